@@ -1,0 +1,419 @@
+"""Host-side schedule of the MFM training step over the CUDA primitive set.
+
+The reference runs ``MFM.forward`` (mfm_model.py:522-555) as ~20 000 tiny
+torch ops per step and lets autograd replay them.  Here the step is a fixed
+schedule of a few dozen hand-written sm_100a kernels (``csrc/``, reached
+through the C ABI in ``include/mfm_b200.h``): every time-parallel contraction
+is hoisted out of the recurrences into large GEMMs over all T*B rows, each
+recurrence (9 LSTM cells, the MFN memory) runs as one kernel with the
+timestep loop inside, and the backward pass is the hand-derived adjoint of the
+same schedule.  This file only decides *which* kernel runs on *which* buffer;
+it does no arithmetic itself and has no CPU path: ``ops`` is the CUDA binding
+(``factorized_b200.cuda_ops.CudaOps``).  Tests may inject another object with
+the same primitive interface to check this schedule against autograd on a
+machine without a GPU.
+
+Buffer naming: ``[T*B, n]`` matrices are time-major row blocks (row t*B+b);
+state histories have T+1 blocks with block 0 the zero initial state.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
+
+# dropout sites (index mixed into the counter-based RNG seed)
+SITE_ATT1, SITE_ATT2, SITE_G1, SITE_G2, SITE_FY, SITE_FL, SITE_FA, SITE_FV, SITE_Y = range(1, 10)
+
+TAGS = "lav"
+
+
+class Dims:
+    """Sizes read from the reference's six config dicts (mfm_model.py:472-489,96-114)."""
+
+    def __init__(self, configs, T: int, B: int, head: str = "l1"):
+        config, nn1, nn2, g1, g2, out = configs
+        if config.get("windowsize", 2) != 2:
+            raise ValueError("windowsize must be 2: MFN concatenates exactly (c_{t-1}, c_t) (mfm_model.py:171-173)")
+        self.T, self.B = int(T), int(B)
+        self.d = [int(v) for v in config["input_dims"]]
+        self.D = sum(self.d)
+        self.off = [0, self.d[0], self.d[0] + self.d[1]]
+        self.hm = [int(v) for v in config["h_dims"]]
+        self.H = sum(self.hm)
+        self.hoff = [0, self.hm[0], self.hm[0] + self.hm[1]]
+        self.z = [int(config["zl_size"]), int(config["za_size"]), int(config["zv_size"])]
+        self.zy = int(config["zy_size"])
+        self.f = [int(config["fl_size"]), int(config["fa_size"]), int(config["fv_size"])]
+        self.fy = int(config["fy_size"])
+        self.hd = [self.fy + f for f in self.f]
+        self.mem = int(config["memsize"])
+        self.a1, self.a2 = int(nn1["shapes"]), int(nn2["shapes"])
+        self.g1, self.g2 = int(g1["shapes"]), int(g2["shapes"])
+        self.out = int(config["output_dim"])
+        self.p_att1, self.p_att2 = float(nn1["drop"]), float(nn2["drop"])
+        self.p_g1, self.p_g2 = float(g1["drop"]), float(g2["drop"])
+        self.p_f = [float(config["zl_to_fl_dropout"]), float(config["za_to_fa_dropout"]), float(config["zv_to_fv_dropout"])]
+        self.p_fy = float(config["zy_to_fy_dropout"])
+        self.p_y = float(config["fy_to_y_dropout"])
+        self.lda = [float(config.get("lda_xl", 1.0)), float(config.get("lda_xa", 1.0)), float(config.get("lda_xv", 1.0))]
+        self.lda_mmd = float(config.get("lda_mmd", 1.0))
+        if head not in ("l1", "ce"):
+            raise ValueError(head)
+        self.head = head
+
+
+class Engine:
+    """One (T, B) instance of the schedule with its HBM workspace."""
+
+    def __init__(self, configs, T: int, B: int, device, ops, head: str = "l1"):
+        self.dm = Dims(configs, T, B, head)
+        self.device = torch.device(device)
+        self.ops = ops
+        self.ws: Dict[str, torch.Tensor] = {}
+        self.train = False
+        self.loss_buf = torch.zeros(16, dtype=torch.float32, device=self.device)
+        # loss_buf: 0 disc, 1..3 mse_l/a/v, 4..7 mmd per latent (unweighted), 8 total (weighted)
+
+    # -- workspace -----------------------------------------------------------------
+    def buf(self, name: str, *shape) -> torch.Tensor:
+        t = self.ws.get(name)
+        if t is None:
+            t = torch.zeros(*shape, dtype=torch.float32, device=self.device)
+            self.ws[name] = t
+        return t
+
+    def workspace_bytes(self) -> int:
+        return sum(t.numel() * 4 for t in self.ws.values())
+
+    # -- forward -------------------------------------------------------------------
+    def forward(self, P: Dict[str, torch.Tensor], x: torch.Tensor, noise: Sequence[torch.Tensor],
+                train: bool = False, rng: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """MFM.forward (mfm_model.py:522-555).  ``x`` is [T,B,D] contiguous fp32,
+        ``noise`` the four Gaussian samples of loss_MMD (order zl,za,zv,zy).
+        Returns views into the workspace: x_l_hat,x_a_hat,x_v_hat [T*B,d], y_hat
+        [B,out], latents; MMD parts go to loss_buf[4:8]."""
+        dm, ops, buf = self.dm, self.ops, self.buf
+        T, B, H, mem = dm.T, dm.B, dm.H, dm.mem
+        TB = T * B
+        if tuple(x.shape) != (T, B, dm.D) or not x.is_contiguous() or x.dtype != torch.float32:
+            raise ValueError("x must be contiguous fp32 [T=%d,B=%d,D=%d], got %s" % (T, B, dm.D, tuple(x.shape)))
+        self.train = bool(train)
+        self.x = x
+        self.noise = list(noise)
+        self.rng = rng
+        X2 = x.view(TB, dm.D)
+        xs = [X2[:, dm.off[m]:dm.off[m] + dm.d[m]] for m in range(3)]
+        self.xs = xs
+        drop = (lambda p, site: (p, site) if (train and p > 0.0) else None)
+
+        # (1) hoisted input projections  G_x = X W_ih^T + b_ih + b_hh   (encoders :56, MFN :167-169)
+        for m, tag in enumerate(TAGS):
+            e, n = "encoder_%s.lstm" % tag, "mfn_encoder.lstm_%s" % tag
+            ops.gemm("nt", xs[m], P[e + ".weight_ih"], buf("GxE%d" % m, TB, 4 * dm.z[m]),
+                     bias=P[e + ".bias_ih"], bias2=P[e + ".bias_hh"])
+            ops.gemm("nt", xs[m], P[n + ".weight_ih"], buf("GxN%d" % m, TB, 4 * dm.hm[m]),
+                     bias=P[n + ".bias_ih"], bias2=P[n + ".bias_hh"])
+
+        # (2) six recurrences in one launch: h W_hh^T + G_x[t] -> gates -> (h, c)
+        Hall = buf("Hall", (T + 1) * B, H)
+        Call = buf("Call", (T + 1) * B, H)
+        cells = []
+        for m, tag in enumerate(TAGS):
+            cells.append(dict(T=T, B=B, h=dm.z[m], gx=self.ws["GxE%d" % m], gx_steps=T, bias_rest=None,
+                              W=P["encoder_%s.lstm.weight_hh" % tag],
+                              hs=buf("hsE%d" % m, (T + 1) * B, dm.z[m]), cs=buf("csE%d" % m, (T + 1) * B, dm.z[m]),
+                              gates=buf("gatesE%d" % m, TB, 4 * dm.z[m])))
+        for m, tag in enumerate(TAGS):
+            o = dm.hoff[m]
+            cells.append(dict(T=T, B=B, h=dm.hm[m], gx=self.ws["GxN%d" % m], gx_steps=T, bias_rest=None,
+                              W=P["mfn_encoder.lstm_%s.weight_hh" % tag],
+                              hs=Hall[:, o:o + dm.hm[m]], cs=Call[:, o:o + dm.hm[m]],
+                              gates=buf("gatesN%d" % m, TB, 4 * dm.hm[m])))
+        ops.lstm_fwd(cells)
+
+        # (3) z_m = fc1(h_T), no activation (:60-61)
+        Z = []
+        for m, tag in enumerate(TAGS):
+            zt = buf("Z%d" % m, B, dm.z[m])
+            ops.gemm("nt", self.ws["hsE%d" % m][TB:], P["encoder_%s.fc1.weight" % tag], zt,
+                     bias=P["encoder_%s.fc1.bias" % tag])
+            Z.append(zt)
+
+        # (4) MFN attention for all T at once (:171-176); only gamma*_fc1's memory columns are sequential
+        pre = "mfn_encoder."
+        cStar = buf("cStar", TB, 2 * H)
+        ops.copy2d(Call[:TB], cStar[:, :H])
+        ops.copy2d(Call[B:], cStar[:, H:])
+        H1 = buf("H1", TB, dm.a1)
+        ops.gemm("nt", cStar, P[pre + "att1_fc1.weight"], H1, bias=P[pre + "att1_fc1.bias"], act=ACT_RELU,
+                 drop=drop(dm.p_att1, SITE_ATT1), rng=rng)
+        Att = buf("Att", TB, 2 * H)
+        ops.gemm("nt", H1, P[pre + "att1_fc2.weight"], Att, bias=P[pre + "att1_fc2.bias"])
+        Attended = buf("Attended", TB, 2 * H)
+        ops.softmax_gate_fwd(Att, cStar, Attended)
+        H2 = buf("H2", TB, dm.a2)
+        ops.gemm("nt", Attended, P[pre + "att2_fc1.weight"], H2, bias=P[pre + "att2_fc1.bias"], act=ACT_RELU,
+                 drop=drop(dm.p_att2, SITE_ATT2), rng=rng)
+        cHat = buf("cHat", TB, mem)
+        ops.gemm("nt", H2, P[pre + "att2_fc2.weight"], cHat, bias=P[pre + "att2_fc2.bias"], act=ACT_TANH)
+        G1pre = buf("G1pre", TB, dm.g1)
+        G2pre = buf("G2pre", TB, dm.g2)
+        Wg1, Wg2 = P[pre + "gamma1_fc1.weight"], P[pre + "gamma2_fc1.weight"]
+        ops.gemm("nt", Attended, Wg1[:, :2 * H], G1pre, bias=P[pre + "gamma1_fc1.bias"])
+        ops.gemm("nt", Attended, Wg2[:, :2 * H], G2pre, bias=P[pre + "gamma2_fc1.bias"])
+
+        # (5) the memory recurrence (:177-180), T steps in one kernel
+        mems = buf("mems", (T + 1) * B, mem)
+        ops.mfn_mem_fwd(dict(
+            T=T, B=B, mem=mem, g1=dm.g1, g2=dm.g2, G1pre=G1pre, G2pre=G2pre, cHat=cHat,
+            W1m=Wg1[:, 2 * H:], W2m=Wg2[:, 2 * H:],
+            W12=P[pre + "gamma1_fc2.weight"], b12=P[pre + "gamma1_fc2.bias"],
+            W22=P[pre + "gamma2_fc2.weight"], b22=P[pre + "gamma2_fc2.bias"],
+            mems=mems, U1=buf("U1", TB, dm.g1), U2=buf("U2", TB, dm.g2),
+            Gam1=buf("Gam1", TB, mem), Gam2=buf("Gam2", TB, mem),
+            drop1=drop(dm.p_g1, SITE_G1), drop2=drop(dm.p_g2, SITE_G2), rng=rng))
+
+        # (6) zy = last_to_zy_fc1(cat(h_T^l, h_T^a, h_T^v, mem_T))  (:194-198, :535)
+        ZY = buf("ZY", B, dm.zy)
+        Wzy = P["last_to_zy_fc1.weight"]
+        ops.gemm("nt", Hall[TB:], Wzy[:, :H], ZY, bias=P["last_to_zy_fc1.bias"])
+        ops.gemm("nt", mems[TB:], Wzy[:, H:], ZY, accumulate=True)
+
+        # (7) MMD of each latent against its Gaussian sample (:25-34, :536)
+        lat = Z + [ZY]
+        for k in range(4):
+            ops.mmd_fwd(lat[k], self.noise[k], self.loss_buf[4 + k:5 + k])
+
+        # (8) factor MLPs (:539-542) written straight into the decoder inputs cat(fy, f_m) (:544-546)
+        FY = buf("FY", B, dm.fy)
+        F1y = buf("F1y", B, dm.fy)
+        ops.gemm("nt", ZY, P["zy_to_fy_fc1.weight"], F1y, bias=P["zy_to_fy_fc1.bias"], act=ACT_RELU,
+                 drop=drop(dm.p_fy, SITE_FY), rng=rng)
+        ops.gemm("nt", F1y, P["zy_to_fy_fc2.weight"], FY, bias=P["zy_to_fy_fc2.bias"], act=ACT_RELU)
+        EMB = []
+        for m, tag in enumerate(TAGS):
+            nm = "z%s_to_f%s" % (tag, tag)
+            F1 = buf("F1_%d" % m, B, dm.f[m])
+            emb = buf("EMB%d" % m, B, dm.hd[m])
+            ops.gemm("nt", Z[m], P[nm + "_fc1.weight"], F1, bias=P[nm + "_fc1.bias"], act=ACT_RELU,
+                     drop=drop(dm.p_f[m], SITE_FL + m), rng=rng)
+            ops.gemm("nt", F1, P[nm + "_fc2.weight"], emb[:, dm.fy:], bias=P[nm + "_fc2.bias"], act=ACT_RELU)
+            ops.copy2d(FY, emb[:, :dm.fy])
+            EMB.append(emb)
+
+        # (9) decoders (:72-91): step 0 eats the embedding; for t>=1 the input IS h_{t-1}, so the two
+        #     gate GEMMs collapse into one with W_ih + W_hh
+        cells = []
+        for m, tag in enumerate(TAGS):
+            d_ = "decoder_%s.lstm" % tag
+            hd = dm.hd[m]
+            G0 = buf("G0_%d" % m, B, 4 * hd)
+            ops.gemm("nt", EMB[m], P[d_ + ".weight_ih"], G0, bias=P[d_ + ".bias_ih"], bias2=P[d_ + ".bias_hh"])
+            Wm = buf("Wm%d" % m, 4 * hd, hd)
+            ops.add(P[d_ + ".weight_ih"], P[d_ + ".weight_hh"], Wm)
+            bs = buf("bsumD%d" % m, 1, 4 * hd)
+            ops.add(P[d_ + ".bias_ih"].view(1, -1), P[d_ + ".bias_hh"].view(1, -1), bs)
+            cells.append(dict(T=T, B=B, h=hd, gx=G0, gx_steps=1, bias_rest=bs.view(-1), W=Wm,
+                              hs=buf("hsD%d" % m, (T + 1) * B, hd), cs=buf("csD%d" % m, (T + 1) * B, hd),
+                              gates=buf("gatesD%d" % m, TB, 4 * hd)))
+        ops.lstm_fwd(cells)
+
+        # (10) reconstructions  x_hat = fc1(all hiddens)  (:88-90)
+        Xhat = []
+        for m, tag in enumerate(TAGS):
+            xh = buf("Xhat%d" % m, TB, dm.d[m])
+            ops.gemm("nt", self.ws["hsD%d" % m][B:], P["decoder_%s.fc1.weight" % tag], xh,
+                     bias=P["decoder_%s.fc1.bias" % tag])
+            Xhat.append(xh)
+
+        # (11) discriminative head (:552)
+        Y1 = buf("Y1", B, dm.fy)
+        Yhat = buf("Yhat", B, dm.out)
+        ops.gemm("nt", FY, P["fy_to_y_fc1.weight"], Y1, bias=P["fy_to_y_fc1.bias"], act=ACT_RELU,
+                 drop=drop(dm.p_y, SITE_Y), rng=rng)
+        ops.gemm("nt", Y1, P["fy_to_y_fc2.weight"], Yhat, bias=P["fy_to_y_fc2.bias"])
+        return dict(x_l_hat=Xhat[0], x_a_hat=Xhat[1], x_v_hat=Xhat[2], y_hat=Yhat,
+                    zl=Z[0], za=Z[1], zv=Z[2], zy=ZY, fy=FY, mmd_parts=self.loss_buf[4:8])
+
+    # -- losses (the fused training path) ------------------------------------------
+    def losses(self, y: torch.Tensor):
+        """Loss terms of mfm_mosi.py:432-439 (L1) / mfm_mosi_acc.py:441-451 (CE) and
+        their gradients w.r.t. the forward outputs, written to dXhat*/dYhat.
+        loss_buf[0..3] = disc, mse_l, mse_a, mse_v (means); loss_buf[8] = total."""
+        dm, ops, buf = self.dm, self.ops, self.buf
+        TB = dm.T * dm.B
+        ops.zero(self.loss_buf[0:4])
+        dX = []
+        for m in range(3):
+            n = float(TB * dm.d[m])
+            dxh = buf("dXhat%d" % m, TB, dm.d[m])
+            ops.mse_fwd_bwd(self.ws["Xhat%d" % m], self.xs[m], 1.0 / n, 2.0 * dm.lda[m] / n,
+                            self.loss_buf[1 + m:2 + m], dxh)
+            dX.append(dxh)
+        dY = buf("dYhat", dm.B, dm.out)
+        if dm.head == "l1":
+            y2 = y.view(dm.B, dm.out)
+            ops.l1_fwd_bwd(self.ws["Yhat"], y2, 1.0 / (dm.B * dm.out), self.loss_buf[0:1], dY)
+        else:
+            ops.ce_fwd_bwd(self.ws["Yhat"], y, 1.0 / dm.B, self.loss_buf[0:1], dY)
+        ops.loss_total(self.loss_buf, dm.lda[0], dm.lda[1], dm.lda[2], dm.lda_mmd)
+        return dX, dY
+
+    # -- backward ------------------------------------------------------------------
+    def backward(self, P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], dXhat: Sequence[torch.Tensor],
+                 dYhat: torch.Tensor, mmd_scale: float, zero_grads: bool = True):
+        """Adjoint of ``forward``.  ``dXhat[m]`` [T*B,d_m] and ``dYhat`` [B,out] are
+        d(loss)/d(output); ``mmd_scale`` = d(loss)/d(mmd).  Parameter gradients are
+        ACCUMULATED into ``G`` (same names as ``P``)."""
+        dm, ops, buf, ws = self.dm, self.ops, self.buf, self.ws
+        T, B, H, mem = dm.T, dm.B, dm.H, dm.mem
+        TB = T * B
+        relu_scale = (lambda p: 1.0 / (1.0 - p) if (self.train and p > 0.0) else 1.0)
+
+        def wgrad(dY, A, name):            # dW[N,K] += dY[M,N]^T A[M,K]
+            ops.gemm("tn", dY, A, G[name], accumulate=True)
+
+        def bgrad(dY, name):
+            ops.colsum(dY, G[name])
+
+        def lin_bwd(dY, A, name, dA=None, accumulate=False, mask=None, mask_scale=1.0):
+            """y = A W^T + b: dW, db and (optionally) dA = (dY W) [* relu/dropout mask of A]."""
+            wgrad(dY, A, name + ".weight")
+            bgrad(dY, name + ".bias")
+            if dA is not None:
+                ops.gemm("nn", dY, P[name + ".weight"], dA, accumulate=accumulate, mask=mask, mask_scale=mask_scale)
+
+        # (11') discriminative head
+        dY1 = buf("dY1", B, dm.fy)
+        lin_bwd(dYhat, ws["Y1"], "fy_to_y_fc2", dY1, mask=ws["Y1"], mask_scale=relu_scale(dm.p_y))
+        dFY = buf("dFY", B, dm.fy)
+        lin_bwd(dY1, ws["FY"], "fy_to_y_fc1", dFY)
+
+        # (10') + (9') decoders
+        cells = []
+        for m, tag in enumerate(TAGS):
+            hd = dm.hd[m]
+            dHd = buf("dHd%d" % m, TB, hd)
+            lin_bwd(dXhat[m], ws["hsD%d" % m][B:], "decoder_%s.fc1" % tag, dHd)
+            cells.append(dict(T=T, B=B, h=hd, gates=ws["gatesD%d" % m], cs=ws["csD%d" % m], W=ws["Wm%d" % m],
+                              dh_all=dHd, dh_last=None, dc_ext=None, dG=buf("dGD%d" % m, TB, 4 * hd)))
+        ops.lstm_bwd(cells)
+        dEMB = []
+        for m, tag in enumerate(TAGS):
+            d_ = "decoder_%s.lstm" % tag
+            dG = ws["dGD%d" % m]
+            hprev = ws["hsD%d" % m][:TB]                    # h_{t-1}; block 0 is the zero state
+            wgrad(dG, hprev, d_ + ".weight_hh")
+            wgrad(dG, hprev, d_ + ".weight_ih")              # input == h_{t-1} for t >= 1 (:85)
+            wgrad(dG[:B], ws["EMB%d" % m], d_ + ".weight_ih")  # step 0 input is the embedding (:83)
+            bgrad(dG, d_ + ".bias_ih")
+            bgrad(dG, d_ + ".bias_hh")
+            de = buf("dEMB%d" % m, B, dm.hd[m])
+            ops.gemm("nn", dG[:B], P[d_ + ".weight_ih"], de)
+            ops.copy2d(de[:, :dm.fy], dFY, accumulate=True)
+            dEMB.append(de)
+
+        # (8') factor MLPs;  dZ[k] receives the decoder-side gradient of each latent
+        dZ = [buf("dZ%d" % m, B, dm.z[m]) for m in range(3)]
+        dZY = buf("dZY", B, dm.zy)
+
+        def mlp2_bwd(df, f, F1, zin, nm, p, dz):
+            dpre = buf("dpre_" + nm, f.shape[0], f.shape[1])
+            ops.relu_bwd(df, f, dpre)
+            dF1 = buf("dF1_" + nm, F1.shape[0], F1.shape[1])
+            lin_bwd(dpre, F1, nm + "_fc2", dF1, mask=F1, mask_scale=relu_scale(p))
+            lin_bwd(dF1, zin, nm + "_fc1", dz)
+
+        mlp2_bwd(dFY, ws["FY"], ws["F1y"], ws["ZY"], "zy_to_fy", dm.p_fy, dZY)
+        for m, tag in enumerate(TAGS):
+            mlp2_bwd(dEMB[m][:, dm.fy:], ws["EMB%d" % m][:, dm.fy:], ws["F1_%d" % m], ws["Z%d" % m],
+                     "z%s_to_f%s" % (tag, tag), dm.p_f[m], dZ[m])
+
+        # (7') MMD: gradient flows through K(z,z) and K(g,z) only
+        lat = [ws["Z0"], ws["Z1"], ws["Z2"], ws["ZY"]]
+        dlat = dZ + [dZY]
+        for k in range(4):
+            ops.mmd_bwd(lat[k], self.noise[k], mmd_scale, dlat[k])
+
+        # (6') last_to_zy_fc1 over cat(h_T, mem_T)
+        Wzy = P["last_to_zy_fc1.weight"]
+        Gzy = G["last_to_zy_fc1.weight"]
+        Hall, Call, mems = ws["Hall"], ws["Call"], ws["mems"]
+        ops.gemm("tn", dZY, Hall[TB:], Gzy[:, :H], accumulate=True)
+        ops.gemm("tn", dZY, mems[TB:], Gzy[:, H:], accumulate=True)
+        bgrad(dZY, "last_to_zy_fc1.bias")
+        dHlast = buf("dHlast", B, H)
+        dmemT = buf("dmemT", B, mem)
+        ops.gemm("nn", dZY, Wzy[:, :H], dHlast)
+        ops.gemm("nn", dZY, Wzy[:, H:], dmemT)
+
+        # (5') memory recurrence, reversed
+        pre = "mfn_encoder."
+        Wg1, Wg2 = P[pre + "gamma1_fc1.weight"], P[pre + "gamma2_fc1.weight"]
+        dU1, dU2 = buf("dU1", TB, dm.g1), buf("dU2", TB, dm.g2)
+        dP1, dP2 = buf("dP1", TB, mem), buf("dP2", TB, mem)
+        dPc = buf("dPc", TB, mem)
+        ops.mfn_mem_bwd(dict(
+            T=T, B=B, mem=mem, g1=dm.g1, g2=dm.g2, cHat=ws["cHat"], mems=mems, U1=ws["U1"], U2=ws["U2"],
+            Gam1=ws["Gam1"], Gam2=ws["Gam2"], W1m=Wg1[:, 2 * H:], W2m=Wg2[:, 2 * H:],
+            W12=P[pre + "gamma1_fc2.weight"], W22=P[pre + "gamma2_fc2.weight"],
+            scale1=relu_scale(dm.p_g1), scale2=relu_scale(dm.p_g2),
+            dmem_last=dmemT, dU1=dU1, dU2=dU2, dP1=dP1, dP2=dP2, dPc=dPc))
+        wgrad(dP1, ws["U1"], pre + "gamma1_fc2.weight")
+        bgrad(dP1, pre + "gamma1_fc2.bias")
+        wgrad(dP2, ws["U2"], pre + "gamma2_fc2.weight")
+        bgrad(dP2, pre + "gamma2_fc2.bias")
+        Attended, cStar, Att = ws["Attended"], ws["cStar"], ws["Att"]
+        dAtt = buf("dAttended", TB, 2 * H)
+        for (dU, Wg, nm, first) in ((dU1, Wg1, "gamma1_fc1", True), (dU2, Wg2, "gamma2_fc1", False)):
+            Gw = G[pre + nm + ".weight"]
+            ops.gemm("tn", dU, Attended, Gw[:, :2 * H], accumulate=True)
+            ops.gemm("tn", dU, mems[:TB], Gw[:, 2 * H:], accumulate=True)
+            bgrad(dU, pre + nm + ".bias")
+            ops.gemm("nn", dU, Wg[:, :2 * H], dAtt, accumulate=not first)
+
+        # (4') attention MLPs, time-parallel
+        dH2 = buf("dH2", TB, dm.a2)
+        lin_bwd(dPc, ws["H2"], pre + "att2_fc2", dH2, mask=ws["H2"], mask_scale=relu_scale(dm.p_att2))
+        lin_bwd(dH2, Attended, pre + "att2_fc1", dAtt, accumulate=True)
+        dL = buf("dL", TB, 2 * H)
+        dcStar = buf("dcStar", TB, 2 * H)
+        ops.softmax_gate_bwd(dAtt, Att, cStar, dL, dcStar)
+        dH1 = buf("dH1", TB, dm.a1)
+        lin_bwd(dL, ws["H1"], pre + "att1_fc2", dH1, mask=ws["H1"], mask_scale=relu_scale(dm.p_att1))
+        lin_bwd(dH1, cStar, pre + "att1_fc1", dcStar, accumulate=True)
+        # c_t enters cStar twice: as "new" at step t and as "prev" at step t+1
+        dCext = buf("dCext", TB, H)                          # row block t = grad wrt c of cell step t
+        ops.copy2d(dcStar[:, H:], dCext)
+        if T > 1:
+            ops.copy2d(dcStar[B:, :H], dCext[:TB - B], accumulate=True)
+
+        # (3') encoder heads, then (2') the six recurrences reversed
+        cells = []
+        for m, tag in enumerate(TAGS):
+            dhl = buf("dhE%d" % m, B, dm.z[m])
+            lin_bwd(dZ[m], ws["hsE%d" % m][TB:], "encoder_%s.fc1" % tag, dhl)
+            cells.append(dict(T=T, B=B, h=dm.z[m], gates=ws["gatesE%d" % m], cs=ws["csE%d" % m],
+                              W=P["encoder_%s.lstm.weight_hh" % tag], dh_all=None, dh_last=dhl, dc_ext=None,
+                              dG=buf("dGE%d" % m, TB, 4 * dm.z[m])))
+        for m, tag in enumerate(TAGS):
+            o = dm.hoff[m]
+            cells.append(dict(T=T, B=B, h=dm.hm[m], gates=ws["gatesN%d" % m], cs=Call[:, o:o + dm.hm[m]],
+                              W=P["mfn_encoder.lstm_%s.weight_hh" % tag], dh_all=None,
+                              dh_last=dHlast[:, o:o + dm.hm[m]], dc_ext=dCext[:, o:o + dm.hm[m]],
+                              dG=buf("dGN%d" % m, TB, 4 * dm.hm[m])))
+        ops.lstm_bwd(cells)
+
+        # (1') weight gradients of the 6 input-side cells, all T at once
+        for m, tag in enumerate(TAGS):
+            for (nm, dGn, hs) in (("encoder_%s.lstm" % tag, "dGE%d" % m, ws["hsE%d" % m][:TB]),
+                                  ("mfn_encoder.lstm_%s" % tag, "dGN%d" % m,
+                                   Hall[:TB, dm.hoff[m]:dm.hoff[m] + dm.hm[m]])):
+                dG = ws[dGn]
+                wgrad(dG, self.xs[m], nm + ".weight_ih")
+                wgrad(dG, hs, nm + ".weight_hh")
+                bgrad(dG, nm + ".bias_ih")
+                bgrad(dG, nm + ".bias_hh")

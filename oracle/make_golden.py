@@ -1,0 +1,171 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference -- TEST INFRASTRUCTURE.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU
+box):  ``python oracle/make_golden.py``
+
+It imports ``/root/reference/mfm_model.py`` under Python 3 with
+``torch.Tensor.cuda`` neutralised (the reference hard-codes ``.cuda()``,
+mfm_model.py:29,51-52,76-77,147-153; there is no GPU here), runs the
+reference ``MFM`` through the py3 restatement of the 25-line train step
+(mfm_mosi.py:427-441; CE head mfm_mosi_acc.py:441-452), and stores inputs,
+outputs, losses, gradients and post-Adam parameters.  It also checks the
+oracle restatement (oracle/mfm_oracle.py) against the live reference and
+refuses to write fixtures if they disagree.
+"""
+import os
+import sys
+
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+from oracle import mfm_oracle as O
+
+REF = "/root/reference"
+
+
+def import_reference():
+    if not os.path.isdir(REF):
+        raise SystemExit("reference tree not present; golden vectors can only be made in the build container")
+    sys.path.insert(0, REF)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    import mfm_model as ref  # noqa
+    return ref
+
+
+def run_reference(ref, configs, seed, T, n, head, data_seed, noise_seed):
+    torch.manual_seed(seed)
+    model = ref.MFM(*configs).eval()              # eval(): the 9 dropouts become identity
+    params0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    x, y = O.synthetic_batch(configs, T, n, data_seed, head)
+    lat = {}
+    hooks = dict(zl=model.encoder_l.fc1, za=model.encoder_a.fc1, zv=model.encoder_v.fc1, zy=model.last_to_zy_fc1)
+    for k, m in hooks.items():
+        m.register_forward_hook(lambda mod, i, o, k=k: lat.__setitem__(k, o.detach().clone()))
+    opt = torch.optim.Adam(model.parameters())     # mfm_mosi.py:403
+    opt.zero_grad()
+    torch.manual_seed(noise_seed)                   # fixes loss_MMD's four randn draws
+    decoded, mmd, missing = model.forward(x)
+    x_l_hat, x_a_hat, x_v_hat, y_hat = decoded
+    c = configs[0]
+    d_l, d_a, d_v = c["input_dims"]
+    F = torch.nn.functional
+    yh = y_hat.squeeze(1) if y_hat.shape[1] == 1 else y_hat
+    mse = [F.mse_loss(x_l_hat, x[:, :, :d_l]), F.mse_loss(x_a_hat, x[:, :, d_l:d_l + d_a]),
+           F.mse_loss(x_v_hat, x[:, :, d_l + d_a:])]
+    gen = c["lda_xl"] * mse[0] + c["lda_xa"] * mse[1] + c["lda_xv"] * mse[2]
+    disc = F.l1_loss(yh, y) if head == "l1" else F.cross_entropy(yh, y.long())
+    mmd_w = c["lda_mmd"] * mmd
+    loss = disc + gen + mmd_w + missing
+    loss.backward()
+    grads = {k: (None if p.grad is None else p.grad.detach().clone()) for k, p in model.named_parameters()}
+    opt.step()
+    params1 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    return dict(params0=params0, params1=params1, grads=grads, x=x, y=y, lat=lat,
+                x_l_hat=x_l_hat.detach(), x_a_hat=x_a_hat.detach(), x_v_hat=x_v_hat.detach(), y_hat=y_hat.detach(),
+                losses=dict(total=float(loss), disc=float(disc), gen=float(gen), mmd=float(mmd_w),
+                            mse_l=float(mse[0]), mse_a=float(mse[1]), mse_v=float(mse[2])))
+
+
+def check_oracle(r, configs, seed, n, head, noise_seed, tag):
+    """oracle restatement vs live reference; returns the max abs diff seen."""
+    P = O.init_params(configs, seed)
+    worst = 0.0
+    for k, v in r["params0"].items():
+        dd = float((P[k] - v).abs().max())
+        worst = max(worst, dd)
+    assert worst == 0.0, "init_params does not reproduce the reference's init (max diff %g)" % worst
+    noise = O.draw_mmd_noise(configs, n, noise_seed)
+    newP, losses, G, out = O.train_step(P, r["x"], r["y"], configs, noise, {}, head=head)
+    def rel(a, b):
+        return float((a - b).norm() / (b.norm() + 1e-30))
+    errs = {}
+    for k in ("zl", "za", "zv", "zy"):
+        errs[k] = rel(out[k], r["lat"][k])
+    for k in ("x_l_hat", "x_a_hat", "x_v_hat", "y_hat"):
+        errs[k] = rel(out[k], r[k])
+    for k, v in r["losses"].items():
+        errs["loss." + k] = abs(losses[k] - v) / (abs(v) + 1e-30)
+    gmax = 0.0
+    for k, g in r["grads"].items():
+        if g is None:
+            assert G[k] is None, k
+            continue
+        gmax = max(gmax, rel(G[k], g))
+    errs["grads(max rel-L2)"] = gmax
+    pmax = max(rel(newP[k], v) for k, v in r["params1"].items())
+    errs["params1(max rel-L2)"] = pmax
+    w = max(errs.values())
+    print("[%s] oracle vs live reference: worst rel err %.3g" % (tag, w))
+    for k, v in errs.items():
+        if v > 1e-6:
+            print("    %-24s %.3g" % (k, v))
+    assert w < 2e-5, "oracle restatement disagrees with the reference"
+    return w
+
+
+def main():
+    ref = import_reference()
+    outdir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(outdir, exist_ok=True)
+
+    # ---- (1) tiny awkward config, everything stored, L1 head and CE head -------------
+    for head, od in (("l1", 1), ("ce", 3), ("l1", 4)):
+        configs = O.tiny_configs(output_dim=od)
+        seed, T, n, data_seed, noise_seed = 321, 4, 6, 11, 77
+        r = run_reference(ref, configs, seed, T, n, head, data_seed, noise_seed)
+        check_oracle(r, configs, seed, n, head, noise_seed, "tiny/%s/out%d" % (head, od))
+        blob = dict(meta=np.array([seed, T, n, data_seed, noise_seed, od]), x=r["x"].numpy(), y=r["y"].numpy())
+        for k, v in r["params0"].items():
+            blob["p0/" + k] = v.numpy()
+        for k, v in r["params1"].items():
+            blob["p1/" + k] = v.numpy()
+        for k, v in r["grads"].items():
+            if v is not None:
+                blob["g/" + k] = v.numpy()
+        for k, v in r["lat"].items():
+            blob["lat/" + k] = v.numpy()
+        for k in ("x_l_hat", "x_a_hat", "x_v_hat", "y_hat"):
+            blob[k] = r[k].numpy()
+        for k, v in r["losses"].items():
+            blob["loss/" + k] = np.float64(v)
+        np.savez_compressed(os.path.join(outdir, "tiny_%s_out%d.npz" % (head, od)), **blob)
+
+    # ---- (2) BASELINE configs[0]: MOSI shapes, best_acc dims, B=32, T=20 --------------
+    # parameters are regenerated from the seed (2.9 MB otherwise); the fixture keeps
+    # outputs, latents, losses, per-parameter gradient norms and a few raw slices.
+    configs = O.best_acc_configs(dropout=False)
+    seed, T, n, data_seed, noise_seed = 123, 20, 32, 1234, 999
+    r = run_reference(ref, configs, seed, T, n, "l1", data_seed, noise_seed)
+    check_oracle(r, configs, seed, n, "l1", noise_seed, "mosi_b32")
+    blob = dict(meta=np.array([seed, T, n, data_seed, noise_seed, 1]))
+    for k, v in r["lat"].items():
+        blob["lat/" + k] = v.numpy()
+    blob["y_hat"] = r["y_hat"].numpy()
+    blob["x_a_hat"] = r["x_a_hat"].numpy()
+    blob["x_l_hat_t0"] = r["x_l_hat"][0].numpy()
+    blob["x_l_hat_tlast"] = r["x_l_hat"][-1].numpy()
+    blob["x_v_hat_tlast"] = r["x_v_hat"][-1].numpy()
+    for k, v in r["losses"].items():
+        blob["loss/" + k] = np.float64(v)
+    names = [k for k, v in r["grads"].items() if v is not None]
+    blob["grad_names"] = np.array(names)
+    blob["grad_norms"] = np.array([float(r["grads"][k].double().norm()) for k in names])
+    blob["grad_sums"] = np.array([float(r["grads"][k].double().sum()) for k in names])
+    blob["p0_norms"] = np.array([float(r["params0"][k].double().norm()) for k in names])
+    blob["p1_minus_p0_norms"] = np.array([float((r["params1"][k] - r["params0"][k]).double().norm()) for k in names])
+    blob["g/last_to_zy_fc1.weight"] = r["grads"]["last_to_zy_fc1.weight"].numpy()
+    blob["g/encoder_a.lstm.weight_ih"] = r["grads"]["encoder_a.lstm.weight_ih"].numpy()
+    blob["g/decoder_v.lstm.weight_hh"] = r["grads"]["decoder_v.lstm.weight_hh"].numpy()
+    blob["g/mfn_encoder.gamma1_fc1.bias"] = r["grads"]["mfn_encoder.gamma1_fc1.bias"].numpy()
+    np.savez_compressed(os.path.join(outdir, "mosi_b32.npz"), **blob)
+    for f in sorted(os.listdir(outdir)):
+        print("%-28s %8.1f KB" % (f, os.path.getsize(os.path.join(outdir, f)) / 1024))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,36 @@
+"""Shared helpers for the test-suite (golden loading, comparisons)."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from oracle import mfm_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def golden_params(g, prefix="p0/"):
+    return OrderedDict((k[len(prefix):], torch.from_numpy(v.copy())) for k, v in g.items() if k.startswith(prefix))
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def tiny_case(head="l1", od=1):
+    g = load_golden("tiny_%s_out%d.npz" % (head, od))
+    seed, T, n, data_seed, noise_seed, od_ = [int(v) for v in g["meta"]]
+    configs = O.tiny_configs(output_dim=od)
+    P = golden_params(g)
+    x = torch.from_numpy(g["x"].copy())
+    y = torch.from_numpy(g["y"].copy())
+    noise = O.draw_mmd_noise(configs, n, noise_seed)
+    return g, configs, P, x, y, noise, T, n

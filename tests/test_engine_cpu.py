@@ -1,0 +1,84 @@
+"""Host schedule + hand-derived backward (factorized_b200.engine) checked against
+the golden vectors / oracle autograd with the torch statement of the primitive
+set injected (tests/emu_ops.py).  CPU only: this tests the HOST LOGIC, the CUDA
+kernels are tested against the same statements under -m gpu."""
+from collections import OrderedDict
+
+import pytest
+import torch
+
+from oracle import mfm_oracle as O
+from factorized_b200.engine import Engine
+from emu_ops import EmuOps
+from helpers import rel_l2, tiny_case
+
+
+def run_engine(configs, P, x, y, noise, T, n, head, dtype=torch.float32, train=False, rng=None):
+    P = OrderedDict((k, v.to(dtype)) for k, v in P.items())
+    eng = Engine(configs, T, n, "cpu", EmuOps(), head=head)
+    if dtype != torch.float32:
+        pytest.skip("engine workspace is fp32")
+    out = eng.forward(P, x.contiguous(), noise, train=train, rng=rng)
+    dX, dY = eng.losses(y)
+    G = OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    eng.backward(P, G, dX, dY, eng.dm.lda_mmd)
+    return eng, out, G
+
+
+@pytest.mark.parametrize("head,od", [("l1", 1), ("ce", 3), ("l1", 4)])
+def test_engine_matches_reference_golden(head, od):
+    g, configs, P, x, y, noise, T, n = tiny_case(head, od)
+    eng, out, G = run_engine(configs, P, x, y, noise, T, n, head)
+    tol = 1e-4
+    for k in ("zl", "za", "zv", "zy"):
+        assert rel_l2(out[k], g["lat/" + k]) < tol, k
+    for k, d in (("x_l_hat", 0), ("x_a_hat", 1), ("x_v_hat", 2)):
+        assert rel_l2(out[k].view(T, n, -1), g[k]) < tol, k
+    assert rel_l2(out["y_hat"], g["y_hat"]) < tol
+    lb = eng.loss_buf
+    assert abs(float(lb[0]) - float(g["loss/disc"])) < tol * abs(float(g["loss/disc"])) + 1e-7
+    assert abs(float(lb[1]) - float(g["loss/mse_l"])) < tol * float(g["loss/mse_l"])
+    assert abs(float(lb[8]) - float(g["loss/total"])) < tol * abs(float(g["loss/total"]))
+    bad = []
+    for k in P:
+        if "g/" + k in g:
+            e = rel_l2(G[k], g["g/" + k])
+            if e > 2e-4:
+                bad.append((k, e))
+        else:
+            assert float(G[k].abs().max()) == 0.0
+    assert not bad, bad
+
+
+def test_engine_dropout_masks_replay():
+    """train=True: the counter-based masks the schedule applies are replayed
+    through the oracle (explicit keep-masks) and forward+backward must agree."""
+    from emu_ops import keep_mask
+    from factorized_b200 import engine as E
+    g, configs, P, x, y, noise, T, n = tiny_case("l1", 1)
+    configs = [dict(c) for c in configs]
+    configs[0].update(zy_to_fy_dropout=0.3, zl_to_fl_dropout=0.2, za_to_fa_dropout=0.5, zv_to_fv_dropout=0.4,
+                      fy_to_y_dropout=0.25)
+    for c, p in zip(configs[1:5], (0.5, 0.3, 0.2, 0.4)):
+        c["drop"] = p
+    rng = torch.tensor([12345, 7], dtype=torch.int64)
+    eng, out, G = run_engine(configs, P, x, y, noise, T, n, "l1", train=True, rng=rng)
+    c = configs[0]
+    nn1, nn2, g1, g2 = configs[1:5]
+    masks = dict(
+        att1=keep_mask(rng, E.SITE_ATT1, nn1["drop"], T * n, nn1["shapes"]).view(T, n, -1),
+        att2=keep_mask(rng, E.SITE_ATT2, nn2["drop"], T * n, nn2["shapes"]).view(T, n, -1),
+        gamma1=keep_mask(rng, E.SITE_G1, g1["drop"], T * n, g1["shapes"]).view(T, n, -1),
+        gamma2=keep_mask(rng, E.SITE_G2, g2["drop"], T * n, g2["shapes"]).view(T, n, -1),
+        fy=keep_mask(rng, E.SITE_FY, c["zy_to_fy_dropout"], n, c["fy_size"]),
+        fl=keep_mask(rng, E.SITE_FL, c["zl_to_fl_dropout"], n, c["fl_size"]),
+        fa=keep_mask(rng, E.SITE_FA, c["za_to_fa_dropout"], n, c["fa_size"]),
+        fv=keep_mask(rng, E.SITE_FV, c["zv_to_fv_dropout"], n, c["fv_size"]),
+        y=keep_mask(rng, E.SITE_Y, c["fy_to_y_dropout"], n, c["fy_size"]),
+    )
+    newP, losses, Go, outo = O.train_step(P, x, y, configs, noise, {}, head="l1", train=True, masks=masks)
+    assert rel_l2(out["zy"], outo["zy"]) < 1e-4
+    assert rel_l2(out["y_hat"], outo["y_hat"]) < 1e-4
+    assert abs(float(eng.loss_buf[8]) - losses["total"]) < 1e-4 * abs(losses["total"])
+    bad = [(k, rel_l2(G[k], Go[k])) for k in P if Go[k] is not None and rel_l2(G[k], Go[k]) > 3e-4]
+    assert not bad, bad

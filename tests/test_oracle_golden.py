@@ -1,0 +1,66 @@
+"""The oracle restatement against golden vectors produced by the UNMODIFIED
+reference (oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mfm_oracle as O
+from helpers import load_golden, golden_params, rel_l2, tiny_case
+
+TOL = 2e-5   # fp32 op-order noise between two torch formulations of the same math
+
+
+@pytest.mark.parametrize("head,od", [("l1", 1), ("ce", 3), ("l1", 4)])
+def test_tiny_full_step(head, od):
+    g, configs, P, x, y, noise, T, n = tiny_case(head, od)
+    # init_params reproduces torch.manual_seed(seed); MFM(*configs) bit-exactly
+    P2 = O.init_params(configs, int(g["meta"][0]))
+    assert list(P2) == list(P)
+    for k in P:
+        assert torch.equal(P[k], P2[k]), k
+    newP, losses, G, out = O.train_step(P, x, y, configs, noise, {}, head=head)
+    for k in ("zl", "za", "zv", "zy"):
+        assert rel_l2(out[k], g["lat/" + k]) < TOL, k
+    for k in ("x_l_hat", "x_a_hat", "x_v_hat", "y_hat"):
+        assert rel_l2(out[k], g[k]) < TOL, k
+    for k, v in losses.items():
+        assert abs(v - float(g["loss/" + k])) <= TOL * abs(float(g["loss/" + k])) + 1e-7, k
+    n_grads = 0
+    for k in P:
+        if "g/" + k in g:
+            assert rel_l2(G[k], g["g/" + k]) < TOL, k
+            n_grads += 1
+        else:
+            assert G[k] is None and k in O.UNUSED_PARAMS
+    assert n_grads == 86
+    for k in P:
+        assert rel_l2(newP[k], g["p1/" + k]) < TOL, k
+
+
+def test_mosi_b32_digest():
+    """BASELINE configs[0]: MOSI shapes, best_acc hyper-parameters, B=32, T=20."""
+    g = load_golden("mosi_b32.npz")
+    seed, T, n, data_seed, noise_seed, od = [int(v) for v in g["meta"]]
+    configs = O.best_acc_configs(dropout=False)
+    P = O.init_params(configs, seed)
+    assert sum(v.numel() for v in P.values()) == 717719
+    x, y = O.synthetic_batch(configs, T, n, data_seed)
+    noise = O.draw_mmd_noise(configs, n, noise_seed)
+    newP, losses, G, out = O.train_step(P, x, y, configs, noise, {}, head="l1")
+    for k in ("zl", "za", "zv", "zy"):
+        assert rel_l2(out[k], g["lat/" + k]) < TOL, k
+    assert rel_l2(out["y_hat"], g["y_hat"]) < TOL
+    assert rel_l2(out["x_a_hat"], g["x_a_hat"]) < TOL
+    assert rel_l2(out["x_l_hat"][0], g["x_l_hat_t0"]) < TOL
+    assert rel_l2(out["x_l_hat"][-1], g["x_l_hat_tlast"]) < TOL
+    for k, v in losses.items():
+        assert abs(v - float(g["loss/" + k])) <= TOL * abs(float(g["loss/" + k])), k
+    names = [str(s) for s in g["grad_names"]]
+    assert len(names) == 86
+    norms = np.array([float(G[k].double().norm()) for k in names])
+    assert np.allclose(norms, g["grad_norms"], rtol=1e-4, atol=1e-9)
+    for k in ("last_to_zy_fc1.weight", "encoder_a.lstm.weight_ih", "decoder_v.lstm.weight_hh",
+              "mfn_encoder.gamma1_fc1.bias"):
+        assert rel_l2(G[k], g["g/" + k]) < 1e-4, k
+    dn = np.array([float((newP[k] - P[k]).double().norm()) for k in names])
+    assert np.allclose(dn, g["p1_minus_p0_norms"], rtol=1e-3)
