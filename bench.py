@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- MFM train samples/sec on synthetic CMU-MOSI shapes (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B_per_gpu] [--impl ours|reference]
+
+One "step" = one MFM training step (forward, L1 + sum(lambda*MSE) + lambda*MMD, backward, [all-reduce], Adam) on one
+synthetic batch [T=20, B, D=325] per GPU, best_acc hyper-parameters (mfm_mosi.py:1239-1286), dropout ACTIVE
+(model.train(), like the reference's loop).  Weak scaling: B per GPU is fixed, value = N*B*K / max-over-ranks time.
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GATE_TRAIN_FLOPS_PER_SAMPLE = {20: 40.55e6}     # SURVEY.md section 8d (MOSI T=20, reference formulation, x3 for training)
+T_STEPS, B_DEFAULT = 20, 2048
+
+
+def gate_train_flops_per_sample(configs, T):
+    """3 * sum over the 9 LSTM cells of T*2*4h*(d_in+h), counted on the reference's two-GEMM formulation."""
+    c = configs[0]
+    d, hm = c["input_dims"], c["h_dims"]
+    z = [c["zl_size"], c["za_size"], c["zv_size"]]
+    hd = [c["fy_size"] + f for f in (c["fl_size"], c["fa_size"], c["fv_size"])]
+    f = 0
+    for m in range(3):
+        f += T * 8 * z[m] * (d[m] + z[m]) + T * 8 * hm[m] * (d[m] + hm[m]) + T * 8 * hd[m] * (2 * hd[m])
+    return 3.0 * f
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], bf16=j["bf16_tflops"], bf16_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([s.strip() for s in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx or None, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def cpu_reference_leg(configs, T, B, steps, warmup):
+    """The reference's own CPU path for this workload, timed on this box's host cores: the oracle port of
+    MFM + the 25-line train step (forward, loss, backward, Adam) in torch fp32 on all host threads.
+    (/root/reference cannot travel to the GPU box; the oracle is pinned to it by tests/golden.)"""
+    import torch
+    from oracle import mfm_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    P = O.init_params(configs, 123)
+    x, y = O.synthetic_batch(configs, T, B, 1234)
+    state = {}
+    times = []
+    for i in range(warmup + steps):
+        noise = O.draw_mmd_noise(configs, B, 999 + i)
+        t0 = time.perf_counter()
+        P, losses, _, _ = O.train_step(P, x, y, configs, noise, state, train=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return dict(value=B / sec, unit="samples/s", cores=torch.get_num_threads(), kind="port",
+                sample="%d warm-up + %d timed steps of batch %d (T=%d), oracle port of mfm_mosi.py:427-441, torch fp32, "
+                       "%.2f s/step" % (warmup, steps, B, T, sec)), sec
+
+
+def profile_primitives(trainer, reps=3):
+    """Per-primitive device time inside one eager step (CUDA events on the launching stream), used to name the
+    dominant kernel and its achieved FLOP rate.  Not part of the timed region."""
+    import torch
+    ops = trainer.ops
+    rec = []
+    flops_of = {}
+
+    def wrap(name, fn):
+        def inner(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            fl = 0.0
+            tag = name
+            if name == "gemm":
+                C = a[3]
+                Kd = a[1].shape[1] if a[0] in ("nt", "nn") else a[1].shape[0]
+                fl = 2.0 * C.shape[0] * C.shape[1] * Kd
+                tag = "gemm_" + a[0]
+            elif name in ("lstm_fwd", "lstm_bwd"):
+                fl = sum(2.0 * c["T"] * c["B"] * 4 * c["h"] * c["h"] for c in a[0])
+                tag = name + ("_dec" if (a[0][0].get("gx_steps", 0) == 1 or a[0][0].get("dh_all") is not None) else "_enc_mfn")
+            elif name in ("mfn_mem_fwd", "mfn_mem_bwd"):
+                d = a[0]
+                fl = 2.0 * d["T"] * d["B"] * 2 * (d["mem"] * (d["g1"] + d["g2"]))
+            elif name in ("mmd_fwd", "mmd_bwd"):
+                Bn, dim = a[0].shape
+                fl = (9.0 if name == "mmd_fwd" else 8.0) * Bn * Bn * dim
+            rec.append((tag, e0, e1, fl))
+            return r
+        return inner
+    names = ["gemm", "lstm_fwd", "lstm_bwd", "mfn_mem_fwd", "mfn_mem_bwd", "softmax_gate_fwd", "softmax_gate_bwd", "mmd_fwd",
+             "mmd_bwd", "copy2d", "add", "zero", "colsum", "relu_bwd", "mse_fwd_bwd", "l1_fwd_bwd", "ce_fwd_bwd",
+             "loss_total", "adam", "randn", "rng_tick"]
+    orig = {n: getattr(ops, n) for n in names}
+    agg = {}
+    try:
+        for n in names:
+            setattr(ops, n, wrap(n, orig[n]))
+        for _ in range(reps):
+            rec.clear()
+            trainer._schedule()
+            torch.cuda.synchronize()
+        for tag, e0, e1, fl in rec:
+            a = agg.setdefault(tag, [0.0, 0.0, 0])
+            a[0] += e0.elapsed_time(e1)
+            a[1] += fl
+            a[2] += 1
+    finally:
+        for n in names:
+            try:
+                delattr(ops, n)
+            except AttributeError:
+                pass
+    return agg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=B_DEFAULT, help="batch per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    T, B = T_STEPS, args.batch
+
+    from oracle import mfm_oracle as O          # configs + (rank 0 only) the CPU baseline leg; never on the GPU path
+    configs = O.best_acc_configs(dropout=True)
+    gate_fl = gate_train_flops_per_sample(configs, T)
+    workload = "synthetic CMU-MOSI shapes: text 300 / audio 5 / visual 20, T=20, batch %d per GPU, best_acc hyper-parameters " \
+               "(mfm_mosi.py:1239-1286), fp32, dropout active, L1 head" % B
+    base = dict(metric="MFM train samples/sec (MOSI seq_len=20)", unit="samples/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, higher_is_better=True, scaling="weak", vs_baseline=None, data="synthetic",
+                config=dict(workload=workload, batch_per_gpu=B, global_batch=B * max(world, 1), seq_len=T,
+                            parallelism="dp%d" % max(world, 1),
+                            l2="4 distinct input batches rotate (213 MB) and the step streams a ~1.8 GB workspace, both > 126 MB L2; no explicit flush"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        cb, sec = cpu_reference_leg(configs, T, B, steps, min(args.warmup, 1))
+        line = dict(base, impl="reference", value=cb["value"], ms_per_step=sec * 1e3, dtype="f32", cpu_baseline=cb,
+                    steps=steps, warmup=min(args.warmup, 1),
+                    e2e=dict(value=cb["value"], unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0, n_gpus=args.gpus)
+        print(json.dumps(line))
+        return
+
+    import torch
+    import factorized_b200 as F
+    from factorized_b200.train import MFMTrainer
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(123)
+    model = F.MFM(*configs).to(dev).train()
+    trainer = MFMTrainer(model, T, B, head="l1", use_graph=not args.no_graph, seed=123 + rank)
+    D = trainer.eng.dm.D
+    gen = torch.Generator().manual_seed(1234 + rank)
+    NB = 4
+    xs_host = [torch.randn(T, B, D, generator=gen).pin_memory() for _ in range(NB)]
+    ys_host = [torch.randn(B, generator=gen).pin_memory() for _ in range(NB)]
+    xs_dev = [t.to(dev) for t in xs_host]
+    ys_dev = [t.to(dev) for t in ys_host]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            return float(t)
+        return ms
+
+    # ---- (A) inputs resident in HBM -------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        trainer.x.copy_(xs_dev[i % NB]); trainer.y.copy_(ys_dev[i % NB]); trainer.step_device()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as cs:
+        e0.record()
+        for i in range(args.steps):
+            trainer.x.copy_(xs_dev[i % NB]); trainer.y.copy_(ys_dev[i % NB]); trainer.step_device()
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        # ---- (B) end to end through the public API: pinned host batch -> H2D -> step -> D2H loss, every step ----------
+        loss_host = torch.zeros(args.steps, 16).pin_memory()
+        for i in range(min(args.warmup, 3)):
+            trainer.step(xs_host[i % NB], ys_host[i % NB])
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(args.steps):
+            lb = trainer.step(xs_host[i % NB], ys_host[i % NB])
+            loss_host[i].copy_(lb, non_blocking=True)
+        f1.record()
+        barrier()
+        ms_e2e = max_over_ranks(f0.elapsed_time(f1))
+    clocks = cs.summary()
+    final_loss = float(loss_host[-1][8])
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    pk = peaks()
+
+    # ---- dominant kernel + roofline (rank 0, outside the timed region) --------------------------------------------------
+    roof, kernels = None, None
+    if rank == 0:
+        agg = profile_primitives(trainer)
+        tot = sum(v[0] for v in agg.values())
+        kernels = {k: dict(ms_per_step=round(v[0] / 3, 4), share=round(v[0] / tot, 4), launches=v[2] // 3,
+                           tflops=(round(v[1] / (v[0] * 1e-3) / 1e12, 3) if v[1] else None)) for k, v in
+                   sorted(agg.items(), key=lambda kv: -kv[1][0])}
+        top = next(iter(kernels))
+        tv = agg[top]
+        ach = tv[1] / (tv[0] * 1e-3) / 1e12 if tv[1] else 0.0
+        roof = dict(bound="tensor", kernel=top, achieved=round(ach, 3), peak=pk["bf16"], unit="TFLOP/s",
+                    frac=round(ach / pk["bf16"], 5), traffic=None, peak_source=pk["src"] + " bf16 dense (burst; kernel timed alone)",
+                    step_gate_gemm=dict(achieved=round(gate_fl * value / max(world, 1) / 1e12, 3), peak=pk["bf16_sustained"],
+                                        frac=round(gate_fl * value / max(world, 1) / 1e12 / pk["bf16_sustained"], 5),
+                                        note="whole step per GPU: algorithmic gate-GEMM train FLOPs/sample (%.2f M) x samples/s "
+                                             "over sustained bf16 peak" % (gate_fl / 1e6)))
+    line = dict(base, value=value, ms_per_step=ms / args.steps, dtype="f32",
+                e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=(T * B * D + B) * 4 * world,
+                         d2h_bytes_per_step=64 * world, ms_per_step=ms_e2e / args.steps),
+                gpu_launches=trainer.launches_per_step * args.steps, launches_per_step=trainer.launches_per_step,
+                cuda_graph=not args.no_graph, clocks=clocks, roofline=roof, kernels=kernels, final_loss=final_loss,
+                workspace_mb=round(trainer.eng.workspace_bytes() / 2 ** 20, 1))
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cb, _ = cpu_reference_leg(configs, T, B, 2, 1)
+            except Exception as ex:   # e.g. host OOM on the reference's [B,B,dim] MMD tensors
+                cb, _ = cpu_reference_leg(configs, T, 256, 3, 1)
+                cb["sample"] += " (batch %d failed on this host: %s)" % (B, type(ex).__name__)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,31 @@
+// C-ABI glue: library version, launch counter, GEMM path selection and dispatch.
+#include "common.cuh"
+
+unsigned long long g_mfm_launches = 0;
+static int g_gemm_path = MFM_PATH_SIMT_FP32;
+
+int gemm_simt_launch(int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
+                     float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
+                     const float* mask, long long ldmask, float mask_scale, float drop_p, int drop_site,
+                     const long long* rng, cudaStream_t st);
+
+extern "C" int mfm_version(void) { return MFM_B200_VERSION; }
+extern "C" unsigned long long mfm_launch_count(void) { return g_mfm_launches; }
+extern "C" int mfm_set_gemm_path(int path) {
+  if (path != MFM_PATH_SIMT_FP32) return MFM_ERR_UNSUPPORTED;
+  g_gemm_path = path;
+  return MFM_OK;
+}
+extern "C" int mfm_get_gemm_path(void) { return g_gemm_path; }
+
+extern "C" int mfm_gemm(int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
+                        float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
+                        const float* mask, long long ldmask, float mask_scale, float drop_p, int drop_site,
+                        const long long* rng, void* stream) {
+  MFM_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C);
+  MFM_REQUIRE(mode == MFM_GEMM_NT || mode == MFM_GEMM_NN || mode == MFM_GEMM_TN);
+  MFM_REQUIRE(act >= MFM_ACT_NONE && act <= MFM_ACT_SIGMOID);
+  MFM_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f && (drop_p == 0.0f || rng));
+  return gemm_simt_launch(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale,
+                          drop_p, drop_site, rng, (cudaStream_t)stream);
+}

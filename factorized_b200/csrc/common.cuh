@@ -1,0 +1,73 @@
+// Shared device helpers for libmfm_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/mfm_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libmfm_b200 targets sm_100a (B200) only"
+#endif
+
+extern unsigned long long g_mfm_launches;   // host-side counter, see abi.cu
+
+#define MFM_LAUNCH_CHECK()                                   \
+  do {                                                       \
+    ++g_mfm_launches;                                        \
+    cudaError_t e__ = cudaGetLastError();                    \
+    if (e__ != cudaSuccess) return (int)e__;                 \
+  } while (0)
+
+#define MFM_REQUIRE(cond) \
+  do { if (!(cond)) return MFM_ERR_ARG; } while (0)
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case MFM_ACT_RELU: return fmaxf(v, 0.0f);
+    case MFM_ACT_TANH: return tanhf(v);
+    case MFM_ACT_SIGMOID: return sigmoidf_acc(v);
+    default: return v;
+  }
+}
+
+// ---- counter-based dropout RNG (stateless; backward never needs the mask: relu+dropout output > 0 <=> kept) ----
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ uint32_t site_seed(const long long* rng, int site) {
+  uint32_t seed = (uint32_t)rng[0], step = (uint32_t)rng[1];
+  return seed + step * 0x9E3779B1u + (uint32_t)site * 0x7F4A7C15u;
+}
+__device__ __forceinline__ bool drop_keep(uint32_t sseed, uint32_t idx, float p) {
+  uint32_t h = fmix32(idx * 0x9E3779B1u + sseed);
+  float u = (float)(h >> 8) * (1.0f / 16777216.0f);
+  return u >= p;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; result valid in thread 0. `red` is >= 32 floats of shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = 0.0f;
+  if (w == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    r = lane < nw ? red[lane] : 0.0f;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}

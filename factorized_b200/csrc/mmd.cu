@@ -1,0 +1,163 @@
+// Tiled MMD (mfm_model.py:14-34): K(x,y)[i,j] = exp(-|x_i - y_j|^2 / dim^2) over all B*B pairs without
+// materialising the reference's [B,B,dim] tensor (1.34 GB for z_v at B=2048).
+//   fwd :  *out = mean K(g,g) + mean K(z,z) - 2 mean K(g,z)
+//   bwd :  dz_i += scale * (2c/B^2) * [ sum_j Kzz_ij (z_i - z_j) - sum_j Kgz_ji (z_i - g_j) ],  c = -2/dim^2
+// A CTA owns MMD_RI rows i and sweeps all j in tiles of MMD_TJ rows staged in shared memory.
+#include "common.cuh"
+
+#define MMD_THREADS 256
+#define MMD_RI 16
+#define MMD_TJ 64
+#define MMD_MAXDIM 256
+
+// distance phase: thread computes pairs (i = p / TJ, j = p % TJ); K written to Ks[i][j]
+__device__ __forceinline__ float mmd_pair_phase(const float* xi, const float* yj, float* Ks, int dimp, int dim,
+                                                int ni, int nj, float inv_d2) {
+  float local = 0.0f;
+  for (int p = threadIdx.x; p < MMD_RI * MMD_TJ; p += MMD_THREADS) {
+    const int i = p / MMD_TJ, j = p - i * MMD_TJ;
+    float k = 0.0f;
+    if (i < ni && j < nj) {
+      float d2 = 0.0f;
+      const float* a = xi + i * dimp;
+      const float* b = yj + j * dimp;
+      for (int d = 0; d < dim; ++d) {
+        const float df = a[d] - b[d];
+        d2 = fmaf(df, df, d2);
+      }
+      k = expf(-d2 * inv_d2);
+    }
+    if (Ks) Ks[p] = k;
+    local += k;
+  }
+  return local;
+}
+
+__device__ __forceinline__ void mmd_load_tile(float* dst, const float* src, long long ld, int row0, int nrows_total,
+                                              int tile_rows, int dim, int dimp) {
+  for (int idx = threadIdx.x; idx < tile_rows * dim; idx += MMD_THREADS) {
+    const int r = idx / dim, d = idx - r * dim;
+    dst[r * dimp + d] = (row0 + r < nrows_total) ? __ldg(src + (long long)(row0 + r) * ld + d) : 0.0f;
+  }
+}
+
+__global__ void __launch_bounds__(MMD_THREADS) mmd_fwd_kernel(int B, int dim, const float* __restrict__ z, long long ldz,
+                                                              const float* __restrict__ g, long long ldg,
+                                                              float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[32];
+  const int dimp = dim | 1;                          // odd row pitch: conflict-free column walks
+  float* zi = smem;                                  // [RI][dimp]
+  float* gi = zi + MMD_RI * dimp;                    // [RI][dimp]
+  float* tj = gi + MMD_RI * dimp;                    // [TJ][dimp]
+  const int i0 = blockIdx.x * MMD_RI;
+  const int ni = min(MMD_RI, B - i0);
+  const float inv_d2 = 1.0f / ((float)dim * (float)dim);
+  mmd_load_tile(zi, z, ldz, i0, B, MMD_RI, dim, dimp);
+  mmd_load_tile(gi, g, ldg, i0, B, MMD_RI, dim, dimp);
+  float acc = 0.0f;
+  for (int j0 = 0; j0 < B; j0 += MMD_TJ) {
+    const int nj = min(MMD_TJ, B - j0);
+    __syncthreads();
+    mmd_load_tile(tj, z, ldz, j0, B, MMD_TJ, dim, dimp);
+    __syncthreads();
+    acc += mmd_pair_phase(zi, tj, nullptr, dimp, dim, ni, nj, inv_d2);          // K(z,z)
+    acc -= 2.0f * mmd_pair_phase(gi, tj, nullptr, dimp, dim, ni, nj, inv_d2);   // K(g,z)
+    __syncthreads();
+    mmd_load_tile(tj, g, ldg, j0, B, MMD_TJ, dim, dimp);
+    __syncthreads();
+    acc += mmd_pair_phase(gi, tj, nullptr, dimp, dim, ni, nj, inv_d2);          // K(g,g)
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, tot / ((float)B * (float)B));
+}
+
+__global__ void __launch_bounds__(MMD_THREADS) mmd_bwd_kernel(int B, int dim, const float* __restrict__ z, long long ldz,
+                                                              const float* __restrict__ g, long long ldg, float coef,
+                                                              const float* __restrict__ scale_dev,
+                                                              float* __restrict__ dz, long long lddz) {
+  extern __shared__ __align__(16) float smem[];
+  const int dimp = dim | 1;
+  float* zi = smem;                                  // [RI][dimp]
+  float* tj = zi + MMD_RI * dimp;                    // [TJ][dimp]
+  float* Ks = tj + MMD_TJ * dimp;                    // [RI][TJ]
+  const int i0 = blockIdx.x * MMD_RI;
+  const int ni = min(MMD_RI, B - i0);
+  const float inv_d2 = 1.0f / ((float)dim * (float)dim);
+  mmd_load_tile(zi, z, ldz, i0, B, MMD_RI, dim, dimp);
+  const float sdev = scale_dev ? __ldg(scale_dev) : 1.0f;
+  constexpr int MAXI = (MMD_RI * MMD_MAXDIM + MMD_THREADS - 1) / MMD_THREADS;
+  float acc[MAXI];
+#pragma unroll
+  for (int q = 0; q < MAXI; ++q) acc[q] = 0.0f;
+  for (int pass = 0; pass < 2; ++pass) {            // pass 0: j over z (+), pass 1: j over g (-)
+    const float* src = pass == 0 ? z : g;
+    const long long ld = pass == 0 ? ldz : ldg;
+    const float sgn = pass == 0 ? 1.0f : -1.0f;
+    for (int j0 = 0; j0 < B; j0 += MMD_TJ) {
+      const int nj = min(MMD_TJ, B - j0);
+      __syncthreads();
+      mmd_load_tile(tj, src, ld, j0, B, MMD_TJ, dim, dimp);
+      __syncthreads();
+      mmd_pair_phase(zi, tj, Ks, dimp, dim, ni, nj, inv_d2);
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < MAXI; ++q) {
+        const int item = threadIdx.x + q * MMD_THREADS;
+        if (item < MMD_RI * dim) {
+          const int i = item / dim, d = item - i * dim;
+          const float zv = zi[i * dimp + d];
+          float s = 0.0f;
+          for (int j = 0; j < nj; ++j) s = fmaf(Ks[i * MMD_TJ + j], zv - tj[j * dimp + d], s);
+          acc[q] = fmaf(sgn, s, acc[q]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < MAXI; ++q) {
+    const int item = threadIdx.x + q * MMD_THREADS;
+    if (item < MMD_RI * dim) {
+      const int i = item / dim, d = item - i * dim;
+      if (i < ni) dz[(long long)(i0 + i) * lddz + d] += coef * sdev * acc[q];
+    }
+  }
+}
+
+extern "C" int mfm_mmd_fwd(int B, int dim, const float* z, long long ldz, const float* g, long long ldg, float* out,
+                           void* stream) {
+  MFM_REQUIRE(B > 0 && dim > 0 && dim <= MMD_MAXDIM && z && g && out);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  const int dimp = dim | 1;
+  const size_t smem = (size_t)(2 * MMD_RI + MMD_TJ) * dimp * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    e = cudaFuncSetAttribute(mmd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  mmd_fwd_kernel<<<(B + MMD_RI - 1) / MMD_RI, MMD_THREADS, smem, st>>>(B, dim, z, ldz, g, ldg, out);
+  MFM_LAUNCH_CHECK();
+  return MFM_OK;
+}
+
+extern "C" int mfm_mmd_bwd(int B, int dim, const float* z, long long ldz, const float* g, long long ldg, float scale,
+                           const float* scale_dev, float* dz, long long lddz, void* stream) {
+  MFM_REQUIRE(B > 0 && dim > 0 && dim <= MMD_MAXDIM && z && g && dz);
+  const int dimp = dim | 1;
+  const size_t smem = ((size_t)(MMD_RI + MMD_TJ) * dimp + MMD_RI * MMD_TJ) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(mmd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const float c = -2.0f / ((float)dim * (float)dim);
+  const float coef = scale * 2.0f * c / ((float)B * (float)B);
+  mmd_bwd_kernel<<<(B + MMD_RI - 1) / MMD_RI, MMD_THREADS, smem, (cudaStream_t)stream>>>(B, dim, z, ldz, g, ldg, coef,
+                                                                                         scale_dev, dz, lddz);
+  MFM_LAUNCH_CHECK();
+  return MFM_OK;
+}

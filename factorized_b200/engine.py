@@ -68,8 +68,11 @@ class Dims:
 class Engine:
     """One (T, B) instance of the schedule with its HBM workspace."""
 
-    def __init__(self, configs, T: int, B: int, device, ops, head: str = "l1"):
+    def __init__(self, configs, T: int, B: int, device, ops, head: str = "l1", mfn_only: bool = False,
+                 mfn_prefix: str = "mfn_encoder."):
         self.dm = Dims(configs, T, B, head)
+        self.mfn_only = bool(mfn_only)          # standalone MFN module: only steps (1,2,4,5) on the MFN cells
+        self.pre = mfn_prefix
         self.device = torch.device(device)
         self.ops = ops
         self.ws: Dict[str, torch.Tensor] = {}
@@ -110,10 +113,12 @@ class Engine:
         drop = (lambda p, site: (p, site) if (train and p > 0.0) else None)
 
         # (1) hoisted input projections  G_x = X W_ih^T + b_ih + b_hh   (encoders :56, MFN :167-169)
+        full = not self.mfn_only
         for m, tag in enumerate(TAGS):
-            e, n = "encoder_%s.lstm" % tag, "mfn_encoder.lstm_%s" % tag
-            ops.gemm("nt", xs[m], P[e + ".weight_ih"], buf("GxE%d" % m, TB, 4 * dm.z[m]),
-                     bias=P[e + ".bias_ih"], bias2=P[e + ".bias_hh"])
+            e, n = "encoder_%s.lstm" % tag, self.pre + "lstm_%s" % tag
+            if full:
+                ops.gemm("nt", xs[m], P[e + ".weight_ih"], buf("GxE%d" % m, TB, 4 * dm.z[m]),
+                         bias=P[e + ".bias_ih"], bias2=P[e + ".bias_hh"])
             ops.gemm("nt", xs[m], P[n + ".weight_ih"], buf("GxN%d" % m, TB, 4 * dm.hm[m]),
                      bias=P[n + ".bias_ih"], bias2=P[n + ".bias_hh"])
 
@@ -121,7 +126,7 @@ class Engine:
         Hall = buf("Hall", (T + 1) * B, H)
         Call = buf("Call", (T + 1) * B, H)
         cells = []
-        for m, tag in enumerate(TAGS):
+        for m, tag in enumerate(TAGS if full else ""):
             cells.append(dict(T=T, B=B, h=dm.z[m], gx=self.ws["GxE%d" % m], gx_steps=T, bias_rest=None,
                               W=P["encoder_%s.lstm.weight_hh" % tag],
                               hs=buf("hsE%d" % m, (T + 1) * B, dm.z[m]), cs=buf("csE%d" % m, (T + 1) * B, dm.z[m]),
@@ -129,21 +134,21 @@ class Engine:
         for m, tag in enumerate(TAGS):
             o = dm.hoff[m]
             cells.append(dict(T=T, B=B, h=dm.hm[m], gx=self.ws["GxN%d" % m], gx_steps=T, bias_rest=None,
-                              W=P["mfn_encoder.lstm_%s.weight_hh" % tag],
+                              W=P[self.pre + "lstm_%s.weight_hh" % tag],
                               hs=Hall[:, o:o + dm.hm[m]], cs=Call[:, o:o + dm.hm[m]],
                               gates=buf("gatesN%d" % m, TB, 4 * dm.hm[m])))
         ops.lstm_fwd(cells)
 
         # (3) z_m = fc1(h_T), no activation (:60-61)
         Z = []
-        for m, tag in enumerate(TAGS):
+        for m, tag in enumerate(TAGS if full else ""):
             zt = buf("Z%d" % m, B, dm.z[m])
             ops.gemm("nt", self.ws["hsE%d" % m][TB:], P["encoder_%s.fc1.weight" % tag], zt,
                      bias=P["encoder_%s.fc1.bias" % tag])
             Z.append(zt)
 
         # (4) MFN attention for all T at once (:171-176); only gamma*_fc1's memory columns are sequential
-        pre = "mfn_encoder."
+        pre = self.pre
         cStar = buf("cStar", TB, 2 * H)
         ops.copy2d(Call[:TB], cStar[:, :H])
         ops.copy2d(Call[B:], cStar[:, H:])
@@ -175,6 +180,12 @@ class Engine:
             mems=mems, U1=buf("U1", TB, dm.g1), U2=buf("U2", TB, dm.g2),
             Gam1=buf("Gam1", TB, mem), Gam2=buf("Gam2", TB, mem),
             drop1=drop(dm.p_g1, SITE_G1), drop2=drop(dm.p_g2, SITE_G2), rng=rng))
+
+        if self.mfn_only:                                     # MFN.forward returns cat(h_T^l,h_T^a,h_T^v,mem_T) (:194-198)
+            last = buf("mfn_last", B, H + mem)
+            ops.copy2d(Hall[TB:], last[:, :H])
+            ops.copy2d(mems[TB:], last[:, H:])
+            return dict(mfn_last=last)
 
         # (6) zy = last_to_zy_fc1(cat(h_T^l, h_T^a, h_T^v, mem_T))  (:194-198, :535)
         ZY = buf("ZY", B, dm.zy)
@@ -264,10 +275,12 @@ class Engine:
 
     # -- backward ------------------------------------------------------------------
     def backward(self, P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], dXhat: Sequence[torch.Tensor],
-                 dYhat: torch.Tensor, mmd_scale: float, zero_grads: bool = True):
+                 dYhat: torch.Tensor, mmd_scale: float, mmd_scale_dev: Optional[torch.Tensor] = None,
+                 d_mfn_last: Optional[torch.Tensor] = None):
         """Adjoint of ``forward``.  ``dXhat[m]`` [T*B,d_m] and ``dYhat`` [B,out] are
-        d(loss)/d(output); ``mmd_scale`` = d(loss)/d(mmd).  Parameter gradients are
-        ACCUMULATED into ``G`` (same names as ``P``)."""
+        d(loss)/d(output); d(loss)/d(mmd) = ``mmd_scale`` (host float) times the optional
+        device scalar ``mmd_scale_dev``.  Parameter gradients are ACCUMULATED into ``G``
+        (same names as ``P``), which the caller zeroes."""
         dm, ops, buf, ws = self.dm, self.ops, self.buf, self.ws
         T, B, H, mem = dm.T, dm.B, dm.H, dm.mem
         TB = T * B
@@ -285,6 +298,11 @@ class Engine:
             bgrad(dY, name + ".bias")
             if dA is not None:
                 ops.gemm("nn", dY, P[name + ".weight"], dA, accumulate=accumulate, mask=mask, mask_scale=mask_scale)
+
+        if self.mfn_only:
+            dHlast, dmemT = d_mfn_last[:, :H], d_mfn_last[:, H:]
+            self._backward_mfn(P, G, dHlast, dmemT, [], wgrad, bgrad, lin_bwd, relu_scale)
+            return
 
         # (11') discriminative head
         dY1 = buf("dY1", B, dm.fy)
@@ -336,7 +354,7 @@ class Engine:
         lat = [ws["Z0"], ws["Z1"], ws["Z2"], ws["ZY"]]
         dlat = dZ + [dZY]
         for k in range(4):
-            ops.mmd_bwd(lat[k], self.noise[k], mmd_scale, dlat[k])
+            ops.mmd_bwd(lat[k], self.noise[k], mmd_scale, dlat[k], mmd_scale_dev)
 
         # (6') last_to_zy_fc1 over cat(h_T, mem_T)
         Wzy = P["last_to_zy_fc1.weight"]
@@ -350,8 +368,25 @@ class Engine:
         ops.gemm("nn", dZY, Wzy[:, :H], dHlast)
         ops.gemm("nn", dZY, Wzy[:, H:], dmemT)
 
+        enc_cells = []
+        for m, tag in enumerate(TAGS):                       # (3') encoder heads
+            dhl = buf("dhE%d" % m, B, dm.z[m])
+            lin_bwd(dZ[m], ws["hsE%d" % m][TB:], "encoder_%s.fc1" % tag, dhl)
+            enc_cells.append(dict(T=T, B=B, h=dm.z[m], gates=ws["gatesE%d" % m], cs=ws["csE%d" % m],
+                                  W=P["encoder_%s.lstm.weight_hh" % tag], dh_all=None, dh_last=dhl, dc_ext=None,
+                                  dG=buf("dGE%d" % m, TB, 4 * dm.z[m])))
+        self._backward_mfn(P, G, dHlast, dmemT, enc_cells, wgrad, bgrad, lin_bwd, relu_scale)
+
+    def _backward_mfn(self, P, G, dHlast, dmemT, enc_cells, wgrad, bgrad, lin_bwd, relu_scale):
+        """Adjoint of steps (5),(4),(2),(1): memory recurrence, attention MLPs, then the MFN cells together
+        with any encoder cells handed in (one launch), then all input-side weight gradients."""
+        dm, ops, buf, ws = self.dm, self.ops, self.buf, self.ws
+        T, B, H, mem = dm.T, dm.B, dm.H, dm.mem
+        TB = T * B
+        Hall, Call, mems = ws["Hall"], ws["Call"], ws["mems"]
+
         # (5') memory recurrence, reversed
-        pre = "mfn_encoder."
+        pre = self.pre
         Wg1, Wg2 = P[pre + "gamma1_fc1.weight"], P[pre + "gamma2_fc1.weight"]
         dU1, dU2 = buf("dU1", TB, dm.g1), buf("dU2", TB, dm.g2)
         dP1, dP2 = buf("dP1", TB, mem), buf("dP2", TB, mem)
@@ -391,27 +426,22 @@ class Engine:
         if T > 1:
             ops.copy2d(dcStar[B:, :H], dCext[:TB - B], accumulate=True)
 
-        # (3') encoder heads, then (2') the six recurrences reversed
-        cells = []
-        for m, tag in enumerate(TAGS):
-            dhl = buf("dhE%d" % m, B, dm.z[m])
-            lin_bwd(dZ[m], ws["hsE%d" % m][TB:], "encoder_%s.fc1" % tag, dhl)
-            cells.append(dict(T=T, B=B, h=dm.z[m], gates=ws["gatesE%d" % m], cs=ws["csE%d" % m],
-                              W=P["encoder_%s.lstm.weight_hh" % tag], dh_all=None, dh_last=dhl, dc_ext=None,
-                              dG=buf("dGE%d" % m, TB, 4 * dm.z[m])))
+        # (2') the recurrences reversed, one launch
+        cells = list(enc_cells)
         for m, tag in enumerate(TAGS):
             o = dm.hoff[m]
             cells.append(dict(T=T, B=B, h=dm.hm[m], gates=ws["gatesN%d" % m], cs=Call[:, o:o + dm.hm[m]],
-                              W=P["mfn_encoder.lstm_%s.weight_hh" % tag], dh_all=None,
+                              W=P[pre + "lstm_%s.weight_hh" % tag], dh_all=None,
                               dh_last=dHlast[:, o:o + dm.hm[m]], dc_ext=dCext[:, o:o + dm.hm[m]],
                               dG=buf("dGN%d" % m, TB, 4 * dm.hm[m])))
         ops.lstm_bwd(cells)
 
         # (1') weight gradients of the 6 input-side cells, all T at once
         for m, tag in enumerate(TAGS):
-            for (nm, dGn, hs) in (("encoder_%s.lstm" % tag, "dGE%d" % m, ws["hsE%d" % m][:TB]),
-                                  ("mfn_encoder.lstm_%s" % tag, "dGN%d" % m,
-                                   Hall[:TB, dm.hoff[m]:dm.hoff[m] + dm.hm[m]])):
+            jobs = [(pre + "lstm_%s" % tag, "dGN%d" % m, Hall[:TB, dm.hoff[m]:dm.hoff[m] + dm.hm[m]])]
+            if enc_cells:
+                jobs.append(("encoder_%s.lstm" % tag, "dGE%d" % m, ws["hsE%d" % m][:TB]))
+            for (nm, dGn, hs) in jobs:
                 dG = ws[dGn]
                 wgrad(dG, self.xs[m], nm + ".weight_ih")
                 wgrad(dG, hs, nm + ".weight_hh")

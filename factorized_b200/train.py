@@ -1,0 +1,229 @@
+"""The fused MFM training step and the ``train_mfm`` entry point.
+
+``MFMTrainer.step`` is the inner loop body of the reference's ``train_mfm``
+(mfm_mosi.py:427-442: zero_grad, forward, L1/CE + sum(lambda*MSE) + lambda*MMD,
+backward, Adam) as ONE fixed kernel schedule: forward with the loss heads fused,
+the hand-derived backward into a flat gradient buffer, an optional NCCL
+all-reduce of that buffer when the batch is sharded over ranks, and a fused
+flat-buffer Adam.  The schedule is captured into a CUDA graph on first use and
+replayed afterwards.
+
+``train_mfm`` keeps the reference signature
+``(X_train, y_train, X_valid, y_valid, X_test, y_test, configs)`` and epoch
+logic (shuffle once, time-major swap, Adam default lr, ReduceLROnPlateau on the
+validation L1, save-best / reload, score) -- mfm_mosi.py:386-503.
+"""
+from __future__ import annotations
+
+import math
+import os
+import random
+import tempfile
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import engine as E
+from .mfm_model import MFM, UNUSED, _ops
+
+SITE_NOISE = 20   # RNG sites 20..23: the four MMD Gaussian samples
+
+
+class MFMTrainer:
+    """Owns flat parameter / gradient / Adam buffers for one MFM module and runs fused steps.
+
+    The module's nn.Parameters are re-pointed at views of the flat parameter buffer, so
+    ``state_dict`` / ``torch.save(model)`` keep working and see the trained weights.
+    """
+
+    def __init__(self, model: MFM, T: int, B: int, head: str = "l1", lr: float = 1e-3, betas=(0.9, 0.999),
+                 eps: float = 1e-8, use_graph: bool = True, process_group=None, seed: int = 123):
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("MFMTrainer: model must be on a CUDA device (model.to('cuda')); no CPU path exists")
+        self.model, self.dev = model, dev
+        self.ops = _ops()
+        self.T, self.B = int(T), int(B)
+        self.betas, self.eps = betas, eps
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        pd = dict(model.named_parameters())
+        self.names = [k for k in pd if k not in UNUSED]
+        n = sum(pd[k].numel() for k in self.names)
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.P: Dict[str, torch.Tensor] = OrderedDict()
+        self.G: Dict[str, torch.Tensor] = OrderedDict()
+        o = 0
+        with torch.no_grad():
+            for k in self.names:
+                p = pd[k]
+                view = self.flat_p[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                self.P[k] = view
+                self.G[k] = self.flat_g[o:o + p.numel()].view(p.shape)
+                o += p.numel()
+        self.eng = E.Engine(model._cfg, T, B, dev, self.ops, head=head)
+        dm = self.eng.dm
+        self.x = torch.zeros(T, B, dm.D, dtype=torch.float32, device=dev)
+        if head == "ce":
+            self.y = torch.zeros(B, dtype=torch.int64, device=dev)
+        else:
+            self.y = torch.zeros(B * dm.out, dtype=torch.float32, device=dev)
+        self.noise = [torch.zeros(B, k, dtype=torch.float32, device=dev) for k in (dm.z[0], dm.z[1], dm.z[2], dm.zy)]
+        self.rng = torch.tensor([int(seed), 0], dtype=torch.int64, device=dev)
+        self.adam_state = torch.tensor([lr, 0.0, 0.0, 0.0], dtype=torch.float32, device=dev)
+        self.use_graph = use_graph
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
+        self.steps_done = 0
+
+    # ------------------------------------------------------------------
+    def set_lr(self, lr: float):
+        self.adam_state[0:1].fill_(float(lr))
+
+    def _schedule(self):
+        """One training step on the static buffers (x, y)."""
+        ops, eng = self.ops, self.eng
+        ops.rng_tick(self.rng)
+        for k in range(4):                                    # loss_MMD's Gaussian samples (mfm_model.py:26)
+            ops.randn(self.noise[k], self.rng, SITE_NOISE + k)
+        eng.forward(self.P, self.x, self.noise, train=True, rng=self.rng)
+        dX, dY = eng.losses(self.y)
+        ops.zero(self.flat_g)
+        eng.backward(self.P, self.G, dX, dY, eng.dm.lda_mmd)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.pg)      # NCCL sum over NVLink; 1/world folded into Adam
+        ops.adam(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.adam_state, grad_scale=1.0 / self.world,
+                 betas=self.betas, eps=self.eps)
+
+    def _run(self):
+        if not self.use_graph:
+            n0 = self.ops.launches
+            self._schedule()
+            self.launches_per_step = self.ops.launches - n0
+            return
+        if self.graph is None:
+            # warm up on a side stream (lazy module loads, cudaFuncSetAttribute, NCCL init), then capture
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            snap = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self.adam_state, self.rng)]
+            with torch.cuda.stream(s):
+                self._schedule()
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            torch.cuda.synchronize(self.dev)
+            for t, c in zip((self.flat_p, self.flat_m, self.flat_v, self.adam_state, self.rng), snap):
+                t.copy_(c)
+            g = torch.cuda.CUDAGraph()
+            n0 = self.ops.launches
+            with torch.cuda.graph(g):
+                self._schedule()
+            self.launches_per_step = self.ops.launches - n0
+            self.graph = g
+        self.graph.replay()
+
+    def step_device(self):
+        """Run one step on whatever is in self.x / self.y (already on the device)."""
+        self._run()
+        self.steps_done += 1
+
+    def step(self, x, y):
+        """x: [T,B,D] fp32, y: targets; host (ideally pinned) or device tensors.  Returns the device loss buffer
+        (index 0 = discriminative loss, 1..3 = MSE l/a/v, 4..7 = MMD parts, 8 = total); reading it syncs."""
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y.reshape(self.y.shape), non_blocking=True)
+        self.step_device()
+        return self.eng.loss_buf
+
+
+def _to_time_major(X):
+    return np.ascontiguousarray(np.swapaxes(np.asarray(X, dtype=np.float32), 0, 1))
+
+
+def train_mfm(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, head: str = "l1", verbose: bool = True,
+              save_dir: Optional[str] = None):
+    """Drop-in for the reference's train_mfm (mfm_mosi.py:386-503); CE head: mfm_mosi_acc.py:396-503.
+    X_* are numpy [n,T,D]; y_* [n] (or [n,out]).  Returns a dict with the trained model and scores."""
+    config = configs[0]
+    if config.get("type", "mfm") == "kl":
+        raise NotImplementedError("MFM_KL is outside the accelerated path (SURVEY.md section 2, row 9)")
+    p = np.random.permutation(X_train.shape[0])                     # :387-389
+    X_train, y_train = np.asarray(X_train)[p], np.asarray(y_train)[p]
+    Xt, Xv, Xte = _to_time_major(X_train), _to_time_major(X_valid), _to_time_major(X_test)    # :391-393
+    dev = torch.device("cuda")
+    model = MFM(*configs).to(dev)                                    # :401,414
+    model.mmd_noise = "cuda"
+    T, total_n = Xt.shape[0], Xt.shape[1]
+    bs = int(config["batchsize"])
+    num_batches = total_n // bs                                      # :423 (py2 integer division: drops the tail)
+    lr = 1e-3                                                        # optim.Adam(model.parameters()) default, :403
+    trainer = MFMTrainer(model, T, bs, head=head, lr=lr)
+    sched_opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=lr)   # carrier for ReduceLROnPlateau only
+    scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(sched_opt, "min")   # :417
+    ydt = np.int64 if head == "ce" else np.float32
+    Xpin = torch.from_numpy(Xt).pin_memory()
+    ypin = torch.from_numpy(np.asarray(y_train, dtype=ydt)).pin_memory()
+
+    def evaluate(X, y):                                              # :445-455
+        model.eval()
+        with torch.no_grad():
+            bx = torch.from_numpy(X).to(dev)
+            decoded, _, _ = model.forward(bx)
+            y_hat = decoded[3]
+            y_hat = y_hat.squeeze(1) if y_hat.shape[1] == 1 else y_hat
+            by = torch.from_numpy(np.asarray(y, dtype=ydt)).to(dev)
+            if head == "ce":
+                return torch.nn.functional.cross_entropy(y_hat, by).item()
+            return torch.nn.functional.l1_loss(y_hat, by).item()
+
+    def predict(X):                                                  # :457-465
+        model.eval()
+        with torch.no_grad():
+            decoded, _, _ = model.forward(torch.from_numpy(X).to(dev))
+            y_hat = decoded[3]
+            return (y_hat.squeeze(1) if y_hat.shape[1] == 1 else y_hat).cpu().numpy()
+
+    best_valid = 999999.0
+    save_dir = save_dir or tempfile.mkdtemp(prefix="res_mfm2_")
+    path = os.path.join(save_dir, "mfn_%d.pt" % random.randint(0, 100000))
+    history = []
+    for epoch in range(int(config["num_epochs"])):
+        model.train()
+        acc = torch.zeros((), dtype=torch.float32, device=dev)
+        for b in range(num_batches):
+            lb = trainer.step(Xpin[:, b * bs:(b + 1) * bs], ypin[b * bs:(b + 1) * bs])
+            acc += lb[0]                                             # device-side; the reference syncs here (:442)
+        train_loss = float(acc) / max(num_batches, 1)
+        valid_loss = evaluate(Xv, y_valid)
+        scheduler.step(valid_loss)
+        trainer.set_lr(sched_opt.param_groups[0]["lr"])
+        history.append((epoch, train_loss, valid_loss))
+        if valid_loss <= best_valid:
+            best_valid = valid_loss
+            torch.save(model, path)                                  # :477 whole-module pickle
+            if verbose:
+                print(epoch, train_loss, valid_loss, "saving model")
+        elif verbose:
+            print(epoch, train_loss, valid_loss)
+    if os.path.exists(path):
+        model = torch.load(path, weights_only=False)                 # :481
+    y_hat = predict(Xte)
+    scores = {}
+    y_test = np.asarray(y_test)
+    if head == "l1" and y_hat.ndim == 1:
+        scores["mae"] = float(np.mean(np.absolute(y_hat - y_test)))                            # :484
+        scores["corr"] = float(np.corrcoef(y_hat, y_test)[0][1])                               # :486
+        scores["mult_acc"] = float(np.mean(np.round(y_hat) == np.round(y_test)))               # :488
+        scores["binary_acc"] = float(np.mean((y_hat >= 0) == (y_test >= 0)))                   # :492-498
+    elif head == "ce":
+        scores["acc"] = float(np.mean(np.argmax(y_hat, 1) == y_test))
+    if verbose:
+        print(scores)
+    return dict(model=model, scores=scores, history=history, best_valid=best_valid, checkpoint=path, predictions=y_hat)

@@ -195,8 +195,10 @@ class EmuOps:
         self.launches += 1
         out[0] = self._k(g, g).mean() + self._k(z, z).mean() - 2.0 * self._k(g, z).mean()
 
-    def mmd_bwd(self, z, g, scale, dz):
+    def mmd_bwd(self, z, g, scale, dz, scale_dev=None):
         self.launches += 1
+        if scale_dev is not None:
+            scale = scale * float(scale_dev)
         n, dim = z.shape
         c = -2.0 / float(dim * dim)
         kzz = self._k(z, z)
@@ -256,7 +258,7 @@ class EmuOps:
         lb[8] = lb[0] + l0 * lb[1] + l1 * lb[2] + l2 * lb[3] + lmmd * (lb[4] + lb[5] + lb[6] + lb[7])
 
     def adam(self, p, g, m, v, state, grad_scale=1.0, betas=(0.9, 0.999), eps=1e-8):
-        """state: float tensor [lr, step] on device; step is incremented here."""
+        """state: float tensor [lr, step, scratch, scratch]; step is incremented here."""
         self.launches += 1
         state[1] += 1
         t = float(state[1])
@@ -267,3 +269,18 @@ class EmuOps:
         v.mul_(b2).addcmul_(gg, gg, value=1 - b2)
         denom = v.sqrt() / (1 - b2 ** t) ** 0.5 + eps
         p -= (lr / (1 - b1 ** t)) * (m / denom)
+
+    def rng_tick(self, rng):
+        self.launches += 1
+        rng[1] += 1
+
+    def randn(self, out, rng, site):
+        self.launches += 1
+        n = out.numel()
+        i = torch.arange(n, dtype=torch.int64)
+        ss = site_seed(rng, site)
+        h1 = _fmix32((((2 * i) & M32) * 0x9E3779B1 + ss) & M32)
+        h2 = _fmix32((((2 * i + 1) & M32) * 0x9E3779B1 + ss) & M32)
+        u1 = ((h1 >> 8).to(torch.float32) + 1.0) * (1.0 / 16777216.0)
+        u2 = (h2 >> 8).to(torch.float32) * (1.0 / 16777216.0)
+        out.view(-1).copy_(torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(2.0 * torch.pi * u2))

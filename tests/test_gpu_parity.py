@@ -1,0 +1,268 @@
+"""Parity of the CUDA path (through the C ABI) against the golden vectors of the unmodified reference and
+against the oracle on the same seeded inputs.  Tolerance: 1e-3 relative (BASELINE.json north_star), fp32."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mfm_oracle as O
+from helpers import load_golden, rel_l2, tiny_case
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def cuda_engine_step(configs, P, x, y, noise, T, n, head):
+    from factorized_b200.engine import Engine
+    from factorized_b200.cuda_ops import CudaOps
+    ops = CudaOps()
+    dev = torch.device("cuda")
+    Pd = OrderedDict((k, v.to(dev)) for k, v in P.items())
+    eng = Engine(configs, T, n, dev, ops, head=head)
+    out = eng.forward(Pd, x.to(dev).contiguous(), [t.to(dev) for t in noise], train=False)
+    dX, dY = eng.losses(y.to(dev))
+    G = OrderedDict((k, torch.zeros_like(v)) for k, v in Pd.items())
+    eng.backward(Pd, G, dX, dY, eng.dm.lda_mmd)
+    torch.cuda.synchronize()
+    return eng, out, G
+
+
+@pytest.mark.parametrize("head,od", [("l1", 1), ("ce", 3), ("l1", 4)])
+def test_tiny_golden(head, od):
+    g, configs, P, x, y, noise, T, n = tiny_case(head, od)
+    eng, out, G = cuda_engine_step(configs, P, x, y, noise, T, n, head)
+    report = {}
+    for k in ("zl", "za", "zv", "zy"):
+        report[k] = rel_l2(out[k], g["lat/" + k])
+    for k in ("x_l_hat", "x_a_hat", "x_v_hat"):
+        report[k] = rel_l2(out[k].view(T, n, -1), g[k])
+    report["y_hat"] = rel_l2(out["y_hat"], g["y_hat"])
+    lb = eng.loss_buf.cpu()
+    for i, k in ((0, "disc"), (1, "mse_l"), (2, "mse_a"), (3, "mse_v"), (8, "total")):
+        report["loss." + k] = abs(float(lb[i]) - float(g["loss/" + k])) / abs(float(g["loss/" + k]))
+    mmd_w = float(lb[4:8].sum()) * configs[0]["lda_mmd"]
+    report["loss.mmd"] = abs(mmd_w - float(g["loss/mmd"])) / abs(float(g["loss/mmd"]))
+    for k in P:
+        if "g/" + k in g:
+            report["grad." + k] = rel_l2(G[k], g["g/" + k])
+    bad = {k: v for k, v in report.items() if not (v < TOL)}
+    assert not bad, bad
+
+
+def _oracle_case(configs, seed, T, n, data_seed, noise_seed, head):
+    P = O.init_params(configs, seed)
+    x, y = O.synthetic_batch(configs, T, n, data_seed, head)
+    noise = O.draw_mmd_noise(configs, n, noise_seed)
+    newP, losses, Go, outo = O.train_step(P, x, y, configs, noise, {}, head=head)
+    return P, x, y, noise, newP, losses, Go, outo
+
+
+def _compare_to_oracle(configs, T, n, head, seed=123, data_seed=1234, noise_seed=999):
+    P, x, y, noise, newP, losses, Go, outo = _oracle_case(configs, seed, T, n, data_seed, noise_seed, head)
+    eng, out, G = cuda_engine_step(configs, P, x, y, noise, T, n, head)
+    report = {}
+    for k in ("zl", "za", "zv", "zy", "y_hat"):
+        report[k] = rel_l2(out[k], outo[k])
+    for k in ("x_l_hat", "x_a_hat", "x_v_hat"):
+        report[k] = rel_l2(out[k].view(T, n, -1), outo[k])
+    lb = eng.loss_buf.cpu()
+    for i, k in ((0, "disc"), (1, "mse_l"), (2, "mse_a"), (3, "mse_v"), (8, "total")):
+        report["loss." + k] = abs(float(lb[i]) - losses[k]) / abs(losses[k])
+    report["loss.mmd"] = abs(float(lb[4:8].sum()) * configs[0]["lda_mmd"] - losses["mmd"]) / abs(losses["mmd"])
+    for k, go in Go.items():
+        if go is not None:
+            report["grad." + k] = rel_l2(G[k], go)
+    # one fused Adam step on the flat buffers against the oracle's post-step parameters
+    from factorized_b200.cuda_ops import CudaOps
+    ops = CudaOps()
+    names = [k for k in P if Go[k] is not None]
+    fp = torch.cat([P[k].reshape(-1) for k in names]).cuda()
+    fg = torch.cat([G[k].reshape(-1) for k in names])
+    m, v = torch.zeros_like(fp), torch.zeros_like(fp)
+    st = torch.tensor([1e-3, 0, 0, 0], dtype=torch.float32).cuda()
+    ops.adam(fp, fg, m, v, st)
+    ref_delta = torch.cat([(newP[k] - P[k]).reshape(-1) for k in names])
+    got_delta = fp.cpu() - torch.cat([P[k].reshape(-1) for k in names])
+    report["adam.delta"] = rel_l2(got_delta, ref_delta)
+    return report
+
+
+def test_mosi_b32_golden_digest():
+    """BASELINE configs[0] shapes against the digest the unmodified reference produced."""
+    g = load_golden("mosi_b32.npz")
+    seed, T, n, data_seed, noise_seed, od = [int(v) for v in g["meta"]]
+    configs = O.best_acc_configs(dropout=False)
+    P = O.init_params(configs, seed)
+    x, y = O.synthetic_batch(configs, T, n, data_seed)
+    noise = O.draw_mmd_noise(configs, n, noise_seed)
+    eng, out, G = cuda_engine_step(configs, P, x, y, noise, T, n, "l1")
+    report = {k: rel_l2(out[k], g["lat/" + k]) for k in ("zl", "za", "zv", "zy")}
+    report["y_hat"] = rel_l2(out["y_hat"], g["y_hat"])
+    report["x_a_hat"] = rel_l2(out["x_a_hat"].view(T, n, -1), g["x_a_hat"])
+    report["x_l_hat_t0"] = rel_l2(out["x_l_hat"].view(T, n, -1)[0], g["x_l_hat_t0"])
+    report["x_l_hat_tlast"] = rel_l2(out["x_l_hat"].view(T, n, -1)[-1], g["x_l_hat_tlast"])
+    lb = eng.loss_buf.cpu()
+    for i, k in ((0, "disc"), (1, "mse_l"), (2, "mse_a"), (3, "mse_v"), (8, "total")):
+        report["loss." + k] = abs(float(lb[i]) - float(g["loss/" + k])) / abs(float(g["loss/" + k]))
+    names = [str(s) for s in g["grad_names"]]
+    norms = np.array([float(G[k].double().norm()) for k in names])
+    report["grad_norms"] = float(np.max(np.abs(norms - g["grad_norms"]) / (g["grad_norms"] + 1e-12)))
+    for k in ("last_to_zy_fc1.weight", "encoder_a.lstm.weight_ih", "decoder_v.lstm.weight_hh", "mfn_encoder.gamma1_fc1.bias"):
+        report["grad." + k] = rel_l2(G[k], g["g/" + k])
+    bad = {k: v for k, v in report.items() if not (v < TOL)}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("name,input_dims,T,n,head,od", [
+    ("mosi_b256", (300, 5, 20), 20, 256, "l1", 1),          # BASELINE configs[1]
+    ("mosei_b64", (300, 74, 35), 50, 64, "l1", 1),          # configs[2] shapes, one rank's shard
+    ("iemocap_b256", (300, 74, 35), 20, 256, "ce", 4),      # configs[3]
+    ("pom_b96", (300, 43, 43), 100, 96, "l1", 16),          # configs[4] shapes (ragged batch)
+])
+def test_full_step_vs_oracle(name, input_dims, T, n, head, od):
+    configs = O.best_acc_configs(input_dims=input_dims, output_dim=od, dropout=False)
+    report = _compare_to_oracle(configs, T, n, head)
+    bad = {k: v for k, v in report.items() if not (v < TOL)}
+    worst = max(report, key=report.get)
+    print("%s: worst %s = %.3g" % (name, worst, report[worst]))
+    assert not bad, bad
+
+
+def test_dropin_module_autograd_and_trainer():
+    """The nn.Module boundary: MFM.forward + torch losses + loss.backward() (the reference's own loop body,
+    mfm_mosi.py:430-441) against the oracle; then MFMTrainer's fused step against the same."""
+    import factorized_b200 as F
+    from factorized_b200.train import MFMTrainer
+    g, configs, P, x, y, noise, T, n = tiny_case("l1", 1)
+    torch.manual_seed(int(g["meta"][0]))
+    model = F.MFM(*configs).cuda().eval()
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), P[k]), k
+    torch.manual_seed(int(g["meta"][4]))                   # same CPU generator state as the reference run
+    xd, yd = x.cuda(), y.cuda()
+    decoded, mmd, missing = model.forward(xd)
+    c = configs[0]
+    d_l, d_a, d_v = c["input_dims"]
+    Fn = torch.nn.functional
+    gen = c["lda_xl"] * Fn.mse_loss(decoded[0], xd[:, :, :d_l]) + c["lda_xa"] * Fn.mse_loss(decoded[1], xd[:, :, d_l:d_l + d_a]) \
+        + c["lda_xv"] * Fn.mse_loss(decoded[2], xd[:, :, d_l + d_a:])
+    loss = Fn.l1_loss(decoded[3].squeeze(1), yd) + gen + c["lda_mmd"] * mmd + missing
+    loss.backward()
+    assert missing == 0.0
+    assert abs(float(loss) - float(g["loss/total"])) < TOL * abs(float(g["loss/total"]))
+    for k in ("zl", "za", "zv", "zy"):
+        assert rel_l2(model.latents[k], g["lat/" + k]) < TOL
+    bad = {}
+    for k, p in model.named_parameters():
+        if "g/" + k in g:
+            e = rel_l2(p.grad, g["g/" + k])
+            if not e < TOL:
+                bad[k] = e
+        else:
+            assert p.grad is None, k
+    assert not bad, bad
+    # whole-module pickle round trip (mfm_mosi.py:477,481)
+    import io
+    b = io.BytesIO()
+    torch.save(model, b)
+    b.seek(0)
+    m2 = torch.load(b, weights_only=False)
+    torch.manual_seed(int(g["meta"][4]))
+    d2, _, _ = m2.forward(xd)
+    assert torch.equal(d2[3], decoded[3])
+
+    # fused trainer step: same math, noise injected, no dropout in this config
+    torch.manual_seed(int(g["meta"][0]))
+    model2 = F.MFM(*configs).cuda()
+    tr = MFMTrainer(model2, T, n, head="l1", use_graph=False)
+    tr.x.copy_(xd)
+    tr.y.copy_(yd.reshape(-1))
+    for k in range(4):
+        tr.noise[k].copy_(noise[k])
+    tr.ops.randn = lambda *a, **kw: None                  # keep the injected noise for the parity check
+    tr.step_device()
+    torch.cuda.synchronize()
+    assert abs(float(tr.eng.loss_buf[8]) - float(g["loss/total"])) < TOL * abs(float(g["loss/total"]))
+    sd = model2.state_dict()
+    bad = {k: rel_l2(sd[k].cpu() - P[k], g["p1/" + k] - P[k].numpy()) for k in P if "g/" + k in g}
+    bad = {k: v for k, v in bad.items() if not v < 5e-3}
+    assert not bad, bad
+
+
+def test_trainer_graph_replay_trains():
+    """CUDA-graph replay of the fused step: loss decreases on a fixed batch and matches the eager schedule."""
+    import factorized_b200 as F
+    from factorized_b200.train import MFMTrainer
+    configs = O.best_acc_configs(dropout=True)
+    T, n = 20, 64
+    x, y = O.synthetic_batch(configs, T, n, 7)
+    res = []
+    for use_graph in (False, True):
+        torch.manual_seed(5)
+        model = F.MFM(*configs).cuda()
+        tr = MFMTrainer(model, T, n, use_graph=use_graph, seed=77)
+        ls = []
+        for i in range(6):
+            lb = tr.step(x, y)
+            ls.append(float(lb[8]))
+        res.append(ls)
+        assert tr.launches_per_step > 50
+    assert res[0][-1] < res[0][0]
+    assert np.allclose(res[0], res[1], rtol=2e-3), res
+
+
+def test_standalone_modules_vs_oracle():
+    import factorized_b200 as F
+    configs = O.tiny_configs()
+    T, n = 5, 7
+    x, _ = O.synthetic_batch(configs, T, n, 3)
+    P = O.init_params(configs, 11)
+    # encoderLSTM on a strided modality slice, with grad to the input
+    enc = F.encoderLSTM(3, 3).cuda()
+    enc.load_state_dict({k[len("encoder_a."):]: v for k, v in P.items() if k.startswith("encoder_a.")})
+    xa = x[:, :, 7:10].clone().requires_grad_(True)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    z_ref = O.encoder_lstm(xa, Pg, "encoder_a")
+    z_ref.square().sum().backward()
+    xg = x.cuda()[:, :, 7:10]
+    xg.requires_grad_(True)
+    z = enc.forward(xg)
+    z.square().sum().backward()
+    assert rel_l2(z, z_ref) < TOL
+    assert rel_l2(enc.lstm.weight_ih.grad, Pg["encoder_a.lstm.weight_ih"].grad) < TOL
+    assert rel_l2(enc.lstm.bias_hh.grad, Pg["encoder_a.lstm.bias_hh"].grad) < TOL
+    assert rel_l2(xg.grad, xa.grad) < TOL
+    # decoderLSTM
+    dec = F.decoderLSTM(7, 3).cuda()
+    dec.load_state_dict({k[len("decoder_a."):]: v for k, v in P.items() if k.startswith("decoder_a.")})
+    emb = torch.randn(n, 7, generator=torch.Generator().manual_seed(1))
+    e1 = emb.clone().requires_grad_(True)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    r_ref = O.decoder_lstm(e1, T, Pg, "decoder_a")
+    r_ref.square().sum().backward()
+    e2 = emb.cuda().requires_grad_(True)
+    r = dec.forward(e2, T)
+    r.square().sum().backward()
+    assert rel_l2(r, r_ref) < TOL and rel_l2(e2.grad, e1.grad) < TOL
+    assert rel_l2(dec.lstm.weight_ih.grad, Pg["decoder_a.lstm.weight_ih"].grad) < TOL
+    assert rel_l2(dec.lstm.weight_hh.grad, Pg["decoder_a.lstm.weight_hh"].grad) < TOL
+    assert rel_l2(dec.fc1.weight.grad, Pg["decoder_a.fc1.weight"].grad) < TOL
+    # MFN
+    mfn = F.MFN(*configs).cuda().eval()
+    mfn.load_state_dict({k[len("mfn_encoder."):]: v for k, v in P.items() if k.startswith("mfn_encoder.")})
+    Pg = {k: v.clone().requires_grad_(k not in O.UNUSED_PARAMS) for k, v in P.items()}
+    last_ref = O.mfn_encoder(x, Pg, configs)
+    last_ref.square().sum().backward()
+    last = mfn.forward(x.cuda())
+    last.square().sum().backward()
+    assert rel_l2(last, last_ref) < TOL
+    bad = {}
+    for k, p in mfn.named_parameters():
+        gr = Pg["mfn_encoder." + k].grad
+        if gr is None:
+            assert p.grad is None
+        elif not rel_l2(p.grad, gr) < TOL:
+            bad[k] = rel_l2(p.grad, gr)
+    assert not bad, bad

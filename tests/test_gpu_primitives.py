@@ -1,0 +1,289 @@
+"""Each CUDA primitive (through the C ABI / ctypes binding) against its torch statement in emu_ops.py on
+seeded random inputs, including ragged / awkward sizes.  Needs a B200: run with -m gpu."""
+import pytest
+import torch
+
+from emu_ops import EmuOps, keep_mask
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from factorized_b200.cuda_ops import CudaOps
+    return CudaOps()
+
+
+def g(*shape, seed=0, scale=1.0):
+    gen = torch.Generator().manual_seed(seed + sum(shape))
+    return torch.randn(*shape, generator=gen) * scale
+
+
+def both(fn_name, cpu_args, ops, emu=None, **kw):
+    """run emu on cpu tensors and cuda op on device copies; returns (cpu_args, gpu_args)."""
+    emu = emu or EmuOps()
+    dev = [a.cuda() if isinstance(a, torch.Tensor) else a for a in cpu_args]
+    getattr(emu, fn_name)(*cpu_args, **kw)
+    kw2 = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
+    getattr(ops, fn_name)(*dev, **kw2)
+    torch.cuda.synchronize()
+    return cpu_args, dev
+
+
+@pytest.mark.parametrize("mode", ["nt", "nn", "tn"])
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (5, 3, 7), (64, 64, 16), (70, 130, 33), (640, 128, 300), (37, 400, 128),
+                                   (12, 20, 5000)])
+def test_gemm_plain(ops, mode, M, N, K):
+    A = g(M, K, seed=1) if mode != "tn" else g(K, M, seed=1)
+    B = g(N, K, seed=2) if mode == "nt" else g(K, N, seed=2)
+    C0 = g(M, N, seed=3)
+    for acc in (False, True):
+        if mode == "tn" and not acc and K >= 1024:
+            pass
+        c_cpu, c_gpu = C0.clone(), C0.clone().cuda()
+        EmuOps().gemm(mode, A, B, c_cpu, accumulate=acc)
+        ops.gemm(mode, A.cuda(), B.cuda(), c_gpu, accumulate=acc)
+        assert rel_l2(c_gpu, c_cpu) < TOL, (mode, M, N, K, acc)
+
+
+def test_gemm_strided_views_and_epilogues(ops):
+    T_B, D = 96, 41
+    X = g(T_B, D, seed=5)
+    W = g(24, 30, seed=6)            # use a column slice of both
+    bias, bias2 = g(24, seed=7), g(24, seed=8)
+    rng = torch.tensor([99, 3], dtype=torch.int64)
+    for act in (0, 1, 2, 3):
+        for drop in (None, (0.4, 5)):
+            out_cpu = torch.zeros(T_B, 50)
+            out_gpu = out_cpu.clone().cuda()
+            EmuOps().gemm("nt", X[:, 7:27], W[:, 3:23], out_cpu[:, 10:34], bias=bias, bias2=bias2, act=act, drop=drop, rng=rng)
+            ops.gemm("nt", X.cuda()[:, 7:27], W.cuda()[:, 3:23], out_gpu[:, 10:34], bias=bias.cuda(), bias2=bias2.cuda(),
+                     act=act, drop=drop, rng=rng.cuda())
+            assert rel_l2(out_gpu, out_cpu) < TOL, (act, drop)
+            assert float(out_gpu[:, :10].abs().max()) == 0 and float(out_gpu[:, 34:].abs().max()) == 0
+    # relu/dropout mask epilogue of the data-gradient GEMM
+    dY, Wn, Hm = g(T_B, 24, seed=9), g(24, 17, seed=10), torch.relu(g(T_B, 17, seed=11))
+    o_cpu, o_gpu = torch.zeros(T_B, 17), torch.zeros(T_B, 17).cuda()
+    EmuOps().gemm("nn", dY, Wn, o_cpu, mask=Hm, mask_scale=2.0)
+    ops.gemm("nn", dY.cuda(), Wn.cuda(), o_gpu, mask=Hm.cuda(), mask_scale=2.0)
+    assert rel_l2(o_gpu, o_cpu) < TOL
+
+
+def _lstm_case(T, B, h, gx_steps, seed, ld_extra=0):
+    W = g(4 * h, h, seed=seed, scale=0.3)
+    gx = g(gx_steps * B, 4 * h, seed=seed + 1)
+    bias_rest = g(4 * h, seed=seed + 2) if gx_steps < T else None
+    hs = torch.full(((T + 1) * B, h + ld_extra), 7.0)
+    cs = torch.full(((T + 1) * B, h + ld_extra), 7.0)
+    gates = torch.zeros(T * B, 4 * h)
+    return dict(T=T, B=B, h=h, gx=gx, gx_steps=gx_steps, bias_rest=bias_rest, W=W,
+                hs=hs[:, ld_extra:], cs=cs[:, ld_extra:], gates=gates)
+
+
+def _to_dev(c):
+    return {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in c.items()}
+
+
+def _dev_view(c_cpu, key, base_cpu, base_gpu):
+    return None
+
+
+@pytest.mark.parametrize("T,B,h,gx_steps,ld_extra", [(3, 5, 6, 3, 0), (4, 19, 32, 4, 3), (5, 33, 104, 1, 0), (2, 9, 8, 2, 0),
+                                                     (3, 17, 128, 3, 0), (2, 6, 300, 1, 0), (20, 70, 88, 20, 112)])
+def test_lstm_fwd_bwd(ops, T, B, h, gx_steps, ld_extra):
+    c = _lstm_case(T, B, h, gx_steps, seed=T + B + h, ld_extra=ld_extra)
+    # device copies that preserve the strided views
+    hs_full = torch.full(((T + 1) * B, h + ld_extra), 7.0).cuda()
+    cs_full = torch.full(((T + 1) * B, h + ld_extra), 7.0).cuda()
+    cg = _to_dev({k: v for k, v in c.items() if k not in ("hs", "cs")})
+    cg["hs"], cg["cs"] = hs_full[:, ld_extra:], cs_full[:, ld_extra:]
+    EmuOps().lstm_fwd([c])
+    ops.lstm_fwd([cg])
+    torch.cuda.synchronize()
+    for k in ("hs", "cs", "gates"):
+        assert rel_l2(cg[k], c[k]) < TOL, (k, T, B, h)
+    if ld_extra:
+        assert float((hs_full[:, :ld_extra] - 7.0).abs().max()) == 0.0      # neighbours untouched
+    # backward on the emulator's forward state
+    for variant in range(3):
+        dh_all = g(T * B, h, seed=11) if variant in (0, 2) else None
+        dh_last = g(B, h, seed=12) if variant in (1, 2) else None
+        dc_ext = g(T * B, h, seed=13) if variant == 2 else None
+        cb = dict(T=T, B=B, h=h, gates=c["gates"], cs=c["cs"], W=c["W"], dh_all=dh_all, dh_last=dh_last, dc_ext=dc_ext,
+                  dG=torch.zeros(T * B, 4 * h))
+        cbg = _to_dev({k: v for k, v in cb.items() if k != "cs"})
+        cs_dev = torch.zeros((T + 1) * B, h + ld_extra).cuda()
+        cs_dev[:, ld_extra:] = c["cs"].cuda()
+        cbg["cs"] = cs_dev[:, ld_extra:]
+        EmuOps().lstm_bwd([cb])
+        ops.lstm_bwd([cbg])
+        torch.cuda.synchronize()
+        assert rel_l2(cbg["dG"], cb["dG"]) < 5e-5, (variant, T, B, h)
+
+
+def test_lstm_multi_cell_launch(ops):
+    cells = [_lstm_case(6, 40, h, gs, seed=h) for h, gs in ((32, 6), (8, 6), (80, 6), (24, 1))]
+    dev = [_to_dev(c) for c in cells]
+    EmuOps().lstm_fwd(cells)
+    ops.lstm_fwd(dev)
+    torch.cuda.synchronize()
+    for c, d in zip(cells, dev):
+        for k in ("hs", "cs", "gates"):
+            assert rel_l2(d[k], c[k]) < TOL, (k, c["h"])
+
+
+@pytest.mark.parametrize("T,B,mem,g1,g2,drop", [(3, 5, 9, 12, 13, False), (4, 21, 64, 128, 128, True), (2, 7, 300, 256, 32, False),
+                                                (20, 64, 64, 128, 128, False)])
+def test_mfn_mem_fwd_bwd(ops, T, B, mem, g1, g2, drop):
+    TB = T * B
+    Wg1, Wg2 = g(g1, 20 + mem, seed=1, scale=0.2), g(g2, 20 + mem, seed=2, scale=0.2)
+    rng = torch.tensor([5, 2], dtype=torch.int64)
+    a = dict(T=T, B=B, mem=mem, g1=g1, g2=g2, G1pre=g(TB, g1, seed=3), G2pre=g(TB, g2, seed=4),
+             cHat=torch.tanh(g(TB, mem, seed=5)), W1m=Wg1[:, 20:], W2m=Wg2[:, 20:],
+             W12=g(mem, g1, seed=6, scale=0.2), b12=g(mem, seed=7), W22=g(mem, g2, seed=8, scale=0.2), b22=g(mem, seed=9),
+             mems=torch.zeros((T + 1) * B, mem), U1=torch.zeros(TB, g1), U2=torch.zeros(TB, g2),
+             Gam1=torch.zeros(TB, mem), Gam2=torch.zeros(TB, mem),
+             drop1=(0.5, 3) if drop else None, drop2=(0.3, 4) if drop else None, rng=rng)
+    ad = _to_dev(a)
+    ad["W1m"], ad["W2m"] = Wg1.cuda()[:, 20:], Wg2.cuda()[:, 20:]
+    EmuOps().mfn_mem_fwd(a)
+    ops.mfn_mem_fwd(ad)
+    torch.cuda.synchronize()
+    for k in ("mems", "U1", "U2", "Gam1", "Gam2"):
+        assert rel_l2(ad[k], a[k]) < TOL, k
+    b = dict(a)
+    b.update(scale1=2.0 if drop else 1.0, scale2=1.0 / 0.7 if drop else 1.0, dmem_last=g(B, mem, seed=10),
+             dU1=torch.zeros(TB, g1), dU2=torch.zeros(TB, g2), dP1=torch.zeros(TB, mem), dP2=torch.zeros(TB, mem),
+             dPc=torch.zeros(TB, mem))
+    bd = _to_dev(b)
+    bd["W1m"], bd["W2m"] = Wg1.cuda()[:, 20:], Wg2.cuda()[:, 20:]
+    EmuOps().mfn_mem_bwd(b)
+    ops.mfn_mem_bwd(bd)
+    torch.cuda.synchronize()
+    for k in ("dU1", "dU2", "dP1", "dP2", "dPc"):
+        assert rel_l2(bd[k], b[k]) < 5e-5, k
+
+
+@pytest.mark.parametrize("M,N", [(1, 1), (7, 30), (100, 400), (33, 1000)])
+def test_softmax_gate(ops, M, N):
+    L, cs = g(M, N, seed=1, scale=3.0), g(M, N, seed=2)
+    att_cpu, att_gpu = L.clone(), L.clone().cuda()
+    o_cpu, o_gpu = torch.zeros(M, N), torch.zeros(M, N).cuda()
+    EmuOps().softmax_gate_fwd(att_cpu, cs, o_cpu)
+    ops.softmax_gate_fwd(att_gpu, cs.cuda(), o_gpu)
+    assert rel_l2(att_gpu, att_cpu) < TOL and rel_l2(o_gpu, o_cpu) < TOL
+    dA = g(M, N, seed=3)
+    dL_c, dc_c = torch.zeros(M, N), torch.zeros(M, N)
+    dL_g, dc_g = torch.zeros(M, N).cuda(), torch.zeros(M, N).cuda()
+    EmuOps().softmax_gate_bwd(dA, att_cpu, cs, dL_c, dc_c)
+    ops.softmax_gate_bwd(dA.cuda(), att_cpu.cuda(), cs.cuda(), dL_g, dc_g)
+    assert rel_l2(dL_g, dL_c) < 5e-5 and rel_l2(dc_g, dc_c) < TOL
+
+
+@pytest.mark.parametrize("B,dim", [(1, 1), (6, 3), (33, 8), (100, 80), (257, 32), (64, 256)])
+def test_mmd(ops, B, dim):
+    zfull = g(B, dim + 5, seed=1)
+    z, n = zfull[:, 2:2 + dim], g(B, dim, seed=2)
+    o_cpu, o_gpu = torch.zeros(1), torch.full((1,), 5.0).cuda()
+    EmuOps().mmd_fwd(z, n, o_cpu)
+    ops.mmd_fwd(zfull.cuda()[:, 2:2 + dim], n.cuda(), o_gpu)
+    assert abs(float(o_gpu) - float(o_cpu)) < 1e-5 * max(1.0, abs(float(o_cpu))), (float(o_gpu), float(o_cpu))
+    dz_c, dz_g = torch.ones(B, dim), torch.ones(B, dim).cuda()
+    EmuOps().mmd_bwd(z, n, 0.7, dz_c)
+    ops.mmd_bwd(zfull.cuda()[:, 2:2 + dim], n.cuda(), 0.7, dz_g)
+    assert rel_l2(dz_g - 1.0, dz_c - 1.0) < 1e-4
+    sd = torch.tensor([0.5]).cuda()
+    dz_g2 = torch.ones(B, dim).cuda()
+    ops.mmd_bwd(zfull.cuda()[:, 2:2 + dim], n.cuda(), 1.4, dz_g2, scale_dev=sd)
+    assert rel_l2(dz_g2, dz_g) < 1e-6
+
+
+def test_small_kernels(ops):
+    emu = EmuOps()
+    src = g(37, 50, seed=1)
+    for acc in (False, True):
+        d_c, d_g = torch.ones(37, 64), torch.ones(37, 64).cuda()
+        emu.copy2d(src[:, 5:25], d_c[:, 10:30], accumulate=acc)
+        ops.copy2d(src.cuda()[:, 5:25], d_g[:, 10:30], accumulate=acc)
+        assert torch.equal(d_g.cpu(), d_c)
+    a, b = g(1000, seed=2), g(1000, seed=3)
+    o = torch.zeros(1000).cuda()
+    ops.add(a.cuda(), b.cuda(), o)
+    assert torch.equal(o.cpu(), a + b)
+    ops.zero(o)
+    assert float(o.abs().max()) == 0.0
+    A = g(5000, 77, seed=4)
+    out_c, out_g = torch.ones(77), torch.ones(77).cuda()
+    emu.colsum(A[:, 3:70], out_c[:67])
+    ops.colsum(A.cuda()[:, 3:70], out_g[:67])
+    assert rel_l2(out_g, out_c) < 1e-5
+    dy, y = g(33, 21, seed=5), torch.relu(g(33, 21, seed=6))
+    r_c, r_g = torch.zeros(33, 21), torch.zeros(33, 21).cuda()
+    emu.relu_bwd(dy, y, r_c)
+    ops.relu_bwd(dy.cuda(), y.cuda(), r_g)
+    assert torch.equal(r_g.cpu(), r_c)
+
+
+def test_loss_heads_and_adam(ops):
+    emu = EmuOps()
+    xh, x = g(640, 20, seed=1), g(640, 45, seed=2)
+    s_c, s_g = torch.zeros(1), torch.zeros(1).cuda()
+    d_c, d_g = torch.zeros(640, 20), torch.zeros(640, 20).cuda()
+    emu.mse_fwd_bwd(xh, x[:, 5:25], 1.0 / 12800, 2.0 * 0.5 / 12800, s_c, d_c)
+    ops.mse_fwd_bwd(xh.cuda(), x.cuda()[:, 5:25], 1.0 / 12800, 2.0 * 0.5 / 12800, s_g, d_g)
+    assert abs(float(s_g) - float(s_c)) < 1e-5 * float(s_c) and rel_l2(d_g, d_c) < 1e-6
+    yh, y = g(77, 4, seed=3), g(77, 4, seed=4)
+    s_c, s_g = torch.zeros(1), torch.zeros(1).cuda()
+    d_c, d_g = torch.zeros(77, 4), torch.zeros(77, 4).cuda()
+    emu.l1_fwd_bwd(yh, y, 1.0 / 308, s_c, d_c)
+    ops.l1_fwd_bwd(yh.cuda(), y.cuda(), 1.0 / 308, s_g, d_g)
+    assert abs(float(s_g) - float(s_c)) < 1e-5 * float(s_c) and rel_l2(d_g, d_c) < 1e-6
+    lab = torch.randint(0, 4, (77,), generator=torch.Generator().manual_seed(1))
+    s_c, s_g = torch.zeros(1), torch.zeros(1).cuda()
+    emu.ce_fwd_bwd(yh, lab, 1.0 / 77, s_c, d_c)
+    ops.ce_fwd_bwd(yh.cuda(), lab.cuda(), 1.0 / 77, s_g, d_g)
+    assert abs(float(s_g) - float(s_c)) < 1e-5 * float(s_c) and rel_l2(d_g, d_c) < 1e-5
+    lb_c = torch.arange(16, dtype=torch.float32) * 0.1
+    lb_g = lb_c.clone().cuda()
+    emu.loss_total(lb_c, 1.0, 0.01, 0.5, 0.7)
+    ops.loss_total(lb_g, 1.0, 0.01, 0.5, 0.7)
+    assert abs(float(lb_g[8]) - float(lb_c[8])) < 1e-6
+    # Adam: three steps against torch.optim.Adam itself
+    p0, grads = g(5000, seed=5), [g(5000, seed=6 + i) for i in range(3)]
+    pt = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([pt])
+    pg, m, v = p0.clone().cuda(), torch.zeros(5000).cuda(), torch.zeros(5000).cuda()
+    st = torch.tensor([1e-3, 0, 0, 0], dtype=torch.float32).cuda()
+    for gi in grads:
+        pt.grad = gi.clone()
+        opt.step()
+        ops.adam(pg, (gi * 4.0).cuda(), m, v, st, grad_scale=0.25)
+    assert rel_l2(pg - p0.cuda(), pt.detach() - p0) < 1e-4
+    assert float(st[1]) == 3.0
+
+
+def test_randn_and_rng(ops):
+    rng = torch.tensor([42, 0], dtype=torch.int64)
+    rg = rng.clone().cuda()
+    ops.rng_tick(rg)
+    assert rg.cpu().tolist() == [42, 1]
+    out_g, out_c = torch.zeros(100000).cuda(), torch.zeros(100000)
+    ops.randn(out_g, rg, 20)
+    EmuOps().randn(out_c, rg.cpu(), 20)
+    assert float((out_g.cpu() - out_c).abs().max()) < 1e-4
+    assert abs(float(out_g.mean())) < 0.02 and abs(float(out_g.std()) - 1.0) < 0.02
+    k = keep_mask(rg.cpu(), 7, 0.3, 100, 50)
+    assert abs(float(k.mean()) - 0.7) < 0.03
+
+
+def test_bad_arguments_fail_loudly(ops):
+    from factorized_b200.cuda_ops import MfmCudaError
+    with pytest.raises(MfmCudaError):
+        ops.gemm("nt", torch.zeros(4, 4), torch.zeros(4, 4).cuda(), torch.zeros(4, 4).cuda())     # CPU tensor
+    with pytest.raises(MfmCudaError):
+        ops.gemm("nt", torch.zeros(4, 5).cuda(), torch.zeros(4, 4).cuda(), torch.zeros(4, 4).cuda())  # K mismatch
+    with pytest.raises(MfmCudaError):
+        ops.mmd_fwd(torch.zeros(4, 300).cuda(), torch.zeros(4, 300).cuda(), torch.zeros(1).cuda())   # dim > 256
