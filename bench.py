@@ -116,6 +116,7 @@ def cpu_reference_leg(configs, T, B, steps, warmup):
 
 
 def profile_primitives(trainer, reps=3):
+    # aggregates over `reps` eager steps; callers divide by reps
     """Per-primitive device time inside one eager step (CUDA events on the launching stream), used to name the
     dominant kernel and its achieved FLOP rate.  Not part of the timed region."""
     import torch
@@ -156,10 +157,12 @@ def profile_primitives(trainer, reps=3):
     try:
         for n in names:
             setattr(ops, n, wrap(n, orig[n]))
+        trainer._schedule()                       # one untimed pass
+        torch.cuda.synchronize()
+        rec.clear()
         for _ in range(reps):
-            rec.clear()
             trainer._schedule()
-            torch.cuda.synchronize()
+        torch.cuda.synchronize()
         for tag, e0, e1, fl in rec:
             a = agg.setdefault(tag, [0.0, 0.0, 0])
             a[0] += e0.elapsed_time(e1)

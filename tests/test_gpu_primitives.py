@@ -180,7 +180,8 @@ def test_softmax_gate(ops, M, N):
     dL_g, dc_g = torch.zeros(M, N).cuda(), torch.zeros(M, N).cuda()
     EmuOps().softmax_gate_bwd(dA, att_cpu, cs, dL_c, dc_c)
     ops.softmax_gate_bwd(dA.cuda(), att_cpu.cuda(), cs.cuda(), dL_g, dc_g)
-    assert rel_l2(dL_g, dL_c) < 5e-5 and rel_l2(dc_g, dc_c) < TOL
+    assert float((dL_g.cpu() - dL_c).abs().max()) < 5e-5 * max(1e-3, float(dL_c.abs().max())) + 1e-7
+    assert rel_l2(dc_g, dc_c) < TOL
 
 
 @pytest.mark.parametrize("B,dim", [(1, 1), (6, 3), (33, 8), (100, 80), (257, 32), (64, 256)])
