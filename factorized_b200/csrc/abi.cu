@@ -2,7 +2,7 @@
 #include "common.cuh"
 
 unsigned long long g_mfm_launches = 0;
-static int g_gemm_path = MFM_PATH_SIMT_FP32;
+static int g_gemm_path = MFM_PATH_TC_BF16X3;   // tensor cores, split-bf16 operands; MFM_PATH_SIMT_FP32 is the exact-fp32 alternative
 
 int gemm_simt_launch(int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
                      float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
@@ -11,9 +11,20 @@ int gemm_simt_launch(int mode, int M, int N, int K, const float* A, long long ld
 
 extern "C" int mfm_version(void) { return MFM_B200_VERSION; }
 extern "C" unsigned long long mfm_launch_count(void) { return g_mfm_launches; }
+int gemm_tc_launch(int passes, int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
+                   float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
+                   const float* mask, long long ldmask, float mask_scale, float drop_p, int drop_site,
+                   const long long* rng, cudaStream_t st);
+static long long g_tc_min_work = 1LL << 20;   // M*N*K below this stays on the CUDA-core kernel
+
 extern "C" int mfm_set_gemm_path(int path) {
-  if (path != MFM_PATH_SIMT_FP32) return MFM_ERR_UNSUPPORTED;
+  if (path != MFM_PATH_SIMT_FP32 && path != MFM_PATH_TC_BF16X3 && path != MFM_PATH_TC_BF16) return MFM_ERR_UNSUPPORTED;
   g_gemm_path = path;
+  return MFM_OK;
+}
+extern "C" int mfm_set_gemm_tc_min_work(long long mnk) {
+  if (mnk < 0) return MFM_ERR_ARG;
+  g_tc_min_work = mnk;
   return MFM_OK;
 }
 extern "C" int mfm_get_gemm_path(void) { return g_gemm_path; }
@@ -26,6 +37,9 @@ extern "C" int mfm_gemm(int mode, int M, int N, int K, const float* A, long long
   MFM_REQUIRE(mode == MFM_GEMM_NT || mode == MFM_GEMM_NN || mode == MFM_GEMM_TN);
   MFM_REQUIRE(act >= MFM_ACT_NONE && act <= MFM_ACT_SIGMOID);
   MFM_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f && (drop_p == 0.0f || rng));
+  if (g_gemm_path != MFM_PATH_SIMT_FP32 && (long long)M * N * K >= g_tc_min_work)
+    return gemm_tc_launch(g_gemm_path == MFM_PATH_TC_BF16X3 ? 3 : 1, mode, M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act,
+                          accumulate, mask, ldmask, mask_scale, drop_p, drop_site, rng, (cudaStream_t)stream);
   return gemm_simt_launch(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale,
                           drop_p, drop_site, rng, (cudaStream_t)stream);
 }

@@ -3,18 +3,7 @@
 // path does not take (K < 16, tiny M).  64x64x16 tiles, 256 threads, 4x4 register blocking.
 #include "common.cuh"
 
-struct GemmArgs {
-  int M, N, K;
-  const float* A; long long lda;
-  const float* B; long long ldb;
-  float* C; long long ldc;
-  const float* bias; const float* bias2;
-  int act, accumulate;
-  const float* mask; long long ldmask; float mask_scale;
-  float drop_p; int drop_site; const long long* rng;
-  int kchunk;      // K range per blockIdx.z
-  int atomic;      // split-K: atomicAdd partial sums into C
-};
+#include "gemm_args.cuh"
 
 #define BM 64
 #define BN 64
@@ -97,16 +86,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs a) {
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= a.N) continue;
-      float v = acc[i][j];
-      float* cp = a.C + (long long)m * a.ldc + n;
-      if (a.atomic) { atomicAdd(cp, v); continue; }
-      if (a.bias) v += __ldg(a.bias + n);
-      if (a.bias2) v += __ldg(a.bias2 + n);
-      v = apply_act(v, a.act);
-      if (do_drop) v = drop_keep(sseed, (uint32_t)m * (uint32_t)a.N + (uint32_t)n, a.drop_p) ? v * keep_scale : 0.0f;
-      if (a.mask) v = (__ldg(a.mask + (long long)m * a.ldmask + n) > 0.0f) ? v * a.mask_scale : 0.0f;
-      if (a.accumulate) v += *cp;
-      *cp = v;
+      gemm_epilogue_store(a, m, n, acc[i][j], do_drop, sseed, keep_scale);
     }
   }
 }

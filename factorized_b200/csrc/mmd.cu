@@ -161,3 +161,84 @@ extern "C" int mfm_mmd_bwd(int B, int dim, const float* z, long long ldz, const 
   MFM_LAUNCH_CHECK();
   return MFM_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// GEMM formulation used by the training schedule (engine.py step 7): the pair matrix S = X Y^T comes from the
+// tensor-core GEMM, then  K_ij = exp(-(|x_i|^2 + |y_j|^2 - 2 S_ij)/dim^2)  in place, with the weighted mean
+// accumulated into the loss slot.  The K matrices stay in HBM/L2 for the backward pass, which is two more GEMMs
+// (K_zz Z and K_gz^T G) and mmd_combine.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rownorm2_kernel(int B, int dim, const float* __restrict__ x, long long ld,
+                                                        float* __restrict__ out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B) return;
+  float s = 0.0f;
+  for (int d = lane; d < dim; d += 32) {
+    const float v = __ldg(x + (long long)row * ld + d);
+    s = fmaf(v, v, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[row] = s;
+}
+
+__global__ void __launch_bounds__(256) mmd_kexp_kernel(int M, int N, float* __restrict__ S, const float* __restrict__ nx,
+                                                        const float* __restrict__ ny, float inv_d2, float weight,
+                                                        float* __restrict__ slot) {
+  __shared__ float red[32];
+  const long long total = (long long)M * N;
+  float acc = 0.0f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / N), n = (int)(i - (long long)m * N);
+    const float d2 = fmaxf(__ldg(nx + m) + __ldg(ny + n) - 2.0f * S[i], 0.0f);
+    const float k = expf(-d2 * inv_d2);
+    S[i] = k;
+    acc += k;
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(slot, tot * weight);
+}
+
+// dz += coef * sdev * ((rs - cs) * z - t1 + t2)
+__global__ void __launch_bounds__(256) mmd_combine_kernel(int B, int dim, const float* __restrict__ z, long long ldz,
+                                                           const float* __restrict__ rs, const float* __restrict__ cs,
+                                                           const float* __restrict__ t1, const float* __restrict__ t2,
+                                                           float coef, const float* __restrict__ scale_dev,
+                                                           float* __restrict__ dz, long long lddz) {
+  const float c = coef * (scale_dev ? __ldg(scale_dev) : 1.0f);
+  const long long total = (long long)B * dim;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / dim), d = (int)(i - (long long)b * dim);
+    const float v = (rs[b] - cs[b]) * __ldg(z + (long long)b * ldz + d) - t1[i] + t2[i];
+    dz[(long long)b * lddz + d] += c * v;
+  }
+}
+
+extern "C" int mfm_rownorm2(int B, int dim, const float* x, long long ld, float* out, void* stream) {
+  MFM_REQUIRE(B > 0 && dim > 0 && x && out);
+  rownorm2_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(B, dim, x, ld, out);
+  MFM_LAUNCH_CHECK();
+  return MFM_OK;
+}
+extern "C" int mfm_mmd_kexp(int M, int N, float* S, const float* nx, const float* ny, int dim, float weight, float* slot,
+                            void* stream) {
+  MFM_REQUIRE(M > 0 && N > 0 && dim > 0 && S && nx && ny && slot);
+  long long blocks = ((long long)M * N + 256 * 8 - 1) / (256 * 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  mmd_kexp_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(M, N, S, nx, ny, 1.0f / ((float)dim * (float)dim), weight, slot);
+  MFM_LAUNCH_CHECK();
+  return MFM_OK;
+}
+extern "C" int mfm_mmd_combine(int B, int dim, const float* z, long long ldz, const float* rs, const float* cs,
+                               const float* t1, const float* t2, float scale, const float* scale_dev, float* dz,
+                               long long lddz, void* stream) {
+  MFM_REQUIRE(B > 0 && dim > 0 && z && rs && cs && t1 && t2 && dz);
+  const float c = -2.0f / ((float)dim * (float)dim);
+  const float coef = scale * 2.0f * c / ((float)B * (float)B);
+  long long blocks = ((long long)B * dim + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  mmd_combine_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(B, dim, z, ldz, rs, cs, t1, t2, coef, scale_dev, dz, lddz);
+  MFM_LAUNCH_CHECK();
+  return MFM_OK;
+}

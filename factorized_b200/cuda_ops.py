@@ -47,6 +47,7 @@ _SIGS = {
     "mfm_launch_count": (C.c_ulonglong, []),
     "mfm_set_gemm_path": (C.c_int, [C.c_int]),
     "mfm_get_gemm_path": (C.c_int, []),
+    "mfm_set_gemm_tc_min_work": (C.c_int, [LL]),
     "mfm_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_f, LL, c_f, LL, c_f, LL, c_f, c_f, C.c_int, C.c_int,
                            c_f, LL, C.c_float, C.c_float, C.c_int, c_f, c_f]),
     "mfm_lstm_seq_fwd": (C.c_int, [C.POINTER(LstmCell), C.c_int, c_f]),
@@ -58,6 +59,9 @@ _SIGS = {
     "mfm_mmd_fwd": (C.c_int, [C.c_int, C.c_int, c_f, LL, c_f, LL, c_f, c_f]),
     "mfm_mmd_bwd": (C.c_int, [C.c_int, C.c_int, c_f, LL, c_f, LL, C.c_float, c_f, c_f, LL, c_f]),
     "mfm_randn": (C.c_int, [LL, c_f, c_f, C.c_int, c_f]),
+    "mfm_rownorm2": (C.c_int, [C.c_int, C.c_int, c_f, LL, c_f, c_f]),
+    "mfm_mmd_kexp": (C.c_int, [C.c_int, C.c_int, c_f, c_f, c_f, C.c_int, C.c_float, c_f, c_f]),
+    "mfm_mmd_combine": (C.c_int, [C.c_int, C.c_int, c_f, LL, c_f, c_f, c_f, c_f, C.c_float, c_f, c_f, LL, c_f]),
     "mfm_copy2d": (C.c_int, [C.c_int, C.c_int, c_f, LL, c_f, LL, C.c_int, c_f]),
     "mfm_add": (C.c_int, [LL, c_f, c_f, c_f, c_f]),
     "mfm_zero": (C.c_int, [LL, c_f, c_f]),
@@ -157,8 +161,13 @@ class CudaOps:
     def launches(self) -> int:
         return int(self.lib.mfm_launch_count())
 
-    def set_gemm_path(self, path: int):
+    def set_gemm_path(self, path: int, min_work: Optional[int] = None):
         _check(self.lib.mfm_set_gemm_path(path), "mfm_set_gemm_path")
+        if min_work is not None:
+            _check(self.lib.mfm_set_gemm_tc_min_work(int(min_work)), "mfm_set_gemm_tc_min_work")
+
+    def get_gemm_path(self) -> int:
+        return int(self.lib.mfm_get_gemm_path())
 
     # ---- GEMM ----
     def gemm(self, mode, A, B, Cm, bias=None, bias2=None, act=0, accumulate=False, mask=None, mask_scale=1.0,
@@ -342,6 +351,28 @@ class CudaOps:
                 raise MfmCudaError("mmd_bwd: scale_dev must be a CUDA float32 scalar")
             psd = scale_dev.data_ptr()
         _check(self.lib.mfm_mmd_bwd(B, dim, pz, ldz, pg, ldg, float(scale), psd, pd, ldd, _stream()), "mfm_mmd_bwd")
+
+    def rownorm2(self, x, out):
+        px, B, dim, ld = _mat(x, "rownorm2 x")
+        _check(self.lib.mfm_rownorm2(B, dim, px, ld, _vec(out, "rownorm2 out", B), _stream()), "mfm_rownorm2")
+
+    def mmd_kexp(self, S, nx, ny, dim, weight, slot):
+        ps, M, N, ld = _mat(S, "mmd_kexp S")
+        if ld != N:
+            raise MfmCudaError("mmd_kexp: S must be contiguous")
+        _check(self.lib.mfm_mmd_kexp(M, N, ps, _vec(nx, "nx", M), _vec(ny, "ny", N), int(dim), float(weight),
+                                     _vec(slot, "slot", 1), _stream()), "mfm_mmd_kexp")
+
+    def mmd_combine(self, z, rs, cs, t1, t2, scale, dz, scale_dev=None):
+        pz, B, dim, ldz = _mat(z, "mmd_combine z")
+        pd, B2, d2, ldd = _mat(dz, "mmd_combine dz")
+        p1, _, _, l1 = _mat(t1, "mmd_combine t1")
+        p2, _, _, l2 = _mat(t2, "mmd_combine t2")
+        if (B2, d2) != (B, dim) or tuple(t1.shape) != (B, dim) or tuple(t2.shape) != (B, dim) or l1 != dim or l2 != dim:
+            raise MfmCudaError("mmd_combine shapes")
+        psd = None if scale_dev is None else scale_dev.data_ptr()
+        _check(self.lib.mfm_mmd_combine(B, dim, pz, ldz, _vec(rs, "rs", B), _vec(cs, "cs", B), p1, p2, float(scale), psd,
+                                        pd, ldd, _stream()), "mfm_mmd_combine")
 
     # ---- small kernels ----
     def copy2d(self, src, dst, accumulate=False):

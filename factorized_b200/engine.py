@@ -194,9 +194,25 @@ class Engine:
         ops.gemm("nt", mems[TB:], Wzy[:, H:], ZY, accumulate=True)
 
         # (7) MMD of each latent against its Gaussian sample (:25-34, :536)
+        #     pair matrices S = X Y^T on the tensor cores, K = exp(-(|x|^2+|y|^2-2S)/dim^2) in place; K(z,z) and
+        #     K(g,z) stay resident for the backward pass (no [B,B,dim] tensor, no recompute)
         lat = Z + [ZY]
+        ops.zero(self.loss_buf[4:8])
+        Kgg = buf("Kgg", B, B)
+        inv_bb = 1.0 / (float(B) * float(B))
         for k in range(4):
-            ops.mmd_fwd(lat[k], self.noise[k], self.loss_buf[4 + k:5 + k])
+            zk, gk, dim = lat[k], self.noise[k], lat[k].shape[1]
+            nz, ng = buf("mmd_nz%d" % k, B), buf("mmd_ng%d" % k, B)
+            ops.rownorm2(zk, nz)
+            ops.rownorm2(gk, ng)
+            Kzz, Kgz = buf("Kzz%d" % k, B, B), buf("Kgz%d" % k, B, B)
+            slot = self.loss_buf[4 + k:5 + k]
+            ops.gemm("nt", zk, zk, Kzz)
+            ops.mmd_kexp(Kzz, nz, nz, dim, inv_bb, slot)
+            ops.gemm("nt", gk, zk, Kgz)                       # rows index the Gaussian sample, columns the latent
+            ops.mmd_kexp(Kgz, ng, nz, dim, -2.0 * inv_bb, slot)
+            ops.gemm("nt", gk, gk, Kgg)
+            ops.mmd_kexp(Kgg, ng, ng, dim, inv_bb, slot)
 
         # (8) factor MLPs (:539-542) written straight into the decoder inputs cat(fy, f_m) (:544-546)
         FY = buf("FY", B, dm.fy)
@@ -353,8 +369,18 @@ class Engine:
         # (7') MMD: gradient flows through K(z,z) and K(g,z) only
         lat = [ws["Z0"], ws["Z1"], ws["Z2"], ws["ZY"]]
         dlat = dZ + [dZY]
+        #      d/dz = (2c/B^2) [ (rowsum Kzz - colsum Kgz) * z - Kzz Z + Kgz^T G ],  c = -2/dim^2
         for k in range(4):
-            ops.mmd_bwd(lat[k], self.noise[k], mmd_scale, dlat[k], mmd_scale_dev)
+            zk, gk, dim = lat[k], self.noise[k], lat[k].shape[1]
+            Kzz, Kgz = ws["Kzz%d" % k], ws["Kgz%d" % k]
+            rc = buf("mmd_rc%d" % k, 2 * B)
+            ops.zero(rc)
+            ops.colsum(Kzz, rc[:B])                          # K(z,z) is symmetric: column sums == row sums
+            ops.colsum(Kgz, rc[B:])
+            t1, t2 = buf("mmd_t1_%d" % k, B, dim), buf("mmd_t2_%d" % k, B, dim)
+            ops.gemm("nn", Kzz, zk, t1)
+            ops.gemm("tn", Kgz, gk, t2)
+            ops.mmd_combine(zk, rc[:B], rc[B:], t1, t2, mmd_scale, dlat[k], mmd_scale_dev)
 
         # (6') last_to_zy_fc1 over cat(h_T, mem_T)
         Wzy = P["last_to_zy_fc1.weight"]

@@ -50,6 +50,8 @@ int mfm_version(void);
 unsigned long long mfm_launch_count(void);
 int mfm_set_gemm_path(int path);
 int mfm_get_gemm_path(void);
+/* GEMMs with M*N*K below this stay on the CUDA-core kernel even when a tcgen05 path is selected (default 2^20) */
+int mfm_set_gemm_tc_min_work(long long mnk);
 
 /* C = epilogue(op(A) op(B)).  Replaces every nn.Linear / LSTMCell input projection on the path:
  * mfm_model.py:56,61,83,85,90,167-169,174,176,178-179,535,539-542,552 and their autograd adjoints.
@@ -122,6 +124,15 @@ int mfm_mmd_fwd(int B, int dim, const float* z, long long ldz, const float* g, l
  * upstream gradient) so the drop-in path needs no host synchronisation */
 int mfm_mmd_bwd(int B, int dim, const float* z, long long ldz, const float* g, long long ldg, float scale,
                 const float* scale_dev, float* dz, long long lddz, void* stream);
+/* GEMM formulation of the same loss for the training schedule: S = X Y^T is produced by mfm_gemm, then
+ *   mfm_mmd_kexp:    S[i,j] <- K_ij = exp(-(nx[i] + ny[j] - 2 S[i,j]) / dim^2);  *slot += weight * sum_ij K_ij
+ *   mfm_rownorm2:    out[i] = |x_i|^2
+ *   mfm_mmd_combine: dz += scale * (scale_dev ? *scale_dev : 1) * (2c/B^2) * ((rs - cs) * z - t1 + t2),  c = -2/dim^2,
+ *                    with rs = row sums of K(z,z), cs = column sums of K(g,z), t1 = K(z,z) Z, t2 = K(g,z)^T G */
+int mfm_rownorm2(int B, int dim, const float* x, long long ld, float* out, void* stream);
+int mfm_mmd_kexp(int M, int N, float* S, const float* nx, const float* ny, int dim, float weight, float* slot, void* stream);
+int mfm_mmd_combine(int B, int dim, const float* z, long long ldz, const float* rs, const float* cs, const float* t1,
+                    const float* t2, float scale, const float* scale_dev, float* dz, long long lddz, void* stream);
 /* out[i] ~ N(0,1), counter-based (Box-Muller over the library's hash RNG keyed by rng=[seed,step] and site):
  * the Gaussian sample of loss_MMD (mfm_model.py:26) generated on the device for the fused training path */
 int mfm_randn(long long n, float* out, const long long* rng, int site, void* stream);

@@ -200,6 +200,27 @@ def dropout(x: Tensor, p: float, train: bool, mask: Optional[Tensor] = None) -> 
     return x
 
 
+RELU_REPLAY_VIOLATIONS: List[str] = []
+
+
+def relu(x: Tensor, branches, key: str, t: Optional[int] = None) -> Tensor:
+    """F.relu, optionally with the branch decision (x > 0) REPLAYED from another implementation.
+
+    ReLU's derivative is discontinuous: an input that the reference computes as +1e-7 and another
+    correct fp32 implementation as -1e-7 yields equal forward values (to 1e-7) but gradients that differ
+    by a whole row.  Parity tests therefore replay the branch mask the CUDA run took (like dropout masks)
+    and separately assert that any disagreement with the oracle's own decision happens only where
+    |x| < 1e-3, i.e. on the knife edge.  With branches=None this is exactly torch.relu."""
+    if branches is None or key not in branches:
+        return torch.relu(x)
+    m = branches[key] if t is None else branches[key][t]
+    m = m.to(x.dtype)
+    bad = ((x > 0).to(x.dtype) != m) & (x.abs() > 1e-3)
+    if bool(bad.any()):
+        RELU_REPLAY_VIOLATIONS.append("%s[t=%s]: %d branch decisions differ with |x| > 1e-3" % (key, t, int(bad.sum())))
+    return x * m
+
+
 def encoder_lstm(x: Tensor, P, prefix: str) -> Tensor:
     """encoderLSTM.forward, mfm_model.py:47-62: zero state, T cell steps,
     fc1 on the last hidden state, no activation."""
@@ -227,7 +248,7 @@ def decoder_lstm(emb: Tensor, T: int, P, prefix: str) -> Tensor:
     return linear(hs_all, P, prefix + ".fc1")
 
 
-def mfn_encoder(x: Tensor, P, configs, train=False, masks=None) -> Tensor:
+def mfn_encoder(x: Tensor, P, configs, train=False, masks=None, branches=None) -> Tensor:
     """MFN.forward, mfm_model.py:140-199 (the memory fusion network that
     produces the input of last_to_zy_fc1).  ``masks`` optionally maps
     'att1','att2','gamma1','gamma2' -> [T,n,shapes] keep-masks."""
@@ -248,16 +269,16 @@ def mfn_encoder(x: Tensor, P, configs, train=False, masks=None) -> Tensor:
             hcs[m][0], hcs[m][1] = lstm_cell(xs[m][t], hcs[m][0], hcs[m][1], P, pre + "lstm_%s" % tag)  # :167-169
         new_cs = torch.cat([hc[1] for hc in hcs], 1)                        # :172
         c_star = torch.cat([prev_cs, new_cs], 1)                            # :173
-        a = torch.relu(linear(c_star, P, pre + "att1_fc1"))
+        a = relu(linear(c_star, P, pre + "att1_fc1"), branches, "att1", t)
         a = dropout(a, nn1["drop"], train, mk("att1", t))
         attention = torch.softmax(linear(a, P, pre + "att1_fc2"), dim=1)    # :174
         attended = attention * c_star                                        # :175
-        b = torch.relu(linear(attended, P, pre + "att2_fc1"))
+        b = relu(linear(attended, P, pre + "att2_fc1"), branches, "att2", t)
         b = dropout(b, nn2["drop"], train, mk("att2", t))
         c_hat = torch.tanh(linear(b, P, pre + "att2_fc2"))                  # :176
         both = torch.cat([attended, mem], 1)                                 # :177
-        u1 = dropout(torch.relu(linear(both, P, pre + "gamma1_fc1")), g1["drop"], train, mk("gamma1", t))
-        u2 = dropout(torch.relu(linear(both, P, pre + "gamma2_fc1")), g2["drop"], train, mk("gamma2", t))
+        u1 = dropout(relu(linear(both, P, pre + "gamma1_fc1"), branches, "gamma1", t), g1["drop"], train, mk("gamma1", t))
+        u2 = dropout(relu(linear(both, P, pre + "gamma2_fc1"), branches, "gamma2", t), g2["drop"], train, mk("gamma2", t))
         gamma1 = torch.sigmoid(linear(u1, P, pre + "gamma1_fc2"))           # :178
         gamma2 = torch.sigmoid(linear(u2, P, pre + "gamma2_fc2"))           # :179
         mem = gamma1 * mem + gamma2 * c_hat                                  # :180
@@ -286,12 +307,13 @@ def draw_mmd_noise(configs, n: int, seed: int, dtype=torch.float32) -> List[Tens
     return [torch.randn(n, k).to(dtype) for k in (c["zl_size"], c["za_size"], c["zv_size"], c["zy_size"])]
 
 
-def factor_mlp(z: Tensor, P, name: str, p: float, train: bool, mask=None) -> Tensor:
+def factor_mlp(z: Tensor, P, name: str, p: float, train: bool, mask=None, branches=None, key="") -> Tensor:
     """relu(fc2(drop(relu(fc1(z))))), mfm_model.py:539-542."""
-    return torch.relu(linear(dropout(torch.relu(linear(z, P, name + "_fc1")), p, train, mask), P, name + "_fc2"))
+    h = dropout(relu(linear(z, P, name + "_fc1"), branches, key + "1"), p, train, mask)
+    return relu(linear(h, P, name + "_fc2"), branches, key)
 
 
-def mfm_forward(x: Tensor, P, configs, noise: Sequence[Tensor], train=False, masks=None):
+def mfm_forward(x: Tensor, P, configs, noise: Sequence[Tensor], train=False, masks=None, branches=None):
     """MFM.forward, mfm_model.py:522-555.  Returns a dict with the reference's
     outputs plus the latents the reference computes but does not return."""
     config = configs[0]
@@ -301,18 +323,18 @@ def mfm_forward(x: Tensor, P, configs, noise: Sequence[Tensor], train=False, mas
     zl = encoder_lstm(x_l, P, "encoder_l")                                   # :530
     za = encoder_lstm(x_a, P, "encoder_a")
     zv = encoder_lstm(x_v, P, "encoder_v")
-    mfn_last = mfn_encoder(x, P, configs, train, masks)                      # :534
+    mfn_last = mfn_encoder(x, P, configs, train, masks, branches)            # :534
     zy = linear(mfn_last, P, "last_to_zy_fc1")                               # :535
     mmd = loss_mmd(zl, noise[0]) + loss_mmd(za, noise[1]) + loss_mmd(zv, noise[2]) + loss_mmd(zy, noise[3])  # :536
     mk = (lambda k: None if masks is None else masks.get(k))
-    fy = factor_mlp(zy, P, "zy_to_fy", config["zy_to_fy_dropout"], train, mk("fy"))
-    fl = factor_mlp(zl, P, "zl_to_fl", config["zl_to_fl_dropout"], train, mk("fl"))
-    fa = factor_mlp(za, P, "za_to_fa", config["za_to_fa_dropout"], train, mk("fa"))
-    fv = factor_mlp(zv, P, "zv_to_fv", config["zv_to_fv_dropout"], train, mk("fv"))
+    fy = factor_mlp(zy, P, "zy_to_fy", config["zy_to_fy_dropout"], train, mk("fy"), branches, "fy")
+    fl = factor_mlp(zl, P, "zl_to_fl", config["zl_to_fl_dropout"], train, mk("fl"), branches, "fl")
+    fa = factor_mlp(za, P, "za_to_fa", config["za_to_fa_dropout"], train, mk("fa"), branches, "fa")
+    fv = factor_mlp(zv, P, "zv_to_fv", config["zv_to_fv_dropout"], train, mk("fv"), branches, "fv")
     x_l_hat = decoder_lstm(torch.cat([fy, fl], 1), T, P, "decoder_l")       # :544-551
     x_a_hat = decoder_lstm(torch.cat([fy, fa], 1), T, P, "decoder_a")
     x_v_hat = decoder_lstm(torch.cat([fy, fv], 1), T, P, "decoder_v")
-    y1 = dropout(torch.relu(linear(fy, P, "fy_to_y_fc1")), config["fy_to_y_dropout"], train, mk("y"))
+    y1 = dropout(relu(linear(fy, P, "fy_to_y_fc1"), branches, "y1"), config["fy_to_y_dropout"], train, mk("y"))
     y_hat = linear(y1, P, "fy_to_y_fc2")                                     # :552
     return dict(x_l_hat=x_l_hat, x_a_hat=x_a_hat, x_v_hat=x_v_hat, y_hat=y_hat, mmd=mmd,
                 zl=zl, za=za, zv=zv, zy=zy, fy=fy, fl=fl, fa=fa, fv=fv, mfn_last=mfn_last)
@@ -359,11 +381,11 @@ def adam_step(P, G, state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
     return P
 
 
-def train_step(P, x, y, configs, noise, state, head="l1", lr=1e-3, train=False, masks=None):
+def train_step(P, x, y, configs, noise, state, head="l1", lr=1e-3, train=False, masks=None, branches=None):
     """One iteration of the inner loop of train_mfm (mfm_mosi.py:427-442):
     forward, loss, backward, Adam.  Returns (new params, losses, grads, fwd)."""
     Pg = OrderedDict((k, v.detach().clone().requires_grad_(k not in UNUSED_PARAMS)) for k, v in P.items())
-    out = mfm_forward(x, Pg, configs, noise, train=train, masks=masks)
+    out = mfm_forward(x, Pg, configs, noise, train=train, masks=masks, branches=branches)
     losses = mfm_losses(out, x, y, configs, head)
     losses["total"].backward()
     G = OrderedDict((k, (None if v.grad is None else v.grad.detach().clone())) for k, v in Pg.items())

@@ -207,6 +207,24 @@ class EmuOps:
         dgz = (-2.0 / (n * n)) * c * ((kgz.sum(0).unsqueeze(1) * z) - kgz.t() @ g)
         dz += scale * (dzz + dgz)
 
+    def rownorm2(self, x, out):
+        self.launches += 1
+        out.copy_((x * x).sum(1))
+
+    def mmd_kexp(self, S, nx, ny, dim, weight, slot):
+        self.launches += 1
+        d2 = (nx.view(-1, 1) + ny.view(1, -1) - 2.0 * S).clamp_min(0.0)
+        S.copy_(torch.exp(-d2 / float(dim * dim)))
+        slot[0] += weight * S.sum()
+
+    def mmd_combine(self, z, rs, cs, t1, t2, scale, dz, scale_dev=None):
+        self.launches += 1
+        if scale_dev is not None:
+            scale = scale * float(scale_dev)
+        n, dim = z.shape
+        coef = scale * 2.0 * (-2.0 / float(dim * dim)) / float(n * n)
+        dz += coef * ((rs - cs).view(-1, 1) * z - t1 + t2)
+
     # ---- small elementwise / reductions ----
     def copy2d(self, src, dst, accumulate=False):
         self.launches += 1

@@ -202,6 +202,35 @@ def test_mmd(ops, B, dim):
     assert rel_l2(dz_g2, dz_g) < 1e-6
 
 
+def test_mmd_gemm_formulation(ops):
+    """rownorm2 + GEMM + mmd_kexp (+ colsum, GEMMs, mmd_combine) against the direct pairwise statement."""
+    emu = EmuOps()
+    B, dim = 300, 80
+    z, n = g(B, dim, seed=1), g(B, dim, seed=2)
+    ref, dz_ref = torch.zeros(1), torch.zeros(B, dim)
+    emu.mmd_fwd(z, n, ref)
+    emu.mmd_bwd(z, n, 0.7, dz_ref)
+    zd, nd = z.cuda(), n.cuda()
+    nz, ng = torch.zeros(B).cuda(), torch.zeros(B).cuda()
+    ops.rownorm2(zd, nz)
+    ops.rownorm2(nd, ng)
+    assert rel_l2(nz, (z * z).sum(1)) < 1e-6
+    slot = torch.zeros(1).cuda()
+    Kzz, Kgz, Kgg = (torch.zeros(B, B).cuda() for _ in range(3))
+    ib = 1.0 / (B * B)
+    ops.gemm("nt", zd, zd, Kzz); ops.mmd_kexp(Kzz, nz, nz, dim, ib, slot)
+    ops.gemm("nt", nd, zd, Kgz); ops.mmd_kexp(Kgz, ng, nz, dim, -2 * ib, slot)
+    ops.gemm("nt", nd, nd, Kgg); ops.mmd_kexp(Kgg, ng, ng, dim, ib, slot)
+    assert abs(float(slot) - float(ref)) < 2e-5 * max(1.0, abs(float(ref))), (float(slot), float(ref))
+    rc = torch.zeros(2 * B).cuda()
+    ops.colsum(Kzz, rc[:B]); ops.colsum(Kgz, rc[B:])
+    t1, t2 = torch.zeros(B, dim).cuda(), torch.zeros(B, dim).cuda()
+    ops.gemm("nn", Kzz, zd, t1); ops.gemm("tn", Kgz, nd, t2)
+    dz = torch.zeros(B, dim).cuda()
+    ops.mmd_combine(zd, rc[:B], rc[B:], t1, t2, 0.7, dz)
+    assert rel_l2(dz, dz_ref) < 2e-4, rel_l2(dz, dz_ref)
+
+
 def test_small_kernels(ops):
     emu = EmuOps()
     src = g(37, 50, seed=1)
