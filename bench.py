@@ -122,7 +122,7 @@ def profile_primitives(trainer, reps=3):
     import torch
     ops = trainer.ops
     rec = []
-    flops_of = {}
+    shapes = []
 
     def wrap(name, fn):
         def inner(*a, **k):
@@ -137,6 +137,7 @@ def profile_primitives(trainer, reps=3):
                 Kd = a[1].shape[1] if a[0] in ("nt", "nn") else a[1].shape[0]
                 fl = 2.0 * C.shape[0] * C.shape[1] * Kd
                 tag = "gemm_" + a[0]
+                shapes.append(("%s %dx%dx%d%s" % (a[0], C.shape[0], C.shape[1], Kd, " acc" if k.get("accumulate") else ""), e0, e1))
             elif name in ("lstm_fwd", "lstm_bwd"):
                 fl = sum(2.0 * c["T"] * c["B"] * 4 * c["h"] * c["h"] for c in a[0])
                 tag = name + ("_dec" if (a[0][0].get("gx_steps", 0) == 1 or a[0][0].get("dh_all") is not None) else "_enc_mfn")
@@ -160,6 +161,7 @@ def profile_primitives(trainer, reps=3):
         trainer._schedule()                       # one untimed pass
         torch.cuda.synchronize()
         rec.clear()
+        shapes.clear()
         for _ in range(reps):
             trainer._schedule()
         torch.cuda.synchronize()
@@ -174,6 +176,12 @@ def profile_primitives(trainer, reps=3):
                 delattr(ops, n)
             except AttributeError:
                 pass
+    by_shape = {}
+    for key, e0, e1 in shapes:
+        v = by_shape.setdefault(key, [0.0, 0])
+        v[0] += e0.elapsed_time(e1) / reps
+        v[1] += 1
+    agg["_gemm_shapes"] = {k: [round(v[0], 4), v[1] // reps] for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:40]}
     return agg
 
 
@@ -280,6 +288,7 @@ def main():
     roof, kernels = None, None
     if rank == 0:
         agg = profile_primitives(trainer)
+        gemm_shapes = agg.pop("_gemm_shapes")
         tot = sum(v[0] for v in agg.values())
         kernels = {k: dict(ms_per_step=round(v[0] / 3, 4), share=round(v[0] / tot, 4), launches=v[2] // 3,
                            tflops=(round(v[1] / (v[0] * 1e-3) / 1e12, 3) if v[1] else None)) for k, v in
@@ -299,6 +308,8 @@ def main():
                 gpu_launches=trainer.launches_per_step * args.steps, launches_per_step=trainer.launches_per_step,
                 cuda_graph=not args.no_graph, clocks=clocks, roofline=roof, kernels=kernels, final_loss=final_loss,
                 workspace_mb=round(trainer.eng.workspace_bytes() / 2 ** 20, 1))
+    if rank == 0 and os.environ.get("MFM_BENCH_GEMM_SHAPES"):
+        line["gemm_shapes_ms"] = gemm_shapes
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:

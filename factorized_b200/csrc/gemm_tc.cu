@@ -12,16 +12,20 @@
 //   MN-major operand (K x cols, cols contiguous in HBM): byte(k,c) = (k/8)*LBO + (c/8)*128 + (k%8)*16 + (c%8)*2
 // so all three GEMM modes (NT forward, NN data-gradient, TN weight-gradient) run without a transpose pass.
 // One elected thread issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN<=256, K=16); completion is tracked
-// with tcgen05.commit -> mbarrier; two shared-memory stages overlap the loads of chunk c+1 with the MMAs of chunk c;
-// the epilogue reads the accumulator with tcgen05.ld (32x32b.x16) and applies the fused epilogue of mfm_gemm.
-#include <cuda_bf16.h>
+// with tcgen05.commit -> mbarrier.  256 threads: the raw fp32 of chunk c+1 is prefetched into registers while chunk c
+// is converted, fenced and multiplied; two shared-memory stages let the MMAs of chunk c overlap the conversion of c+1.
+// The epilogue reads the accumulator with tcgen05.ld, transposes 32x32 blocks through shared memory so that every
+// store / split-K reduction is a coalesced 128 B row segment, and applies the fused epilogue of mfm_gemm.
 #include "gemm_args.cuh"
+#include "tc_common.cuh"
 
 #define TC_BM 128
 #define TC_BK 32
-#define TC_THREADS 128
+#define TC_THREADS 256
 #define TC_STAGES 2
 #define TC_A_PLANE (4 * (TC_BM * 16 + 32))        // bytes of one A plane (K-major with 32 B slab padding; MN-major needs less)
+#define TC_NA 2                                   // A items (8 fp32 each) per thread per chunk: 128 rows * 4 slabs / 256
+#define TC_NB 4                                   // B items per thread per chunk (BN <= 256)
 
 struct TcArgs {
   GemmArgs g;
@@ -30,137 +34,46 @@ struct TcArgs {
   int tmem_cols;   // power of two >= max(32, BN)
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-// bounded wait: a barrier that never completes traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  // cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_NONE
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// 8 consecutive fp32 along the contiguous dimension at (row, col..col+7); zero outside [0,nrows) x [0,ncols)
-__device__ __forceinline__ void load8(const float* __restrict__ src, long long ld, int row, int nrows, int col, int ncols,
-                                      bool vec_ok, float v[8]) {
-  if (row < nrows && col + 8 <= ncols) {
-    const float* p = src + (long long)row * ld + col;
-    if (vec_ok) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
+// One operand tile of a K chunk travels HBM -> registers (raw fp32) -> split-bf16 planes in shared memory.
+// The two halves are separate calls so the loads of chunk c+1 are in flight while chunk c is converted,
+// fenced, and multiplied (register-level software pipelining; nothing waits on a load it just issued).
+//   K-major  source [rows, K] (K contiguous):  item = (row r, 8-wide k slab)
+//   MN-major source [K, cols] (cols contiguous): item = (k row, 8-wide column group)
+template <bool MN, int NI>
+__device__ __forceinline__ void tile_fetch(float (&v)[NI][8], const float* __restrict__ src, long long ld, int mn0, int mn_max,
+                                           int k0, int kend, int tile_mn, bool vec_ok) {
+  const int items = MN ? ((((tile_mn >> 3) + 3) & ~3) * TC_BK) : tile_mn * 4;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = __ldg(p + i);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.0f;
-    if (row < nrows) {
-      const float* p = src + (long long)row * ld + col;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (col + i < ncols) v[i] = __ldg(p + i);
+  for (int u = 0; u < NI; ++u) {
+    const int idx = u * TC_THREADS + threadIdx.x;
+    if (idx < items) {
+      if (MN) {
+        const int k = (idx & 7) + 8 * ((idx >> 5) & 3), mg = ((idx >> 3) & 3) + 4 * (idx >> 7);
+        if (mg < (tile_mn >> 3)) load8(src, ld, k0 + k, kend, mn0 + mg * 8, mn_max, vec_ok, v[u]);
+      } else {
+        const int slab = idx & 3, r = idx >> 2;
+        load8(src, ld, mn0 + r, mn_max, k0 + slab * 8, kend, vec_ok, v[u]);
+      }
     }
   }
 }
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);      // .x = a (low address), .y = b
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-
-// fp32 x8 -> 16 B of bf16 "hi" and (optionally) 16 B of bf16 "lo" = bf16(x - hi)
-__device__ __forceinline__ void split_store(const float v[8], unsigned char* hi_dst, unsigned char* lo_dst, bool want_lo) {
-  uint4 h;
-  h.x = pack_bf16(v[0], v[1]); h.y = pack_bf16(v[2], v[3]); h.z = pack_bf16(v[4], v[5]); h.w = pack_bf16(v[6], v[7]);
-  *reinterpret_cast<uint4*>(hi_dst) = h;
-  if (want_lo) {
-    float r[8];
-    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      r[2 * i] = v[2 * i] - __uint_as_float(hw[i] << 16);
-      r[2 * i + 1] = v[2 * i + 1] - __uint_as_float(hw[i] & 0xFFFF0000u);
-    }
-    uint4 l;
-    l.x = pack_bf16(r[0], r[1]); l.y = pack_bf16(r[2], r[3]); l.z = pack_bf16(r[4], r[5]); l.w = pack_bf16(r[6], r[7]);
-    *reinterpret_cast<uint4*>(lo_dst) = l;
-  }
-}
-
-// source [rows, K] with K contiguous -> K-major planes.  item = (row r, 8-wide k slab)
-__device__ __forceinline__ void load_kmajor(const float* __restrict__ src, long long ld, int row0, int nrows, int k0, int kend,
-                                            int tile_rows, unsigned char* hi, unsigned char* lo, int lbo, bool vec_ok,
+template <bool MN, int NI>
+__device__ __forceinline__ void tile_commit(const float (&v)[NI][8], unsigned char* hi, unsigned char* lo, int lbo, int tile_mn,
                                             bool want_lo) {
-  const int items = tile_rows * 4;
-  for (int base = 0; base < items; base += TC_THREADS * 4) {
-    float v[4][8];
+  const int items = MN ? ((((tile_mn >> 3) + 3) & ~3) * TC_BK) : tile_mn * 4;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int idx = base + u * TC_THREADS + threadIdx.x;
-      const int slab = idx & 3, r = idx >> 2;
-      if (idx < items) load8(src, ld, row0 + r, nrows, k0 + slab * 8, kend, vec_ok, v[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int idx = base + u * TC_THREADS + threadIdx.x;
-      const int slab = idx & 3, r = idx >> 2;
-      if (idx < items) split_store(v[u], hi + slab * lbo + r * 16, lo + slab * lbo + r * 16, want_lo);
-    }
-  }
-}
-
-// source [K, cols] with cols contiguous -> MN-major planes.  item = (k row, 8-wide column group)
-__device__ __forceinline__ void load_mnmajor(const float* __restrict__ src, long long ld, int k0, int kend, int col0, int ncols,
-                                             int tile_cols, unsigned char* hi, unsigned char* lo, int lbo, bool vec_ok,
-                                             bool want_lo) {
-  const int groups = tile_cols >> 3;
-  const int items = ((groups + 3) & ~3) * TC_BK;
-  for (int base = 0; base < items; base += TC_THREADS * 4) {
-    float v[4][8];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int idx = base + u * TC_THREADS + threadIdx.x;
-      const int k = (idx & 7) + 8 * ((idx >> 5) & 3), mg = ((idx >> 3) & 3) + 4 * (idx >> 7);
-      if (idx < items && mg < groups) load8(src, ld, k0 + k, kend, col0 + mg * 8, ncols, vec_ok, v[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int idx = base + u * TC_THREADS + threadIdx.x;
-      const int k = (idx & 7) + 8 * ((idx >> 5) & 3), mg = ((idx >> 3) & 3) + 4 * (idx >> 7);
-      if (idx < items && mg < groups) {
-        const int off = (k >> 3) * lbo + mg * 128 + (k & 7) * 16;
-        split_store(v[u], hi + off, lo + off, want_lo);
+  for (int u = 0; u < NI; ++u) {
+    const int idx = u * TC_THREADS + threadIdx.x;
+    if (idx < items) {
+      if (MN) {
+        const int k = (idx & 7) + 8 * ((idx >> 5) & 3), mg = ((idx >> 3) & 3) + 4 * (idx >> 7);
+        if (mg < (tile_mn >> 3)) {
+          const int off = (k >> 3) * lbo + mg * 128 + (k & 7) * 16;
+          split_store(v[u], hi + off, lo + off, want_lo);
+        }
+      } else {
+        const int slab = idx & 3, r = idx >> 2;
+        split_store(v[u], hi + slab * lbo + r * 16, lo + slab * lbo + r * 16, want_lo);
       }
     }
   }
@@ -197,6 +110,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // first chunk's loads go out before anything else waits
+  float va[TC_NA][8], vb[TC_NB][8];
+  const int nchunks = (kend - kbeg + TC_BK - 1) / TC_BK;
+  if (nchunks > 0) {
+    tile_fetch<A_MN, TC_NA>(va, a.A, a.lda, m0, a.M, kbeg, kend, TC_BM, vecA);
+    tile_fetch<B_MN, TC_NB>(vb, a.B, a.ldb, n0, a.N, kbeg, kend, BN, vecB);
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -206,7 +126,6 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
-  const int nchunks = (kend - kbeg + TC_BK - 1) / TC_BK;
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1;
     unsigned char* st = smem + s * stage_bytes;
@@ -215,11 +134,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
     unsigned char* Bhi = st + 2 * TC_A_PLANE;
     unsigned char* Blo = Bhi + b_plane;
     if (c >= TC_STAGES) mbar_wait(smem_u32(&bars[s]), (uint32_t)((c / TC_STAGES - 1) & 1));   // MMAs that read this stage are done
-    const int k0 = kbeg + c * TC_BK;
-    if (A_MN) load_mnmajor(a.A, a.lda, k0, kend, m0, a.M, TC_BM, Ahi, Alo, lboA, vecA, want_lo);
-    else      load_kmajor(a.A, a.lda, m0, a.M, k0, kend, TC_BM, Ahi, Alo, lboA, vecA, want_lo);
-    if (B_MN) load_mnmajor(a.B, a.ldb, k0, kend, n0, a.N, BN, Bhi, Blo, lboB, vecB, want_lo);
-    else      load_kmajor(a.B, a.ldb, n0, a.N, k0, kend, BN, Bhi, Blo, lboB, vecB, want_lo);
+    tile_commit<A_MN, TC_NA>(va, Ahi, Alo, lboA, TC_BM, want_lo);
+    tile_commit<B_MN, TC_NB>(vb, Bhi, Blo, lboB, BN, want_lo);
+    if (c + 1 < nchunks) {
+      const int k1 = kbeg + (c + 1) * TC_BK;
+      tile_fetch<A_MN, TC_NA>(va, a.A, a.lda, m0, a.M, k1, kend, TC_BM, vecA);
+      tile_fetch<B_MN, TC_NB>(vb, a.B, a.ldb, n0, a.N, k1, kend, BN, vecB);
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
     __syncthreads();
     if (tid == 0) {
@@ -246,29 +167,46 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 == tile rows
+  // ---- epilogue.  Warp w reads TMEM lanes 32*(w%4).. (tile rows) for the column half w/4, transposes 32x32 blocks
+  //      through the (now idle) stage memory, and writes 128 B row segments: coalesced stores / reductions.
   uint32_t sseed = 0;
   const bool do_drop = a.drop_p > 0.0f;
   if (do_drop) sseed = site_seed(a.rng, a.drop_site);
   const float keep_scale = do_drop ? 1.0f / (1.0f - a.drop_p) : 1.0f;
-  const int m = m0 + warp * 32 + lane;
-  for (int c0 = 0; c0 < BN; c0 += 16) {
-    uint32_t r[16];
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (m < a.M && nchunks > 0) {
+  float* scratch = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+  const int quad = warp & 3, half = warp >> 2;
+  const int cbeg = half * (BN >> 1), cend = cbeg + (BN >> 1);
+  const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+  for (int c0 = cbeg; c0 < cend; c0 += 32) {
+    float v[32];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = n0 + c0 + j;
-        if (n < a.N) gemm_epilogue_store(a, m, n, __uint_as_float(r[j]), do_drop, sseed, keep_scale);
+    for (int q = 0; q < 4; ++q) {
+      if (c0 + 8 * q < cend) {          // warp-uniform
+        uint32_t r[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(tlane + (uint32_t)(c0 + 8 * q))
+                     : "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 * q + i] = __uint_as_float(r[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 * q + i] = 0.0f;
       }
     }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = v[j];
+    __syncwarp();
+    const int n = n0 + c0 + lane;
+    if (c0 + lane < cend && n < a.N && nchunks > 0) {
+      for (int rr = 0; rr < 32; ++rr) {
+        const int m = m0 + quad * 32 + rr;
+        if (m >= a.M) break;
+        gemm_epilogue_store(a, m, n, scratch[rr * 33 + lane], do_drop, sseed, keep_scale);
+      }
+    }
+    __syncwarp();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

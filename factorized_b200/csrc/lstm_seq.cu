@@ -269,9 +269,20 @@ static int smem_optin_limit() {
   return lim;
 }
 
+int lstm_tc_fwd_launch(const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* rest, int* nrest, cudaStream_t st);
+
 extern "C" int mfm_lstm_seq_fwd(const mfm_lstm_cell* cells, int ncells, void* stream) {
   int rc = lstm_validate(cells, ncells, false);
   if (rc) return rc;
+  mfm_lstm_cell rest[MFM_MAX_CELLS];
+  if (mfm_get_gemm_path() != MFM_PATH_SIMT_FP32) {      // tensor-core recurrence for every cell that fits on chip
+    int nrest = 0;
+    rc = lstm_tc_fwd_launch(cells, ncells, rest, &nrest, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (nrest == 0) return MFM_OK;
+    cells = rest;
+    ncells = nrest;
+  }
   LstmBatch bt;
   bt.n = ncells;
   bt.smem_limit = smem_optin_limit();

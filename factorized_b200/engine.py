@@ -377,9 +377,11 @@ class Engine:
             ops.zero(rc)
             ops.colsum(Kzz, rc[:B])                          # K(z,z) is symmetric: column sums == row sums
             ops.colsum(Kgz, rc[B:])
-            t1, t2 = buf("mmd_t1_%d" % k, B, dim), buf("mmd_t2_%d" % k, B, dim)
-            ops.gemm("nn", Kzz, zk, t1)
-            ops.gemm("tn", Kgz, gk, t2)
+            t12 = buf("mmd_t12_%d" % k, 2 * B, dim)
+            t1, t2 = t12[:B], t12[B:]
+            ops.zero(t12)                                    # accumulate form lets the GEMM split K = B over CTAs
+            ops.gemm("nn", Kzz, zk, t1, accumulate=True)
+            ops.gemm("tn", Kgz, gk, t2, accumulate=True)
             ops.mmd_combine(zk, rc[:B], rc[B:], t1, t2, mmd_scale, dlat[k], mmd_scale_dev)
 
         # (6') last_to_zy_fc1 over cat(h_T, mem_T)

@@ -104,7 +104,7 @@ def test_lstm_fwd_bwd(ops, T, B, h, gx_steps, ld_extra):
     ops.lstm_fwd([cg])
     torch.cuda.synchronize()
     for k in ("hs", "cs", "gates"):
-        assert rel_l2(cg[k], c[k]) < TOL, (k, T, B, h)
+        assert rel_l2(cg[k], c[k]) < 1e-4, (k, T, B, h, rel_l2(cg[k], c[k]))      # tensor-core recurrence: bf16x3
     if ld_extra:
         assert float((hs_full[:, :ld_extra] - 7.0).abs().max()) == 0.0      # neighbours untouched
     # backward on the emulator's forward state
@@ -132,7 +132,7 @@ def test_lstm_multi_cell_launch(ops):
     torch.cuda.synchronize()
     for c, d in zip(cells, dev):
         for k in ("hs", "cs", "gates"):
-            assert rel_l2(d[k], c[k]) < TOL, (k, c["h"])
+            assert rel_l2(d[k], c[k]) < 1e-4, (k, c["h"], rel_l2(d[k], c[k]))
 
 
 @pytest.mark.parametrize("T,B,mem,g1,g2,drop", [(3, 5, 9, 12, 13, False), (4, 21, 64, 128, 128, True), (2, 7, 300, 256, 32, False),
