@@ -22,6 +22,24 @@ extern unsigned long long g_mfm_launches;   // host-side counter, see abi.cu
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Gate activations of the recurrences.  The cell update is transcendental-bound (5 per hidden unit per step), so
+// these use the SFU directly: ex2.approx (2 ulp) and rcp.approx (1 ulp); absolute error <= ~2e-7, far inside the
+// 1e-3 parity budget, ~4x cheaper than expf/tanhf.  Arguments are clamped so 1+e never overflows.
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float gate_sigmoid(float x) {
+  x = fminf(fmaxf(x, -30.0f), 30.0f);
+  return rcp_fast(1.0f + __expf(-x));
+}
+__device__ __forceinline__ float gate_tanh(float x) {
+  x = fminf(fmaxf(x, -15.0f), 15.0f);
+  const float e = __expf(-2.0f * x);
+  return (1.0f - e) * rcp_fast(1.0f + e);
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
     case MFM_ACT_RELU: return fmaxf(v, 0.0f);

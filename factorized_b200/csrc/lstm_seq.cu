@@ -141,13 +141,13 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_seq_fwd_kernel(LstmBatch bt
         for (int r = 0; r < LSTM_R; ++r) {
           const int row = row0 + rbase + r;
           if (row >= B) continue;
-          const float ig = sigmoidf_acc(acc[r][0]);
-          const float fg = sigmoidf_acc(acc[r][1]);
-          const float gg = tanhf(acc[r][2]);
-          const float og = sigmoidf_acc(acc[r][3]);
+          const float ig = gate_sigmoid(acc[r][0]);
+          const float fg = gate_sigmoid(acc[r][1]);
+          const float gg = gate_tanh(acc[r][2]);
+          const float og = gate_sigmoid(acc[r][3]);
           const float cp = c.cs[((long long)t * B + row) * c.ld_cs + j];
           const float cn = fg * cp + ig * gg;
-          const float hn = og * tanhf(cn);
+          const float hn = og * gate_tanh(cn);
           float* gp = c.gates + ((long long)t * B + row) * H4 + j;
           gp[0] = ig; gp[h] = fg; gp[2 * h] = gg; gp[3 * h] = og;
           c.cs[((long long)(t + 1) * B + row) * c.ld_cs + j] = cn;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_seq_bwd_kernel(LstmBatch bt
           const float ig = gp[0], fg = gp[h], gg = gp[2 * h], og = gp[3 * h];
           const float cp = c.cs[tr * c.ld_cs + j];
           const float cn = c.cs[(tr + B) * c.ld_cs + j];
-          const float tc = tanhf(cn);
+          const float tc = gate_tanh(cn);
           float dc = dcs[(rbase + r) * h + j] + dh * og * (1.0f - tc * tc);
           if (c.dc_ext) dc += __ldg(c.dc_ext + tr * c.ld_dc_ext + j);
           const float d_o = dh * tc * og * (1.0f - og);
@@ -309,9 +309,20 @@ extern "C" int mfm_lstm_seq_fwd(const mfm_lstm_cell* cells, int ncells, void* st
   return MFM_OK;
 }
 
+int lstm_tc_bwd_launch(const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* rest, int* nrest, cudaStream_t st);
+
 extern "C" int mfm_lstm_seq_bwd(const mfm_lstm_cell* cells, int ncells, void* stream) {
   int rc = lstm_validate(cells, ncells, true);
   if (rc) return rc;
+  mfm_lstm_cell rest[MFM_MAX_CELLS];
+  if (mfm_get_gemm_path() != MFM_PATH_SIMT_FP32) {
+    int nrest = 0;
+    rc = lstm_tc_bwd_launch(cells, ncells, rest, &nrest, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (nrest == 0) return MFM_OK;
+    cells = rest;
+    ncells = nrest;
+  }
   LstmBatch bt;
   bt.n = ncells;
   bt.smem_limit = smem_optin_limit();

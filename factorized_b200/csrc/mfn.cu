@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(MEM_THREADS) mfn_mem_fwd_kernel(mfm_mem_args a
         for (int k = 0; k < g1; ++k) s1 = fmaf(us[k], __ldg(a.W12 + (long long)j * g1 + k), s1);
         for (int k = 0; k < g2; ++k) s2 = fmaf(us[g1 + k], __ldg(a.W22 + (long long)j * g2 + k), s2);
       }
-      const float ga1 = sigmoidf_acc(s1), ga2 = sigmoidf_acc(s2);
+      const float ga1 = gate_sigmoid(s1), ga2 = gate_sigmoid(s2);
       float nm = 0.0f;
       if (row < B) {
         const long long tr = (long long)t * B + row;

@@ -27,7 +27,7 @@ class LstmCell(C.Structure):
                 ("gx", c_f), ("bias_rest", c_f), ("W", c_f),
                 ("hs", c_f), ("ld_hs", LL), ("cs", c_f), ("ld_cs", LL), ("gates", c_f),
                 ("dh_all", c_f), ("ld_dh_all", LL), ("dh_last", c_f), ("ld_dh_last", LL),
-                ("dc_ext", c_f), ("ld_dc_ext", LL), ("dG", c_f)]
+                ("dc_ext", c_f), ("ld_dc_ext", LL), ("dG", c_f), ("dc_scratch", c_f)]
 
 
 class MemArgs(C.Structure):
@@ -241,6 +241,11 @@ class CudaOps:
                 if (dr, dc_) != (c["T"] * c["B"], h4) or ldd != h4:
                     raise MfmCudaError("lstm dG must be contiguous [T*B,4h]")
                 s.dG = pd
+                if c.get("dc_scratch") is not None:
+                    p_, r_, c_, l_ = _mat(c["dc_scratch"], "lstm dc_scratch")
+                    if (r_, c_) != (c["B"], c["h"]) or (r_ > 1 and l_ != c["h"]):
+                        raise MfmCudaError("lstm dc_scratch must be contiguous [B,h]")
+                    s.dc_scratch = p_
                 if c.get("dh_all") is not None:
                     p_, r_, c_, l_ = _mat(c["dh_all"], "lstm dh_all")
                     if (r_, c_) != (c["T"] * c["B"], c["h"]):

@@ -333,7 +333,8 @@ class Engine:
             dHd = buf("dHd%d" % m, TB, hd)
             lin_bwd(dXhat[m], ws["hsD%d" % m][B:], "decoder_%s.fc1" % tag, dHd)
             cells.append(dict(T=T, B=B, h=hd, gates=ws["gatesD%d" % m], cs=ws["csD%d" % m], W=ws["Wm%d" % m],
-                              dh_all=dHd, dh_last=None, dc_ext=None, dG=buf("dGD%d" % m, TB, 4 * hd)))
+                              dh_all=dHd, dh_last=None, dc_ext=None, dG=buf("dGD%d" % m, TB, 4 * hd),
+                              dc_scratch=buf("dcSD%d" % m, B, hd)))
         ops.lstm_bwd(cells)
         dEMB = []
         for m, tag in enumerate(TAGS):
@@ -402,7 +403,7 @@ class Engine:
             lin_bwd(dZ[m], ws["hsE%d" % m][TB:], "encoder_%s.fc1" % tag, dhl)
             enc_cells.append(dict(T=T, B=B, h=dm.z[m], gates=ws["gatesE%d" % m], cs=ws["csE%d" % m],
                                   W=P["encoder_%s.lstm.weight_hh" % tag], dh_all=None, dh_last=dhl, dc_ext=None,
-                                  dG=buf("dGE%d" % m, TB, 4 * dm.z[m])))
+                                  dG=buf("dGE%d" % m, TB, 4 * dm.z[m]), dc_scratch=buf("dcSE%d" % m, B, dm.z[m])))
         self._backward_mfn(P, G, dHlast, dmemT, enc_cells, wgrad, bgrad, lin_bwd, relu_scale)
 
     def _backward_mfn(self, P, G, dHlast, dmemT, enc_cells, wgrad, bgrad, lin_bwd, relu_scale):
@@ -461,7 +462,7 @@ class Engine:
             cells.append(dict(T=T, B=B, h=dm.hm[m], gates=ws["gatesN%d" % m], cs=Call[:, o:o + dm.hm[m]],
                               W=P[pre + "lstm_%s.weight_hh" % tag], dh_all=None,
                               dh_last=dHlast[:, o:o + dm.hm[m]], dc_ext=dCext[:, o:o + dm.hm[m]],
-                              dG=buf("dGN%d" % m, TB, 4 * dm.hm[m])))
+                              dG=buf("dGN%d" % m, TB, 4 * dm.hm[m]), dc_scratch=buf("dcSN%d" % m, B, dm.hm[m])))
         ops.lstm_bwd(cells)
 
         # (1') weight gradients of the 6 input-side cells, all T at once

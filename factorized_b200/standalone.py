@@ -65,7 +65,8 @@ class _EncoderFn(torch.autograd.Function):
         dh = _new((N, h), dev)
         ops.gemm("nn", dz, fw, dh)
         dG = _new((T * N, 4 * h), dev)
-        ops.lstm_bwd([dict(T=T, B=N, h=h, gates=gates, cs=cs, W=w_hh, dh_all=None, dh_last=dh, dc_ext=None, dG=dG)])
+        ops.lstm_bwd([dict(T=T, B=N, h=h, gates=gates, cs=cs, W=w_hh, dh_all=None, dh_last=dh, dc_ext=None, dG=dG,
+                           dc_scratch=_new((N, h), dev))])
         g_ih, g_hh, g_b = z0(4 * h, d), z0(4 * h, h), z0(4 * h)
         ops.gemm("tn", dG, X2, g_ih, accumulate=True)
         ops.gemm("tn", dG, hs[:T * N], g_hh, accumulate=True)
@@ -119,7 +120,8 @@ class _DecoderFn(torch.autograd.Function):
         dH = _new((T * N, h), dev)
         ops.gemm("nn", dX, fw, dH)
         dG = _new((T * N, 4 * h), dev)
-        ops.lstm_bwd([dict(T=T, B=N, h=h, gates=gates, cs=cs, W=Wm, dh_all=dH, dh_last=None, dc_ext=None, dG=dG)])
+        ops.lstm_bwd([dict(T=T, B=N, h=h, gates=gates, cs=cs, W=Wm, dh_all=dH, dh_last=None, dc_ext=None, dG=dG,
+                           dc_scratch=_new((N, h), dev))])
         g_ih, g_hh, g_b = z0(4 * h, h), z0(4 * h, h), z0(4 * h)
         ops.gemm("tn", dG, hs[:T * N], g_hh, accumulate=True)
         ops.gemm("tn", dG, hs[:T * N], g_ih, accumulate=True)

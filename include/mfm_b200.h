@@ -81,6 +81,8 @@ typedef struct mfm_lstm_cell {
   const float* dh_last; long long ld_dh_last; /* [B, h]   dL/dh_{T-1} from outside, or NULL         */
   const float* dc_ext; long long ld_dc_ext;   /* [T*B, h] dL/dc_t from outside, or NULL             */
   float* dG;                /* [T*B, 4h] contiguous: dL/d(pre-activation gates)                      */
+  float* dc_scratch;        /* [B, h] contiguous workspace (carried dc) for the tensor-core backward;
+                               NULL selects the CUDA-core kernel                                      */
 } mfm_lstm_cell;
 #define MFM_MAX_CELLS 8
 /* all cells of one call run concurrently (blockIdx.y = cell) */

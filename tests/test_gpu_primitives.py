@@ -113,7 +113,7 @@ def test_lstm_fwd_bwd(ops, T, B, h, gx_steps, ld_extra):
         dh_last = g(B, h, seed=12) if variant in (1, 2) else None
         dc_ext = g(T * B, h, seed=13) if variant == 2 else None
         cb = dict(T=T, B=B, h=h, gates=c["gates"], cs=c["cs"], W=c["W"], dh_all=dh_all, dh_last=dh_last, dc_ext=dc_ext,
-                  dG=torch.zeros(T * B, 4 * h))
+                  dG=torch.zeros(T * B, 4 * h), dc_scratch=torch.zeros(B, h))
         cbg = _to_dev({k: v for k, v in cb.items() if k != "cs"})
         cs_dev = torch.zeros((T + 1) * B, h + ld_extra).cuda()
         cs_dev[:, ld_extra:] = c["cs"].cuda()
@@ -121,7 +121,7 @@ def test_lstm_fwd_bwd(ops, T, B, h, gx_steps, ld_extra):
         EmuOps().lstm_bwd([cb])
         ops.lstm_bwd([cbg])
         torch.cuda.synchronize()
-        assert rel_l2(cbg["dG"], cb["dG"]) < 5e-5, (variant, T, B, h)
+        assert rel_l2(cbg["dG"], cb["dG"]) < 1e-4, (variant, T, B, h, rel_l2(cbg["dG"], cb["dG"]))
 
 
 def test_lstm_multi_cell_launch(ops):
