@@ -178,7 +178,11 @@ __global__ void __launch_bounds__(LT_THREADS) lstm_tc_fwd_kernel(LstmTcBatch bt)
 #pragma unroll
           for (int g = 0; g < 4; ++g) ld8_global(c.bias_rest + g * h + j0, vec_b, nv, x[g]);
         }
-        ld8_global(c.cs + tr * c.ld_cs + j0, vec_cs, nv, cp);
+        if (t > 0) ld8_global(c.cs + tr * c.ld_cs + j0, vec_cs, nv, cp);     // written by this same thread at step t-1
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cp[i] = 0.0f;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float ig = gate_sigmoid(a[0][i] + x[0][i]);

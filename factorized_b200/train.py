@@ -39,12 +39,15 @@ class MFMTrainer:
     """
 
     def __init__(self, model: MFM, T: int, B: int, head: str = "l1", lr: float = 1e-3, betas=(0.9, 0.999),
-                 eps: float = 1e-8, use_graph: bool = True, process_group=None, seed: int = 123):
+                 eps: float = 1e-8, use_graph: bool = True, process_group=None, seed: int = 123, _test_ops=None):
         dev = next(model.parameters()).device
-        if dev.type != "cuda":
+        if dev.type != "cuda" and _test_ops is None:
             raise RuntimeError("MFMTrainer: model must be on a CUDA device (model.to('cuda')); no CPU path exists")
         self.model, self.dev = model, dev
-        self.ops = _ops()
+        # _test_ops: tests inject a statement of the primitive set to check the multi-rank host logic without a GPU
+        self.ops = _test_ops if _test_ops is not None else _ops()
+        if _test_ops is not None:
+            use_graph = False
         self.T, self.B = int(T), int(B)
         self.betas, self.eps = betas, eps
         self.pg = process_group
