@@ -13,6 +13,7 @@ struct GemmArgs {
   float drop_p; int drop_site; const long long* rng;
   int kchunk;      // K range per blockIdx.z
   int atomic;      // split-K: atomicAdd partial sums into C
+  float* colsum_out;   // TN only (tensor-core kernel): colsum_out[m] += sum_k A[k,m]  (bias gradient fused as a ones column of B)
 };
 
 // epilogue of include/mfm_b200.h::mfm_gemm for one output element

@@ -96,7 +96,7 @@ int gemm_simt_launch(int mode, int M, int N, int K, const float* A, long long ld
                      const float* mask, long long ldmask, float mask_scale, float drop_p, int drop_site,
                      const long long* rng, cudaStream_t st) {
   GemmArgs a{M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale,
-             drop_p, drop_site, rng, K, 0};
+             drop_p, drop_site, rng, K, 0, nullptr};
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, 1);
   // split K over CTAs for the weight-gradient shape (tiny M,N; K = T*B rows), plain sums only
   const bool plain = !bias && !bias2 && act == MFM_ACT_NONE && !mask && drop_p <= 0.0f && accumulate;

@@ -41,7 +41,7 @@ struct TcArgs {
 //   MN-major source [K, cols] (cols contiguous): item = (k row, 8-wide column group)
 template <bool MN, int NI>
 __device__ __forceinline__ void tile_fetch(float (&v)[NI][8], const float* __restrict__ src, long long ld, int mn0, int mn_max,
-                                           int k0, int kend, int tile_mn, bool vec_ok) {
+                                           int k0, int kend, int tile_mn, bool vec_ok, int ones_col = -1) {
   const int items = MN ? ((((tile_mn >> 3) + 3) & ~3) * TC_BK) : tile_mn * 4;
 #pragma unroll
   for (int u = 0; u < NI; ++u) {
@@ -49,7 +49,14 @@ __device__ __forceinline__ void tile_fetch(float (&v)[NI][8], const float* __res
     if (idx < items) {
       if (MN) {
         const int k = (idx & 7) + 8 * ((idx >> 5) & 3), mg = ((idx >> 3) & 3) + 4 * (idx >> 7);
-        if (mg < (tile_mn >> 3)) load8(src, ld, k0 + k, kend, mn0 + mg * 8, mn_max, vec_ok, v[u]);
+        if (mg < (tile_mn >> 3)) {
+          load8(src, ld, k0 + k, kend, mn0 + mg * 8, mn_max, vec_ok, v[u]);
+          if (ones_col >= 0 && k0 + k < kend) {       // virtual all-ones column: column sums of the other operand
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (mn0 + mg * 8 + i == ones_col) v[u][i] = 1.0f;
+          }
+        }
       } else {
         const int slab = idx & 3, r = idx >> 2;
         load8(src, ld, mn0 + r, mn_max, k0 + slab * 8, kend, vec_ok, v[u]);
@@ -99,6 +106,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
   const int stage_bytes = 2 * TC_A_PLANE + 2 * b_plane;
   const bool vecA = ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0) && ((a.lda & 3) == 0);
   const bool vecB = ((reinterpret_cast<uintptr_t>(a.B) & 15) == 0) && ((a.ldb & 3) == 0);
+  const int ones_col = (MODE == MFM_GEMM_TN && a.colsum_out) ? a.N : -1;
 
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
@@ -115,7 +123,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
   const int nchunks = (kend - kbeg + TC_BK - 1) / TC_BK;
   if (nchunks > 0) {
     tile_fetch<A_MN, TC_NA>(va, a.A, a.lda, m0, a.M, kbeg, kend, TC_BM, vecA);
-    tile_fetch<B_MN, TC_NB>(vb, a.B, a.ldb, n0, a.N, kbeg, kend, BN, vecB);
+    tile_fetch<B_MN, TC_NB>(vb, a.B, a.ldb, n0, a.N, kbeg, kend, BN, vecB, ones_col);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -139,7 +147,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
     if (c + 1 < nchunks) {
       const int k1 = kbeg + (c + 1) * TC_BK;
       tile_fetch<A_MN, TC_NA>(va, a.A, a.lda, m0, a.M, k1, kend, TC_BM, vecA);
-      tile_fetch<B_MN, TC_NB>(vb, a.B, a.ldb, n0, a.N, k1, kend, BN, vecB);
+      tile_fetch<B_MN, TC_NB>(vb, a.B, a.ldb, n0, a.N, k1, kend, BN, vecB, ones_col);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
     __syncthreads();
@@ -199,11 +207,38 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
     for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = v[j];
     __syncwarp();
     const int n = n0 + c0 + lane;
-    if (c0 + lane < cend && n < a.N && nchunks > 0) {
+    if (ones_col >= 0 && n == ones_col && c0 + lane < cend && nchunks > 0) {      // the ones column: bias gradient
       for (int rr = 0; rr < 32; ++rr) {
         const int m = m0 + quad * 32 + rr;
-        if (m >= a.M) break;
-        gemm_epilogue_store(a, m, n, scratch[rr * 33 + lane], do_drop, sseed, keep_scale);
+        if (m < a.M) atomicAdd(a.colsum_out + m, scratch[rr * 33 + lane]);
+      }
+    }
+    if (c0 + lane < cend && n < a.N && nchunks > 0) {
+      // per-column terms once; per-row global reads (accumulate / mask) issued 8 rows at a time ahead of their use
+      const float bsum = (a.bias ? __ldg(a.bias + n) : 0.0f) + (a.bias2 ? __ldg(a.bias2 + n) : 0.0f);
+      const int mbase = m0 + quad * 32;
+#pragma unroll 1
+      for (int rr0 = 0; rr0 < 32; rr0 += 8) {
+        float cv[8], mk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = mbase + rr0 + i;
+          const bool ok = m < a.M;
+          cv[i] = (ok && a.accumulate && !a.atomic) ? a.C[(long long)m * a.ldc + n] : 0.0f;
+          mk[i] = (ok && a.mask) ? __ldg(a.mask + (long long)m * a.ldmask + n) : 1.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = mbase + rr0 + i;
+          if (m >= a.M) continue;
+          float v = scratch[(rr0 + i) * 33 + lane];
+          float* cp = a.C + (long long)m * a.ldc + n;
+          if (a.atomic) { atomicAdd(cp, v); continue; }
+          v = apply_act(v + bsum, a.act);
+          if (do_drop) v = drop_keep(sseed, (uint32_t)m * (uint32_t)a.N + (uint32_t)n, a.drop_p) ? v * keep_scale : 0.0f;
+          if (a.mask) v = mk[i] > 0.0f ? v * a.mask_scale : 0.0f;
+          *cp = v + cv[i];
+        }
       }
     }
     __syncwarp();
@@ -221,19 +256,19 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 int gemm_tc_launch(int passes, int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
                    float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
                    const float* mask, long long ldmask, float mask_scale, float drop_p, int drop_site,
-                   const long long* rng, cudaStream_t st) {
+                   const long long* rng, float* colsum_out, cudaStream_t st) {
   TcArgs ta;
   ta.g = GemmArgs{M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale,
-                  drop_p, drop_site, rng, K, 0};
+                  drop_p, drop_site, rng, K, 0, colsum_out};
   ta.passes = passes;
-  // tile N: the whole (padded) N when it fits 256 columns, else near-equal tiles
-  const int n16 = round_up(N, 16);
+  // tile N: the whole (padded) N when it fits 256 columns, else near-equal tiles (+1 virtual ones column for colsum_out)
+  const int n16 = round_up(N + (colsum_out ? 1 : 0), 16);
   const int ntiles = (n16 + 255) / 256;
   ta.BN = round_up((n16 + ntiles - 1) / ntiles, 16);
   int cols = 32;
   while (cols < ta.BN) cols <<= 1;
   ta.tmem_cols = cols;
-  dim3 grid((N + ta.BN - 1) / ta.BN, (M + TC_BM - 1) / TC_BM, 1);
+  dim3 grid((N + (colsum_out ? 1 : 0) + ta.BN - 1) / ta.BN, (M + TC_BM - 1) / TC_BM, 1);
   const bool plain = !bias && !bias2 && act == MFM_ACT_NONE && !mask && drop_p <= 0.0f && accumulate;
   if (plain && K >= 2048) {
     long long tiles = (long long)grid.x * grid.y;

@@ -49,7 +49,7 @@ _SIGS = {
     "mfm_get_gemm_path": (C.c_int, []),
     "mfm_set_gemm_tc_min_work": (C.c_int, [LL]),
     "mfm_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_f, LL, c_f, LL, c_f, LL, c_f, c_f, C.c_int, C.c_int,
-                           c_f, LL, C.c_float, C.c_float, C.c_int, c_f, c_f]),
+                           c_f, LL, C.c_float, C.c_float, C.c_int, c_f, c_f, c_f]),
     "mfm_lstm_seq_fwd": (C.c_int, [C.POINTER(LstmCell), C.c_int, c_f]),
     "mfm_lstm_seq_bwd": (C.c_int, [C.POINTER(LstmCell), C.c_int, c_f]),
     "mfm_mfn_mem_fwd": (C.c_int, [C.POINTER(MemArgs), c_f]),
@@ -171,7 +171,7 @@ class CudaOps:
 
     # ---- GEMM ----
     def gemm(self, mode, A, B, Cm, bias=None, bias2=None, act=0, accumulate=False, mask=None, mask_scale=1.0,
-             drop=None, rng=None):
+             drop=None, rng=None, colsum_out=None):
         pa, ar, ac, lda = _mat(A, "gemm A")
         pb, br, bc, ldb = _mat(B, "gemm B")
         pc, M, N, ldc = _mat(Cm, "gemm C")
@@ -201,7 +201,8 @@ class CudaOps:
             prng = rng.data_ptr()
         _check(self.lib.mfm_gemm(GEMM_MODE[mode], M, N, K, pa, lda, pb, ldb, pc, ldc, _vec(bias, "bias", N),
                                  _vec(bias2, "bias2", N), act, int(accumulate), pm, ldm, float(mask_scale),
-                                 float(p), int(site), prng, _stream()), "mfm_gemm")
+                                 float(p), int(site), prng,
+                                 None if colsum_out is None else _vec(colsum_out, "colsum_out", M), _stream()), "mfm_gemm")
 
     # ---- LSTM ----
     @staticmethod

@@ -309,9 +309,9 @@ class Engine:
             ops.colsum(dY, G[name])
 
         def lin_bwd(dY, A, name, dA=None, accumulate=False, mask=None, mask_scale=1.0):
-            """y = A W^T + b: dW, db and (optionally) dA = (dY W) [* relu/dropout mask of A]."""
-            wgrad(dY, A, name + ".weight")
-            bgrad(dY, name + ".bias")
+            """y = A W^T + b: dW and db in one GEMM (db rides along as a ones column), and (optionally)
+            dA = (dY W) [* relu/dropout mask of A]."""
+            ops.gemm("tn", dY, A, G[name + ".weight"], accumulate=True, colsum_out=G[name + ".bias"])
             if dA is not None:
                 ops.gemm("nn", dY, P[name + ".weight"], dA, accumulate=accumulate, mask=mask, mask_scale=mask_scale)
 
@@ -341,11 +341,10 @@ class Engine:
             d_ = "decoder_%s.lstm" % tag
             dG = ws["dGD%d" % m]
             hprev = ws["hsD%d" % m][:TB]                    # h_{t-1}; block 0 is the zero state
-            wgrad(dG, hprev, d_ + ".weight_hh")
-            wgrad(dG, hprev, d_ + ".weight_ih")              # input == h_{t-1} for t >= 1 (:85)
+            ops.gemm("tn", dG, hprev, G[d_ + ".weight_hh"], accumulate=True, colsum_out=G[d_ + ".bias_hh"])
+            ops.gemm("tn", dG, hprev, G[d_ + ".weight_ih"], accumulate=True,        # input == h_{t-1} for t >= 1 (:85)
+                     colsum_out=G[d_ + ".bias_ih"])
             wgrad(dG[:B], ws["EMB%d" % m], d_ + ".weight_ih")  # step 0 input is the embedding (:83)
-            bgrad(dG, d_ + ".bias_ih")
-            bgrad(dG, d_ + ".bias_hh")
             de = buf("dEMB%d" % m, B, dm.hd[m])
             ops.gemm("nn", dG[:B], P[d_ + ".weight_ih"], de)
             ops.copy2d(de[:, :dm.fy], dFY, accumulate=True)
@@ -426,17 +425,14 @@ class Engine:
             W12=P[pre + "gamma1_fc2.weight"], W22=P[pre + "gamma2_fc2.weight"],
             scale1=relu_scale(dm.p_g1), scale2=relu_scale(dm.p_g2),
             dmem_last=dmemT, dU1=dU1, dU2=dU2, dP1=dP1, dP2=dP2, dPc=dPc))
-        wgrad(dP1, ws["U1"], pre + "gamma1_fc2.weight")
-        bgrad(dP1, pre + "gamma1_fc2.bias")
-        wgrad(dP2, ws["U2"], pre + "gamma2_fc2.weight")
-        bgrad(dP2, pre + "gamma2_fc2.bias")
+        ops.gemm("tn", dP1, ws["U1"], G[pre + "gamma1_fc2.weight"], accumulate=True, colsum_out=G[pre + "gamma1_fc2.bias"])
+        ops.gemm("tn", dP2, ws["U2"], G[pre + "gamma2_fc2.weight"], accumulate=True, colsum_out=G[pre + "gamma2_fc2.bias"])
         Attended, cStar, Att = ws["Attended"], ws["cStar"], ws["Att"]
         dAtt = buf("dAttended", TB, 2 * H)
         for (dU, Wg, nm, first) in ((dU1, Wg1, "gamma1_fc1", True), (dU2, Wg2, "gamma2_fc1", False)):
             Gw = G[pre + nm + ".weight"]
-            ops.gemm("tn", dU, Attended, Gw[:, :2 * H], accumulate=True)
+            ops.gemm("tn", dU, Attended, Gw[:, :2 * H], accumulate=True, colsum_out=G[pre + nm + ".bias"])
             ops.gemm("tn", dU, mems[:TB], Gw[:, 2 * H:], accumulate=True)
-            bgrad(dU, pre + nm + ".bias")
             ops.gemm("nn", dU, Wg[:, :2 * H], dAtt, accumulate=not first)
 
         # (4') attention MLPs, time-parallel
@@ -472,7 +468,5 @@ class Engine:
                 jobs.append(("encoder_%s.lstm" % tag, "dGE%d" % m, ws["hsE%d" % m][:TB]))
             for (nm, dGn, hs) in jobs:
                 dG = ws[dGn]
-                wgrad(dG, self.xs[m], nm + ".weight_ih")
-                wgrad(dG, hs, nm + ".weight_hh")
-                bgrad(dG, nm + ".bias_ih")
-                bgrad(dG, nm + ".bias_hh")
+                ops.gemm("tn", dG, self.xs[m], G[nm + ".weight_ih"], accumulate=True, colsum_out=G[nm + ".bias_ih"])
+                ops.gemm("tn", dG, hs, G[nm + ".weight_hh"], accumulate=True, colsum_out=G[nm + ".bias_hh"])

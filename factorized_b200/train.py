@@ -94,6 +94,11 @@ class MFMTrainer:
 
     def _schedule(self):
         """One training step on the static buffers (x, y)."""
+        self._schedule_compute()
+        self._schedule_update()
+
+    def _schedule_compute(self):
+        """forward + losses + backward into the flat gradient buffer (no communication)."""
         ops, eng = self.ops, self.eng
         ops.rng_tick(self.rng)
         for k in range(4):                                    # loss_MMD's Gaussian samples (mfm_model.py:26)
@@ -102,8 +107,12 @@ class MFMTrainer:
         dX, dY = eng.losses(self.y)
         ops.zero(self.flat_g)
         eng.backward(self.P, self.G, dX, dY, eng.dm.lda_mmd)
+
+    def _schedule_update(self):
+        """[all-reduce of the flat gradient buffer over NCCL/NVLink] + fused Adam (1/world folded in)."""
+        ops = self.ops
         if self.world > 1:
-            torch.distributed.all_reduce(self.flat_g, group=self.pg)      # NCCL sum over NVLink; 1/world folded into Adam
+            torch.distributed.all_reduce(self.flat_g, group=self.pg)
         ops.adam(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.adam_state, grad_scale=1.0 / self.world,
                  betas=self.betas, eps=self.eps)
 
@@ -124,13 +133,20 @@ class MFMTrainer:
             torch.cuda.synchronize(self.dev)
             for t, c in zip((self.flat_p, self.flat_m, self.flat_v, self.adam_state, self.rng), snap):
                 t.copy_(c)
+            # single rank: the whole step is one graph.  Multi-rank: the compute part is a graph, the NCCL
+            # all-reduce + Adam (3 launches) stay eager on the same stream -- the collective is not captured.
             g = torch.cuda.CUDAGraph()
             n0 = self.ops.launches
             with torch.cuda.graph(g):
-                self._schedule()
-            self.launches_per_step = self.ops.launches - n0
+                if self.world > 1:
+                    self._schedule_compute()
+                else:
+                    self._schedule()
+            self.launches_per_step = self.ops.launches - n0 + (2 if self.world > 1 else 0)
             self.graph = g
         self.graph.replay()
+        if self.world > 1:
+            self._schedule_update()
 
     def step_device(self):
         """Run one step on whatever is in self.x / self.y (already on the device)."""

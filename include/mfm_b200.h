@@ -57,12 +57,14 @@ int mfm_set_gemm_tc_min_work(long long mnk);
  * mfm_model.py:56,61,83,85,90,167-169,174,176,178-179,535,539-542,552 and their autograd adjoints.
  * epilogue, in order: + bias[n] + bias2[n]; activation; counter-based dropout (drop_p > 0:
  * keep iff u(rng, drop_site, m*N+n) >= drop_p, scaled 1/(1-p));  * (mask[m,n] > 0) * mask_scale;
- * + C if accumulate.  MFM_GEMM_TN may split K across CTAs and then needs accumulate=1. */
+ * + C if accumulate.  MFM_GEMM_TN may split K across CTAs and then needs accumulate=1.
+ * colsum_out (MFM_GEMM_TN only, may be NULL): colsum_out[m] += sum_k A[k,m] -- the bias gradient that always
+ * accompanies a weight gradient dW = dY^T X, fused as a virtual all-ones column of X. */
 int mfm_gemm(int mode, int M, int N, int K,
              const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
              const float* bias, const float* bias2, int act, int accumulate,
              const float* mask, long long ldmask, float mask_scale,
-             float drop_p, int drop_site, const long long* rng, void* stream);
+             float drop_p, int drop_site, const long long* rng, float* colsum_out, void* stream);
 
 /* One LSTM cell unrolled over T steps inside the kernel (encoderLSTM.forward mfm_model.py:47-62,
  * decoderLSTM.forward :72-91, the three cells of MFN.forward :167-169).

@@ -42,8 +42,11 @@ class EmuOps:
 
     # ---- GEMM with fused epilogue ----
     def gemm(self, mode, A, B, C, bias=None, bias2=None, act=0, accumulate=False, mask=None, mask_scale=1.0,
-             drop=None, rng=None):
+             drop=None, rng=None, colsum_out=None):
         self.launches += 1
+        if colsum_out is not None:
+            assert mode == "tn"
+            colsum_out += A.sum(0)
         if mode == "nt":
             v = A @ B.t()
         elif mode == "nn":

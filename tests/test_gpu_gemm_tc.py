@@ -94,3 +94,14 @@ def test_tc_gemm_plain_bf16_path():
         assert 1e-4 < e < 1e-2, e           # one bf16 pass: ~2^-9 per operand
     finally:
         ops.set_gemm_path(old, min_work=1 << 20)
+
+
+@pytest.mark.parametrize("K,M,N", [(40960, 128, 400), (700, 352, 300), (5000, 96, 255), (640, 416, 104), (300, 16, 16)])
+def test_tc_gemm_fused_bias_gradient(tc_ops, K, M, N):
+    """TN GEMM with colsum_out: dW += dY^T X and db += colsum(dY) in one launch (ones column of X)."""
+    dY, X = g(K, M, seed=1), g(K, N, seed=2)
+    w_cpu, w_gpu = torch.ones(M, N).double(), torch.ones(M, N).cuda()
+    b_cpu, b_gpu = torch.ones(M).double(), torch.ones(M).cuda()
+    EmuOps().gemm("tn", dY.double(), X.double(), w_cpu, accumulate=True, colsum_out=b_cpu)
+    tc_ops.gemm("tn", dY.cuda(), X.cuda(), w_gpu, accumulate=True, colsum_out=b_gpu)
+    assert rel_l2(w_gpu, w_cpu) < 5e-5 and rel_l2(b_gpu, b_cpu) < 5e-5, (rel_l2(w_gpu, w_cpu), rel_l2(b_gpu, b_cpu))
