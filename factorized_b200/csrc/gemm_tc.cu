@@ -16,6 +16,7 @@
 // is converted, fenced and multiplied; two shared-memory stages let the MMAs of chunk c overlap the conversion of c+1.
 // The epilogue reads the accumulator with tcgen05.ld, transposes 32x32 blocks through shared memory so that every
 // store / split-K reduction is a coalesced 128 B row segment, and applies the fused epilogue of mfm_gemm.
+#include <cstdlib>
 #include "gemm_args.cuh"
 #include "tc_common.cuh"
 
@@ -32,6 +33,7 @@ struct TcArgs {
   int BN;          // tile N (multiple of 16, <= 256)
   int passes;      // 3 = hi/lo split, 1 = plain bf16
   int tmem_cols;   // power of two >= max(32, BN)
+  int dbg;         // experiment switches (env MFM_TC_DEBUG): 1 skip MMA, 2 skip convert/store, 4 skip epilogue, 8 skip loads
 };
 
 // One operand tile of a K chunk travels HBM -> registers (raw fp32) -> split-bf16 planes in shared memory.
@@ -94,8 +96,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
   const GemmArgs& a = ta.g;
   const int BN = ta.BN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-  const int kbeg = blockIdx.z * a.kchunk;
+  // block indices pinned in registers: the compiler otherwise re-reads SR_CTAID (S2UR, long latency) inside the K loop
+  unsigned bx, by, bz;
+  asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bx));
+  asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(by));
+  asm volatile("mov.u32 %0, %%ctaid.z;" : "=r"(bz));
+  const int m0 = by * TC_BM, n0 = bx * BN;
+  const int kbeg = bz * a.kchunk;
   const int kend = min(a.K, kbeg + a.kchunk);
   const bool want_lo = ta.passes == 3;
   constexpr bool A_MN = (MODE == MFM_GEMM_TN);
@@ -121,10 +128,48 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
   // first chunk's loads go out before anything else waits
   float va[TC_NA][8], vb[TC_NB][8];
   const int nchunks = (kend - kbeg + TC_BK - 1) / TC_BK;
-  if (nchunks > 0) {
-    tile_fetch<A_MN, TC_NA>(va, a.A, a.lda, m0, a.M, kbeg, kend, TC_BM, vecA);
-    tile_fetch<B_MN, TC_NB>(vb, a.B, a.ldb, n0, a.N, kbeg, kend, BN, vecB, ones_col);
+  // interior fast path (aligned, tile fully in bounds): per-thread item pointers computed once, advanced per chunk
+  const bool fastA = vecA && (m0 + TC_BM <= a.M), fastB = vecB && (n0 + BN <= a.N) && ones_col < 0;
+  const float* pa[TC_NA];
+  const float* pb[TC_NB];
+  bool okb[TC_NB];
+#pragma unroll
+  for (int u = 0; u < TC_NA; ++u) {
+    const int idx = u * TC_THREADS + tid;
+    if (A_MN) pa[u] = a.A + (long long)(kbeg + (idx & 7) + 8 * ((idx >> 5) & 3)) * a.lda + m0 + (((idx >> 3) & 3) + 4 * (idx >> 7)) * 8;
+    else      pa[u] = a.A + (long long)(m0 + (idx >> 2)) * a.lda + kbeg + (idx & 3) * 8;
   }
+#pragma unroll
+  for (int u = 0; u < TC_NB; ++u) {
+    const int idx = u * TC_THREADS + tid;
+    if (B_MN) {
+      const int mg = ((idx >> 3) & 3) + 4 * (idx >> 7);
+      okb[u] = mg < (BN >> 3);
+      pb[u] = a.B + (long long)(kbeg + (idx & 7) + 8 * ((idx >> 5) & 3)) * a.ldb + n0 + mg * 8;
+    } else {
+      okb[u] = idx < BN * 4;
+      pb[u] = a.B + (long long)(n0 + (idx >> 2)) * a.ldb + kbeg + (idx & 3) * 8;
+    }
+  }
+  const long long stepA = A_MN ? (long long)TC_BK * a.lda : TC_BK, stepB = B_MN ? (long long)TC_BK * a.ldb : TC_BK;
+  auto fetch = [&](int c) {
+    const int k1 = kbeg + c * TC_BK;
+    const bool kfull = k1 + TC_BK <= kend;
+    if (fastA && kfull) {
+#pragma unroll
+      for (int u = 0; u < TC_NA; ++u) load8_fast(pa[u] + c * stepA, va[u]);
+    } else {
+      tile_fetch<A_MN, TC_NA>(va, a.A, a.lda, m0, a.M, k1, kend, TC_BM, vecA);
+    }
+    if (fastB && kfull) {
+#pragma unroll
+      for (int u = 0; u < TC_NB; ++u)
+        if (okb[u]) load8_fast(pb[u] + c * stepB, vb[u]);
+    } else {
+      tile_fetch<B_MN, TC_NB>(vb, a.B, a.ldb, n0, a.N, k1, kend, BN, vecB, ones_col);
+    }
+  };
+  if (nchunks > 0) fetch(0);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -141,17 +186,18 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
     unsigned char* Alo = st + TC_A_PLANE;
     unsigned char* Bhi = st + 2 * TC_A_PLANE;
     unsigned char* Blo = Bhi + b_plane;
-    if (c >= TC_STAGES) mbar_wait(smem_u32(&bars[s]), (uint32_t)((c / TC_STAGES - 1) & 1));   // MMAs that read this stage are done
-    tile_commit<A_MN, TC_NA>(va, Ahi, Alo, lboA, TC_BM, want_lo);
-    tile_commit<B_MN, TC_NB>(vb, Bhi, Blo, lboB, BN, want_lo);
-    if (c + 1 < nchunks) {
-      const int k1 = kbeg + (c + 1) * TC_BK;
-      tile_fetch<A_MN, TC_NA>(va, a.A, a.lda, m0, a.M, k1, kend, TC_BM, vecA);
-      tile_fetch<B_MN, TC_NB>(vb, a.B, a.ldb, n0, a.N, k1, kend, BN, vecB, ones_col);
+    if (c >= TC_STAGES && !(ta.dbg & 1)) mbar_wait(smem_u32(&bars[s]), (uint32_t)((c / TC_STAGES - 1) & 1));   // MMAs that read this stage are done
+    if (!(ta.dbg & 2)) {
+      tile_commit<A_MN, TC_NA>(va, Ahi, Alo, lboA, TC_BM, want_lo);
+      tile_commit<B_MN, TC_NB>(vb, Bhi, Blo, lboB, BN, want_lo);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
+    // generic-proxy stores -> visible to the tensor core.  The fence lowers to MEMBAR.ALL.CTA, which waits for ALL of
+    // this thread's outstanding memory operations: it must come BEFORE the prefetch loads are issued, or every chunk
+    // pays the full HBM latency at the fence and nothing overlaps.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (c + 1 < nchunks && !(ta.dbg & 8)) fetch(c + 1);
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && !(ta.dbg & 1)) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t aH = smem_u32(Ahi), aL = smem_u32(Alo), bH = smem_u32(Bhi), bL = smem_u32(Blo);
 #pragma unroll
@@ -169,7 +215,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
     }
   }
   // all MMAs complete when the last commit lands (commits are ordered)
-  if (nchunks > 0) {
+  if (nchunks > 0 && !(ta.dbg & 1)) {
     const int c = nchunks - 1;
     mbar_wait(smem_u32(&bars[c & 1]), (uint32_t)((c / TC_STAGES) & 1));
   }
@@ -182,10 +228,15 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
   if (do_drop) sseed = site_seed(a.rng, a.drop_site);
   const float keep_scale = do_drop ? 1.0f / (1.0f - a.drop_p) : 1.0f;
   float* scratch = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+  // epilogue parameters pinned in registers (the fully generic per-element form cost ~30 instructions per output)
+  float* const e_C = a.C;
+  const long long e_ldc = a.ldc;
+  const int e_M = a.M, e_N = a.N, e_act = a.act;
+  const bool e_atomic = a.atomic != 0, e_acc = a.accumulate != 0, e_simple = !a.mask && !do_drop;
   const int quad = warp & 3, half = warp >> 2;
   const int cbeg = half * (BN >> 1), cend = cbeg + (BN >> 1);
   const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
-  for (int c0 = cbeg; c0 < cend; c0 += 32) {
+  for (int c0 = cbeg; c0 < cend && !(ta.dbg & 4); c0 += 32) {
     float v[32];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -207,37 +258,49 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
     for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = v[j];
     __syncwarp();
     const int n = n0 + c0 + lane;
-    if (ones_col >= 0 && n == ones_col && c0 + lane < cend && nchunks > 0) {      // the ones column: bias gradient
-      for (int rr = 0; rr < 32; ++rr) {
-        const int m = m0 + quad * 32 + rr;
-        if (m < a.M) atomicAdd(a.colsum_out + m, scratch[rr * 33 + lane]);
-      }
-    }
-    if (c0 + lane < cend && n < a.N && nchunks > 0) {
-      // per-column terms once; per-row global reads (accumulate / mask) issued 8 rows at a time ahead of their use
-      const float bsum = (a.bias ? __ldg(a.bias + n) : 0.0f) + (a.bias2 ? __ldg(a.bias2 + n) : 0.0f);
-      const int mbase = m0 + quad * 32;
-#pragma unroll 1
-      for (int rr0 = 0; rr0 < 32; rr0 += 8) {
-        float cv[8], mk[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = mbase + rr0 + i;
-          const bool ok = m < a.M;
-          cv[i] = (ok && a.accumulate && !a.atomic) ? a.C[(long long)m * a.ldc + n] : 0.0f;
-          mk[i] = (ok && a.mask) ? __ldg(a.mask + (long long)m * a.ldmask + n) : 1.0f;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = mbase + rr0 + i;
-          if (m >= a.M) continue;
-          float v = scratch[(rr0 + i) * 33 + lane];
-          float* cp = a.C + (long long)m * a.ldc + n;
-          if (a.atomic) { atomicAdd(cp, v); continue; }
-          v = apply_act(v + bsum, a.act);
-          if (do_drop) v = drop_keep(sseed, (uint32_t)m * (uint32_t)a.N + (uint32_t)n, a.drop_p) ? v * keep_scale : 0.0f;
-          if (a.mask) v = mk[i] > 0.0f ? v * a.mask_scale : 0.0f;
-          *cp = v + cv[i];
+    const int mbase = m0 + quad * 32;
+    const int nrows = max(0, min(32, e_M - mbase));
+    const float* sp = scratch + lane;
+    if (nchunks > 0 && c0 + lane < cend) {
+      if (ones_col >= 0 && n == ones_col) {                 // the ones column: bias gradient
+        for (int rr = 0; rr < nrows; ++rr) atomicAdd(a.colsum_out + mbase + rr, sp[rr * 33]);
+      } else if (n < e_N) {
+        float* cp = e_C + (long long)mbase * e_ldc + n;
+        if (e_atomic) {
+          for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) atomicAdd(cp, sp[rr * 33]);
+        } else if (e_simple) {                              // bias + activation (+ C): the common case, lean loops
+          const float bsum = (a.bias ? __ldg(a.bias + n) : 0.0f) + (a.bias2 ? __ldg(a.bias2 + n) : 0.0f);
+          if (e_acc) {
+            int rr = 0;
+            for (; rr + 4 <= nrows; rr += 4, cp += 4 * e_ldc) {
+              const float c0v = cp[0], c1v = cp[e_ldc], c2v = cp[2 * e_ldc], c3v = cp[3 * e_ldc];
+              cp[0] = apply_act(sp[rr * 33] + bsum, e_act) + c0v;
+              cp[e_ldc] = apply_act(sp[(rr + 1) * 33] + bsum, e_act) + c1v;
+              cp[2 * e_ldc] = apply_act(sp[(rr + 2) * 33] + bsum, e_act) + c2v;
+              cp[3 * e_ldc] = apply_act(sp[(rr + 3) * 33] + bsum, e_act) + c3v;
+            }
+            for (; rr < nrows; ++rr, cp += e_ldc) cp[0] = apply_act(sp[rr * 33] + bsum, e_act) + cp[0];
+          } else if (e_act == MFM_ACT_NONE) {
+#pragma unroll 8
+            for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) cp[0] = sp[rr * 33] + bsum;
+          } else if (e_act == MFM_ACT_RELU) {
+#pragma unroll 8
+            for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) cp[0] = fmaxf(sp[rr * 33] + bsum, 0.0f);
+          } else {
+#pragma unroll 4
+            for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) cp[0] = apply_act(sp[rr * 33] + bsum, e_act);
+          }
+        } else {                                            // dropout and/or ReLU-mask epilogues
+          const float bsum = (a.bias ? __ldg(a.bias + n) : 0.0f) + (a.bias2 ? __ldg(a.bias2 + n) : 0.0f);
+          const float* mp = a.mask ? a.mask + (long long)mbase * a.ldmask + n : nullptr;
+#pragma unroll 2
+          for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) {
+            float v = apply_act(sp[rr * 33] + bsum, e_act);
+            const int m = mbase + rr;
+            if (do_drop) v = drop_keep(sseed, (uint32_t)m * (uint32_t)e_N + (uint32_t)n, a.drop_p) ? v * keep_scale : 0.0f;
+            if (mp) v = __ldg(mp + (long long)rr * a.ldmask) > 0.0f ? v * a.mask_scale : 0.0f;
+            cp[0] = e_acc ? v + cp[0] : v;
+          }
         }
       }
     }
@@ -261,6 +324,9 @@ int gemm_tc_launch(int passes, int mode, int M, int N, int K, const float* A, lo
   ta.g = GemmArgs{M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale,
                   drop_p, drop_site, rng, K, 0, colsum_out};
   ta.passes = passes;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("MFM_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+  ta.dbg = dbg;
   // tile N: the whole (padded) N when it fits 256 columns, else near-equal tiles (+1 virtual ones column for colsum_out)
   const int n16 = round_up(N + (colsum_out ? 1 : 0), 16);
   const int ntiles = (n16 + 255) / 256;

@@ -42,6 +42,13 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// interior fast path: 16 B-aligned, fully in bounds, no predicates
+__device__ __forceinline__ void load8_fast(const float* __restrict__ p, float v[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 // 8 consecutive fp32 along the contiguous dimension at (row, col..col+7); zero outside [0,nrows) x [0,ncols)
 __device__ __forceinline__ void load8(const float* __restrict__ src, long long ld, int row, int nrows, int col, int ncols,
                                       bool vec_ok, float v[8]) {
