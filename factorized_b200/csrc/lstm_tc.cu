@@ -1,56 +1,40 @@
-// LSTM recurrence on the tensor cores: the gate GEMM h_{t-1} W^T is a tcgen05.mma per timestep, fused with the
-// sigmoid/tanh/Hadamard cell update, T steps inside the kernel  (mfm_model.py:56,83,85,167-169).
+// LSTM recurrences on the tensor cores, forward and backward (mfm_model.py:56,83,85,167-169 and their adjoint).
 //
-// A CTA owns MT (128, or 64 when shared memory is tight) batch rows of one cell for the whole sequence:
-//   * W (the recurrent weight, [4h,h]) is converted ONCE to split-bf16 (hi+lo) and stays resident in shared memory
-//     as the K-major B operand (no-swizzle canonical layout, see gemm_tc.cu);
-//   * h_{t-1} is the A operand: the epilogue of step t-1 writes it (hi+lo bf16) straight into shared memory in the
-//     canonical K-major layout, so the recurrence never round-trips through HBM;
-//   * per step: one elected thread issues ceil(4h/256) x (hp/16) x 3 MMAs (bf16x3: hi*hi + lo*hi + hi*lo) into a
-//     [MT x 4h] fp32 accumulator in TMEM and commits to an mbarrier; every thread (one batch row each) then reads
-//     its row's i,f,g,o pre-activations with tcgen05.ld, adds the hoisted x-projection G_x[t] (HBM), applies the
-//     gates, updates c, and stores gates / c_t / h_t (the stash the backward pass needs) and the next A operand.
-// Cells whose weights do not fit (4h > 512 TMEM columns or > 227 KB shared memory) run on lstm_seq.cu instead.
+// The gate GEMM is issued TRANSPOSED:   D^T[gate-unit n, batch b] = W[n, :] . h_{t-1}[b, :]
+//   A operand = W (M = 128 gate-units per MMA tile, K-major = W's own row-major layout), resident in shared memory as
+//               split-bf16 (hi + lo) for the whole sequence;
+//   B operand = h_{t-1} for the CTA's NB batch rows (N = NB), written by the previous step's epilogue straight into
+//               shared memory in the canonical K-major layout (the recurrence never leaves the SM);
+//   D         = fp32 in TMEM: lane = gate-unit, column = batch row; 3 MMAs per k-step (hi*hi + lo*hi + hi*lo).
+// Why transposed: an epilogue thread owns a TMEM lane.  With lane = gate-unit, the 32 lanes of a warp touch 32
+// CONSECUTIVE floats of one row of the row-major stashes (G_x, gates, dG, c, h), i.e. one 128 B line per access.
+// The first version had lane = batch row: every access hit 32 different lines and the kernels were bound by L1
+// wavefronts (64 cycles per 512 B), 8x slower than the tensor-core work they wrapped.
+// A thread sees ONE gate of a unit, so the four gates meet through a small shared-memory exchange (8 batch columns at
+// a time), after which (unit, batch) items finish the cell update, again unit-fastest (coalesced).
+//
+// Backward:  dh^T[unit j, batch b] = sum_k' W^T[j, k'] dG[b, k'],  k' = 4*unit + gate (unit-major so the four gate
+// gradients of a unit are 8 contiguous bytes of the B operand); thread (unit j, 8 or 4 batch columns) keeps the
+// carried dc in registers, reads dh from TMEM, and all its global traffic is unit-fastest as well.
+// Cells with h > 128 (TMEM lanes / shared memory) run on lstm_seq.cu instead.
 #include "tc_common.cuh"
 
-#define LT_THREADS 512       // 16 warps: TMEM lane quadrant = warp%4, unit-chunk group = warp/4
+#define L2_THREADS 512
+#define L2_CC 8            // batch columns per exchange chunk (forward)
 
-struct LstmTcCell {
+struct Lstm2Cell {
   mfm_lstm_cell c;
-  int mt;        // rows per CTA: 128 or 64
-  int tiles;     // ceil(B / mt)
-  int hp8;       // h rounded up to 8
-  int hp16;      // h rounded up to 16 (MMA K)
-  int n4;        // 4h rounded up to 16 (MMA N)
-  int bn;        // N per MMA block (<= 256, multiple of 16)
-  int nblk;
+  int nb;          // batch rows per CTA = UMMA N (32 or 16)
+  int tiles;       // ceil(B / nb)
+  int kp;          // forward: h rounded up to 16 (MMA K).  backward: 4 * (h rounded up to 8)
+  int mtiles;      // forward: ceil(4h / 128)
   int tmem_cols;
 };
-struct LstmTcBatch {
-  LstmTcCell c[MFM_MAX_CELLS];
+struct Lstm2Batch {
+  Lstm2Cell c[MFM_MAX_CELLS];
   int n;
 };
 
-__device__ __forceinline__ void ld8_global(const float* __restrict__ p, bool vec, int nvalid, float v[8]) {
-  if (vec && nvalid >= 8) {
-    const float4 a = *reinterpret_cast<const float4*>(p);
-    const float4 b = *(reinterpret_cast<const float4*>(p) + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = i < nvalid ? p[i] : 0.0f;
-  }
-}
-__device__ __forceinline__ void st8_global(float* __restrict__ p, bool vec, int nvalid, const float v[8]) {
-  if (vec && nvalid >= 8) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    *(reinterpret_cast<float4*>(p) + 1) = make_float4(v[4], v[5], v[6], v[7]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < nvalid) p[i] = v[i];
-  }
-}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -60,25 +44,41 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float v[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ unsigned short bf16_bits(float x) {
+  __nv_bfloat16 b = __float2bfloat16_rn(x);
+  return *reinterpret_cast<unsigned short*>(&b);
+}
 
-__global__ void __launch_bounds__(LT_THREADS) lstm_tc_fwd_kernel(LstmTcBatch bt) {
+// ----------------------------------------------------------------------------------------------------------------
+// forward
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(L2_THREADS, 1) lstm_tc_fwd_kernel(Lstm2Batch bt) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar;
   __shared__ uint32_t tmem_holder;
-  const LstmTcCell& lc = bt.c[blockIdx.y];
+  const Lstm2Cell& lc = bt.c[blockIdx.y];
   if ((int)blockIdx.x >= lc.tiles) return;
   const mfm_lstm_cell& c = lc.c;
   const int h = c.h, B = c.B, T = c.T, H4 = 4 * c.h;
-  const int MT = lc.mt, hp8 = lc.hp8, hp16 = lc.hp16, n4 = lc.n4;
-  const int slabs = hp16 >> 3;
-  const int lboW = n4 * 16 + 32, lboH = MT * 16 + 32;
+  const int NB = lc.nb, KP = lc.kp, mtiles = lc.mtiles;
+  const int slabs = KP >> 3;
+  const int lboA = H4 * 16 + 32, lboH = NB * 16 + 32;
   unsigned char* Whi = smem;
-  unsigned char* Wlo = Whi + slabs * lboW;
-  unsigned char* Hhi = Wlo + slabs * lboW;
+  unsigned char* Wlo = Whi + slabs * lboA;
+  unsigned char* Hhi = Wlo + slabs * lboA;                 // the last MMA tile may read up to 127 rows past W: lands here, ignored lanes
   unsigned char* Hlo = Hhi + slabs * lboH;
+  float* Gs = reinterpret_cast<float*>(Hlo + slabs * lboH + 2048);     // [4h][L2_CC + 1] activated gates of one column chunk
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row0 = blockIdx.x * MT;
+  const int row0 = blockIdx.x * NB;
 
   if (tid == 0) {
     mbar_init(smem_u32(&bar), 1);
@@ -90,15 +90,24 @@ __global__ void __launch_bounds__(LT_THREADS) lstm_tc_fwd_kernel(LstmTcBatch bt)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // W [4h,h] fp32 -> resident split-bf16 K-major B operand (rows >= 4h and k >= h are zero)
+  // W [4h,h] fp32 -> resident split-bf16 K-major A operand (k >= h zero)
   {
-    const bool vecW = aligned16(c.W) && ((h & 3) == 0);
-    const int items = n4 * slabs;
-    for (int idx = tid; idx < items; idx += LT_THREADS) {
+    const bool vecW = ((reinterpret_cast<uintptr_t>(c.W) & 15) == 0) && ((h & 3) == 0);
+    for (int idx = tid; idx < H4 * slabs; idx += L2_THREADS) {
       const int slab = idx % slabs, n = idx / slabs;
       float v[8];
       load8(c.W, h, n, H4, slab * 8, h, vecW, v);
-      split_store(v, Whi + slab * lboW + n * 16, Wlo + slab * lboW + n * 16, true);
+      split_store(v, Whi + slab * lboA + n * 16, Wlo + slab * lboA + n * 16, true);
+    }
+    for (int idx = tid * 16; idx < 2 * slabs * lboH + 2048; idx += L2_THREADS * 16)
+      *reinterpret_cast<uint4*>(Hhi + idx) = make_uint4(0, 0, 0, 0);       // h_{-1} = 0, K padding = 0
+  }
+  // block 0 of the histories is the zero initial state
+  for (int idx = tid; idx < NB * h; idx += L2_THREADS) {
+    const int b = row0 + idx / h, j = idx % h;
+    if (b < B) {
+      c.hs[(long long)b * c.ld_hs + j] = 0.0f;
+      c.cs[(long long)b * c.ld_cs + j] = 0.0f;
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -106,42 +115,54 @@ __global__ void __launch_bounds__(LT_THREADS) lstm_tc_fwd_kernel(LstmTcBatch bt)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_holder;
-  const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MT >> 4) << 24);
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
-  // this thread's batch row: TMEM lane 32*warp+lane holds tile row 32*warp+lane (MT=128) or 16*warp+lane (MT=64, lane<16)
-  const int quad = warp & 3, cg = warp >> 2;
-  const bool owns = (MT == 128) || (lane < 16);
-  const int r = (MT == 128) ? (quad * 32 + lane) : (quad * 16 + lane);
-  const int row = row0 + r;
-  const bool valid = owns && row < B;
-  const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
-  const bool vec_gx = aligned16(c.gx) && ((h & 3) == 0);
-  const bool vec_gt = aligned16(c.gates) && ((h & 3) == 0);
-  const bool vec_hs = aligned16(c.hs) && ((c.ld_hs & 3) == 0);
-  const bool vec_cs = aligned16(c.cs) && ((c.ld_cs & 3) == 0);
-  const bool vec_b = c.bias_rest && aligned16(c.bias_rest) && ((h & 3) == 0);
-
-  if (valid && cg == 0) {   // block 0 of the histories is the zero initial state
-    for (int j = 0; j < h; ++j) {
-      c.hs[(long long)row * c.ld_hs + j] = 0.0f;
-      c.cs[(long long)row * c.ld_cs + j] = 0.0f;
-    }
+  // phase-1 identity: MMA tile mt, TMEM lane quadrant q, gate-unit n
+  const int mt = warp >> 2, q = warp & 3;
+  const int n = mt * 128 + q * 32 + lane;
+  const bool tile_on = mt < mtiles;              // warp-uniform
+  const bool n_on = tile_on && n < H4;
+  const bool is_tanh = n_on && (n / h == 2);
+  const float bias_n = (n_on && c.bias_rest) ? __ldg(c.bias_rest + n) : 0.0f;
+  const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NB);
+  // phase-2 identity: items (cc, j) of a column chunk, unit j fastest; at most 2 per thread (8*h <= 1024)
+  int it_cc[2], it_j[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int item = tid + k * L2_THREADS;
+    it_cc[k] = item < L2_CC * h ? item / h : -1;
+    it_j[k] = item % h;
   }
+  float cprev[4][2];                              // c_{t-1} of this thread's items, per column chunk
+#pragma unroll
+  for (int a = 0; a < 4; ++a) cprev[a][0] = cprev[a][1] = 0.0f;
+  const int nchunk = NB / L2_CC;                  // 4 (NB=32) or 2 (NB=16)
 
   for (int t = 0; t < T; ++t) {
+    // G_x[t] (or the decoder's constant bias) for this thread's gate-unit and all NB columns: issued before the MMA wait
+    float gxv[32];
+    if (n_on) {
+      if (t < c.gx_steps) {
+#pragma unroll
+        for (int cc = 0; cc < 32; ++cc) {
+          const int b = row0 + cc;
+          gxv[cc] = (cc < NB && b < B) ? __ldg(c.gx + ((long long)t * B + b) * H4 + n) : 0.0f;
+        }
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < 32; ++cc) gxv[cc] = bias_n;
+      }
+    }
     if (t > 0) {
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t aH = smem_u32(Hhi), aL = smem_u32(Hlo), bH = smem_u32(Whi), bL = smem_u32(Wlo);
-        for (int b = 0; b < lc.nblk; ++b) {
-          const int nb0 = b * lc.bn;
-          const int nsz = min(lc.bn, n4 - nb0);
-          const uint32_t idesc = idesc_base | ((uint32_t)(nsz >> 3) << 17);
-          const uint32_t dcol = tmem_base + (uint32_t)nb0;
-          for (int kk = 0; kk < (hp16 >> 4); ++kk) {
-            const uint32_t ao = kk * 2 * lboH, bo = kk * 2 * lboW + nb0 * 16;
-            const uint64_t dAh = make_smem_desc(aH + ao, lboH, 128), dAl = make_smem_desc(aL + ao, lboH, 128);
-            const uint64_t dBh = make_smem_desc(bH + bo, lboW, 128), dBl = make_smem_desc(bL + bo, lboW, 128);
+        const uint32_t aH = smem_u32(Whi), aL = smem_u32(Wlo), bH = smem_u32(Hhi), bL = smem_u32(Hlo);
+        for (int m = 0; m < mtiles; ++m) {
+          const uint32_t dcol = tmem_base + (uint32_t)(m * NB);
+          for (int kk = 0; kk < (KP >> 4); ++kk) {
+            const uint32_t ao = m * 128 * 16 + kk * 2 * lboA, bo = kk * 2 * lboH;
+            const uint64_t dAh = make_smem_desc(aH + ao, lboA, 128), dAl = make_smem_desc(aL + ao, lboA, 128);
+            const uint64_t dBh = make_smem_desc(bH + bo, lboH, 128), dBl = make_smem_desc(bL + bo, lboH, 128);
             umma_bf16(dcol, dAh, dBh, idesc, kk > 0 ? 1u : 0u);
             umma_bf16(dcol, dAl, dBh, idesc, 1u);
             umma_bf16(dcol, dAh, dBl, idesc, 1u);
@@ -152,57 +173,55 @@ __global__ void __launch_bounds__(LT_THREADS) lstm_tc_fwd_kernel(LstmTcBatch bt)
       mbar_wait(smem_u32(&bar), (uint32_t)((t - 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    const long long tr = (long long)t * B + row;
-    for (int j0 = 8 * cg; j0 < hp8; j0 += 32) {     // the four warps of a lane quadrant interleave the unit chunks
-      float a[4][8];
-      if (t > 0) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) tmem_ld8(tlane + (uint32_t)(g * h + j0), a[g]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      } else {
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) a[g][i] = 0.0f;
-      }
-      float hv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) hv[i] = 0.0f;
-      if (valid) {
-        const int nv = min(8, h - j0);
-        float x[4][8], cp[8], cn[8];
-        if (t < c.gx_steps) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) ld8_global(c.gx + tr * H4 + g * h + j0, vec_gx, nv, x[g]);
+    for (int ch = 0; ch < 4; ++ch) {
+      if (ch >= nchunk) break;
+      const int bc0 = ch * L2_CC;
+      // phase 1: activate this thread's gate for 8 batch columns; stash it; hand it to the exchange buffer
+      if (tile_on) {
+        float acc[8];
+        if (t > 0) {
+          tmem_ld8(tlane + (uint32_t)bc0, acc);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         } else {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) ld8_global(c.bias_rest + g * h + j0, vec_b, nv, x[g]);
+          for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
         }
-        if (t > 0) ld8_global(c.cs + tr * c.ld_cs + j0, vec_cs, nv, cp);     // written by this same thread at step t-1
-        else {
+        if (n_on) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) cp[i] = 0.0f;
+          for (int cc = 0; cc < 8; ++cc) {
+            const float pre = acc[cc] + gxv[bc0 + cc];
+            const float av = is_tanh ? gate_tanh(pre) : gate_sigmoid(pre);
+            const int b = row0 + bc0 + cc;
+            if (b < B) c.gates[((long long)t * B + b) * H4 + n] = av;
+            Gs[n * (L2_CC + 1) + cc] = av;
+          }
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float ig = gate_sigmoid(a[0][i] + x[0][i]);
-          const float fg = gate_sigmoid(a[1][i] + x[1][i]);
-          const float gg = gate_tanh(a[2][i] + x[2][i]);
-          const float og = gate_sigmoid(a[3][i] + x[3][i]);
-          cn[i] = fg * cp[i] + ig * gg;
-          hv[i] = i < nv ? og * gate_tanh(cn[i]) : 0.0f;
-          x[0][i] = ig; x[1][i] = fg; x[2][i] = gg; x[3][i] = og;
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) st8_global(c.gates + tr * H4 + g * h + j0, vec_gt, nv, x[g]);
-        st8_global(c.cs + (tr + B) * c.ld_cs + j0, vec_cs, nv, cn);
-        st8_global(c.hs + (tr + B) * c.ld_hs + j0, vec_hs, nv, hv);
       }
-      if (owns) split_store(hv, Hhi + (j0 >> 3) * lboH + r * 16, Hlo + (j0 >> 3) * lboH + r * 16, true);
-    }
-    if (hp16 > hp8 && owns && cg == 0) {
-      const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      split_store(z, Hhi + (hp8 >> 3) * lboH + r * 16, Hlo + (hp8 >> 3) * lboH + r * 16, true);
+      __syncthreads();
+      // phase 2: (column, unit) items: c_t, h_t, histories, and h_t as next step's B operand
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int cc = it_cc[k], j = it_j[k];
+        if (cc < 0) continue;
+        const int bl = bc0 + cc, b = row0 + bl;
+        float hn = 0.0f;
+        if (b < B) {
+          const float ig = Gs[j * (L2_CC + 1) + cc], fg = Gs[(h + j) * (L2_CC + 1) + cc];
+          const float gg = Gs[(2 * h + j) * (L2_CC + 1) + cc], og = Gs[(3 * h + j) * (L2_CC + 1) + cc];
+          const float cn = fg * cprev[ch][k] + ig * gg;
+          hn = og * gate_tanh(cn);
+          cprev[ch][k] = cn;
+          c.cs[((long long)(t + 1) * B + b) * c.ld_cs + j] = cn;
+          c.hs[((long long)(t + 1) * B + b) * c.ld_hs + j] = hn;
+        }
+        const unsigned short hb = bf16_bits(hn);
+        const float hr = hn - __uint_as_float((uint32_t)hb << 16);
+        const int off = (j >> 3) * lboH + bl * 16 + (j & 7) * 2;
+        *reinterpret_cast<unsigned short*>(Hhi + off) = hb;
+        *reinterpret_cast<unsigned short*>(Hlo + off) = bf16_bits(hr);
+      }
+      if (ch + 1 < nchunk) __syncthreads();        // Gs is rewritten by the next chunk
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -214,50 +233,31 @@ __global__ void __launch_bounds__(LT_THREADS) lstm_tc_fwd_kernel(LstmTcBatch bt)
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// backward recurrence on the tensor cores.  Per step (t = T-1 .. 0), per CTA (MT batch rows of one cell):
-//   elementwise: dh = dh_rec (TMEM, from the previous step's MMAs) + external dh;  dc += dh o (1-tanh^2 c) + external dc;
-//                dG_t = (d_i, d_f, d_g, d_o) pre-activation gradients -> HBM (stash for the weight-gradient GEMMs) and,
-//                split to bf16 hi/lo, into shared memory as the next A operand;  dc carry (dc*f) -> a [B,h] scratch row;
-//   MMA:         dh_rec[MT, h] = dG_t[MT, 4h] W[4h, h]   (K = 4h) into the other half of a double-buffered TMEM tile.
-// K is ordered unit-major (k' = 4*j + gate) so the gradients of a group of units form a contiguous K range: the A
-// operand is produced and consumed in slots of 32 units while later units are still being computed.
-// W^T stays resident in shared memory as the K-major B operand in the same k' order.
-// ------------------------------------------------------------------------------------------------------------------
-#define LB_SLOT_UNITS 32
-
-struct LstmTcBwdCell {
-  mfm_lstm_cell c;
-  int mt, tiles, hp8, npad, nslot, tmem_cols;
-};
-struct LstmTcBwdBatch {
-  LstmTcBwdCell c[MFM_MAX_CELLS];
-  int n;
-};
-
-__global__ void __launch_bounds__(LT_THREADS) lstm_tc_bwd_kernel(LstmTcBwdBatch bt) {
+// ----------------------------------------------------------------------------------------------------------------
+// backward
+// ----------------------------------------------------------------------------------------------------------------
+template <int CPT>      // batch columns per thread: 8 (NB = 32) or 4 (NB = 16)
+__global__ void __launch_bounds__(L2_THREADS, 1) lstm_tc_bwd_kernel(Lstm2Batch bt) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long slotbar[2];
-  __shared__ __align__(8) unsigned long long stepbar;
+  __shared__ __align__(8) unsigned long long bar;
   __shared__ uint32_t tmem_holder;
-  const LstmTcBwdCell& lc = bt.c[blockIdx.y];
+  const Lstm2Cell& lc = bt.c[blockIdx.y];
   if ((int)blockIdx.x >= lc.tiles) return;
   const mfm_lstm_cell& c = lc.c;
   const int h = c.h, B = c.B, T = c.T, H4 = 4 * c.h;
-  const int MT = lc.mt, hp8 = lc.hp8, npad = lc.npad, nslot = lc.nslot;
-  const int kslabs = hp8 >> 1;                        // K' = 4*hp8, 8 per slab
-  const int lboB = npad * 16 + 32, lboA = MT * 16 + 32;
-  const int slot_bytes = (LB_SLOT_UNITS / 2) * lboA;  // one plane of one slot: 16 slabs
-  unsigned char* Bhi = smem;
-  unsigned char* Blo = Bhi + kslabs * lboB;
-  unsigned char* Aring = Blo + kslabs * lboB;         // [nslot][hi|lo][16 slabs]
+  constexpr int NB = 4 * CPT;
+  const int KP = lc.kp;                               // 4 * hp8, a multiple of 32
+  const int slabs = KP >> 3;
+  const int lboA = h * 16 + 32, lboB = NB * 16 + 32;
+  unsigned char* Ahi = smem;                          // W^T: A[j][k'], k' = 4*unit + gate
+  unsigned char* Alo = Ahi + slabs * lboA;
+  unsigned char* Bhi = Alo + slabs * lboA + 2048;     // the MMA tile reads rows j in [h,128): lands in valid memory, lanes ignored
+  unsigned char* Blo = Bhi + slabs * lboB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row0 = blockIdx.x * MT;
+  const int row0 = blockIdx.x * NB;
 
   if (tid == 0) {
-    mbar_init(smem_u32(&slotbar[0]), 1);
-    mbar_init(smem_u32(&slotbar[1]), 1);
-    mbar_init(smem_u32(&stepbar), 1);
+    mbar_init(smem_u32(&bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -266,145 +266,111 @@ __global__ void __launch_bounds__(LT_THREADS) lstm_tc_bwd_kernel(LstmTcBwdBatch 
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // B operand: B[n, k'=4j+g] = W[g*h + j][n]  (zero for j >= h or n >= h); item = (n, slab): 8 gathered values
-  for (int idx = tid; idx < npad * kslabs; idx += LT_THREADS) {
-    const int n = idx % npad, slab = idx / npad;
+  // A[j][k' = 4*jj + g] = W[g*h + jj][j]; item = (j, slab): 8 gathered values, j fastest (coalesced)
+  for (int idx = tid; idx < h * slabs; idx += L2_THREADS) {
+    const int j = idx % h, slab = idx / h;
     float v[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int j = 2 * slab + (q >> 2), g = q & 3;
-      v[q] = (j < h && n < h) ? __ldg(c.W + (long long)(g * h + j) * h + n) : 0.0f;
+    for (int e = 0; e < 8; ++e) {
+      const int jj = 2 * slab + (e >> 2), g = e & 3;
+      v[e] = jj < h ? __ldg(c.W + (long long)(g * h + jj) * h + j) : 0.0f;
     }
-    split_store(v, Bhi + slab * lboB + n * 16, Blo + slab * lboB + n * 16, true);
+    split_store(v, Ahi + slab * lboA + j * 16, Alo + slab * lboA + j * 16, true);
   }
+  for (int idx = tid * 16; idx < 2 * slabs * lboB; idx += L2_THREADS * 16)
+    *reinterpret_cast<uint4*>(Bhi + idx) = make_uint4(0, 0, 0, 0);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_holder;
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
-  const int quad = warp & 3, cg = warp >> 2;
-  const bool owns = (MT == 128) || (lane < 16);
-  const int r = (MT == 128) ? (quad * 32 + lane) : (quad * 16 + lane);
-  const int row = row0 + r;
-  const bool valid = owns && row < B;
-  const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
-  const bool hv4 = (h & 3) == 0;
-  const bool vec_gt = aligned16(c.gates) && hv4, vec_dg = aligned16(c.dG) && hv4;
-  const bool vec_cs = aligned16(c.cs) && ((c.ld_cs & 3) == 0);
-  const bool vec_sc = aligned16(c.dc_scratch) && hv4;
-  const bool vec_dha = c.dh_all && aligned16(c.dh_all) && ((c.ld_dh_all & 3) == 0);
-  const bool vec_dhl = c.dh_last && aligned16(c.dh_last) && ((c.ld_dh_last & 3) == 0);
-  const bool vec_dce = c.dc_ext && aligned16(c.dc_ext) && ((c.ld_dc_ext & 3) == 0);
-  const int nslots_per_step = (hp8 + LB_SLOT_UNITS - 1) / LB_SLOT_UNITS;
-  int slot_uses[2] = {0, 0};
-  int step_commits = 0;
+  // thread = (unit j = TMEM lane, CPT batch columns)
+  const int q = warp & 3, cg = warp >> 2;
+  const int j = q * 32 + lane;
+  const bool j_on = j < h;
+  const int hp8 = KP >> 2;
+  const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * CPT);
+  float dc[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) dc[i] = 0.0f;
 
   for (int t = T - 1; t >= 0; --t) {
-    const uint32_t dprev = tlane + (uint32_t)(((t + 1) & 1) * npad);
-    const uint32_t dcur = tmem_base + (uint32_t)((t & 1) * npad);
-    if (t < T - 1) {                       // dh_rec of this step = result of the previous step's MMAs
-      mbar_wait(smem_u32(&stepbar), (uint32_t)((step_commits - 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-    const long long tr = (long long)t * B + row;
-    for (int u = 0; u < nslots_per_step; ++u) {
-      const int sl = (nslot == 2) ? (u & 1) : 0;
-      unsigned char* Ahi = Aring + sl * 2 * slot_bytes;
-      unsigned char* Alo = Ahi + slot_bytes;
-      if (slot_uses[sl] > 0) mbar_wait(smem_u32(&slotbar[sl]), (uint32_t)((slot_uses[sl] - 1) & 1));   // MMAs that read it are done
-      const int j0 = u * LB_SLOT_UNITS + 8 * cg;
-      if (j0 < hp8) {
-        float dh[8];
-        if (t < T - 1) {
-          tmem_ld8(dprev + (uint32_t)j0, dh);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        } else {
+    // everything that does not depend on the recurrence is loaded before the MMA wait
+    float ig[CPT], fg[CPT], gg[CPT], og[CPT], cp[CPT], cn[CPT], dhx[CPT], dcx[CPT];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dh[i] = 0.0f;
-        }
-        float dg[4][8];
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dg[g][i] = 0.0f;
-        if (valid) {
-          const int nv = min(8, h - j0);
-          float x[4][8], cp[8], cn[8], e[8], dc[8];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) ld8_global(c.gates + tr * H4 + g * h + j0, vec_gt, nv, x[g]);
-          ld8_global(c.cs + tr * c.ld_cs + j0, vec_cs, nv, cp);
-          ld8_global(c.cs + (tr + B) * c.ld_cs + j0, vec_cs, nv, cn);
-          if (c.dh_all) {
-            ld8_global(c.dh_all + tr * c.ld_dh_all + j0, vec_dha, nv, e);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dh[i] += e[i];
-          }
-          if (c.dh_last && t == T - 1) {
-            ld8_global(c.dh_last + (long long)row * c.ld_dh_last + j0, vec_dhl, nv, e);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dh[i] += e[i];
-          }
-          if (t < T - 1) ld8_global(c.dc_scratch + (long long)row * h + j0, vec_sc, nv, dc);
-          else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dc[i] = 0.0f;
-          }
-          if (c.dc_ext) {
-            ld8_global(c.dc_ext + tr * c.ld_dc_ext + j0, vec_dce, nv, e);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dc[i] += e[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float ig = x[0][i], fg = x[1][i], gg = x[2][i], og = x[3][i];
-            const float tc = gate_tanh(cn[i]);
-            const float dci = dc[i] + dh[i] * og * (1.0f - tc * tc);
-            const bool ok = i < nv;
-            dg[0][i] = ok ? dci * gg * ig * (1.0f - ig) : 0.0f;
-            dg[1][i] = ok ? dci * cp[i] * fg * (1.0f - fg) : 0.0f;
-            dg[2][i] = ok ? dci * ig * (1.0f - gg * gg) : 0.0f;
-            dg[3][i] = ok ? dh[i] * tc * og * (1.0f - og) : 0.0f;
-            dc[i] = dci * fg;
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) st8_global(c.dG + tr * H4 + g * h + j0, vec_dg, nv, dg[g]);
-          if (t > 0) st8_global(c.dc_scratch + (long long)row * h + j0, vec_sc, nv, dc);
-        }
-        if (owns && t > 0) {               // A operand: slab q of this chunk = units (j0+2q, j0+2q+1) x gates (i,f,g,o)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float v[8] = {dg[0][2 * q], dg[1][2 * q], dg[2][2 * q], dg[3][2 * q],
-                                dg[0][2 * q + 1], dg[1][2 * q + 1], dg[2][2 * q + 1], dg[3][2 * q + 1]};
-            const int off = (4 * cg + q) * lboA + r * 16;
-            split_store(v, Ahi + off, Alo + off, true);
-          }
-        }
+    for (int i = 0; i < CPT; ++i) {
+      const int b = row0 + cg * CPT + i;
+      ig[i] = fg[i] = gg[i] = og[i] = cp[i] = cn[i] = dhx[i] = dcx[i] = 0.0f;
+      if (j_on && b < B) {
+        const long long tr = (long long)t * B + b;
+        const float* gp = c.gates + tr * H4 + j;
+        ig[i] = gp[0]; fg[i] = gp[h]; gg[i] = gp[2 * h]; og[i] = gp[3 * h];
+        cp[i] = c.cs[tr * c.ld_cs + j];
+        cn[i] = c.cs[(tr + B) * c.ld_cs + j];
+        if (c.dh_all) dhx[i] = __ldg(c.dh_all + tr * c.ld_dh_all + j);
+        if (c.dh_last && t == T - 1) dhx[i] += __ldg(c.dh_last + (long long)b * c.ld_dh_last + j);
+        if (c.dc_ext) dcx[i] = __ldg(c.dc_ext + tr * c.ld_dc_ext + j);
       }
-      if (t > 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const int units = min(LB_SLOT_UNITS, hp8 - u * LB_SLOT_UNITS);
-          const int ksteps = units >> 2;                                  // 4 units = 16 k'
-          const uint32_t aH = smem_u32(Ahi), aL = smem_u32(Alo);
-          const uint32_t bH = smem_u32(Bhi) + (uint32_t)(u * (LB_SLOT_UNITS / 2) * lboB), bL = bH + (uint32_t)(kslabs * lboB);
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint32_t ao = kk * 2 * lboA, bo = kk * 2 * lboB;
-            const uint64_t dAh = make_smem_desc(aH + ao, lboA, 128), dAl = make_smem_desc(aL + ao, lboA, 128);
-            const uint64_t dBh = make_smem_desc(bH + bo, lboB, 128), dBl = make_smem_desc(bL + bo, lboB, 128);
-            umma_bf16(dcur, dAh, dBh, idesc, (u > 0 || kk > 0) ? 1u : 0u);
-            umma_bf16(dcur, dAl, dBh, idesc, 1u);
-            umma_bf16(dcur, dAh, dBl, idesc, 1u);
-          }
-          umma_commit(smem_u32(&slotbar[sl]));
-          if (u == nslots_per_step - 1) umma_commit(smem_u32(&stepbar));
+    }
+    float dh[CPT];
+    if (t < T - 1) {                                  // dh_rec of this step = the previous step's MMAs
+      mbar_wait(smem_u32(&bar), (uint32_t)((T - 2 - t) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t dprev = tlane + (uint32_t)(((t + 1) & 1) * NB);
+      if (CPT == 8) tmem_ld8(dprev, dh); else tmem_ld4(dprev, dh);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    } else {
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) dh[i] = 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      const int bl = cg * CPT + i, b = row0 + bl;
+      float d_i = 0.0f, d_f = 0.0f, d_g = 0.0f, d_o = 0.0f;
+      if (j_on && b < B) {
+        const float dht = dh[i] + dhx[i];
+        const float tc = gate_tanh(cn[i]);
+        const float dci = dc[i] + dht * og[i] * (1.0f - tc * tc) + dcx[i];
+        d_i = dci * gg[i] * ig[i] * (1.0f - ig[i]);
+        d_f = dci * cp[i] * fg[i] * (1.0f - fg[i]);
+        d_g = dci * ig[i] * (1.0f - gg[i] * gg[i]);
+        d_o = dht * tc * og[i] * (1.0f - og[i]);
+        dc[i] = dci * fg[i];
+        float* op = c.dG + ((long long)t * B + b) * H4 + j;
+        op[0] = d_i; op[h] = d_f; op[2 * h] = d_g; op[3 * h] = d_o;
+      }
+      if (j < hp8 && t > 0) {                         // B operand: row = batch column, k' = 4j..4j+3  (8 contiguous bytes)
+        const float v4[4] = {d_i, d_f, d_g, d_o};
+        unsigned short hb[4], lb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          hb[e] = bf16_bits(v4[e]);
+          lb[e] = bf16_bits(v4[e] - __uint_as_float((uint32_t)hb[e] << 16));
         }
-        ++slot_uses[sl];
-        if (u == nslots_per_step - 1) ++step_commits;
+        const int off = (j >> 1) * lboB + bl * 16 + (j & 1) * 8;
+        *reinterpret_cast<uint2*>(Bhi + off) = make_uint2((uint32_t)hb[0] | ((uint32_t)hb[1] << 16), (uint32_t)hb[2] | ((uint32_t)hb[3] << 16));
+        *reinterpret_cast<uint2*>(Blo + off) = make_uint2((uint32_t)lb[0] | ((uint32_t)lb[1] << 16), (uint32_t)lb[2] | ((uint32_t)lb[3] << 16));
+      }
+    }
+    if (t > 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t dcur = tmem_base + (uint32_t)((t & 1) * NB);
+        const uint32_t aH = smem_u32(Ahi), aL = smem_u32(Alo), bH = smem_u32(Bhi), bL = smem_u32(Blo);
+        for (int kk = 0; kk < (KP >> 4); ++kk) {
+          const uint32_t ao = kk * 2 * lboA, bo = kk * 2 * lboB;
+          const uint64_t dAh = make_smem_desc(aH + ao, lboA, 128), dAl = make_smem_desc(aL + ao, lboA, 128);
+          const uint64_t dBh = make_smem_desc(bH + bo, lboB, 128), dBl = make_smem_desc(bL + bo, lboB, 128);
+          umma_bf16(dcur, dAh, dBh, idesc, kk > 0 ? 1u : 0u);
+          umma_bf16(dcur, dAl, dBh, idesc, 1u);
+          umma_bf16(dcur, dAh, dBl, idesc, 1u);
+        }
+        umma_commit(smem_u32(&bar));
       }
     }
   }
@@ -416,122 +382,57 @@ __global__ void __launch_bounds__(LT_THREADS) lstm_tc_bwd_kernel(LstmTcBwdBatch 
   }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------------------------
 static inline int ru(int x, int m) { return (x + m - 1) / m * m; }
 
-static size_t lstm_tc_bwd_smem(int h, int mt, int nslot) {
-  const int hp8 = ru(h, 8), npad = ru(h, 16);
-  return (size_t)2 * (hp8 / 2) * (npad * 16 + 32) + (size_t)nslot * 2 * (LB_SLOT_UNITS / 2) * (mt * 16 + 32) + 128;
+static size_t fwd_smem(int h, int nb) {
+  const int slabs = ru(h, 16) / 8;
+  return (size_t)2 * slabs * (4 * h * 16 + 32) + (size_t)2 * slabs * (nb * 16 + 32) + 2048 + (size_t)4 * h * (L2_CC + 1) * 4 + 128;
 }
-
-static bool lstm_tc_bwd_plan(const mfm_lstm_cell& c, int smem_limit, LstmTcBwdCell& out) {
-  if (c.h > 128 || c.h < 1 || !c.dc_scratch) return false;
-  int mt = 0, nslot = 0;
-  const int cand_mt[2] = {128, 64};
-  for (int a = 0; a < 2 && !mt; ++a) {
-    if (cand_mt[a] == 128 && c.B <= 64) continue;
-    for (int ns = 2; ns >= 1 && !mt; --ns)
-      if (lstm_tc_bwd_smem(c.h, cand_mt[a], ns) <= (size_t)smem_limit) { mt = cand_mt[a]; nslot = ns; }
-  }
-  if (!mt) return false;
-  out.c = c;
-  out.mt = mt;
-  out.nslot = nslot;
-  out.tiles = (c.B + mt - 1) / mt;
-  out.hp8 = ru(c.h, 8);
-  out.npad = ru(c.h, 16);
-  int cols = 32;
-  while (cols < 2 * out.npad) cols <<= 1;
-  out.tmem_cols = cols;
-  return true;
+static size_t bwd_smem(int h, int nb) {
+  const int slabs = 4 * ru(h, 8) / 8;
+  return (size_t)2 * slabs * (h * 16 + 32) + 2048 + (size_t)2 * slabs * (nb * 16 + 32) + 128;
 }
-
-int lstm_tc_bwd_launch(const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* rest, int* nrest, cudaStream_t st) {
+static int smem_limit() {
   static int lim = -1;
   if (lim < 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) lim = 48 * 1024;
-    lim -= 1024;
+    lim -= 1024;      // the opt-in limit covers static + dynamic shared memory
   }
-  LstmTcBwdBatch bt;
-  bt.n = 0;
-  *nrest = 0;
-  size_t smem = 0;
-  int gx = 0;
-  for (int i = 0; i < ncells; ++i) {
-    LstmTcBwdCell lc;
-    if (lstm_tc_bwd_plan(cells[i], lim, lc)) {
-      bt.c[bt.n++] = lc;
-      const size_t s = lstm_tc_bwd_smem(lc.c.h, lc.mt, lc.nslot);
-      if (s > smem) smem = s;
-      if (lc.tiles > gx) gx = lc.tiles;
-    } else {
-      rest[(*nrest)++] = cells[i];
-    }
-  }
-  if (bt.n == 0) return MFM_OK;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
-  lstm_tc_bwd_kernel<<<dim3(gx, bt.n), LT_THREADS, smem, st>>>(bt);
-  MFM_LAUNCH_CHECK();
-  return MFM_OK;
-}
-
-// shared-memory bytes of the forward kernel for (h, mt)
-static size_t lstm_tc_fwd_smem(int h, int mt) {
-  const int hp16 = ru(h, 16), n4 = ru(4 * h, 16), slabs = hp16 / 8;
-  return (size_t)2 * slabs * (n4 * 16 + 32) + (size_t)2 * slabs * (mt * 16 + 32) + 128;
-}
-
-// plan one cell; returns false if it must run on the CUDA-core kernel
-static bool lstm_tc_plan(const mfm_lstm_cell& c, int smem_limit, LstmTcCell& out) {
-  if (4 * c.h > 512 || c.h < 1) return false;
-  int mt = 0;
-  if (c.B > 64 && lstm_tc_fwd_smem(c.h, 128) <= (size_t)smem_limit) mt = 128;
-  else if (lstm_tc_fwd_smem(c.h, 64) <= (size_t)smem_limit) mt = 64;
-  if (!mt) return false;
-  out.c = c;
-  out.mt = mt;
-  out.tiles = (c.B + mt - 1) / mt;
-  out.hp8 = ru(c.h, 8);
-  out.hp16 = ru(c.h, 16);
-  out.n4 = ru(4 * c.h, 16);
-  out.nblk = (out.n4 + 255) / 256;
-  out.bn = ru((out.n4 + out.nblk - 1) / out.nblk, 16);
-  int cols = 32;
-  while (cols < out.n4) cols <<= 1;
-  out.tmem_cols = cols;
-  return true;
+  return lim;
 }
 
 // Launches the tensor-core forward for every cell that fits; cells that do not are returned in `rest`.
 int lstm_tc_fwd_launch(const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* rest, int* nrest, cudaStream_t st) {
-  static int lim = -1;
-  if (lim < 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) lim = 48 * 1024;
-    lim -= 1024;      // the opt-in limit covers static + dynamic shared memory; the kernel has a few static bytes
-  }
-  LstmTcBatch bt;
+  const int lim = smem_limit();
+  Lstm2Batch bt;
   bt.n = 0;
   *nrest = 0;
   size_t smem = 0;
   int gx = 0;
   for (int i = 0; i < ncells; ++i) {
-    LstmTcCell lc;
-    if (lstm_tc_plan(cells[i], lim, lc)) {
-      bt.c[bt.n++] = lc;
-      const size_t s = lstm_tc_fwd_smem(lc.c.h, lc.mt);
-      if (s > smem) smem = s;
-      if (lc.tiles > gx) gx = lc.tiles;
-    } else {
-      rest[(*nrest)++] = cells[i];
+    const mfm_lstm_cell& c = cells[i];
+    int nb = 0;
+    if (c.h >= 1 && c.h <= 128) {
+      if (fwd_smem(c.h, 32) <= (size_t)lim) nb = 32;
+      else if (fwd_smem(c.h, 16) <= (size_t)lim) nb = 16;
     }
+    if (!nb) { rest[(*nrest)++] = c; continue; }
+    Lstm2Cell& lc = bt.c[bt.n++];
+    lc.c = c;
+    lc.nb = nb;
+    lc.tiles = (c.B + nb - 1) / nb;
+    lc.kp = ru(c.h, 16);
+    lc.mtiles = (4 * c.h + 127) / 128;
+    int cols = 32;
+    while (cols < lc.mtiles * nb) cols <<= 1;
+    lc.tmem_cols = cols;
+    smem = smem > fwd_smem(c.h, nb) ? smem : fwd_smem(c.h, nb);
+    gx = gx > lc.tiles ? gx : lc.tiles;
   }
   if (bt.n == 0) return MFM_OK;
   static bool attr = false;
@@ -540,7 +441,51 @@ int lstm_tc_fwd_launch(const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* re
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  lstm_tc_fwd_kernel<<<dim3(gx, bt.n), LT_THREADS, smem, st>>>(bt);
+  lstm_tc_fwd_kernel<<<dim3(gx, bt.n), L2_THREADS, smem, st>>>(bt);
   MFM_LAUNCH_CHECK();
+  return MFM_OK;
+}
+
+int lstm_tc_bwd_launch(const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* rest, int* nrest, cudaStream_t st) {
+  const int lim = smem_limit();
+  Lstm2Batch b32, b16;
+  b32.n = b16.n = 0;
+  *nrest = 0;
+  size_t smem32 = 0, smem16 = 0;
+  int gx32 = 0, gx16 = 0;
+  for (int i = 0; i < ncells; ++i) {
+    const mfm_lstm_cell& c = cells[i];
+    int nb = 0;
+    if (c.h >= 1 && c.h <= 128) {
+      if (bwd_smem(c.h, 32) <= (size_t)lim) nb = 32;
+      else if (bwd_smem(c.h, 16) <= (size_t)lim) nb = 16;
+    }
+    if (!nb) { rest[(*nrest)++] = c; continue; }
+    Lstm2Batch& bt = nb == 32 ? b32 : b16;
+    Lstm2Cell& lc = bt.c[bt.n++];
+    lc.c = c;
+    lc.nb = nb;
+    lc.tiles = (c.B + nb - 1) / nb;
+    lc.kp = 4 * ru(c.h, 8);
+    lc.mtiles = 1;
+    lc.tmem_cols = nb == 32 ? 64 : 32;
+    if (nb == 32) { smem32 = smem32 > bwd_smem(c.h, 32) ? smem32 : bwd_smem(c.h, 32); gx32 = gx32 > lc.tiles ? gx32 : lc.tiles; }
+    else          { smem16 = smem16 > bwd_smem(c.h, 16) ? smem16 : bwd_smem(c.h, 16); gx16 = gx16 > lc.tiles ? gx16 : lc.tiles; }
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(lstm_tc_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_tc_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  if (b32.n) {
+    lstm_tc_bwd_kernel<8><<<dim3(gx32, b32.n), L2_THREADS, smem32, st>>>(b32);
+    MFM_LAUNCH_CHECK();
+  }
+  if (b16.n) {
+    lstm_tc_bwd_kernel<4><<<dim3(gx16, b16.n), L2_THREADS, smem16, st>>>(b16);
+    MFM_LAUNCH_CHECK();
+  }
   return MFM_OK;
 }
