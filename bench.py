@@ -152,9 +152,11 @@ def profile_primitives(trainer, reps=3):
         return inner
     names = ["gemm", "lstm_fwd", "lstm_bwd", "mfn_mem_fwd", "mfn_mem_bwd", "softmax_gate_fwd", "softmax_gate_bwd", "mmd_fwd",
              "mmd_bwd", "copy2d", "add", "zero", "colsum", "relu_bwd", "mse_fwd_bwd", "l1_fwd_bwd", "ce_fwd_bwd",
-             "loss_total", "adam", "randn", "rng_tick"]
+             "loss_total", "adam", "randn", "rng_tick", "rownorm2", "mmd_kexp", "mmd_combine"]
     orig = {n: getattr(ops, n) for n in names}
     agg = {}
+    side = trainer.eng.use_side_stream
+    trainer.eng.use_side_stream = False       # per-kernel timing needs everything on the timed stream
     try:
         for n in names:
             setattr(ops, n, wrap(n, orig[n]))
@@ -171,6 +173,7 @@ def profile_primitives(trainer, reps=3):
             a[1] += fl
             a[2] += 1
     finally:
+        trainer.eng.use_side_stream = side
         for n in names:
             try:
                 delattr(ops, n)

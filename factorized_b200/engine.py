@@ -78,6 +78,9 @@ class Engine:
         self.ws: Dict[str, torch.Tensor] = {}
         self.train = False
         self.loss_buf = torch.zeros(16, dtype=torch.float32, device=self.device)
+        self.use_side_stream = True
+        self._side = None
+        self._side_used = False
         # loss_buf: 0 disc, 1..3 mse_l/a/v, 4..7 mmd per latent (unweighted), 8 total (weighted)
 
     # -- workspace -----------------------------------------------------------------
@@ -289,6 +292,31 @@ class Engine:
         ops.loss_total(self.loss_buf, dm.lda[0], dm.lda[1], dm.lda[2], dm.lda_mmd)
         return dX, dY
 
+    # -- weight-gradient GEMMs run on a side stream ---------------------------------
+    def _wgrad_gemm(self, dY, A, Gout, **kw):
+        """dW += dY^T A (TN GEMM, optionally with the fused bias gradient).  Weight gradients only read stashes and
+        write the flat gradient buffer, so they do not belong on the critical path of the backward chain: they are
+        issued on a side stream that forks from the main stream right after dY is produced and joins before the
+        optimizer step (inside a CUDA graph this becomes a parallel branch)."""
+        ops = self.ops
+        if self.device.type != "cuda" or not self.use_side_stream:
+            ops.gemm("tn", dY, A, Gout, **kw)
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            ops.gemm("tn", dY, A, Gout, **kw)
+        self._side_used = True
+
+    def _join_side(self):
+        if self._side is not None and self._side_used:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            self._side_used = False
+
     # -- backward ------------------------------------------------------------------
     def backward(self, P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], dXhat: Sequence[torch.Tensor],
                  dYhat: torch.Tensor, mmd_scale: float, mmd_scale_dev: Optional[torch.Tensor] = None,
@@ -303,7 +331,7 @@ class Engine:
         relu_scale = (lambda p: 1.0 / (1.0 - p) if (self.train and p > 0.0) else 1.0)
 
         def wgrad(dY, A, name):            # dW[N,K] += dY[M,N]^T A[M,K]
-            ops.gemm("tn", dY, A, G[name], accumulate=True)
+            self._wgrad_gemm( dY, A, G[name], accumulate=True)
 
         def bgrad(dY, name):
             ops.colsum(dY, G[name])
@@ -311,13 +339,14 @@ class Engine:
         def lin_bwd(dY, A, name, dA=None, accumulate=False, mask=None, mask_scale=1.0):
             """y = A W^T + b: dW and db in one GEMM (db rides along as a ones column), and (optionally)
             dA = (dY W) [* relu/dropout mask of A]."""
-            ops.gemm("tn", dY, A, G[name + ".weight"], accumulate=True, colsum_out=G[name + ".bias"])
+            self._wgrad_gemm( dY, A, G[name + ".weight"], accumulate=True, colsum_out=G[name + ".bias"])
             if dA is not None:
                 ops.gemm("nn", dY, P[name + ".weight"], dA, accumulate=accumulate, mask=mask, mask_scale=mask_scale)
 
         if self.mfn_only:
             dHlast, dmemT = d_mfn_last[:, :H], d_mfn_last[:, H:]
             self._backward_mfn(P, G, dHlast, dmemT, [], wgrad, bgrad, lin_bwd, relu_scale)
+            self._join_side()
             return
 
         # (11') discriminative head
@@ -341,8 +370,8 @@ class Engine:
             d_ = "decoder_%s.lstm" % tag
             dG = ws["dGD%d" % m]
             hprev = ws["hsD%d" % m][:TB]                    # h_{t-1}; block 0 is the zero state
-            ops.gemm("tn", dG, hprev, G[d_ + ".weight_hh"], accumulate=True, colsum_out=G[d_ + ".bias_hh"])
-            ops.gemm("tn", dG, hprev, G[d_ + ".weight_ih"], accumulate=True,        # input == h_{t-1} for t >= 1 (:85)
+            self._wgrad_gemm( dG, hprev, G[d_ + ".weight_hh"], accumulate=True, colsum_out=G[d_ + ".bias_hh"])
+            self._wgrad_gemm( dG, hprev, G[d_ + ".weight_ih"], accumulate=True,        # input == h_{t-1} for t >= 1 (:85)
                      colsum_out=G[d_ + ".bias_ih"])
             wgrad(dG[:B], ws["EMB%d" % m], d_ + ".weight_ih")  # step 0 input is the embedding (:83)
             de = buf("dEMB%d" % m, B, dm.hd[m])
@@ -388,8 +417,8 @@ class Engine:
         Wzy = P["last_to_zy_fc1.weight"]
         Gzy = G["last_to_zy_fc1.weight"]
         Hall, Call, mems = ws["Hall"], ws["Call"], ws["mems"]
-        ops.gemm("tn", dZY, Hall[TB:], Gzy[:, :H], accumulate=True)
-        ops.gemm("tn", dZY, mems[TB:], Gzy[:, H:], accumulate=True)
+        self._wgrad_gemm( dZY, Hall[TB:], Gzy[:, :H], accumulate=True)
+        self._wgrad_gemm( dZY, mems[TB:], Gzy[:, H:], accumulate=True)
         bgrad(dZY, "last_to_zy_fc1.bias")
         dHlast = buf("dHlast", B, H)
         dmemT = buf("dmemT", B, mem)
@@ -404,6 +433,7 @@ class Engine:
                                   W=P["encoder_%s.lstm.weight_hh" % tag], dh_all=None, dh_last=dhl, dc_ext=None,
                                   dG=buf("dGE%d" % m, TB, 4 * dm.z[m]), dc_scratch=buf("dcSE%d" % m, B, dm.z[m])))
         self._backward_mfn(P, G, dHlast, dmemT, enc_cells, wgrad, bgrad, lin_bwd, relu_scale)
+        self._join_side()
 
     def _backward_mfn(self, P, G, dHlast, dmemT, enc_cells, wgrad, bgrad, lin_bwd, relu_scale):
         """Adjoint of steps (5),(4),(2),(1): memory recurrence, attention MLPs, then the MFN cells together
@@ -425,14 +455,14 @@ class Engine:
             W12=P[pre + "gamma1_fc2.weight"], W22=P[pre + "gamma2_fc2.weight"],
             scale1=relu_scale(dm.p_g1), scale2=relu_scale(dm.p_g2),
             dmem_last=dmemT, dU1=dU1, dU2=dU2, dP1=dP1, dP2=dP2, dPc=dPc))
-        ops.gemm("tn", dP1, ws["U1"], G[pre + "gamma1_fc2.weight"], accumulate=True, colsum_out=G[pre + "gamma1_fc2.bias"])
-        ops.gemm("tn", dP2, ws["U2"], G[pre + "gamma2_fc2.weight"], accumulate=True, colsum_out=G[pre + "gamma2_fc2.bias"])
+        self._wgrad_gemm( dP1, ws["U1"], G[pre + "gamma1_fc2.weight"], accumulate=True, colsum_out=G[pre + "gamma1_fc2.bias"])
+        self._wgrad_gemm( dP2, ws["U2"], G[pre + "gamma2_fc2.weight"], accumulate=True, colsum_out=G[pre + "gamma2_fc2.bias"])
         Attended, cStar, Att = ws["Attended"], ws["cStar"], ws["Att"]
         dAtt = buf("dAttended", TB, 2 * H)
         for (dU, Wg, nm, first) in ((dU1, Wg1, "gamma1_fc1", True), (dU2, Wg2, "gamma2_fc1", False)):
             Gw = G[pre + nm + ".weight"]
-            ops.gemm("tn", dU, Attended, Gw[:, :2 * H], accumulate=True, colsum_out=G[pre + nm + ".bias"])
-            ops.gemm("tn", dU, mems[:TB], Gw[:, 2 * H:], accumulate=True)
+            self._wgrad_gemm( dU, Attended, Gw[:, :2 * H], accumulate=True, colsum_out=G[pre + nm + ".bias"])
+            self._wgrad_gemm( dU, mems[:TB], Gw[:, 2 * H:], accumulate=True)
             ops.gemm("nn", dU, Wg[:, :2 * H], dAtt, accumulate=not first)
 
         # (4') attention MLPs, time-parallel
@@ -468,5 +498,5 @@ class Engine:
                 jobs.append(("encoder_%s.lstm" % tag, "dGE%d" % m, ws["hsE%d" % m][:TB]))
             for (nm, dGn, hs) in jobs:
                 dG = ws[dGn]
-                ops.gemm("tn", dG, self.xs[m], G[nm + ".weight_ih"], accumulate=True, colsum_out=G[nm + ".bias_ih"])
-                ops.gemm("tn", dG, hs, G[nm + ".weight_hh"], accumulate=True, colsum_out=G[nm + ".bias_hh"])
+                self._wgrad_gemm( dG, self.xs[m], G[nm + ".weight_ih"], accumulate=True, colsum_out=G[nm + ".bias_ih"])
+                self._wgrad_gemm( dG, hs, G[nm + ".weight_hh"], accumulate=True, colsum_out=G[nm + ".bias_hh"])
