@@ -406,6 +406,17 @@ static int smem_limit() {
   return lim;
 }
 
+// CTAs are dispatched in blockIdx order (cell = blockIdx.y slowest): put the long-running cells first so the short
+// ones fill the tail instead of the other way round.
+static void sort_heavy_first(Lstm2Batch& bt) {
+  for (int i = 1; i < bt.n; ++i) {
+    Lstm2Cell key = bt.c[i];
+    int j = i - 1;
+    while (j >= 0 && bt.c[j].c.h < key.c.h) { bt.c[j + 1] = bt.c[j]; --j; }
+    bt.c[j + 1] = key;
+  }
+}
+
 // Launches the tensor-core forward for every cell that fits; cells that do not are returned in `rest`.
 int lstm_tc_fwd_launch(const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* rest, int* nrest, cudaStream_t st) {
   const int lim = smem_limit();
@@ -435,6 +446,7 @@ int lstm_tc_fwd_launch(const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* re
     gx = gx > lc.tiles ? gx : lc.tiles;
   }
   if (bt.n == 0) return MFM_OK;
+  sort_heavy_first(bt);
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(lstm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
@@ -479,6 +491,8 @@ int lstm_tc_bwd_launch(const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* re
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
+  sort_heavy_first(b32);
+  sort_heavy_first(b16);
   if (b32.n) {
     lstm_tc_bwd_kernel<8><<<dim3(gx32, b32.n), L2_THREADS, smem32, st>>>(b32);
     MFM_LAUNCH_CHECK();

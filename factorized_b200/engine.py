@@ -81,6 +81,9 @@ class Engine:
         self.use_side_stream = True
         self._side = None
         self._side_used = False
+        self._aux_stream = None
+        self._aux_used = False
+        self.defer_mmd_join = False      # the fused trainer joins the MMD stream in losses() instead of at the end of forward
         # loss_buf: 0 disc, 1..3 mse_l/a/v, 4..7 mmd per latent (unweighted), 8 total (weighted)
 
     # -- workspace -----------------------------------------------------------------
@@ -199,23 +202,26 @@ class Engine:
         # (7) MMD of each latent against its Gaussian sample (:25-34, :536)
         #     pair matrices S = X Y^T on the tensor cores, K = exp(-(|x|^2+|y|^2-2S)/dim^2) in place; K(z,z) and
         #     K(g,z) stay resident for the backward pass (no [B,B,dim] tensor, no recompute)
+        #     Nothing downstream of the latents waits for it, so it runs on the auxiliary stream, concurrently with the
+        #     factor MLPs and the decoders.
         lat = Z + [ZY]
-        ops.zero(self.loss_buf[4:8])
         Kgg = buf("Kgg", B, B)
         inv_bb = 1.0 / (float(B) * float(B))
-        for k in range(4):
-            zk, gk, dim = lat[k], self.noise[k], lat[k].shape[1]
-            nz, ng = buf("mmd_nz%d" % k, B), buf("mmd_ng%d" % k, B)
-            ops.rownorm2(zk, nz)
-            ops.rownorm2(gk, ng)
-            Kzz, Kgz = buf("Kzz%d" % k, B, B), buf("Kgz%d" % k, B, B)
-            slot = self.loss_buf[4 + k:5 + k]
-            ops.gemm("nt", zk, zk, Kzz)
-            ops.mmd_kexp(Kzz, nz, nz, dim, inv_bb, slot)
-            ops.gemm("nt", gk, zk, Kgz)                       # rows index the Gaussian sample, columns the latent
-            ops.mmd_kexp(Kgz, ng, nz, dim, -2.0 * inv_bb, slot)
-            ops.gemm("nt", gk, gk, Kgg)
-            ops.mmd_kexp(Kgg, ng, ng, dim, inv_bb, slot)
+        bufs = [(buf("mmd_nz%d" % k, B), buf("mmd_ng%d" % k, B), buf("Kzz%d" % k, B, B), buf("Kgz%d" % k, B, B)) for k in range(4)]
+        with self._aux():
+            ops.zero(self.loss_buf[4:8])
+            for k in range(4):
+                zk, gk, dim = lat[k], self.noise[k], lat[k].shape[1]
+                nz, ng, Kzz, Kgz = bufs[k]
+                ops.rownorm2(zk, nz)
+                ops.rownorm2(gk, ng)
+                slot = self.loss_buf[4 + k:5 + k]
+                ops.gemm("nt", zk, zk, Kzz)
+                ops.mmd_kexp(Kzz, nz, nz, dim, inv_bb, slot)
+                ops.gemm("nt", gk, zk, Kgz)                   # rows index the Gaussian sample, columns the latent
+                ops.mmd_kexp(Kgz, ng, nz, dim, -2.0 * inv_bb, slot)
+                ops.gemm("nt", gk, gk, Kgg)
+                ops.mmd_kexp(Kgg, ng, ng, dim, inv_bb, slot)
 
         # (8) factor MLPs (:539-542) written straight into the decoder inputs cat(fy, f_m) (:544-546)
         FY = buf("FY", B, dm.fy)
@@ -265,6 +271,8 @@ class Engine:
         ops.gemm("nt", FY, P["fy_to_y_fc1.weight"], Y1, bias=P["fy_to_y_fc1.bias"], act=ACT_RELU,
                  drop=drop(dm.p_y, SITE_Y), rng=rng)
         ops.gemm("nt", Y1, P["fy_to_y_fc2.weight"], Yhat, bias=P["fy_to_y_fc2.bias"])
+        if not self.defer_mmd_join:
+            self._join_aux()
         return dict(x_l_hat=Xhat[0], x_a_hat=Xhat[1], x_v_hat=Xhat[2], y_hat=Yhat,
                     zl=Z[0], za=Z[1], zv=Z[2], zy=ZY, fy=FY, mmd_parts=self.loss_buf[4:8])
 
@@ -275,6 +283,7 @@ class Engine:
         loss_buf[0..3] = disc, mse_l, mse_a, mse_v (means); loss_buf[8] = total."""
         dm, ops, buf = self.dm, self.ops, self.buf
         TB = dm.T * dm.B
+        self._join_aux()                 # loss_buf[4:8] (MMD parts) come from the auxiliary stream
         ops.zero(self.loss_buf[0:4])
         dX = []
         for m in range(3):
@@ -317,6 +326,40 @@ class Engine:
             torch.cuda.current_stream(self.device).wait_stream(self._side)
             self._side_used = False
 
+    # -- the MMD statistic is off the critical path: it runs on its own stream -------
+    class _Aux:
+        """``with eng._aux():`` runs the body on the auxiliary stream, forked from the main stream at entry."""
+
+        def __init__(self, eng):
+            self.eng, self.ctx = eng, None
+
+        def __enter__(self):
+            e = self.eng
+            if e.device.type != "cuda" or not e.use_side_stream:
+                return self
+            if e._aux_stream is None:
+                e._aux_stream = torch.cuda.Stream(device=e.device)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(e.device))
+            e._aux_stream.wait_event(ev)
+            self.ctx = torch.cuda.stream(e._aux_stream)
+            self.ctx.__enter__()
+            e._aux_used = True
+            return self
+
+        def __exit__(self, *a):
+            if self.ctx is not None:
+                self.ctx.__exit__(*a)
+            return False
+
+    def _aux(self):
+        return Engine._Aux(self)
+
+    def _join_aux(self):
+        if self._aux_stream is not None and self._aux_used:
+            torch.cuda.current_stream(self.device).wait_stream(self._aux_stream)
+            self._aux_used = False
+
     # -- backward ------------------------------------------------------------------
     def backward(self, P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], dXhat: Sequence[torch.Tensor],
                  dYhat: torch.Tensor, mmd_scale: float, mmd_scale_dev: Optional[torch.Tensor] = None,
@@ -348,6 +391,27 @@ class Engine:
             self._backward_mfn(P, G, dHlast, dmemT, [], wgrad, bgrad, lin_bwd, relu_scale)
             self._join_side()
             return
+
+        # (7') MMD: gradient flows through K(z,z) and K(g,z) only and depends on nothing upstream but its scale, so
+        #      it starts now on the auxiliary stream and is added to dZ after the factor MLPs have produced dZ.
+        #      d/dz = (2c/B^2) [ (rowsum Kzz - colsum Kgz) * z - Kzz Z + Kgz^T G ],  c = -2/dim^2
+        lat = [ws["Z0"], ws["Z1"], ws["Z2"], ws["ZY"]]
+        dmmd = [buf("dZmmd%d" % k, B, lat[k].shape[1]) for k in range(4)]
+        mbufs = [(buf("mmd_rc%d" % k, 2 * B), buf("mmd_t12_%d" % k, 2 * B, lat[k].shape[1])) for k in range(4)]
+        with self._aux():
+            for k in range(4):
+                zk, gk, dim = lat[k], self.noise[k], lat[k].shape[1]
+                Kzz, Kgz = ws["Kzz%d" % k], ws["Kgz%d" % k]
+                rc, t12 = mbufs[k]
+                ops.zero(rc)
+                ops.colsum(Kzz, rc[:B])                          # K(z,z) is symmetric: column sums == row sums
+                ops.colsum(Kgz, rc[B:])
+                t1, t2 = t12[:B], t12[B:]
+                ops.zero(t12)                                    # accumulate form lets the GEMM split K = B over CTAs
+                ops.gemm("nn", Kzz, zk, t1, accumulate=True)
+                ops.gemm("tn", Kgz, gk, t2, accumulate=True)
+                ops.zero(dmmd[k])
+                ops.mmd_combine(zk, rc[:B], rc[B:], t1, t2, mmd_scale, dmmd[k], mmd_scale_dev)
 
         # (11') discriminative head
         dY1 = buf("dY1", B, dm.fy)
@@ -395,23 +459,10 @@ class Engine:
             mlp2_bwd(dEMB[m][:, dm.fy:], ws["EMB%d" % m][:, dm.fy:], ws["F1_%d" % m], ws["Z%d" % m],
                      "z%s_to_f%s" % (tag, tag), dm.p_f[m], dZ[m])
 
-        # (7') MMD: gradient flows through K(z,z) and K(g,z) only
-        lat = [ws["Z0"], ws["Z1"], ws["Z2"], ws["ZY"]]
+        self._join_aux()
         dlat = dZ + [dZY]
-        #      d/dz = (2c/B^2) [ (rowsum Kzz - colsum Kgz) * z - Kzz Z + Kgz^T G ],  c = -2/dim^2
         for k in range(4):
-            zk, gk, dim = lat[k], self.noise[k], lat[k].shape[1]
-            Kzz, Kgz = ws["Kzz%d" % k], ws["Kgz%d" % k]
-            rc = buf("mmd_rc%d" % k, 2 * B)
-            ops.zero(rc)
-            ops.colsum(Kzz, rc[:B])                          # K(z,z) is symmetric: column sums == row sums
-            ops.colsum(Kgz, rc[B:])
-            t12 = buf("mmd_t12_%d" % k, 2 * B, dim)
-            t1, t2 = t12[:B], t12[B:]
-            ops.zero(t12)                                    # accumulate form lets the GEMM split K = B over CTAs
-            ops.gemm("nn", Kzz, zk, t1, accumulate=True)
-            ops.gemm("tn", Kgz, gk, t2, accumulate=True)
-            ops.mmd_combine(zk, rc[:B], rc[B:], t1, t2, mmd_scale, dlat[k], mmd_scale_dev)
+            ops.copy2d(dmmd[k], dlat[k], accumulate=True)
 
         # (6') last_to_zy_fc1 over cat(h_T, mem_T)
         Wzy = P["last_to_zy_fc1.weight"]

@@ -74,6 +74,7 @@ class MFMTrainer:
                 self.G[k] = self.flat_g[o:o + p.numel()].view(p.shape)
                 o += p.numel()
         self.eng = E.Engine(model._cfg, T, B, dev, self.ops, head=head)
+        self.eng.defer_mmd_join = True
         dm = self.eng.dm
         self.x = torch.zeros(T, B, dm.D, dtype=torch.float32, device=dev)
         if head == "ce":
@@ -84,6 +85,7 @@ class MFMTrainer:
         self.rng = torch.tensor([int(seed), 0], dtype=torch.int64, device=dev)
         self.adam_state = torch.tensor([lr, 0.0, 0.0, 0.0], dtype=torch.float32, device=dev)
         self.use_graph = use_graph
+        self._copy_stream = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
         self.steps_done = 0
@@ -155,9 +157,38 @@ class MFMTrainer:
 
     def step(self, x, y):
         """x: [T,B,D] fp32, y: targets; host (ideally pinned) or device tensors.  Returns the device loss buffer
-        (index 0 = discriminative loss, 1..3 = MSE l/a/v, 4..7 = MMD parts, 8 = total); reading it syncs."""
-        self.x.copy_(x, non_blocking=True)
-        self.y.copy_(y.reshape(self.y.shape), non_blocking=True)
+        (index 0 = discriminative loss, 1..3 = MSE l/a/v, 4..7 = MMD parts, 8 = total); reading it syncs.
+
+        Host batches travel on a dedicated copy stream into one of two device staging buffers, so the H2D copy of
+        batch n+1 overlaps the compute of batch n (the reference does a blocking pageable copy per step,
+        mfm_mosi.py:428-429).  The call itself never synchronises."""
+        if x.is_cuda or self.dev.type != "cuda":
+            self.x.copy_(x, non_blocking=True)
+            self.y.copy_(y.reshape(self.y.shape), non_blocking=True)
+            self.step_device()
+            return self.eng.loss_buf
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._stage = [(torch.empty_like(self.x), torch.empty_like(self.y)) for _ in range(2)]
+            self._consumed = [None, None]
+            self._stage_idx = 0
+        i = self._stage_idx
+        self._stage_idx ^= 1
+        cs, main = self._copy_stream, torch.cuda.current_stream(self.dev)
+        sx, sy = self._stage[i]
+        if self._consumed[i] is not None:
+            cs.wait_event(self._consumed[i])                 # staging buffer i was read by step n-2
+        with torch.cuda.stream(cs):
+            sx.copy_(x, non_blocking=True)
+            sy.copy_(y.reshape(sy.shape), non_blocking=True)
+            landed = torch.cuda.Event()
+            landed.record(cs)
+        main.wait_event(landed)
+        self.x.copy_(sx)
+        self.y.copy_(sy)
+        done = torch.cuda.Event()
+        done.record(main)
+        self._consumed[i] = done
         self.step_device()
         return self.eng.loss_buf
 
