@@ -157,6 +157,7 @@ def profile_primitives(trainer, reps=3):
     agg = {}
     side = trainer.eng.use_side_stream
     trainer.eng.use_side_stream = False       # per-kernel timing needs everything on the timed stream
+    world, trainer.world = trainer.world, 1   # rank 0 profiles alone: no collective may be issued here
     try:
         for n in names:
             setattr(ops, n, wrap(n, orig[n]))
@@ -174,6 +175,7 @@ def profile_primitives(trainer, reps=3):
             a[2] += 1
     finally:
         trainer.eng.use_side_stream = side
+        trainer.world = world
         for n in names:
             try:
                 delattr(ops, n)
@@ -323,6 +325,7 @@ def main():
             line["cpu_baseline"] = cb
         print(json.dumps(line))
     if world > 1:
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 

@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+NCCL_DEBUG=WARN timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+echo "bench n2 exit $?"; tail -c 1500 gpurun_out/bench_n2.json | cut -c1-1500; tail -5 gpurun_out/bench_n2.err
