@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(MEM_THREADS, 1) mfn_mem_bwd_kernel(mfm_mem_arg
       const float sc = first ? a.scale1 : a.scale2;
       float* ds = first ? du1_s + rg * 8 * g1P : du2_s + rg * 8 * g2P;
       const int up = first ? g1P : g2P;
+      const long long ldu = first ? (a.ld_dU1 ? a.ld_dU1 : g1) : (a.ld_dU2 ? a.ld_dU2 : g2);
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const int row = row0 + rg * 8 + r;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(MEM_THREADS, 1) mfn_mem_bwd_kernel(mfm_mem_arg
         if (row < B) {
           const long long tr = (long long)t * B + row;
           v = (U[tr * gw + uu] > 0.0f) ? acc[r] * sc : 0.0f;
-          dU[tr * gw + uu] = v;
+          dU[tr * ldu + uu] = v;
         }
         ds[r * up + uu] = v;
       }

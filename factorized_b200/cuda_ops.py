@@ -39,7 +39,7 @@ class MemArgs(C.Structure):
                 ("drop_p1", C.c_float), ("drop_p2", C.c_float), ("site1", C.c_int), ("site2", C.c_int), ("rng", c_f),
                 ("scale1", C.c_float), ("scale2", C.c_float),
                 ("dmem_last", c_f), ("ld_dmem_last", LL),
-                ("dU1", c_f), ("dU2", c_f), ("dP1", c_f), ("dP2", c_f), ("dPc", c_f)]
+                ("dU1", c_f), ("dU2", c_f), ("dP1", c_f), ("dP2", c_f), ("dPc", c_f), ("ld_dU1", LL), ("ld_dU2", LL)]
 
 
 _SIGS = {
@@ -306,7 +306,10 @@ class CudaOps:
         else:
             s.scale1, s.scale2 = float(a["scale1"]), float(a["scale2"])
             s.dmem_last, _, _, s.ld_dmem_last = _mat(a["dmem_last"], "mem dmem_last")
-            s.dU1, s.dU2 = dense("dU1", TB, a["g1"]), dense("dU2", TB, a["g2"])
+            s.dU1, r1, c1, s.ld_dU1 = _mat(a["dU1"], "mem dU1")
+            s.dU2, r2, c2, s.ld_dU2 = _mat(a["dU2"], "mem dU2")
+            if (r1, c1) != (TB, a["g1"]) or (r2, c2) != (TB, a["g2"]):
+                raise MfmCudaError("mem dU1/dU2 must be [T*B, g]")
             s.dP1, s.dP2, s.dPc = dense("dP1", TB, a["mem"]), dense("dP2", TB, a["mem"]), dense("dPc", TB, a["mem"])
         return s
 

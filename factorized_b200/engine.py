@@ -313,17 +313,21 @@ class Engine:
             return
         main = torch.cuda.current_stream(self.device)
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+        # independent weight gradients also overlap each other; two GEMMs into the same tensor share a stream
+        st = self._side[(Gout.data_ptr() >> 8) % len(self._side)]
         ev = torch.cuda.Event()
         ev.record(main)
-        self._side.wait_event(ev)
-        with torch.cuda.stream(self._side):
+        st.wait_event(ev)
+        with torch.cuda.stream(st):
             ops.gemm("tn", dY, A, Gout, **kw)
         self._side_used = True
 
     def _join_side(self):
         if self._side is not None and self._side_used:
-            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            main = torch.cuda.current_stream(self.device)
+            for st in self._side:
+                main.wait_stream(st)
             self._side_used = False
 
     # -- the MMD statistic is off the critical path: it runs on its own stream -------
@@ -497,7 +501,10 @@ class Engine:
         # (5') memory recurrence, reversed
         pre = self.pre
         Wg1, Wg2 = P[pre + "gamma1_fc1.weight"], P[pre + "gamma2_fc1.weight"]
-        dU1, dU2 = buf("dU1", TB, dm.g1), buf("dU2", TB, dm.g2)
+        # dU1 | dU2 | dH2 are column blocks of one matrix: the data gradient of `attended` (three products in the
+        # reference's autograd) becomes ONE GEMM against the row-concatenated weights, not three read-modify-write passes
+        dUcat = buf("dUcat", TB, dm.g1 + dm.g2 + dm.a2)
+        dU1, dU2, dH2 = dUcat[:, :dm.g1], dUcat[:, dm.g1:dm.g1 + dm.g2], dUcat[:, dm.g1 + dm.g2:]
         dP1, dP2 = buf("dP1", TB, mem), buf("dP2", TB, mem)
         dPc = buf("dPc", TB, mem)
         ops.mfn_mem_bwd(dict(
@@ -510,16 +517,19 @@ class Engine:
         self._wgrad_gemm( dP2, ws["U2"], G[pre + "gamma2_fc2.weight"], accumulate=True, colsum_out=G[pre + "gamma2_fc2.bias"])
         Attended, cStar, Att = ws["Attended"], ws["cStar"], ws["Att"]
         dAtt = buf("dAttended", TB, 2 * H)
-        for (dU, Wg, nm, first) in ((dU1, Wg1, "gamma1_fc1", True), (dU2, Wg2, "gamma2_fc1", False)):
+        for (dU, nm) in ((dU1, "gamma1_fc1"), (dU2, "gamma2_fc1")):
             Gw = G[pre + nm + ".weight"]
             self._wgrad_gemm( dU, Attended, Gw[:, :2 * H], accumulate=True, colsum_out=G[pre + nm + ".bias"])
             self._wgrad_gemm( dU, mems[:TB], Gw[:, 2 * H:], accumulate=True)
-            ops.gemm("nn", dU, Wg[:, :2 * H], dAtt, accumulate=not first)
 
         # (4') attention MLPs, time-parallel
-        dH2 = buf("dH2", TB, dm.a2)
         lin_bwd(dPc, ws["H2"], pre + "att2_fc2", dH2, mask=ws["H2"], mask_scale=relu_scale(dm.p_att2))
-        lin_bwd(dH2, Attended, pre + "att2_fc1", dAtt, accumulate=True)
+        lin_bwd(dH2, Attended, pre + "att2_fc1")
+        Wcat = buf("WcatAtt", dm.g1 + dm.g2 + dm.a2, 2 * H)
+        ops.copy2d(Wg1[:, :2 * H], Wcat[:dm.g1])
+        ops.copy2d(Wg2[:, :2 * H], Wcat[dm.g1:dm.g1 + dm.g2])
+        ops.copy2d(P[pre + "att2_fc1.weight"], Wcat[dm.g1 + dm.g2:])
+        ops.gemm("nn", dUcat, Wcat, dAtt)
         dL = buf("dL", TB, 2 * H)
         dcStar = buf("dcStar", TB, 2 * H)
         ops.softmax_gate_bwd(dAtt, Att, cStar, dL, dcStar)

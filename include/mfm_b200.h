@@ -112,6 +112,8 @@ typedef struct mfm_mem_args {
   float* dU1; float* dU2;                     /* [T*B, g*]  grad wrt pre-relu gamma*_fc1 output */
   float* dP1; float* dP2;                     /* [T*B, mem] grad wrt pre-sigmoid gamma*_fc2 output */
   float* dPc;                                 /* [T*B, mem] grad wrt pre-tanh att2_fc2 output */
+  long long ld_dU1, ld_dU2;                   /* row pitch of dU1 / dU2 (0 = contiguous): lets them be column blocks of one
+                                                 matrix so the data gradient of `attended` is a single GEMM */
 } mfm_mem_args;
 int mfm_mfn_mem_fwd(const mfm_mem_args* a, void* stream);
 int mfm_mfn_mem_bwd(const mfm_mem_args* a, void* stream);
