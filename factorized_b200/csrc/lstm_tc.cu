@@ -20,7 +20,6 @@
 #include "tc_common.cuh"
 
 #define L2_THREADS 512
-#define L2_CC 8            // batch columns per exchange chunk (forward)
 
 struct Lstm2Cell {
   mfm_lstm_cell c;
@@ -61,9 +60,11 @@ __device__ __forceinline__ unsigned short bf16_bits(float x) {
 // ----------------------------------------------------------------------------------------------------------------
 // forward
 // ----------------------------------------------------------------------------------------------------------------
+// CC = batch columns per gate-exchange chunk: 32 (one exchange per step) when the buffer fits next to W, else 8
+template <int CC>
 __global__ void __launch_bounds__(L2_THREADS, 1) lstm_tc_fwd_kernel(Lstm2Batch bt) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long bar;
+  __shared__ __align__(8) unsigned long long bars[4];       // one per MMA tile: a tile's warps start as soon as it is done
   __shared__ uint32_t tmem_holder;
   const Lstm2Cell& lc = bt.c[blockIdx.y];
   if ((int)blockIdx.x >= lc.tiles) return;
@@ -76,12 +77,12 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_tc_fwd_kernel(Lstm2Batch b
   unsigned char* Wlo = Whi + slabs * lboA;
   unsigned char* Hhi = Wlo + slabs * lboA;                 // the last MMA tile may read up to 127 rows past W: lands here, ignored lanes
   unsigned char* Hlo = Hhi + slabs * lboH;
-  float* Gs = reinterpret_cast<float*>(Hlo + slabs * lboH + 2048);     // [4h][L2_CC + 1] activated gates of one column chunk
+  float* Gs = reinterpret_cast<float*>(Hlo + slabs * lboH + 2048);     // [4h][CC + 1] activated gates of one column chunk
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * NB;
 
   if (tid == 0) {
-    mbar_init(smem_u32(&bar), 1);
+    for (int m = 0; m < 4; ++m) mbar_init(smem_u32(&bars[m]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -125,18 +126,21 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_tc_fwd_kernel(Lstm2Batch b
   const bool is_tanh = n_on && (n / h == 2);
   const float bias_n = (n_on && c.bias_rest) ? __ldg(c.bias_rest + n) : 0.0f;
   const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NB);
-  // phase-2 identity: items (cc, j) of a column chunk, unit j fastest; at most 2 per thread (8*h <= 1024)
-  int it_cc[2], it_j[2];
+  // phase-2 identity: items (cc, j) of a column chunk, unit j fastest; at most ITEMS per thread (CC*h <= CC*128)
+  constexpr int ITEMS = CC * 128 / L2_THREADS, NCH = 32 / CC;
+  int it_cc[ITEMS], it_j[ITEMS];
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < ITEMS; ++k) {
     const int item = tid + k * L2_THREADS;
-    it_cc[k] = item < L2_CC * h ? item / h : -1;
+    it_cc[k] = item < CC * h ? item / h : -1;
     it_j[k] = item % h;
   }
-  float cprev[4][2];                              // c_{t-1} of this thread's items, per column chunk
+  float cprev[NCH][ITEMS];                        // c_{t-1} of this thread's items, per column chunk
 #pragma unroll
-  for (int a = 0; a < 4; ++a) cprev[a][0] = cprev[a][1] = 0.0f;
-  const int nchunk = NB / L2_CC;                  // 4 (NB=32) or 2 (NB=16)
+  for (int a = 0; a < NCH; ++a)
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) cprev[a][k] = 0.0f;
+  const int nchunk = NB / CC;
 
   for (int t = 0; t < T; ++t) {
     // G_x[t] (or the decoder's constant bias) for this thread's gate-unit and all NB columns: issued before the MMA wait
@@ -167,48 +171,54 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_tc_fwd_kernel(Lstm2Batch b
             umma_bf16(dcol, dAl, dBh, idesc, 1u);
             umma_bf16(dcol, dAh, dBl, idesc, 1u);
           }
+          umma_commit(smem_u32(&bars[m]));          // per-tile completion: tile m's warps need not wait for tiles m+1..
         }
-        umma_commit(smem_u32(&bar));
       }
-      mbar_wait(smem_u32(&bar), (uint32_t)((t - 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (tile_on) {
+        mbar_wait(smem_u32(&bars[mt]), (uint32_t)((t - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
     }
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
+    for (int ch = 0; ch < NCH; ++ch) {
       if (ch >= nchunk) break;
-      const int bc0 = ch * L2_CC;
-      // phase 1: activate this thread's gate for 8 batch columns; stash it; hand it to the exchange buffer
+      const int bc0 = ch * CC;
+      // phase 1: activate this thread's gate for CC batch columns; stash it; hand it to the exchange buffer
       if (tile_on) {
-        float acc[8];
-        if (t > 0) {
-          tmem_ld8(tlane + (uint32_t)bc0, acc);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-        }
-        if (n_on) {
+        for (int sub = 0; sub < CC / 8; ++sub) {
+          float acc[8];
+          if (t > 0) {
+            tmem_ld8(tlane + (uint32_t)(bc0 + 8 * sub), acc);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          } else {
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            const float pre = acc[cc] + gxv[bc0 + cc];
-            const float av = is_tanh ? gate_tanh(pre) : gate_sigmoid(pre);
-            const int b = row0 + bc0 + cc;
-            if (b < B) c.gates[((long long)t * B + b) * H4 + n] = av;
-            Gs[n * (L2_CC + 1) + cc] = av;
+            for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+          }
+          if (n_on) {
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              const int col = bc0 + 8 * sub + cc;
+              const float pre = acc[cc] + gxv[col];
+              const float av = is_tanh ? gate_tanh(pre) : gate_sigmoid(pre);
+              const int b = row0 + col;
+              if (b < B) c.gates[((long long)t * B + b) * H4 + n] = av;
+              Gs[n * (CC + 1) + 8 * sub + cc] = av;
+            }
           }
         }
       }
       __syncthreads();
       // phase 2: (column, unit) items: c_t, h_t, histories, and h_t as next step's B operand
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < ITEMS; ++k) {
         const int cc = it_cc[k], j = it_j[k];
         if (cc < 0) continue;
         const int bl = bc0 + cc, b = row0 + bl;
         float hn = 0.0f;
         if (b < B) {
-          const float ig = Gs[j * (L2_CC + 1) + cc], fg = Gs[(h + j) * (L2_CC + 1) + cc];
-          const float gg = Gs[(2 * h + j) * (L2_CC + 1) + cc], og = Gs[(3 * h + j) * (L2_CC + 1) + cc];
+          const float ig = Gs[j * (CC + 1) + cc], fg = Gs[(h + j) * (CC + 1) + cc];
+          const float gg = Gs[(2 * h + j) * (CC + 1) + cc], og = Gs[(3 * h + j) * (CC + 1) + cc];
           const float cn = fg * cprev[ch][k] + ig * gg;
           hn = og * gate_tanh(cn);
           cprev[ch][k] = cn;
@@ -387,9 +397,9 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_tc_bwd_kernel(Lstm2Batch b
 // ----------------------------------------------------------------------------------------------------------------
 static inline int ru(int x, int m) { return (x + m - 1) / m * m; }
 
-static size_t fwd_smem(int h, int nb) {
+static size_t fwd_smem(int h, int nb, int cc) {
   const int slabs = ru(h, 16) / 8;
-  return (size_t)2 * slabs * (4 * h * 16 + 32) + (size_t)2 * slabs * (nb * 16 + 32) + 2048 + (size_t)4 * h * (L2_CC + 1) * 4 + 128;
+  return (size_t)2 * slabs * (4 * h * 16 + 32) + (size_t)2 * slabs * (nb * 16 + 32) + 2048 + (size_t)4 * h * (cc + 1) * 4 + 128;
 }
 static size_t bwd_smem(int h, int nb) {
   const int slabs = 4 * ru(h, 8) / 8;
@@ -420,19 +430,21 @@ static void sort_heavy_first(Lstm2Batch& bt) {
 // Launches the tensor-core forward for every cell that fits; cells that do not are returned in `rest`.
 int lstm_tc_fwd_launch(const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* rest, int* nrest, cudaStream_t st) {
   const int lim = smem_limit();
-  Lstm2Batch bt;
-  bt.n = 0;
+  Lstm2Batch b32, b8;          // by exchange-chunk width
+  b32.n = b8.n = 0;
   *nrest = 0;
-  size_t smem = 0;
-  int gx = 0;
+  size_t smem32 = 0, smem8 = 0;
+  int gx32 = 0, gx8 = 0;
   for (int i = 0; i < ncells; ++i) {
     const mfm_lstm_cell& c = cells[i];
-    int nb = 0;
+    int nb = 0, cc = 0;
     if (c.h >= 1 && c.h <= 128) {
-      if (fwd_smem(c.h, 32) <= (size_t)lim) nb = 32;
-      else if (fwd_smem(c.h, 16) <= (size_t)lim) nb = 16;
+      if (fwd_smem(c.h, 32, 32) <= (size_t)lim) { nb = 32; cc = 32; }
+      else if (fwd_smem(c.h, 32, 8) <= (size_t)lim) { nb = 32; cc = 8; }
+      else if (fwd_smem(c.h, 16, 8) <= (size_t)lim) { nb = 16; cc = 8; }
     }
     if (!nb) { rest[(*nrest)++] = c; continue; }
+    Lstm2Batch& bt = cc == 32 ? b32 : b8;
     Lstm2Cell& lc = bt.c[bt.n++];
     lc.c = c;
     lc.nb = nb;
@@ -442,19 +454,27 @@ int lstm_tc_fwd_launch(const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* re
     int cols = 32;
     while (cols < lc.mtiles * nb) cols <<= 1;
     lc.tmem_cols = cols;
-    smem = smem > fwd_smem(c.h, nb) ? smem : fwd_smem(c.h, nb);
-    gx = gx > lc.tiles ? gx : lc.tiles;
+    const size_t sm = fwd_smem(c.h, nb, cc);
+    if (cc == 32) { smem32 = smem32 > sm ? smem32 : sm; gx32 = gx32 > lc.tiles ? gx32 : lc.tiles; }
+    else          { smem8 = smem8 > sm ? smem8 : sm; gx8 = gx8 > lc.tiles ? gx8 : lc.tiles; }
   }
-  if (bt.n == 0) return MFM_OK;
-  sort_heavy_first(bt);
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaError_t e = cudaFuncSetAttribute(lstm_tc_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_tc_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  lstm_tc_fwd_kernel<<<dim3(gx, bt.n), L2_THREADS, smem, st>>>(bt);
-  MFM_LAUNCH_CHECK();
+  sort_heavy_first(b32);
+  sort_heavy_first(b8);
+  if (b8.n) {        // the widest cells first: they are the long pole
+    lstm_tc_fwd_kernel<8><<<dim3(gx8, b8.n), L2_THREADS, smem8, st>>>(b8);
+    MFM_LAUNCH_CHECK();
+  }
+  if (b32.n) {
+    lstm_tc_fwd_kernel<32><<<dim3(gx32, b32.n), L2_THREADS, smem32, st>>>(b32);
+    MFM_LAUNCH_CHECK();
+  }
   return MFM_OK;
 }
 
