@@ -124,6 +124,10 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_tc_fwd_kernel(Lstm2Batch b
   const bool tile_on = mt < mtiles;              // warp-uniform
   const bool n_on = tile_on && n < H4;
   const bool is_tanh = n_on && (n / h == 2);
+  // sigmoid and tanh share one code path: tanh(x) = 2*sigmoid(2x) - 1  ->  act = aa * rcp(1 + ex2(kk * x)) + bb
+  const float act_k = (is_tanh ? -2.0f : -1.0f) * 1.4426950408889634f, act_a = is_tanh ? 2.0f : 1.0f, act_b = is_tanh ? -1.0f : 0.0f;
+  const float act_clamp = is_tanh ? 15.0f : 30.0f;
+  const bool full = (NB == 32) && (row0 + 32 <= B);     // CTA-uniform
   const float bias_n = (n_on && c.bias_rest) ? __ldg(c.bias_rest + n) : 0.0f;
   const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NB);
   // phase-2 identity: items (cc, j) of a column chunk, unit j fastest; at most ITEMS per thread (CC*h <= CC*128)
@@ -147,10 +151,13 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_tc_fwd_kernel(Lstm2Batch b
     float gxv[32];
     if (n_on) {
       if (t < c.gx_steps) {
+        const float* gp = c.gx + ((long long)t * B + row0) * H4 + n;
+        if (full) {                                  // whole tile in range: no per-element predicates
 #pragma unroll
-        for (int cc = 0; cc < 32; ++cc) {
-          const int b = row0 + cc;
-          gxv[cc] = (cc < NB && b < B) ? __ldg(c.gx + ((long long)t * B + b) * H4 + n) : 0.0f;
+          for (int cc = 0; cc < 32; ++cc) gxv[cc] = __ldg(gp + (long long)cc * H4);
+        } else {
+#pragma unroll
+          for (int cc = 0; cc < 32; ++cc) gxv[cc] = (cc < NB && row0 + cc < B) ? __ldg(gp + (long long)cc * H4) : 0.0f;
         }
       } else {
 #pragma unroll
@@ -196,14 +203,17 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_tc_fwd_kernel(Lstm2Batch b
             for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
           }
           if (n_on) {
+            float* gout = c.gates + ((long long)t * B + row0 + bc0 + 8 * sub) * H4 + n;
+            float* gs = Gs + n * (CC + 1) + 8 * sub;
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {
               const int col = bc0 + 8 * sub + cc;
-              const float pre = acc[cc] + gxv[col];
-              const float av = is_tanh ? gate_tanh(pre) : gate_sigmoid(pre);
-              const int b = row0 + col;
-              if (b < B) c.gates[((long long)t * B + b) * H4 + n] = av;
-              Gs[n * (CC + 1) + 8 * sub + cc] = av;
+              const float pre = fminf(fmaxf(acc[cc] + gxv[col], -act_clamp), act_clamp);
+              float e;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(pre * act_k));
+              const float av = fmaf(act_a, rcp_fast(1.0f + e), act_b);
+              if (full || row0 + col < B) gout[(long long)cc * H4] = av;
+              gs[cc] = av;
             }
           }
         }
