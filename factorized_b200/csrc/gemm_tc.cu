@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include "gemm_args.cuh"
 #include "tc_common.cuh"
+#include "tc_epilogue.cuh"
 
 #define TC_BM 128
 #define TC_BK 32
@@ -28,13 +29,6 @@
 #define TC_NA 2                                   // A items (8 fp32 each) per thread per chunk: 128 rows * 4 slabs / 256
 #define TC_NB 4                                   // B items per thread per chunk (BN <= 256)
 
-struct TcArgs {
-  GemmArgs g;
-  int BN;          // tile N (multiple of 16, <= 256)
-  int passes;      // 3 = hi/lo split, 1 = plain bf16
-  int tmem_cols;   // power of two >= max(32, BN)
-  int dbg;         // experiment switches (env MFM_TC_DEBUG): 1 skip MMA, 2 skip convert/store, 4 skip epilogue, 8 skip loads
-};
 
 // One operand tile of a K chunk travels HBM -> registers (raw fp32) -> split-bf16 planes in shared memory.
 // The two halves are separate calls so the loads of chunk c+1 are in flight while chunk c is converted,
@@ -221,91 +215,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  // ---- epilogue.  Warp w reads TMEM lanes 32*(w%4).. (tile rows) for the column half w/4, transposes 32x32 blocks
-  //      through the (now idle) stage memory, and writes 128 B row segments: coalesced stores / reductions.
-  uint32_t sseed = 0;
-  const bool do_drop = a.drop_p > 0.0f;
-  if (do_drop) sseed = site_seed(a.rng, a.drop_site);
-  const float keep_scale = do_drop ? 1.0f / (1.0f - a.drop_p) : 1.0f;
-  float* scratch = reinterpret_cast<float*>(smem) + warp * (32 * 33);
-  // epilogue parameters pinned in registers (the fully generic per-element form cost ~30 instructions per output)
-  float* const e_C = a.C;
-  const long long e_ldc = a.ldc;
-  const int e_M = a.M, e_N = a.N, e_act = a.act;
-  const bool e_atomic = a.atomic != 0, e_acc = a.accumulate != 0, e_simple = !a.mask && !do_drop;
-  const int quad = warp & 3, half = warp >> 2;
-  const int cbeg = half * (BN >> 1), cend = cbeg + (BN >> 1);
-  const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
-  for (int c0 = cbeg; c0 < cend && !(ta.dbg & 4); c0 += 32) {
-    float v[32];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (c0 + 8 * q < cend) {          // warp-uniform
-        uint32_t r[8];
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                     : "r"(tlane + (uint32_t)(c0 + 8 * q))
-                     : "memory");
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[8 * q + i] = __uint_as_float(r[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[8 * q + i] = 0.0f;
-      }
-    }
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = v[j];
-    __syncwarp();
-    const int n = n0 + c0 + lane;
-    const int mbase = m0 + quad * 32;
-    const int nrows = max(0, min(32, e_M - mbase));
-    const float* sp = scratch + lane;
-    if (nchunks > 0 && c0 + lane < cend) {
-      if (ones_col >= 0 && n == ones_col) {                 // the ones column: bias gradient
-        for (int rr = 0; rr < nrows; ++rr) atomicAdd(a.colsum_out + mbase + rr, sp[rr * 33]);
-      } else if (n < e_N) {
-        float* cp = e_C + (long long)mbase * e_ldc + n;
-        if (e_atomic) {
-          for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) atomicAdd(cp, sp[rr * 33]);
-        } else if (e_simple) {                              // bias + activation (+ C): the common case, lean loops
-          const float bsum = (a.bias ? __ldg(a.bias + n) : 0.0f) + (a.bias2 ? __ldg(a.bias2 + n) : 0.0f);
-          if (e_acc) {
-            int rr = 0;
-            for (; rr + 4 <= nrows; rr += 4, cp += 4 * e_ldc) {
-              const float c0v = cp[0], c1v = cp[e_ldc], c2v = cp[2 * e_ldc], c3v = cp[3 * e_ldc];
-              cp[0] = apply_act(sp[rr * 33] + bsum, e_act) + c0v;
-              cp[e_ldc] = apply_act(sp[(rr + 1) * 33] + bsum, e_act) + c1v;
-              cp[2 * e_ldc] = apply_act(sp[(rr + 2) * 33] + bsum, e_act) + c2v;
-              cp[3 * e_ldc] = apply_act(sp[(rr + 3) * 33] + bsum, e_act) + c3v;
-            }
-            for (; rr < nrows; ++rr, cp += e_ldc) cp[0] = apply_act(sp[rr * 33] + bsum, e_act) + cp[0];
-          } else if (e_act == MFM_ACT_NONE) {
-#pragma unroll 8
-            for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) cp[0] = sp[rr * 33] + bsum;
-          } else if (e_act == MFM_ACT_RELU) {
-#pragma unroll 8
-            for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) cp[0] = fmaxf(sp[rr * 33] + bsum, 0.0f);
-          } else {
-#pragma unroll 4
-            for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) cp[0] = apply_act(sp[rr * 33] + bsum, e_act);
-          }
-        } else {                                            // dropout and/or ReLU-mask epilogues
-          const float bsum = (a.bias ? __ldg(a.bias + n) : 0.0f) + (a.bias2 ? __ldg(a.bias2 + n) : 0.0f);
-          const float* mp = a.mask ? a.mask + (long long)mbase * a.ldmask + n : nullptr;
-#pragma unroll 2
-          for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) {
-            float v = apply_act(sp[rr * 33] + bsum, e_act);
-            const int m = mbase + rr;
-            if (do_drop) v = drop_keep(sseed, (uint32_t)m * (uint32_t)e_N + (uint32_t)n, a.drop_p) ? v * keep_scale : 0.0f;
-            if (mp) v = __ldg(mp + (long long)rr * a.ldmask) > 0.0f ? v * a.mask_scale : 0.0f;
-            cp[0] = e_acc ? v + cp[0] : v;
-          }
-        }
-      }
-    }
-    __syncwarp();
-  }
+  // ---- epilogue (tc_epilogue.cuh): TMEM -> registers -> transposed through the now idle stage memory -> coalesced stores
+  if (!(ta.dbg & 4)) tc_epilogue(ta, tmem_base, reinterpret_cast<float*>(smem), warp, lane, m0, n0, nchunks > 0, ones_col);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
@@ -316,10 +227,20 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(TcArgs ta) {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// gemm_tcp.cu: the pipelined (warp-specialised, cp.async-staged) kernel for 16 B-aligned operands
+bool gemm_tcp_eligible(int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb);
+int gemm_tcp_launch(int passes, int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
+                    float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
+                    const float* mask, long long ldmask, float mask_scale, float drop_p, int drop_site,
+                    const long long* rng, float* colsum_out, cudaStream_t st);
+
 int gemm_tc_launch(int passes, int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
                    float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
                    const float* mask, long long ldmask, float mask_scale, float drop_p, int drop_site,
                    const long long* rng, float* colsum_out, cudaStream_t st) {
+  if (gemm_tcp_eligible(mode, M, N, K, A, lda, B, ldb))
+    return gemm_tcp_launch(passes, mode, M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask,
+                           mask_scale, drop_p, drop_site, rng, colsum_out, st);
   TcArgs ta;
   ta.g = GemmArgs{M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale,
                   drop_p, drop_site, rng, K, 0, colsum_out};

@@ -1,0 +1,143 @@
+// Epilogue shared by the tcgen05 GEMM kernels: TMEM accumulator -> registers -> per-warp shared-memory transpose ->
+// coalesced global stores with the fused epilogue of include/mfm_b200.h::mfm_gemm.
+//
+// 4*nhalves warps take part.  Warp w owns TMEM lanes 32*(w%4).. (tile rows) and the column range w/4 of nhalves.  A 32x32 block is read
+// with tcgen05.ld (lane = row), written to the warp's scratch as float4 (row stride 36 floats: 16 B aligned and
+// conflict-free for both phases), and read back transposed:
+//   * fast path (bias / activation / accumulate, 16 B-aligned C): each lane moves a float4, one store instruction
+//     covers four 128 B row segments;
+//   * general path (split-K reduction, dropout, ReLU mask, ones column, unaligned C): lane = column, 128 B per store.
+#pragma once
+#include "gemm_args.cuh"
+#include "tc_common.cuh"
+
+#define TC_EPI_LD 36                              // scratch row stride in floats
+#define TC_EPI_SCRATCH_BYTES (8 * 32 * TC_EPI_LD * 4)
+
+struct TcArgs {
+  GemmArgs g;
+  int BN;          // tile N (multiple of 16, <= 256)
+  int passes;      // 3 = hi/lo split, 1 = plain bf16
+  int tmem_cols;   // power of two >= max(32, BN)
+  int dbg;         // experiment switches (env MFM_TC_DEBUG): 1 skip MMA, 2 skip convert/store, 4 skip epilogue, 8 skip loads
+};
+
+__device__ __forceinline__ float4 act4(float4 v, float b0, float b1, float b2, float b3, int act) {
+  v.x = apply_act(v.x + b0, act); v.y = apply_act(v.y + b1, act);
+  v.z = apply_act(v.z + b2, act); v.w = apply_act(v.w + b3, act);
+  return v;
+}
+
+// warp, lane: indices within the epilogue warps.  scratch_all: 32*TC_EPI_LD floats of idle shared memory per warp.
+__device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base, float* scratch_all, int warp, int lane,
+                                            int m0, int n0, bool have_acc, int ones_col, int nhalves = 2) {
+  const GemmArgs& a = ta.g;
+  const int BN = ta.BN;
+  uint32_t sseed = 0;
+  const bool do_drop = a.drop_p > 0.0f;
+  if (do_drop) sseed = site_seed(a.rng, a.drop_site);
+  const float keep_scale = do_drop ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+  float* scratch = scratch_all + warp * (32 * TC_EPI_LD);
+  // epilogue parameters pinned in registers (the fully generic per-element form cost ~30 instructions per output)
+  float* const e_C = a.C;
+  const long long e_ldc = a.ldc;
+  const int e_M = a.M, e_N = a.N, e_act = a.act;
+  const bool e_atomic = a.atomic != 0, e_acc = a.accumulate != 0, e_simple = !a.mask && !do_drop;
+  const bool e_vec = e_simple && !e_atomic && ones_col < 0 && ((reinterpret_cast<uintptr_t>(e_C) & 15) == 0) &&
+                     ((e_ldc & 3) == 0) && ((n0 & 3) == 0);
+  const int quad = warp & 3, half = warp >> 2;
+  const int cbeg = half * (BN / nhalves), cend = cbeg + (BN / nhalves);
+  const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+  const int mbase = m0 + quad * 32;
+  const int nrows = max(0, min(32, e_M - mbase));
+  for (int c0 = cbeg; c0 < cend; c0 += 32) {
+    float v[32];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (c0 + 8 * q < cend) {          // warp-uniform
+        uint32_t r[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(tlane + (uint32_t)(c0 + 8 * q))
+                     : "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 * q + i] = __uint_as_float(r[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 * q + i] = 0.0f;
+      }
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(scratch + lane * TC_EPI_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    __syncwarp();
+    if (!have_acc) { __syncwarp(); continue; }
+    if (e_vec) {
+      // lane -> (row within a group of 4, 4-column group); 8 passes cover the 32 rows
+      const int cg = lane & 7, rsub = lane >> 3;
+      const int cl = c0 + cg * 4;                   // column within the tile
+      const int n = n0 + cl;
+      if (cl < cend && n < e_N) {
+        const bool full4 = n + 3 < e_N;
+        float b[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (n + i < e_N) b[i] = (a.bias ? __ldg(a.bias + n + i) : 0.0f) + (a.bias2 ? __ldg(a.bias2 + n + i) : 0.0f);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const int rr = p * 4 + rsub;
+          if (rr < nrows) {
+            float4 t = *reinterpret_cast<const float4*>(scratch + rr * TC_EPI_LD + cg * 4);
+            t = act4(t, b[0], b[1], b[2], b[3], e_act);
+            float* cp = e_C + (long long)(mbase + rr) * e_ldc + n;
+            if (full4) {
+              if (e_acc) {
+                const float4 o = *reinterpret_cast<const float4*>(cp);
+                t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+              }
+              *reinterpret_cast<float4*>(cp) = t;
+            } else {
+              const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (n + i < e_N) cp[i] = e_acc ? tv[i] + cp[i] : tv[i];
+            }
+          }
+        }
+      }
+    } else {
+      const int n = n0 + c0 + lane;
+      const float* sp = scratch + lane;
+      if (c0 + lane < cend) {
+        if (ones_col >= 0 && n == ones_col) {                 // the ones column: bias gradient
+          for (int rr = 0; rr < nrows; ++rr) atomicAdd(a.colsum_out + mbase + rr, sp[rr * TC_EPI_LD]);
+        } else if (n < e_N) {
+          float* cp = e_C + (long long)mbase * e_ldc + n;
+          if (e_atomic) {
+            for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) atomicAdd(cp, sp[rr * TC_EPI_LD]);
+          } else if (e_simple) {                              // bias + activation (+ C) on an unaligned C
+            const float bsum = (a.bias ? __ldg(a.bias + n) : 0.0f) + (a.bias2 ? __ldg(a.bias2 + n) : 0.0f);
+#pragma unroll 4
+            for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) {
+              const float t = apply_act(sp[rr * TC_EPI_LD] + bsum, e_act);
+              cp[0] = e_acc ? t + cp[0] : t;
+            }
+          } else {                                            // dropout and/or ReLU-mask epilogues
+            const float bsum = (a.bias ? __ldg(a.bias + n) : 0.0f) + (a.bias2 ? __ldg(a.bias2 + n) : 0.0f);
+            const float* mp = a.mask ? a.mask + (long long)mbase * a.ldmask + n : nullptr;
+#pragma unroll 2
+            for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) {
+              float t = apply_act(sp[rr * TC_EPI_LD] + bsum, e_act);
+              const int m = mbase + rr;
+              if (do_drop) t = drop_keep(sseed, (uint32_t)m * (uint32_t)e_N + (uint32_t)n, a.drop_p) ? t * keep_scale : 0.0f;
+              if (mp) t = __ldg(mp + (long long)rr * a.ldmask) > 0.0f ? t * a.mask_scale : 0.0f;
+              cp[0] = e_acc ? t + cp[0] : t;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}

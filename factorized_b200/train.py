@@ -56,23 +56,27 @@ class MFMTrainer:
             self.world = torch.distributed.get_world_size(process_group)
         pd = dict(model.named_parameters())
         self.names = [k for k in pd if k not in UNUSED]
-        n = sum(pd[k].numel() for k in self.names)
-        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        # every tensor starts 256 B aligned inside the flat buffers (the cp.async-staged GEMM needs 16 B-aligned
+        # operands); the gaps stay zero in all four buffers, so Adam and the all-reduce leave them zero
+        ALIGN = 64
+        offs, n = {}, 0
+        for k in self.names:
+            offs[k] = n
+            n += (pd[k].numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(n, dtype=torch.float32, device=dev)
         self.P: Dict[str, torch.Tensor] = OrderedDict()
         self.G: Dict[str, torch.Tensor] = OrderedDict()
-        o = 0
         with torch.no_grad():
             for k in self.names:
-                p = pd[k]
+                p, o = pd[k], offs[k]
                 view = self.flat_p[o:o + p.numel()].view(p.shape)
                 view.copy_(p.data)
                 p.data = view
                 self.P[k] = view
                 self.G[k] = self.flat_g[o:o + p.numel()].view(p.shape)
-                o += p.numel()
         self.eng = E.Engine(model._cfg, T, B, dev, self.ops, head=head)
         self.eng.defer_mmd_join = True
         dm = self.eng.dm

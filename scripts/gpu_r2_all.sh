@@ -1,0 +1,5 @@
+#!/bin/bash
+# full GPU test suite + step bench with per-GEMM-shape timings
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x 2>&1 | tail -6
+bash scripts/gpu_bench_only.sh 2>&1 | head -80

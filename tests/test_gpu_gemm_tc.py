@@ -24,7 +24,9 @@ def g(*shape, seed=0):
 
 
 SHAPES = [(128, 16, 16), (128, 128, 32), (256, 256, 64), (1, 1, 1), (5, 3, 7), (70, 130, 33), (640, 128, 300), (300, 400, 128),
-          (1000, 24, 5), (129, 257, 65), (96, 512, 464)]
+          (1000, 24, 5), (129, 257, 65), (96, 512, 464),
+          # 16 B-aligned ragged shapes: these take the pipelined cp.async kernel (gemm_tcp.cu)
+          (72, 132, 36), (1000, 24, 8), (516, 260, 68), (2048, 2048, 32), (4, 4, 4), (132, 20, 2052), (388, 112, 20)]
 
 
 @pytest.mark.parametrize("mode", ["nt", "nn", "tn"])
