@@ -14,7 +14,7 @@ extern "C" unsigned long long mfm_launch_count(void) { return g_mfm_launches; }
 int gemm_tc_launch(int passes, int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
                    float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
                    const float* mask, long long ldmask, float mask_scale, float drop_p, int drop_site,
-                   const long long* rng, float* colsum_out, cudaStream_t st);
+                   const long long* rng, float* colsum_out, void* ws, size_t ws_bytes, cudaStream_t st);
 static long long g_tc_min_work = 1LL << 20;   // M*N*K below this stays on the CUDA-core kernel
 
 extern "C" int mfm_set_gemm_path(int path) {
@@ -33,6 +33,14 @@ extern "C" int mfm_gemm(int mode, int M, int N, int K, const float* A, long long
                         float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
                         const float* mask, long long ldmask, float mask_scale, float drop_p, int drop_site,
                         const long long* rng, float* colsum_out, void* stream) {
+  return mfm_gemm_ws(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale, drop_p,
+                     drop_site, rng, colsum_out, nullptr, 0, stream);
+}
+
+extern "C" int mfm_gemm_ws(int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
+                           float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
+                           const float* mask, long long ldmask, float mask_scale, float drop_p, int drop_site,
+                           const long long* rng, float* colsum_out, void* ws, long long ws_bytes, void* stream) {
   MFM_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C);
   MFM_REQUIRE(!colsum_out || mode == MFM_GEMM_TN);
   MFM_REQUIRE(mode == MFM_GEMM_NT || mode == MFM_GEMM_NN || mode == MFM_GEMM_TN);
@@ -40,7 +48,8 @@ extern "C" int mfm_gemm(int mode, int M, int N, int K, const float* A, long long
   MFM_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f && (drop_p == 0.0f || rng));
   if (g_gemm_path != MFM_PATH_SIMT_FP32 && (long long)M * N * K >= g_tc_min_work)
     return gemm_tc_launch(g_gemm_path == MFM_PATH_TC_BF16X3 ? 3 : 1, mode, M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act,
-                          accumulate, mask, ldmask, mask_scale, drop_p, drop_site, rng, colsum_out, (cudaStream_t)stream);
+                          accumulate, mask, ldmask, mask_scale, drop_p, drop_site, rng, colsum_out, ws, ws_bytes > 0 ? (size_t)ws_bytes : 0,
+                          (cudaStream_t)stream);
   if (colsum_out) {      // CUDA-core path: the column sums are a separate streaming kernel
     int rc = mfm_colsum(K, M, A, lda, colsum_out, stream);
     if (rc) return rc;

@@ -232,15 +232,17 @@ bool gemm_tcp_eligible(int mode, int M, int N, int K, const float* A, long long 
 int gemm_tcp_launch(int passes, int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
                     float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
                     const float* mask, long long ldmask, float mask_scale, float drop_p, int drop_site,
-                    const long long* rng, float* colsum_out, cudaStream_t st);
+                    const long long* rng, float* colsum_out, void* ws, size_t ws_bytes, cudaStream_t st);
 
 int gemm_tc_launch(int passes, int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
                    float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
                    const float* mask, long long ldmask, float mask_scale, float drop_p, int drop_site,
-                   const long long* rng, float* colsum_out, cudaStream_t st) {
-  if (gemm_tcp_eligible(mode, M, N, K, A, lda, B, ldb))
-    return gemm_tcp_launch(passes, mode, M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask,
-                           mask_scale, drop_p, drop_site, rng, colsum_out, st);
+                   const long long* rng, float* colsum_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (gemm_tcp_eligible(mode, M, N, K, A, lda, B, ldb)) {
+    const int rc = gemm_tcp_launch(passes, mode, M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask,
+                                   mask_scale, drop_p, drop_site, rng, colsum_out, ws, ws_bytes, st);
+    if (rc != MFM_ERR_UNSUPPORTED) return rc;       // unsupported operand alignment: the register-prefetch kernel below
+  }
   TcArgs ta;
   ta.g = GemmArgs{M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale,
                   drop_p, drop_site, rng, K, 0, colsum_out};

@@ -3,42 +3,49 @@
 // The step's time-parallel GEMMs are [T*B, <=512] activations against small weights: they are bound by streaming the
 // activation operand from HBM.  gemm_tc.cu keeps one K chunk of prefetch in registers and runs all its threads in
 // lock step (load -> convert -> fence -> barrier -> MMA), so every chunk exposes the whole latency chain.  Here the
-// links of that chain are different warps connected by mbarriers, and the transport is TMA:
+// links of that chain are different warps connected by mbarriers over a ring of 3 stages, and the transport is TMA:
 //
-//   warp 8 (one thread)  PRODUCER    cp.async.bulk.tensor.2d: the raw fp32 box of A and of B for chunk c -> ring stage s,
-//                                    completion by complete_tx on full[s].  The tensor maps describe the operands as
-//                                    they lie in HBM (any 16 B-aligned view); M/N/K tails are zero-filled by the TMA
-//                                    unit.  No thread ever has a load outstanding, several stages are always in flight.
-//   warps 0..7           CONVERTERS  wait full[s]; read 32 B items of the stage, split fp32 -> bf16 hi + lo, store both
-//                                    planes in the tcgen05 no-swizzle canonical layout (plane set p), fence.proxy.async;
-//                                    one arrive per warp on conv[p] and on empty[s].  Warps run ahead independently.
-//   warp 9 (one thread)  MMA         wait conv[p]; tcgen05.mma hi*hi + lo*hi + hi*lo (M=128, N=BN, K=16) into the fp32 TMEM
-//                                    accumulator; tcgen05.commit -> pfree[p] hands the plane set back to the converters.
+//   warp 8 (one thread)  PRODUCER    waits pfree[s]; cp.async.bulk.tensor.2d: the raw fp32 box of A for chunk c -> stage s
+//                                    (the tensor map describes the operand as it lies in HBM, any 16 B-aligned view; M/N/K
+//                                    tails are zero-filled by the TMA unit), and B either the same way or -- when the
+//                                    caller supplied a workspace (weights: NT / NN) -- as ONE bulk copy of the chunk's
+//                                    pre-split bf16 image, already in MMA layout.  Completion: complete_tx on full[s].
+//   warps 0..7           CONVERTERS  wait full[s]; read 32 B items of the raw boxes, split fp32 -> bf16 hi + lo, store both
+//                                    planes in the tcgen05 no-swizzle canonical layout, fence.proxy.async; one arrive per
+//                                    warp on conv[s].  Warps run ahead independently (no CTA-wide barrier in the loop).
+//   warp 9 (one thread)  MMA         wait conv[s]; tcgen05.mma hi*hi + lo*hi + hi*lo (M=128, N=BN, K=16) into the fp32 TMEM
+//                                    accumulator; tcgen05.commit -> pfree[s] hands the stage back to the producer.
 //   warps 0..7           EPILOGUE    after the last commit: tc_epilogue.cuh (TMEM -> transposed through the idle ring ->
 //                                    512 B coalesced stores with bias / activation / dropout / mask / split-K reduction).
 //
-// Two CTAs are resident per SM, so one CTA's epilogue stores overlap the other's loads.  Staging layouts:
-//   K-major operand  [rows, K]:  one dense box [rows][BK] fp32; item (r, slab) = 32 B at r*BK*4 + slab*32
-//                                -> plane byte slab*LBO + r*16, LBO = rows*16 + 128/SLABS (rotates banks: conflict-free)
-//   MN-major operand [K, cols]:  boxes of [BK][32 cols] with the 128 B TMA swizzle (16 B chunk index ^= k%8), so the
-//                                eight k rows of a core matrix are read from eight different bank groups
-//                                -> plane byte (k/8)*LBO + (c/8)*128 + (k%8)*16
+// Pre-split B (gemm_prep_kernel): a weight is the same for all T*B/128 row tiles, so splitting it inside every CTA is
+// T*B/128-fold redundant and costs as much as splitting A.  One small kernel writes, per (N tile, K chunk), the image
+// [hi plane | lo plane] exactly as the MMA wants it in shared memory; with B out of the converters' way a tile can be 256
+// columns wide (A is staged and split once per 256 output columns instead of once per 128).
+//
+// Two CTAs of 320 threads are resident per SM (<= 100 KB each, no static shared memory), so one CTA's epilogue stores
+// overlap the other's loads.  (Three CTAs with four converter warps each were measured slower.)  Raw layouts:
+//   K-major operand  [rows, K]:  one box [rows][16] fp32, 64 B TMA swizzle (16 B chunk ^= (row/2)%4): the two 16 B halves
+//                                of an item (r, slab) are read conflict-free -> plane byte slab*LBO + r*16, LBO = rows*16+64
+//   MN-major operand [K, cols]:  boxes of [16][32 cols], 128 B TMA swizzle (chunk ^= k%8), so the eight k rows of a core
+//                                matrix come from eight different bank groups -> plane byte (k/8)*LBO + (c/8)*128 + (k%8)*16
 // Requirements (else the caller falls back to gemm_tc.cu): A and B 16 B aligned, leading dimensions multiples of 4.
 #include <cuda.h>
 #include <cstdlib>
 #include "tc_epilogue.cuh"
 
 #define P_BM 128
-#define P_MAXBN 128
+#define P_BK 16
+#define P_SLABS 2
+#define P_PAD 64
+#define P_MAXRING 8                 // upper bound of either ring depth
 #define P_NCONV 256                 // converter / epilogue threads (warps 0..7)
 #define P_THREADS (P_NCONV + 64)    // + producer warp + MMA warp
-
-template <int BK> struct PCfg {
-  static constexpr int SLABS = BK / 8;
-  static constexpr int PAD = 128 / SLABS;
-  static constexpr int STAGES = (BK == 16) ? 4 : 2;
-  static constexpr int PSETS = (BK == 16) ? 2 : 1;
-};
+#define P_WPROD (P_NCONV / 32)
+#define P_WMMA (P_NCONV / 32 + 1)
+#define P_BAR_BYTES 384             // mbarriers + TMEM address live at the tail of the dynamic buffer (no static smem)
+#define P_MAXBN_RAW 128             // B staged raw and split in the kernel
+#define P_MAXBN_PRE 256             // B pre-split
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -51,61 +58,80 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void lds8(const unsigned char* p0, const unsigned char* p1, float v[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p0);
   const float4 b = *reinterpret_cast<const float4*>(p1);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-// ---- converter: one operand tile of a stage -> split-bf16 planes ------------------------------------------------------
-template <bool MN, int BK>
-__device__ __forceinline__ void convert_tile(const unsigned char* st, unsigned char* hi, unsigned char* lo, int rows_or_cols,
+// ---- converter: one raw operand tile of a stage -> split-bf16 planes ---------------------------------------------------
+// width = rows (K-major) or columns (MN-major) of the tile, a multiple of 16 and <= 128.
+template <bool MN>
+__device__ __forceinline__ void convert_tile(const unsigned char* st, unsigned char* hi, unsigned char* lo, int width,
                                              int lbo, int tid, bool want_lo, int ones_local, int kvalid) {
-  constexpr int SLABS = BK / 8;
-  constexpr int NI = P_MAXBN * SLABS / P_NCONV;          // items per thread for a 128-wide tile: 1 (BK 16) or 2 (BK 32)
   float v[8];
 #pragma unroll
-  for (int u = 0; u < NI; ++u) {
+  for (int u = 0; u < 256 / P_NCONV; ++u) {                 // up to 256 items of 32 B per tile
     const int idx = u * P_NCONV + tid;
     if (!MN) {
-      const int r = idx / SLABS, slab = idx % SLABS;
-      if (r < rows_or_cols) {
-        const unsigned char* p = st + r * (BK * 4) + slab * 32;
-        lds8(p, p + 16, v);
+      const int r = idx >> 1, slab = idx & 1;               // rows x 2 slabs
+      if (r < width) {
+        const unsigned char* row = st + r * (P_BK * 4);
+        const int sw = (r >> 1) & 3;                        // 64 B swizzle: chunk ^= (byte address >> 7) & 3
+        lds8(row + (((2 * slab) ^ sw) << 4), row + (((2 * slab + 1) ^ sw) << 4), v);
         split_store(v, hi + slab * lbo + r * 16, lo + slab * lbo + r * 16, want_lo);
       }
     } else {
-      const int klo = idx & 7, g = idx >> 3, ng = rows_or_cols >> 3;
+      const int klo = idx & 7, g = idx >> 3, ng = width >> 3;   // 16 k x (width/8) column groups
       const int mg = g % ng, khi = g / ng;
-      if (khi < SLABS) {
+      if (khi < P_SLABS) {
         const int k = khi * 8 + klo;
-        const unsigned char* row = st + (mg >> 2) * (BK * 128) + k * 128;      // box of 32 columns, 128 B rows, swizzled
-        const int ch = (mg & 3) * 2;
+        const unsigned char* row = st + (mg >> 2) * (P_BK * 128) + k * 128;    // box of 32 columns, 128 B rows
+        const int ch = (mg & 3) * 2;                        // 128 B swizzle: chunk ^= k % 8
         lds8(row + ((ch ^ klo) << 4), row + (((ch + 1) ^ klo) << 4), v);
-        if (ones_local >= 0 && (ones_local >> 3) == mg && k < kvalid) {                          // virtual ones column
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i == (ones_local & 7)) v[i] = 1.0f;
-        }
         const int off = khi * lbo + mg * 128 + klo * 16;
         split_store(v, hi + off, lo + off, want_lo);
+        if (ones_local >= 0 && (ones_local >> 3) == mg && k < kvalid)          // virtual ones column (fused bias gradient):
+          *reinterpret_cast<unsigned short*>(hi + off + 2 * (ones_local & 7)) = 0x3F80;   // bf16(1.0); its lo part stays 0
       }
     }
   }
 }
 
-template <int MODE, int BK>
-__global__ void __launch_bounds__(P_THREADS, 2) gemm_tcp_kernel(const TcArgs ta, const __grid_constant__ CUtensorMap tmA,
+// debug trace: per CTA 4 header words (globaltimer at start, smid, nchunks, globaltimer at end) + per chunk 6 stamps
+// (clock64 relative to CTA start): producer issue, converter full-wait done, converter arrive, MMA conv-wait done, MMA commit,
+// producer pfree-wait done.  One writer thread per role; enabled only through mfm_debug_set_gemm_trace.
+#define P_TRACE_CHUNKS 32
+#define P_TRACE_WORDS (4 + 6 * P_TRACE_CHUNKS)
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+struct TcpArgs {
+  TcArgs t;
+  const unsigned char* bimg;     // BPRE: images [N tile][K chunk][hi plane | lo plane]
+  int nchunks_total;             // BPRE: K chunks per N tile in bimg
+  int bar_off;                   // byte offset of the mbarrier block inside the dynamic shared buffer
+  int nraw, nsets;               // ring depths: raw stages (TMA in flight) and plane sets (convert -> MMA)
+  long long* trace;              // debug (mfm_debug_set_gemm_trace): per-CTA clock64 stamps, see scripts/gemm_trace.py
+};
+
+template <int MODE, bool BPRE>
+__global__ void __launch_bounds__(P_THREADS, 2) gemm_tcp_kernel(const TcpArgs pa, const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB) {
-  constexpr int S = PCfg<BK>::STAGES, NP = PCfg<BK>::PSETS, SLABS = PCfg<BK>::SLABS, PAD = PCfg<BK>::PAD;
   constexpr bool A_MN = (MODE == MFM_GEMM_TN);
   constexpr bool B_MN = (MODE != MFM_GEMM_NT);
-  extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long full_bar[S], empty_bar[S], conv_bar[NP], pfree_bar[NP], accum_bar;
-  __shared__ uint32_t tmem_holder;
-  unsigned char* const smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const TcArgs& ta = pa.t;
   const GemmArgs& a = ta.g;
-  const int BN = ta.BN;
+  const int BN = ta.BN, R = pa.nraw, P = pa.nsets;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned bx, by, bz;
   asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bx));
@@ -114,29 +140,40 @@ __global__ void __launch_bounds__(P_THREADS, 2) gemm_tcp_kernel(const TcArgs ta,
   const int m0 = by * P_BM, n0 = bx * BN;
   const int kbeg = bz * a.kchunk;
   const int kend = min(a.K, kbeg + a.kchunk);
-  const int nchunks = (kend - kbeg + BK - 1) / BK;
+  const int nchunks = (kend - kbeg + P_BK - 1) / P_BK;
   const bool want_lo = ta.passes == 3;
-  const int BNb = B_MN ? ((BN + 31) & ~31) : BN;          // MN-major B arrives in boxes of 32 columns
-  const int stA = P_BM * BK * 4, stB = BNb * BK * 4, stage_bytes = stA + stB;
-  const int lboA = A_MN ? (P_BM / 8) * 128 : (P_BM * 16 + PAD);
-  const int lboB = B_MN ? (BN / 8) * 128 : (BN * 16 + PAD);
-  const int plA = SLABS * (P_BM * 16 + PAD), plB = SLABS * (BN * 16 + PAD), pset = 2 * plA + 2 * plB;
-  unsigned char* const planes = smem + S * stage_bytes;
+  // raw ring: R stages of [raw A | raw B (absent when pre-split)], each a multiple of the 1024 B swizzle atom;
+  // plane ring: P sets of [A hi | A lo | B hi | B lo] in MMA layout (a pre-split B image lands here directly)
+  const int BNb = B_MN ? ((BN + 31) & ~31) : BN;          // raw MN-major B arrives in boxes of 32 columns
+  const int stA = P_BM * P_BK * 4, stB = BPRE ? 0 : BNb * P_BK * 4, raw_bytes = stA + stB;
+  const int plA = P_SLABS * (P_BM * 16 + P_PAD), plB = P_SLABS * (BN * 16 + P_PAD), pset = 2 * plA + 2 * plB;
+  unsigned char* const planes = smem + R * raw_bytes;
+  const int lboA = A_MN ? (P_BM / 8) * 128 : (P_BM * 16 + P_PAD);
+  const int lboB = B_MN ? (BN / 8) * 128 : (BN * 16 + P_PAD);
   const int ones_col = (MODE == MFM_GEMM_TN && a.colsum_out) ? a.N : -1;
+  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem + pa.bar_off);
+  unsigned long long* const rfull_bar = bars;                    // [R] raw stage landed (TMA complete_tx)
+  unsigned long long* const rempty_bar = bars + P_MAXRING;       // [R] raw stage read by every converter warp
+  unsigned long long* const conv_bar = bars + 2 * P_MAXRING;     // [P] planes written and fenced by every converter warp
+  unsigned long long* const pfree_bar = bars + 3 * P_MAXRING;    // [P] the MMAs that read plane set p are complete
+  unsigned long long* const bfull_bar = bars + 4 * P_MAXRING;    // [P] pre-split B image landed in plane set p
+  unsigned long long& accum_bar = bars[5 * P_MAXRING];
+  uint32_t& tmem_holder = *reinterpret_cast<uint32_t*>(bars + 5 * P_MAXRING + 1);
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), P_NCONV / 32);
+    for (int s = 0; s < R; ++s) {
+      mbar_init(smem_u32(&rfull_bar[s]), 1);
+      mbar_init(smem_u32(&rempty_bar[s]), P_NCONV / 32);
     }
-    for (int p = 0; p < NP; ++p) {
-      mbar_init(smem_u32(&conv_bar[p]), P_NCONV / 32);
-      mbar_init(smem_u32(&pfree_bar[p]), 1);
+    for (int q = 0; q < P; ++q) {
+      mbar_init(smem_u32(&conv_bar[q]), P_NCONV / 32);
+      mbar_init(smem_u32(&pfree_bar[q]), 1);
+      mbar_init(smem_u32(&bfull_bar[q]), 1);
     }
     mbar_init(smem_u32(&accum_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == P_WMMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
                  "r"((uint32_t)ta.tmem_cols)
                  : "memory");
@@ -146,54 +183,90 @@ __global__ void __launch_bounds__(P_THREADS, 2) gemm_tcp_kernel(const TcArgs ta,
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_holder;
+  long long* const tr = pa.trace ? pa.trace + (size_t)((bz * gridDim.y + by) * gridDim.x + bx) * P_TRACE_WORDS : nullptr;
+  const long long t0 = clock64();
+  if (tr && tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tr[0] = gtimer(); tr[1] = smid; tr[2] = nchunks;
+  }
+#define TRACE(cc, slot) do { if (tr && (cc) < P_TRACE_CHUNKS) tr[4 + 6 * (cc) + (slot)] = clock64() - t0; } while (0)
 
   if (warp < P_NCONV / 32) {
     // ================================ CONVERTERS, then EPILOGUE ================================
-    const int ones_local = ones_col >= 0 ? ones_col - n0 : -1;      // column of the tile that is the virtual ones column
+    const int ones_local = (ones_col >= 0 && ones_col - n0 >= 0 && ones_col - n0 < BN) ? ones_col - n0 : -1;
+    int s = 0, q = 0;
+    uint32_t sph = 0, qph = 0;                               // phase parities of raw stage s / plane set q
     for (int c = 0; c < nchunks; ++c) {
-      const int s = c % S, p = c % NP;
-      const unsigned char* st = smem + s * stage_bytes;
-      unsigned char* Ahi = planes + p * pset;
-      unsigned char* Bhi = Ahi + 2 * plA;
-      mbar_wait(smem_u32(&full_bar[s]), (uint32_t)((c / S) & 1));
-      if (c >= NP) mbar_wait(smem_u32(&pfree_bar[p]), (uint32_t)((c / NP - 1) & 1));
+      const unsigned char* st = smem + s * raw_bytes;
+      unsigned char* ps = planes + q * pset;
+      mbar_wait(smem_u32(&rfull_bar[s]), sph);
+      if (c >= P) mbar_wait(smem_u32(&pfree_bar[q]), qph ^ 1u);              // the MMAs of chunk c-P are done with set q
+      if (tid == 0) TRACE(c, 1);
       if (!(ta.dbg & 2)) {
-        convert_tile<A_MN, BK>(st, Ahi, Ahi + plA, P_BM, lboA, tid, want_lo, -1, 0);
-        convert_tile<B_MN, BK>(st + stA, Bhi, Bhi + plB, BN, lboB, tid, want_lo,
-                               (ones_local >= 0 && ones_local < BN) ? ones_local : -1, kend - (kbeg + c * BK));
+        convert_tile<A_MN>(st, ps, ps + plA, P_BM, lboA, tid, want_lo, -1, 0);
+        if (!BPRE)
+          convert_tile<B_MN>(st + stA, ps + 2 * plA, ps + 2 * plA + plB, BN, lboB, tid, want_lo, ones_local, kend - (kbeg + c * P_BK));
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(smem_u32(&conv_bar[p]));       // this warp's share of the planes is written and fenced
-        mbar_arrive(smem_u32(&empty_bar[s]));      // ... and its share of the stage has been read
+        mbar_arrive(smem_u32(&conv_bar[q]));      // this warp's share of the planes is written and fenced
+        mbar_arrive(smem_u32(&rempty_bar[s]));    // ... and its share of the raw stage has been read
       }
+      if (tid == 0) TRACE(c, 2);
+      if (++s == R) { s = 0; sph ^= 1u; }
+      if (++q == P) { q = 0; qph ^= 1u; }
     }
     if (nchunks > 0) mbar_wait(smem_u32(&accum_bar), 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // every stage has been converted and every MMA has completed: the ring is idle and serves as the transpose scratch
-    if (!(ta.dbg & 4)) tc_epilogue(ta, tmem_base, reinterpret_cast<float*>(smem), warp, lane, m0, n0, nchunks > 0, ones_col, 2);
-  } else if (warp == 8) {
-    // ================================ TMA PRODUCER (one thread) ================================
+    // every chunk has been converted and multiplied: the rings are idle and serve as the transpose scratch
+    if (!(ta.dbg & 4)) tc_epilogue(ta, tmem_base, reinterpret_cast<float*>(smem), warp, lane, m0, n0, nchunks > 0, ones_col, P_NCONV / 128);
+  } else if (warp == P_WPROD) {
+    // ================================ PRODUCER (one thread) ================================
+    // raw(i): TMA boxes of chunk i -> raw stage i%R (runs R chunks ahead of the converters);
+    // image(j): the pre-split B image of chunk j -> plane set j%P (runs P chunks ahead of the MMAs), j = i - (R - P)
     if (lane == 0) {
-      const uint32_t stage0 = smem_u32(smem);
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c % S;
-        if (c >= S) mbar_wait(smem_u32(&empty_bar[s]), (uint32_t)((c / S - 1) & 1));
-        const uint32_t fb = smem_u32(&full_bar[s]);
-        const uint32_t sa = stage0 + s * stage_bytes, sb = sa + stA;
-        const int k0 = kbeg + c * BK;
-        mbar_expect_tx(fb, (uint32_t)stage_bytes);
-        if (A_MN) {
+      const uint32_t stage0 = smem_u32(smem), planes0 = smem_u32(planes);
+      const unsigned char* img = BPRE ? pa.bimg + ((size_t)bx * pa.nchunks_total + kbeg / P_BK) * (size_t)(2 * plB) : nullptr;
+      int s = 0, q = 0, jnext = 0;
+      uint32_t sph = 0, qph = 0;
+      const int lag = R - P;
+      for (int i = 0; i < nchunks + (BPRE ? max(lag, 0) : 0); ++i) {
+        if (i < nchunks) {
+          if (i >= R) mbar_wait(smem_u32(&rempty_bar[s]), sph ^ 1u);        // the converters have read chunk i-R
+          TRACE(i, 5);
+          const uint32_t fb = smem_u32(&rfull_bar[s]);
+          const uint32_t sa = stage0 + s * raw_bytes, sb = sa + stA;
+          const int k0 = kbeg + i * P_BK;
+          mbar_expect_tx(fb, (uint32_t)raw_bytes);
+          if (A_MN) {
 #pragma unroll
-          for (int j = 0; j < P_BM / 32; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, m0 + 32 * j, k0, fb);
-        } else {
-          tma_load_2d(sa, &tmA, k0, m0, fb);
+            for (int j = 0; j < P_BM / 32; ++j) tma_load_2d(sa + j * (P_BK * 128), &tmA, m0 + 32 * j, k0, fb);
+          } else {
+            tma_load_2d(sa, &tmA, k0, m0, fb);
+          }
+          if (!BPRE) {
+            if (B_MN) {
+              for (int j = 0; j < BNb / 32; ++j) tma_load_2d(sb + j * (P_BK * 128), &tmB, n0 + 32 * j, k0, fb);
+            } else {
+              tma_load_2d(sb, &tmB, k0, n0, fb);
+            }
+          }
+          TRACE(i, 0);
+          if (++s == R) { s = 0; sph ^= 1u; }
         }
-        if (B_MN) {
-          for (int j = 0; j < BNb / 32; ++j) tma_load_2d(sb + j * (BK * 128), &tmB, n0 + 32 * j, k0, fb);
-        } else {
-          tma_load_2d(sb, &tmB, k0, n0, fb);
+        if (BPRE) {
+          // images may run up to chunk i - lag; the first P need no wait and go out at once
+          int jmax = max(i - lag, min(P, nchunks) - 1);
+          jmax = min(jmax, nchunks - 1);
+          for (; jnext <= jmax; ++jnext) {
+            if (jnext >= P) mbar_wait(smem_u32(&pfree_bar[q]), qph ^ 1u);   // the MMAs of chunk jnext-P are done with set q
+            const uint32_t bb = smem_u32(&bfull_bar[q]);
+            mbar_expect_tx(bb, (uint32_t)(2 * plB));
+            bulk_load(planes0 + q * pset + 2 * plA, img + (size_t)jnext * (2 * plB), (uint32_t)(2 * plB), bb);
+            if (++q == P) { q = 0; qph ^= 1u; }
+          }
         }
       }
     }
@@ -203,44 +276,94 @@ __global__ void __launch_bounds__(P_THREADS, 2) gemm_tcp_kernel(const TcArgs ta,
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(P_BM >> 4) << 24);
     const uint32_t planes0 = smem_u32(planes);
+    int q = 0;
+    uint32_t qph = 0;
     for (int c = 0; c < nchunks; ++c) {
-      const int p = c % NP;
-      mbar_wait(smem_u32(&conv_bar[p]), (uint32_t)((c / NP) & 1));
+      mbar_wait(smem_u32(&conv_bar[q]), qph);
+      if (BPRE) mbar_wait(smem_u32(&bfull_bar[q]), qph);
+      TRACE(c, 3);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t aH = planes0 + p * pset, aL = aH + plA, bH = aH + 2 * plA, bL = bH + plB;
-#pragma unroll
-      for (int kk = 0; kk < BK / 16; ++kk) {
-        const uint32_t ao = kk * 2 * lboA, bo = kk * 2 * lboB;
-        const uint64_t dAh = make_smem_desc(aH + ao, lboA, 128), dBh = make_smem_desc(bH + bo, lboB, 128);
-        umma_bf16(tmem_base, dAh, dBh, idesc, (c > 0 || kk > 0) ? 1u : 0u);
-        if (want_lo) {
-          const uint64_t dAl = make_smem_desc(aL + ao, lboA, 128), dBl = make_smem_desc(bL + bo, lboB, 128);
-          umma_bf16(tmem_base, dAl, dBh, idesc, 1u);
-          umma_bf16(tmem_base, dAh, dBl, idesc, 1u);
-        }
+      const uint32_t aH = planes0 + q * pset, aL = aH + plA, bH = aH + 2 * plA, bL = bH + plB;
+      const uint64_t dAh = make_smem_desc(aH, lboA, 128), dBh = make_smem_desc(bH, lboB, 128);
+      umma_bf16(tmem_base, dAh, dBh, idesc, c > 0 ? 1u : 0u);
+      if (want_lo) {
+        const uint64_t dAl = make_smem_desc(aL, lboA, 128), dBl = make_smem_desc(bL, lboB, 128);
+        umma_bf16(tmem_base, dAl, dBh, idesc, 1u);
+        umma_bf16(tmem_base, dAh, dBl, idesc, 1u);
       }
-      umma_commit(smem_u32(&pfree_bar[p]));               // plane set p may be rewritten once these MMAs have read it
+      umma_commit(smem_u32(&pfree_bar[q]));               // plane set q may be rewritten once these MMAs have read it
+      TRACE(c, 4);
+      if (++q == P) { q = 0; qph ^= 1u; }
     }
     if (nchunks > 0) umma_commit(smem_u32(&accum_bar));    // all MMAs complete: the accumulator is final
   }
+#undef TRACE
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 9) {
+  if (tr && tid == 0) tr[3] = gtimer();
+  if (warp == P_WMMA) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)ta.tmem_cols)
                  : "memory");
   }
 }
 
+// ---- B pre-split: block (N tile, K chunk) writes that chunk's MMA-ready image [hi plane | lo plane] -------------------
+template <bool MN>
+__global__ void __launch_bounds__(256) gemm_prep_kernel(const float* __restrict__ B, long long ldb, int N, int K, int BN,
+                                                        int nchunks_total, int want_lo, unsigned char* __restrict__ img) {
+  const int bx = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+  const int plB = P_SLABS * (BN * 16 + P_PAD);
+  const int lbo = MN ? (BN / 8) * 128 : (BN * 16 + P_PAD);
+  unsigned char* hi = img + ((size_t)bx * nchunks_total + c) * (size_t)(2 * plB);
+  unsigned char* lo = hi + plB;
+  const bool vec = ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((ldb & 3) == 0);
+  const int n0 = bx * BN, k0 = c * P_BK;
+  float v[8];
+  if (!MN) {                                   // B[N, K]: item (row r, slab)
+    for (int idx = tid; idx < BN * P_SLABS; idx += 256) {
+      const int r = idx >> 1, slab = idx & 1;
+      load8(B, ldb, n0 + r, N, k0 + slab * 8, K, vec, v);
+      split_store(v, hi + slab * lbo + r * 16, lo + slab * lbo + r * 16, want_lo != 0);
+    }
+  } else {                                     // B[K, N]: item (k, column group mg)
+    const int ng = BN >> 3;
+    for (int idx = tid; idx < P_BK * ng; idx += 256) {
+      const int klo = idx & 7, g = idx >> 3, mg = g % ng, khi = g / ng;
+      load8(B, ldb, k0 + khi * 8 + klo, K, n0 + mg * 8, N, vec, v);
+      const int off = khi * lbo + mg * 128 + klo * 16;
+      split_store(v, hi + off, lo + off, want_lo != 0);
+    }
+  }
+}
+
+static long long* g_trace = nullptr;
+static long long g_trace_words = 0;
+extern "C" int mfm_debug_set_gemm_trace(void* buf, long long bytes) {
+  g_trace = static_cast<long long*>(buf);
+  g_trace_words = buf ? bytes / 8 : 0;
+  return MFM_OK;
+}
+
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-template <int BK>
-static size_t tcp_smem_bytes(int BN, bool b_mn) {
+#define P_RING_BUDGET (99 * 1024)    // two CTAs per SM
+struct RingCfg { int R, P; size_t bytes; };
+static RingCfg tcp_ring(int BN, bool b_mn, bool bpre) {
+  static int pset_env = -1;
+  if (pset_env < 0) { const char* e = getenv("MFM_TCP_P"); pset_env = e ? atoi(e) : 0; }
   const int BNb = b_mn ? round_up(BN, 32) : BN;
-  const size_t stage = (size_t)P_BM * BK * 4 + (size_t)BNb * BK * 4;
-  const size_t pset = 2 * (size_t)PCfg<BK>::SLABS * (P_BM * 16 + PCfg<BK>::PAD) + 2 * (size_t)PCfg<BK>::SLABS * (BN * 16 + PCfg<BK>::PAD);
-  size_t tot = PCfg<BK>::STAGES * stage + PCfg<BK>::PSETS * pset;
-  if (tot < TC_EPI_SCRATCH_BYTES) tot = TC_EPI_SCRATCH_BYTES;
-  return tot + 1024;                                     // slack to align the ring to the 1024 B swizzle atom
+  const size_t raw = (size_t)P_BM * P_BK * 4 + (bpre ? 0 : (size_t)BNb * P_BK * 4);
+  const size_t pset = 2 * (size_t)P_SLABS * (P_BM * 16 + P_PAD) + 2 * (size_t)P_SLABS * (BN * 16 + P_PAD);
+  RingCfg c;
+  c.P = pset_env > 0 ? pset_env : ((bpre && BN <= 128) ? 3 : 2);
+  while (c.P > 2 && c.P * pset + 2 * raw > P_RING_BUDGET) --c.P;
+  c.R = (int)((P_RING_BUDGET - c.P * pset) / raw);
+  if (c.R > P_MAXRING) c.R = P_MAXRING;
+  if (c.R < 2) c.R = 2;
+  c.bytes = c.R * raw + c.P * pset;
+  const size_t scratch = (size_t)(P_NCONV / 32) * 32 * TC_EPI_LD * 4;
+  if (c.bytes < scratch) c.bytes = scratch;
+  return c;
 }
 
 // ---- tensor maps (driver entry point resolved at run time: the library does not link libcuda) --------------------------
@@ -261,76 +384,100 @@ static EncodeTiledFn get_encode() {
   }
   return fn;
 }
-// fp32 matrix view [outer, inner] with row pitch ld floats; box [box_outer][box_inner]
-static bool make_map(CUtensorMap* tm, const float* base, long long ld, int inner, int outer, int box_inner, int box_outer,
-                     bool swizzle128) {
+// fp32 matrix view [outer, inner] with row pitch ld floats; box [box_outer][box_inner]; swizzle span = the box row
+static bool make_map(CUtensorMap* tm, const float* base, long long ld, int inner, int outer, int box_inner, int box_outer) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = box_inner * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
-template <int MODE, int BK>
-static int tcp_launch_one(const TcArgs& ta, dim3 grid, cudaStream_t st) {
+template <int MODE, bool BPRE>
+static int tcp_launch_one(const TcpArgs& pa, dim3 grid, cudaStream_t st) {
   constexpr bool A_MN = (MODE == MFM_GEMM_TN), B_MN = (MODE != MFM_GEMM_NT);
-  const GemmArgs& g = ta.g;
+  const GemmArgs& g = pa.t.g;
   CUtensorMap tmA, tmB;
-  bool ok = A_MN ? make_map(&tmA, g.A, g.lda, g.M, g.K, 32, BK, true) : make_map(&tmA, g.A, g.lda, g.K, g.M, BK, P_BM, false);
-  ok = ok && (B_MN ? make_map(&tmB, g.B, g.ldb, g.N, g.K, 32, BK, true) : make_map(&tmB, g.B, g.ldb, g.K, g.N, BK, ta.BN, false));
+  bool ok = A_MN ? make_map(&tmA, g.A, g.lda, g.M, g.K, 32, P_BK) : make_map(&tmA, g.A, g.lda, g.K, g.M, P_BK, P_BM);
+  if (BPRE) tmB = tmA;
+  else ok = ok && (B_MN ? make_map(&tmB, g.B, g.ldb, g.N, g.K, 32, P_BK) : make_map(&tmB, g.B, g.ldb, g.K, g.N, P_BK, pa.t.BN));
   if (!ok) return MFM_ERR_UNSUPPORTED;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcp_kernel<MODE, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)tcp_smem_bytes<BK>(P_MAXBN, B_MN));
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcp_kernel<MODE, BPRE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(P_RING_BUDGET + 16 * 1024 + P_BAR_BYTES));
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  gemm_tcp_kernel<MODE, BK><<<grid, P_THREADS, tcp_smem_bytes<BK>(ta.BN, B_MN), st>>>(ta, tmA, tmB);
+  TcpArgs pb = pa;
+  pb.trace = ((long long)grid.x * grid.y * grid.z * P_TRACE_WORDS <= g_trace_words) ? g_trace : nullptr;
+  const RingCfg rc = tcp_ring(pa.t.BN, B_MN, BPRE);
+  pb.nraw = rc.R;
+  pb.nsets = rc.P;
+  pb.bar_off = (int)rc.bytes;
+  gemm_tcp_kernel<MODE, BPRE><<<grid, P_THREADS, (size_t)pb.bar_off + P_BAR_BYTES, st>>>(pb, tmA, tmB);
   MFM_LAUNCH_CHECK();
   return MFM_OK;
 }
 
-// TMA needs 16 B-aligned bases and row pitches; extents are free (tails are zero-filled by the TMA unit).  The virtual
-// ones column of the fused bias gradient must start a fresh 16 B group, and a split-K range must not end inside a chunk
-// (both hold for the launcher's own choices; N % 4 is checked here).
+// TMA needs 16 B-aligned bases and row pitches; extents are free (tails are zero-filled by the TMA unit).
 bool gemm_tcp_eligible(int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb) {
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("MFM_TCP"); enabled = e ? atoi(e) : 1; }
   if (!enabled || !get_encode()) return false;
-  if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda & 3) || (reinterpret_cast<uintptr_t>(B) & 15) || (ldb & 3)) return false;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda & 3)) return false;
   return true;
 }
 
 int gemm_tcp_launch(int passes, int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
                     float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
                     const float* mask, long long ldmask, float mask_scale, float drop_p, int drop_site,
-                    const long long* rng, float* colsum_out, cudaStream_t st) {
-  TcArgs ta;
+                    const long long* rng, float* colsum_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  TcpArgs pa;
+  TcArgs& ta = pa.t;
   ta.g = GemmArgs{M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale,
                   drop_p, drop_site, rng, K, 0, colsum_out};
   ta.passes = passes;
-  static int dbg = -1, bk = -1;
+  static int dbg = -1, pre = -1;
   if (dbg < 0) { const char* e = getenv("MFM_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-  if (bk < 0) { const char* e = getenv("MFM_TCP_BK"); bk = e ? atoi(e) : 16; }
+  if (pre < 0) { const char* e = getenv("MFM_TCP_PRE"); pre = e ? atoi(e) : 1; }
   ta.dbg = dbg;
-  // tile N: near-equal tiles of at most 128 columns (+1 virtual ones column for colsum_out)
+  pa.bimg = nullptr;
+  pa.nchunks_total = 0;
+  pa.trace = nullptr;
+  const bool plain = !bias && !bias2 && act == MFM_ACT_NONE && !mask && drop_p <= 0.0f && accumulate;
+  const bool splitk = plain && K >= 2048;
+  // pre-split B: weights (NT / NN) against many row tiles, caller-provided workspace, no split-K
+  const int nck = (K + P_BK - 1) / P_BK;
+  bool bpre = pre && mode != MFM_GEMM_TN && !splitk && ws && M >= 4096 && ((reinterpret_cast<uintptr_t>(ws) & 127) == 0);
+  const bool b_ok = ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((ldb & 3) == 0);
+  if (!bpre && !b_ok) return MFM_ERR_UNSUPPORTED;         // raw B goes through TMA: needs the alignment
+  const int maxbn = bpre ? P_MAXBN_PRE : P_MAXBN_RAW;
+  // tile N: near-equal tiles of at most maxbn columns (+1 virtual ones column for colsum_out)
   const int n16 = round_up(N + (colsum_out ? 1 : 0), 16);
-  const int ntiles = (n16 + P_MAXBN - 1) / P_MAXBN;
+  const int ntiles = (n16 + maxbn - 1) / maxbn;
   ta.BN = round_up((n16 + ntiles - 1) / ntiles, 16);
+  if (bpre) {
+    const size_t need = (size_t)ntiles * nck * 2 * P_SLABS * (ta.BN * 16 + P_PAD);
+    if (need > ws_bytes) {
+      if (!b_ok) return MFM_ERR_UNSUPPORTED;
+      return gemm_tcp_launch(passes, mode, M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask,
+                             mask_scale, drop_p, drop_site, rng, colsum_out, nullptr, 0, st);
+    }
+  }
   int cols = 32;
   while (cols < ta.BN) cols <<= 1;
   ta.tmem_cols = cols;
   dim3 grid((N + (colsum_out ? 1 : 0) + ta.BN - 1) / ta.BN, (M + P_BM - 1) / P_BM, 1);
-  const bool plain = !bias && !bias2 && act == MFM_ACT_NONE && !mask && drop_p <= 0.0f && accumulate;
-  if (plain && K >= 2048) {                       // split-K weight gradients: fill both CTA slots of every SM
+  if (splitk) {                                   // split-K weight gradients: one split per resident CTA slot
     long long tiles = (long long)grid.x * grid.y;
-    int splits = (int)((2 * 148 + tiles - 1) / tiles);
+    const int occ = 2;   // __launch_bounds__(P_THREADS, 2), ring budget 99 KB
+    int splits = (int)((occ * 148 + tiles - 1) / tiles);
     int maxs = K / 256;
     if (splits > maxs) splits = maxs;
     if (splits > 1) {
@@ -340,18 +487,19 @@ int gemm_tcp_launch(int passes, int mode, int M, int N, int K, const float* A, l
       grid.z = (K + kc - 1) / kc;
     }
   }
-  if (bk == 32) {
-    switch (mode) {
-      case MFM_GEMM_NT: return tcp_launch_one<MFM_GEMM_NT, 32>(ta, grid, st);
-      case MFM_GEMM_NN: return tcp_launch_one<MFM_GEMM_NN, 32>(ta, grid, st);
-      case MFM_GEMM_TN: return tcp_launch_one<MFM_GEMM_TN, 32>(ta, grid, st);
-    }
-  } else {
-    switch (mode) {
-      case MFM_GEMM_NT: return tcp_launch_one<MFM_GEMM_NT, 16>(ta, grid, st);
-      case MFM_GEMM_NN: return tcp_launch_one<MFM_GEMM_NN, 16>(ta, grid, st);
-      case MFM_GEMM_TN: return tcp_launch_one<MFM_GEMM_TN, 16>(ta, grid, st);
-    }
+  if (bpre) {
+    pa.bimg = static_cast<const unsigned char*>(ws);
+    pa.nchunks_total = nck;
+    dim3 pg(grid.x, nck, 1);
+    if (mode == MFM_GEMM_NT) gemm_prep_kernel<false><<<pg, 256, 0, st>>>(B, ldb, N, K, ta.BN, nck, passes == 3, static_cast<unsigned char*>(ws));
+    else                     gemm_prep_kernel<true><<<pg, 256, 0, st>>>(B, ldb, N, K, ta.BN, nck, passes == 3, static_cast<unsigned char*>(ws));
+    MFM_LAUNCH_CHECK();
+    return mode == MFM_GEMM_NT ? tcp_launch_one<MFM_GEMM_NT, true>(pa, grid, st) : tcp_launch_one<MFM_GEMM_NN, true>(pa, grid, st);
+  }
+  switch (mode) {
+    case MFM_GEMM_NT: return tcp_launch_one<MFM_GEMM_NT, false>(pa, grid, st);
+    case MFM_GEMM_NN: return tcp_launch_one<MFM_GEMM_NN, false>(pa, grid, st);
+    case MFM_GEMM_TN: return tcp_launch_one<MFM_GEMM_TN, false>(pa, grid, st);
   }
   return MFM_ERR_ARG;
 }

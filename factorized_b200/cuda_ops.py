@@ -50,6 +50,9 @@ _SIGS = {
     "mfm_set_gemm_tc_min_work": (C.c_int, [LL]),
     "mfm_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_f, LL, c_f, LL, c_f, LL, c_f, c_f, C.c_int, C.c_int,
                            c_f, LL, C.c_float, C.c_float, C.c_int, c_f, c_f, c_f]),
+    "mfm_gemm_ws": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_f, LL, c_f, LL, c_f, LL, c_f, c_f, C.c_int, C.c_int,
+                              c_f, LL, C.c_float, C.c_float, C.c_int, c_f, c_f, c_f, LL, c_f]),
+    "mfm_debug_set_gemm_trace": (C.c_int, [c_f, LL]),
     "mfm_lstm_seq_fwd": (C.c_int, [C.POINTER(LstmCell), C.c_int, c_f]),
     "mfm_lstm_seq_bwd": (C.c_int, [C.POINTER(LstmCell), C.c_int, c_f]),
     "mfm_mfn_mem_fwd": (C.c_int, [C.POINTER(MemArgs), c_f]),
@@ -154,6 +157,7 @@ class CudaOps:
 
     def __init__(self):
         self.lib = load_library()
+        self._ws = {}
         if not torch.cuda.is_available():
             raise RuntimeError("factorized_b200 needs a CUDA device (B200, sm_100a); none is visible")
 
@@ -199,10 +203,24 @@ class CudaOps:
             if rng is None or rng.dtype != torch.int64 or not rng.is_cuda:
                 raise MfmCudaError("dropout needs a CUDA int64 rng state [seed, step]")
             prng = rng.data_ptr()
-        _check(self.lib.mfm_gemm(GEMM_MODE[mode], M, N, K, pa, lda, pb, ldb, pc, ldc, _vec(bias, "bias", N),
-                                 _vec(bias2, "bias2", N), act, int(accumulate), pm, ldm, float(mask_scale),
-                                 float(p), int(site), prng,
-                                 None if colsum_out is None else _vec(colsum_out, "colsum_out", M), _stream()), "mfm_gemm")
+        ws, ws_bytes = None, 0
+        if mode != "tn" and M >= 4096:          # weight operand against many row tiles: pre-split it once per call
+            ws_bytes = 8 * (N + 64) * (K + 16)
+            ws = self._gemm_workspace(Cm.device, ws_bytes)
+        _check(self.lib.mfm_gemm_ws(GEMM_MODE[mode], M, N, K, pa, lda, pb, ldb, pc, ldc, _vec(bias, "bias", N),
+                                    _vec(bias2, "bias2", N), act, int(accumulate), pm, ldm, float(mask_scale),
+                                    float(p), int(site), prng,
+                                    None if colsum_out is None else _vec(colsum_out, "colsum_out", M),
+                                    ws, ws_bytes, _stream()), "mfm_gemm_ws")
+
+    def _gemm_workspace(self, device, nbytes: int) -> int:
+        """One scratch buffer per (device, stream): calls on a stream are ordered, so the next call may reuse it."""
+        key = (device.index, _stream())
+        t = self._ws.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(nbytes, 4 << 20), dtype=torch.uint8, device=device)
+            self._ws[key] = t
+        return t.data_ptr()
 
     # ---- LSTM ----
     @staticmethod

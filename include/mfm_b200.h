@@ -65,6 +65,19 @@ int mfm_gemm(int mode, int M, int N, int K,
              const float* bias, const float* bias2, int act, int accumulate,
              const float* mask, long long ldmask, float mask_scale,
              float drop_p, int drop_site, const long long* rng, float* colsum_out, void* stream);
+/* The same GEMM with a caller-owned device workspace (128 B aligned, ws_bytes >= 8*(N+64)*(K+16) is always enough; the
+ * library never allocates).  With it, NT / NN GEMMs over many rows (M >= 4096) split the small B operand -- the weight --
+ * into its bf16 hi/lo MMA image once per call instead of once per 128-row tile.  The workspace is only read by kernels
+ * enqueued by this call on `stream`; reuse it for the next call on the same stream, not across streams. */
+/* Debug aid (scripts/gemm_trace.py): while a device buffer is registered, every pipelined-GEMM CTA records clock stamps of
+ * its producer / converter / MMA roles into it (4 + 6*32 int64 words per CTA).  NULL disables.  Not for production use. */
+int mfm_debug_set_gemm_trace(void* device_buf, long long bytes);
+int mfm_gemm_ws(int mode, int M, int N, int K,
+                const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
+                const float* bias, const float* bias2, int act, int accumulate,
+                const float* mask, long long ldmask, float mask_scale,
+                float drop_p, int drop_site, const long long* rng, float* colsum_out,
+                void* ws, long long ws_bytes, void* stream);
 
 /* One LSTM cell unrolled over T steps inside the kernel (encoderLSTM.forward mfm_model.py:47-62,
  * decoderLSTM.forward :72-91, the three cells of MFN.forward :167-169).

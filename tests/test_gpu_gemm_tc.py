@@ -26,7 +26,9 @@ def g(*shape, seed=0):
 SHAPES = [(128, 16, 16), (128, 128, 32), (256, 256, 64), (1, 1, 1), (5, 3, 7), (70, 130, 33), (640, 128, 300), (300, 400, 128),
           (1000, 24, 5), (129, 257, 65), (96, 512, 464),
           # 16 B-aligned ragged shapes: these take the pipelined cp.async kernel (gemm_tcp.cu)
-          (72, 132, 36), (1000, 24, 8), (516, 260, 68), (2048, 2048, 32), (4, 4, 4), (132, 20, 2052), (388, 112, 20)]
+          (72, 132, 36), (1000, 24, 8), (516, 260, 68), (2048, 2048, 32), (4, 4, 4), (132, 20, 2052), (388, 112, 20),
+          # >= 4096 rows: NT / NN pre-split the weight operand into its MMA image (tiles up to 256 columns wide)
+          (4100, 400, 128), (4096, 260, 36), (4608, 32, 8), (5000, 513, 72), (4200, 20, 300)]
 
 
 @pytest.mark.parametrize("mode", ["nt", "nn", "tn"])
@@ -52,8 +54,9 @@ def test_tc_gemm_split_k_weight_gradient(tc_ops):
     assert rel_l2(c_gpu, c_cpu) < 5e-5
 
 
-def test_tc_gemm_views_and_epilogues(tc_ops):
-    TB, D = 700, 325
+@pytest.mark.parametrize("TB", [700, 4300])
+def test_tc_gemm_views_and_epilogues(tc_ops, TB):
+    D = 325
     X = g(TB, D, seed=5)                      # modality slices of x: row pitch 1300 B, not 16 B aligned
     W = g(352, 300, seed=6)
     bias, bias2 = g(352, seed=7), g(352, seed=8)
@@ -65,6 +68,12 @@ def test_tc_gemm_views_and_epilogues(tc_ops):
             EmuOps().gemm("nt", X[:, :300], W, out_cpu[:, 10:362], bias=bias, bias2=bias2, act=act, drop=drop, rng=rng)
             tc_ops.gemm("nt", X.cuda()[:, :300], W.cuda(), out_gpu[:, 10:362], bias=bias.cuda(), bias2=bias2.cuda(),
                         act=act, drop=drop, rng=rng.cuda())
+            # the same product from a 16 B-aligned copy of the slice (TMA-staged kernel; pre-split weight when TB >= 4096)
+            out_al = torch.zeros(TB, 400).cuda()
+            tc_ops.gemm("nt", X[:, :300].contiguous().cuda(), W.cuda(), out_al[:, 12:364], bias=bias.cuda(), bias2=bias2.cuda(),
+                        act=act, drop=drop, rng=rng.cuda())
+            dal = (out_al[:, 12:364] - out_gpu[:, 10:362]).abs()
+            assert float((dal > 2e-3).float().mean()) < 1e-4, (act, drop)
             # relu/dropout decisions can flip for |pre-activation| ~ 1e-5; compare with an absolute allowance
             diff = (out_gpu.cpu() - out_cpu).abs()
             assert float((diff > 2e-3).float().mean()) < 1e-4, (act, drop)
