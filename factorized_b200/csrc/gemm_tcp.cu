@@ -45,7 +45,7 @@
 #define P_WMMA (P_NCONV / 32 + 1)
 #define P_BAR_BYTES 384             // mbarriers + TMEM address live at the tail of the dynamic buffer (no static smem)
 #define P_MAXBN_RAW 128             // B staged raw and split in the kernel
-#define P_MAXBN_PRE 256             // B pre-split
+#define P_MAXBN_PRE 160             // B pre-split: 160 accumulator + 6 x 16 A columns = 256 TMEM columns
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -114,12 +114,54 @@ __device__ __forceinline__ long long gtimer() {
   return t;
 }
 
+// ---- TS mode: the A operand lives in tensor memory -------------------------------------------------------------------
+// Thread (warp w, lane l) owns row 32*(w%4)+l of the tile (= its TMEM lane) and the 8-k slab w/4 of the chunk: it reads
+// its 8 fp32 from the raw stage (conflict-free through the TMA swizzle), splits them, and writes 4 packed hi registers and
+// 4 packed lo registers with tcgen05.st.  No shared-memory store, no proxy fence, and the MMA reads only B from shared
+// memory: per chunk this removes 8.4 KB of plane stores and 12 KB of operand reads from the shared-memory pipe, which
+// is what bounds the SS form.  TMEM image of one plane: lane = row, column j = (k = 2j, 2j+1) packed.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+template <bool MN>
+__device__ __forceinline__ void convert_a_tmem(const unsigned char* st, uint32_t taddr_set, int warp, int lane, bool want_lo) {
+  const int slab = warp >> 2;
+  float v[8];
+  if (!MN) {
+    const int r = 32 * (warp & 3) + lane;
+    const unsigned char* row = st + r * (P_BK * 4);
+    const int sw = (r >> 1) & 3;                            // 64 B swizzle
+    lds8(row + (((2 * slab) ^ sw) << 4), row + (((2 * slab + 1) ^ sw) << 4), v);
+  } else {
+    const unsigned char* box = st + (warp & 3) * (P_BK * 128) + slab * (8 * 128) + (lane & 3) * 4;   // box = 32 columns
+#pragma unroll
+    for (int i = 0; i < 8; ++i)                             // k = 8*slab + i; 128 B swizzle: chunk ^= k % 8 = i
+      v[i] = *reinterpret_cast<const float*>(box + i * 128 + (((lane >> 2) ^ i) << 4));
+  }
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+    l[j] = pack_bf16(v[2 * j] - __uint_as_float(h[j] << 16), v[2 * j + 1] - __uint_as_float(h[j] & 0xFFFF0000u));
+  }
+  const uint32_t ta = taddr_set + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(slab * 4);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+  if (want_lo)
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ta + 8), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+}
+
 struct TcpArgs {
   TcArgs t;
   const unsigned char* bimg;     // BPRE: images [N tile][K chunk][hi plane | lo plane]
   int nchunks_total;             // BPRE: K chunks per N tile in bimg
   int bar_off;                   // byte offset of the mbarrier block inside the dynamic shared buffer
-  int nraw, nsets;               // ring depths: raw stages (TMA in flight) and plane sets (convert -> MMA)
+  int nstages;                   // ring depth
+  int group;                     // chunks the MMA thread issues per mbarrier wait (<= nstages / 2)
   long long* trace;              // debug (mfm_debug_set_gemm_trace): per-CTA clock64 stamps, see scripts/gemm_trace.py
 };
 
@@ -131,7 +173,7 @@ __global__ void __launch_bounds__(P_THREADS, 2) gemm_tcp_kernel(const TcpArgs pa
   extern __shared__ __align__(1024) unsigned char smem[];
   const TcArgs& ta = pa.t;
   const GemmArgs& a = ta.g;
-  const int BN = ta.BN, R = pa.nraw, P = pa.nsets;
+  const int BN = ta.BN, S = pa.nstages;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned bx, by, bz;
   asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bx));
@@ -142,33 +184,28 @@ __global__ void __launch_bounds__(P_THREADS, 2) gemm_tcp_kernel(const TcpArgs pa
   const int kend = min(a.K, kbeg + a.kchunk);
   const int nchunks = (kend - kbeg + P_BK - 1) / P_BK;
   const bool want_lo = ta.passes == 3;
-  // raw ring: R stages of [raw A | raw B (absent when pre-split)], each a multiple of the 1024 B swizzle atom;
-  // plane ring: P sets of [A hi | A lo | B hi | B lo] in MMA layout (a pre-split B image lands here directly)
+  // one ring, S deep.  Stage s = [raw A | pre-split B image]  or  [raw A | raw B | B hi | B lo] in shared memory (a
+  // multiple of the 1024 B swizzle atom) plus 16 tensor-memory columns (A hi 8 | A lo 8) behind the accumulator.
   const int BNb = B_MN ? ((BN + 31) & ~31) : BN;          // raw MN-major B arrives in boxes of 32 columns
-  const int stA = P_BM * P_BK * 4, stB = BPRE ? 0 : BNb * P_BK * 4, raw_bytes = stA + stB;
-  const int plA = P_SLABS * (P_BM * 16 + P_PAD), plB = P_SLABS * (BN * 16 + P_PAD), pset = 2 * plA + 2 * plB;
-  unsigned char* const planes = smem + R * raw_bytes;
-  const int lboA = A_MN ? (P_BM / 8) * 128 : (P_BM * 16 + P_PAD);
+  const int plB = P_SLABS * (BN * 16 + P_PAD);
+  const int stA = P_BM * P_BK * 4, stB = BPRE ? 0 : BNb * P_BK * 4;
+  const int offB = stA + stB;                               // B planes (hi | lo): the landed image, or written by the converters
+  const int stage_bytes = (offB + 2 * plB + 1023) & ~1023;
   const int lboB = B_MN ? (BN / 8) * 128 : (BN * 16 + P_PAD);
+  const uint32_t acol0 = (uint32_t)((BN + 15) & ~15);
   const int ones_col = (MODE == MFM_GEMM_TN && a.colsum_out) ? a.N : -1;
   unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smem + pa.bar_off);
-  unsigned long long* const rfull_bar = bars;                    // [R] raw stage landed (TMA complete_tx)
-  unsigned long long* const rempty_bar = bars + P_MAXRING;       // [R] raw stage read by every converter warp
-  unsigned long long* const conv_bar = bars + 2 * P_MAXRING;     // [P] planes written and fenced by every converter warp
-  unsigned long long* const pfree_bar = bars + 3 * P_MAXRING;    // [P] the MMAs that read plane set p are complete
-  unsigned long long* const bfull_bar = bars + 4 * P_MAXRING;    // [P] pre-split B image landed in plane set p
-  unsigned long long& accum_bar = bars[5 * P_MAXRING];
-  uint32_t& tmem_holder = *reinterpret_cast<uint32_t*>(bars + 5 * P_MAXRING + 1);
+  unsigned long long* const full_bar = bars;                     // [S] stage landed (TMA / bulk complete_tx)
+  unsigned long long* const conv_bar = bars + P_MAXRING;         // [S] stage converted by every converter warp
+  unsigned long long* const done_bar = bars + 2 * P_MAXRING;     // [S] the MMAs that read stage s are complete
+  unsigned long long& accum_bar = bars[3 * P_MAXRING];
+  uint32_t& tmem_holder = *reinterpret_cast<uint32_t*>(bars + 3 * P_MAXRING + 1);
 
   if (tid == 0) {
-    for (int s = 0; s < R; ++s) {
-      mbar_init(smem_u32(&rfull_bar[s]), 1);
-      mbar_init(smem_u32(&rempty_bar[s]), P_NCONV / 32);
-    }
-    for (int q = 0; q < P; ++q) {
-      mbar_init(smem_u32(&conv_bar[q]), P_NCONV / 32);
-      mbar_init(smem_u32(&pfree_bar[q]), 1);
-      mbar_init(smem_u32(&bfull_bar[q]), 1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&conv_bar[s]), P_NCONV / 32);
+      mbar_init(smem_u32(&done_bar[s]), 1);
     }
     mbar_init(smem_u32(&accum_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -194,106 +231,99 @@ __global__ void __launch_bounds__(P_THREADS, 2) gemm_tcp_kernel(const TcpArgs pa
 
   if (warp < P_NCONV / 32) {
     // ================================ CONVERTERS, then EPILOGUE ================================
+    // full[s] also means "the MMAs of chunk c-S are complete" (the producer waited for done[s] before refilling the
+    // stage), so the stage's tensor-memory columns and B planes may be overwritten without a further wait.
     const int ones_local = (ones_col >= 0 && ones_col - n0 >= 0 && ones_col - n0 < BN) ? ones_col - n0 : -1;
-    int s = 0, q = 0;
-    uint32_t sph = 0, qph = 0;                               // phase parities of raw stage s / plane set q
+    int s = 0;
+    uint32_t ph = 0;
     for (int c = 0; c < nchunks; ++c) {
-      const unsigned char* st = smem + s * raw_bytes;
-      unsigned char* ps = planes + q * pset;
-      mbar_wait(smem_u32(&rfull_bar[s]), sph);
-      if (c >= P) mbar_wait(smem_u32(&pfree_bar[q]), qph ^ 1u);              // the MMAs of chunk c-P are done with set q
+      unsigned char* st = smem + s * stage_bytes;
+      mbar_wait(smem_u32(&full_bar[s]), ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (tid == 0) TRACE(c, 1);
       if (!(ta.dbg & 2)) {
-        convert_tile<A_MN>(st, ps, ps + plA, P_BM, lboA, tid, want_lo, -1, 0);
-        if (!BPRE)
-          convert_tile<B_MN>(st + stA, ps + 2 * plA, ps + 2 * plA + plB, BN, lboB, tid, want_lo, ones_local, kend - (kbeg + c * P_BK));
+        convert_a_tmem<A_MN>(st, tmem_base + acol0 + (uint32_t)(s * 16), warp, lane, want_lo);
+        if (!BPRE) {
+          convert_tile<B_MN>(st + stA, st + offB, st + offB + plB, BN, lboB, tid, want_lo, ones_local, kend - (kbeg + c * P_BK));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(smem_u32(&conv_bar[q]));      // this warp's share of the planes is written and fenced
-        mbar_arrive(smem_u32(&rempty_bar[s]));    // ... and its share of the raw stage has been read
-      }
+      if (lane == 0) mbar_arrive(smem_u32(&conv_bar[s]));
       if (tid == 0) TRACE(c, 2);
-      if (++s == R) { s = 0; sph ^= 1u; }
-      if (++q == P) { q = 0; qph ^= 1u; }
+      if (++s == S) { s = 0; ph ^= 1u; }
     }
     if (nchunks > 0) mbar_wait(smem_u32(&accum_bar), 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // every chunk has been converted and multiplied: the rings are idle and serve as the transpose scratch
+    // every chunk has been converted and multiplied: the ring is idle and serves as the transpose scratch
     if (!(ta.dbg & 4)) tc_epilogue(ta, tmem_base, reinterpret_cast<float*>(smem), warp, lane, m0, n0, nchunks > 0, ones_col, P_NCONV / 128);
   } else if (warp == P_WPROD) {
     // ================================ PRODUCER (one thread) ================================
-    // raw(i): TMA boxes of chunk i -> raw stage i%R (runs R chunks ahead of the converters);
-    // image(j): the pre-split B image of chunk j -> plane set j%P (runs P chunks ahead of the MMAs), j = i - (R - P)
     if (lane == 0) {
-      const uint32_t stage0 = smem_u32(smem), planes0 = smem_u32(planes);
+      const uint32_t stage0 = smem_u32(smem);
       const unsigned char* img = BPRE ? pa.bimg + ((size_t)bx * pa.nchunks_total + kbeg / P_BK) * (size_t)(2 * plB) : nullptr;
-      int s = 0, q = 0, jnext = 0;
-      uint32_t sph = 0, qph = 0;
-      const int lag = R - P;
-      for (int i = 0; i < nchunks + (BPRE ? max(lag, 0) : 0); ++i) {
-        if (i < nchunks) {
-          if (i >= R) mbar_wait(smem_u32(&rempty_bar[s]), sph ^ 1u);        // the converters have read chunk i-R
-          TRACE(i, 5);
-          const uint32_t fb = smem_u32(&rfull_bar[s]);
-          const uint32_t sa = stage0 + s * raw_bytes, sb = sa + stA;
-          const int k0 = kbeg + i * P_BK;
-          mbar_expect_tx(fb, (uint32_t)raw_bytes);
-          if (A_MN) {
+      const uint32_t tx = (uint32_t)(stA + (BPRE ? 2 * plB : stB));
+      int s = 0;
+      uint32_t ph = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        if (c >= S) mbar_wait(smem_u32(&done_bar[s]), ph ^ 1u);             // the MMAs of chunk c-S are complete
+        TRACE(c, 5);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        const uint32_t sa = stage0 + s * stage_bytes, sb = sa + stA;
+        const int k0 = kbeg + c * P_BK;
+        mbar_expect_tx(fb, tx);
+        if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < P_BM / 32; ++j) tma_load_2d(sa + j * (P_BK * 128), &tmA, m0 + 32 * j, k0, fb);
-          } else {
-            tma_load_2d(sa, &tmA, k0, m0, fb);
-          }
-          if (!BPRE) {
-            if (B_MN) {
-              for (int j = 0; j < BNb / 32; ++j) tma_load_2d(sb + j * (P_BK * 128), &tmB, n0 + 32 * j, k0, fb);
-            } else {
-              tma_load_2d(sb, &tmB, k0, n0, fb);
-            }
-          }
-          TRACE(i, 0);
-          if (++s == R) { s = 0; sph ^= 1u; }
+          for (int j = 0; j < P_BM / 32; ++j) tma_load_2d(sa + j * (P_BK * 128), &tmA, m0 + 32 * j, k0, fb);
+        } else {
+          tma_load_2d(sa, &tmA, k0, m0, fb);
         }
         if (BPRE) {
-          // images may run up to chunk i - lag; the first P need no wait and go out at once
-          int jmax = max(i - lag, min(P, nchunks) - 1);
-          jmax = min(jmax, nchunks - 1);
-          for (; jnext <= jmax; ++jnext) {
-            if (jnext >= P) mbar_wait(smem_u32(&pfree_bar[q]), qph ^ 1u);   // the MMAs of chunk jnext-P are done with set q
-            const uint32_t bb = smem_u32(&bfull_bar[q]);
-            mbar_expect_tx(bb, (uint32_t)(2 * plB));
-            bulk_load(planes0 + q * pset + 2 * plA, img + (size_t)jnext * (2 * plB), (uint32_t)(2 * plB), bb);
-            if (++q == P) { q = 0; qph ^= 1u; }
-          }
+          bulk_load(sa + offB, img + (size_t)c * (2 * plB), (uint32_t)(2 * plB), fb);
+        } else if (B_MN) {
+          for (int j = 0; j < BNb / 32; ++j) tma_load_2d(sb + j * (P_BK * 128), &tmB, n0 + 32 * j, k0, fb);
+        } else {
+          tma_load_2d(sb, &tmB, k0, n0, fb);
         }
+        TRACE(c, 0);
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
     }
   } else if (lane == 0) {
     // ================================ MMA ISSUE (one thread) ================================
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, majors, N>>3, M>>4
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+    // Its loop is the serial spine of the kernel: one wait, three MMAs, one commit per chunk.
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, A from TMEM (K-major), B major, N>>3, M>>4
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((B_MN ? 1u : 0u) << 16) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(P_BM >> 4) << 24);
-    const uint32_t planes0 = smem_u32(planes);
-    int q = 0;
-    uint32_t qph = 0;
-    for (int c = 0; c < nchunks; ++c) {
-      mbar_wait(smem_u32(&conv_bar[q]), qph);
-      if (BPRE) mbar_wait(smem_u32(&bfull_bar[q]), qph);
-      TRACE(c, 3);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t aH = planes0 + q * pset, aL = aH + plA, bH = aH + 2 * plA, bL = bH + plB;
-      const uint64_t dAh = make_smem_desc(aH, lboA, 128), dBh = make_smem_desc(bH, lboB, 128);
-      umma_bf16(tmem_base, dAh, dBh, idesc, c > 0 ? 1u : 0u);
-      if (want_lo) {
-        const uint64_t dAl = make_smem_desc(aL, lboA, 128), dBl = make_smem_desc(bL, lboB, 128);
-        umma_bf16(tmem_base, dAl, dBh, idesc, 1u);
-        umma_bf16(tmem_base, dAh, dBl, idesc, 1u);
+    const uint32_t stage0 = smem_u32(smem);
+    const int G = pa.group;                      // chunks per wait: converter warps finish chunks in order, so "chunk c+G-1
+    int s = 0;                                   // converted" implies chunks c..c+G-2 are too -- one mbarrier wait per G chunks
+    uint32_t ph = 0;
+    for (int c0 = 0; c0 < nchunks; c0 += G) {
+      const int g = min(G, nchunks - c0);
+      {
+        int sl = s + g - 1;
+        uint32_t pl = ph;
+        if (sl >= S) { sl -= S; pl ^= 1u; }
+        mbar_wait(smem_u32(&conv_bar[sl]), pl);  // converters saw full[] before arriving: the B images are acquired transitively
       }
-      umma_commit(smem_u32(&pfree_bar[q]));               // plane set q may be rewritten once these MMAs have read it
-      TRACE(c, 4);
-      if (++q == P) { q = 0; qph ^= 1u; }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c = c0; c < c0 + g; ++c) {
+        TRACE(c, 3);
+        const uint32_t bH = stage0 + s * stage_bytes + offB, bL = bH + plB;
+        const uint64_t dBh = make_smem_desc(bH, lboB, 128), dBl = make_smem_desc(bL, lboB, 128);
+        const uint32_t tAh = tmem_base + acol0 + (uint32_t)(s * 16), tAl = tAh + 8;
+        umma_bf16_ts(tmem_base, tAh, dBh, idesc, c > 0 ? 1u : 0u);
+        if (want_lo) {
+          umma_bf16_ts(tmem_base, tAl, dBh, idesc, 1u);
+          umma_bf16_ts(tmem_base, tAh, dBl, idesc, 1u);
+        }
+        umma_commit(smem_u32(&done_bar[s]));              // stage s (shared memory and its TMEM columns) may be refilled
+        TRACE(c, 4);
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
     }
     if (nchunks > 0) umma_commit(smem_u32(&accum_bar));    // all MMAs complete: the accumulator is final
   }
@@ -346,23 +376,25 @@ extern "C" int mfm_debug_set_gemm_trace(void* buf, long long bytes) {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-#define P_RING_BUDGET (99 * 1024)    // two CTAs per SM
-struct RingCfg { int R, P; size_t bytes; };
+#define P_RING_BUDGET (110 * 1024)   // two CTAs per SM
+struct RingCfg { int S; size_t bytes; int tmem_cols; };
 static RingCfg tcp_ring(int BN, bool b_mn, bool bpre) {
-  static int pset_env = -1;
-  if (pset_env < 0) { const char* e = getenv("MFM_TCP_P"); pset_env = e ? atoi(e) : 0; }
   const int BNb = b_mn ? round_up(BN, 32) : BN;
-  const size_t raw = (size_t)P_BM * P_BK * 4 + (bpre ? 0 : (size_t)BNb * P_BK * 4);
-  const size_t pset = 2 * (size_t)P_SLABS * (P_BM * 16 + P_PAD) + 2 * (size_t)P_SLABS * (BN * 16 + P_PAD);
+  const size_t plB = (size_t)P_SLABS * (BN * 16 + P_PAD);
+  size_t stage = (size_t)P_BM * P_BK * 4 + (bpre ? 0 : (size_t)BNb * P_BK * 4) + 2 * plB;
+  stage = (stage + 1023) & ~(size_t)1023;
   RingCfg c;
-  c.P = pset_env > 0 ? pset_env : ((bpre && BN <= 128) ? 3 : 2);
-  while (c.P > 2 && c.P * pset + 2 * raw > P_RING_BUDGET) --c.P;
-  c.R = (int)((P_RING_BUDGET - c.P * pset) / raw);
-  if (c.R > P_MAXRING) c.R = P_MAXRING;
-  if (c.R < 2) c.R = 2;
-  c.bytes = c.R * raw + c.P * pset;
+  c.S = (int)(P_RING_BUDGET / stage);
+  // each stage also owns 16 tensor-memory columns behind the accumulator; 256 columns per CTA (two CTAs share the 512)
+  const int by_tmem = (256 - round_up(BN, 16)) / 16;
+  if (c.S > by_tmem) c.S = by_tmem;
+  if (c.S > P_MAXRING) c.S = P_MAXRING;
+  if (c.S < 2) c.S = 2;
+  c.bytes = c.S * stage;
   const size_t scratch = (size_t)(P_NCONV / 32) * 32 * TC_EPI_LD * 4;
   if (c.bytes < scratch) c.bytes = scratch;
+  c.tmem_cols = 32;
+  while (c.tmem_cols < round_up(BN, 16) + 16 * c.S) c.tmem_cols <<= 1;
   return c;
 }
 
@@ -384,6 +416,14 @@ static EncodeTiledFn get_encode() {
   }
   return fn;
 }
+// A K chunk touches only 64 B of each operand row; promoting the L2 fill to 256 B makes DRAM see four chunks' worth of a
+// row at once (one activate instead of four) and the next three chunks hit in L2.
+static CUtensorMapL2promotion l2promo() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MFM_TCP_L2"); v = e ? atoi(e) : 256; }
+  return v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+       : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+}
 // fp32 matrix view [outer, inner] with row pitch ld floats; box [box_outer][box_inner]; swizzle span = the box row
 static bool make_map(CUtensorMap* tm, const float* base, long long ld, int inner, int outer, int box_inner, int box_outer) {
   EncodeTiledFn enc = get_encode();
@@ -394,7 +434,7 @@ static bool make_map(CUtensorMap* tm, const float* base, long long ld, int inner
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapSwizzle sw = box_inner * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, l2promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -410,16 +450,19 @@ static int tcp_launch_one(const TcpArgs& pa, dim3 grid, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcp_kernel<MODE, BPRE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(P_RING_BUDGET + 16 * 1024 + P_BAR_BYTES));
+                                         (int)(P_RING_BUDGET + P_BAR_BYTES));
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
   TcpArgs pb = pa;
   pb.trace = ((long long)grid.x * grid.y * grid.z * P_TRACE_WORDS <= g_trace_words) ? g_trace : nullptr;
   const RingCfg rc = tcp_ring(pa.t.BN, B_MN, BPRE);
-  pb.nraw = rc.R;
-  pb.nsets = rc.P;
+  pb.nstages = rc.S;
+  static int grp = -1;
+  if (grp < 0) { const char* e = getenv("MFM_TCP_G"); grp = e ? atoi(e) : 2; }
+  pb.group = grp < 1 ? 1 : (grp > rc.S / 2 ? (rc.S / 2 > 0 ? rc.S / 2 : 1) : grp);
   pb.bar_off = (int)rc.bytes;
+  pb.t.tmem_cols = rc.tmem_cols;
   gemm_tcp_kernel<MODE, BPRE><<<grid, P_THREADS, (size_t)pb.bar_off + P_BAR_BYTES, st>>>(pb, tmA, tmB);
   MFM_LAUNCH_CHECK();
   return MFM_OK;
@@ -443,9 +486,10 @@ int gemm_tcp_launch(int passes, int mode, int M, int N, int K, const float* A, l
   ta.g = GemmArgs{M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale,
                   drop_p, drop_site, rng, K, 0, colsum_out};
   ta.passes = passes;
-  static int dbg = -1, pre = -1;
+  static int dbg = -1, pre = -1, maxbn_pre = -1;
   if (dbg < 0) { const char* e = getenv("MFM_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
   if (pre < 0) { const char* e = getenv("MFM_TCP_PRE"); pre = e ? atoi(e) : 1; }
+  if (maxbn_pre < 0) { const char* e = getenv("MFM_TCP_MAXBN"); maxbn_pre = e ? atoi(e) : P_MAXBN_PRE; }
   ta.dbg = dbg;
   pa.bimg = nullptr;
   pa.nchunks_total = 0;
@@ -457,7 +501,7 @@ int gemm_tcp_launch(int passes, int mode, int M, int N, int K, const float* A, l
   bool bpre = pre && mode != MFM_GEMM_TN && !splitk && ws && M >= 4096 && ((reinterpret_cast<uintptr_t>(ws) & 127) == 0);
   const bool b_ok = ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((ldb & 3) == 0);
   if (!bpre && !b_ok) return MFM_ERR_UNSUPPORTED;         // raw B goes through TMA: needs the alignment
-  const int maxbn = bpre ? P_MAXBN_PRE : P_MAXBN_RAW;
+  const int maxbn = bpre ? maxbn_pre : P_MAXBN_RAW;
   // tile N: near-equal tiles of at most maxbn columns (+1 virtual ones column for colsum_out)
   const int n16 = round_up(N + (colsum_out ? 1 : 0), 16);
   const int ntiles = (n16 + maxbn - 1) / maxbn;
@@ -470,9 +514,7 @@ int gemm_tcp_launch(int passes, int mode, int M, int N, int K, const float* A, l
                              mask_scale, drop_p, drop_site, rng, colsum_out, nullptr, 0, st);
     }
   }
-  int cols = 32;
-  while (cols < ta.BN) cols <<= 1;
-  ta.tmem_cols = cols;
+  ta.tmem_cols = 0;                                  // set by tcp_launch_one (accumulator + A sets)
   dim3 grid((N + (colsum_out ? 1 : 0) + ta.BN - 1) / ta.BN, (M + P_BM - 1) / P_BM, 1);
   if (splitk) {                                   // split-K weight gradients: one split per resident CTA slot
     long long tiles = (long long)grid.x * grid.y;

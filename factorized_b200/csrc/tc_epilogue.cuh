@@ -4,9 +4,9 @@
 // 4*nhalves warps take part.  Warp w owns TMEM lanes 32*(w%4).. (tile rows) and the column range w/4 of nhalves.  A 32x32 block is read
 // with tcgen05.ld (lane = row), written to the warp's scratch as float4 (row stride 36 floats: 16 B aligned and
 // conflict-free for both phases), and read back transposed:
-//   * fast path (bias / activation / accumulate, 16 B-aligned C): each lane moves a float4, one store instruction
-//     covers four 128 B row segments;
-//   * general path (split-K reduction, dropout, ReLU mask, ones column, unaligned C): lane = column, 128 B per store.
+//   * fast path (16 B-aligned C and mask; bias / activation / dropout / ReLU mask / accumulate): each lane moves a float4,
+//     one store instruction covers four 128 B row segments;
+//   * general path (split-K reduction, ones column, unaligned C or mask): lane = column, 128 B per store.
 #pragma once
 #include "gemm_args.cuh"
 #include "tc_common.cuh"
@@ -43,7 +43,8 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base
   const long long e_ldc = a.ldc;
   const int e_M = a.M, e_N = a.N, e_act = a.act;
   const bool e_atomic = a.atomic != 0, e_acc = a.accumulate != 0, e_simple = !a.mask && !do_drop;
-  const bool e_vec = e_simple && !e_atomic && ones_col < 0 && ((reinterpret_cast<uintptr_t>(e_C) & 15) == 0) &&
+  const bool mask_vec = !a.mask || (((reinterpret_cast<uintptr_t>(a.mask) & 15) == 0) && ((a.ldmask & 3) == 0));
+  const bool e_vec = !e_atomic && ones_col < 0 && mask_vec && ((reinterpret_cast<uintptr_t>(e_C) & 15) == 0) &&
                      ((e_ldc & 3) == 0) && ((n0 & 3) == 0);
   const int quad = warp & 3, half = warp >> 2;
   const int cbeg = half * (BN / nhalves), cend = cbeg + (BN / nhalves);
@@ -90,6 +91,26 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base
           if (rr < nrows) {
             float4 t = *reinterpret_cast<const float4*>(scratch + rr * TC_EPI_LD + cg * 4);
             t = act4(t, b[0], b[1], b[2], b[3], e_act);
+            if (!e_simple) {                                  // dropout and / or ReLU mask, four columns at a time
+              const int m = mbase + rr;
+              if (do_drop) {
+                const uint32_t e0 = (uint32_t)m * (uint32_t)e_N + (uint32_t)n;
+                t.x = drop_keep(sseed, e0, a.drop_p) ? t.x * keep_scale : 0.0f;
+                t.y = drop_keep(sseed, e0 + 1, a.drop_p) ? t.y * keep_scale : 0.0f;
+                t.z = drop_keep(sseed, e0 + 2, a.drop_p) ? t.z * keep_scale : 0.0f;
+                t.w = drop_keep(sseed, e0 + 3, a.drop_p) ? t.w * keep_scale : 0.0f;
+              }
+              if (a.mask) {
+                const float* mp = a.mask + (long long)m * a.ldmask + n;
+                float4 mv;
+                if (full4) mv = __ldg(reinterpret_cast<const float4*>(mp));
+                else { mv.x = __ldg(mp); mv.y = n + 1 < e_N ? __ldg(mp + 1) : 0.0f; mv.z = n + 2 < e_N ? __ldg(mp + 2) : 0.0f; mv.w = 0.0f; }
+                t.x = mv.x > 0.0f ? t.x * a.mask_scale : 0.0f;
+                t.y = mv.y > 0.0f ? t.y * a.mask_scale : 0.0f;
+                t.z = mv.z > 0.0f ? t.z * a.mask_scale : 0.0f;
+                t.w = mv.w > 0.0f ? t.w * a.mask_scale : 0.0f;
+              }
+            }
             float* cp = e_C + (long long)(mbase + rr) * e_ldc + n;
             if (full4) {
               if (e_acc) {
