@@ -131,13 +131,19 @@ def profile_primitives(trainer, reps=3):
             r = fn(*a, **k)
             e1.record()
             fl = 0.0
+            by = 0.0
             tag = name
             if name == "gemm":
                 C = a[3]
                 Kd = a[1].shape[1] if a[0] in ("nt", "nn") else a[1].shape[0]
                 fl = 2.0 * C.shape[0] * C.shape[1] * Kd
+                # algorithmic bytes of one launch: read A and B once, write C once (read it too when accumulating into a
+                # full-size C; a split-K weight gradient's C is tiny either way)
+                by = 4.0 * (a[1].numel() + a[2].numel() + C.numel() * (2 if k.get("accumulate") else 1))
                 tag = "gemm_" + a[0]
-                shapes.append(("%s %dx%dx%d%s" % (a[0], C.shape[0], C.shape[1], Kd, " acc" if k.get("accumulate") else ""), e0, e1))
+                streamed = C.shape[0] * C.shape[1] * Kd >= (1 << 20)   # the tcgen05 path (mfm_set_gemm_tc_min_work default)
+                shapes.append(("%s %dx%dx%d%s" % (a[0], C.shape[0], C.shape[1], Kd, " acc" if k.get("accumulate") else ""),
+                               e0, e1, by, streamed))
             elif name in ("lstm_fwd", "lstm_bwd"):
                 fl = sum(2.0 * c["T"] * c["B"] * 4 * c["h"] * c["h"] for c in a[0])
                 tag = name + ("_dec" if (a[0][0].get("gx_steps", 0) == 1 or a[0][0].get("dh_all") is not None) else "_enc_mfn")
@@ -147,7 +153,7 @@ def profile_primitives(trainer, reps=3):
             elif name in ("mmd_fwd", "mmd_bwd"):
                 Bn, dim = a[0].shape
                 fl = (9.0 if name == "mmd_fwd" else 8.0) * Bn * Bn * dim
-            rec.append((tag, e0, e1, fl))
+            rec.append((tag, e0, e1, fl, by))
             return r
         return inner
     names = ["gemm", "lstm_fwd", "lstm_bwd", "mfn_mem_fwd", "mfn_mem_bwd", "softmax_gate_fwd", "softmax_gate_bwd", "mmd_fwd",
@@ -168,11 +174,12 @@ def profile_primitives(trainer, reps=3):
         for _ in range(reps):
             trainer._schedule()
         torch.cuda.synchronize()
-        for tag, e0, e1, fl in rec:
-            a = agg.setdefault(tag, [0.0, 0.0, 0])
+        for tag, e0, e1, fl, by in rec:
+            a = agg.setdefault(tag, [0.0, 0.0, 0, 0.0])
             a[0] += e0.elapsed_time(e1)
             a[1] += fl
             a[2] += 1
+            a[3] += by
     finally:
         trainer.eng.use_side_stream = side
         trainer.world = world
@@ -182,11 +189,19 @@ def profile_primitives(trainer, reps=3):
             except AttributeError:
                 pass
     by_shape = {}
-    for key, e0, e1 in shapes:
-        v = by_shape.setdefault(key, [0.0, 0])
-        v[0] += e0.elapsed_time(e1) / reps
+    stream_ms, stream_bytes, stream_n = 0.0, 0.0, 0
+    for key, e0, e1, by, streamed in shapes:
+        v = by_shape.setdefault(key, [0.0, 0, by])
+        dt = e0.elapsed_time(e1)
+        v[0] += dt / reps
         v[1] += 1
-    agg["_gemm_shapes"] = {k: [round(v[0], 4), v[1] // reps] for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:40]}
+        if streamed:
+            stream_ms += dt
+            stream_bytes += by
+            stream_n += 1
+    # [total ms per step, launches per step, algorithmic bytes per launch]
+    agg["_gemm_shapes"] = {k: [round(v[0], 4), v[1] // reps, v[2]] for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:40]}
+    agg["_gemm_streamed"] = dict(ms_per_step=stream_ms / reps, bytes_per_step=stream_bytes / reps, launches_per_step=stream_n // reps)
     return agg
 
 
@@ -294,17 +309,35 @@ def main():
     if rank == 0:
         agg = profile_primitives(trainer)
         gemm_shapes = agg.pop("_gemm_shapes")
+        streamed = agg.pop("_gemm_streamed")
         tot = sum(v[0] for v in agg.values())
         kernels = {k: dict(ms_per_step=round(v[0] / 3, 4), share=round(v[0] / tot, 4), launches=v[2] // 3,
-                           tflops=(round(v[1] / (v[0] * 1e-3) / 1e12, 3) if v[1] else None)) for k, v in
+                           tflops=(round(v[1] / (v[0] * 1e-3) / 1e12, 3) if v[1] else None),
+                           gbs=(round(v[3] / (v[0] * 1e-3) / 1e9, 1) if v[3] else None)) for k, v in
                    sorted(agg.items(), key=lambda kv: -kv[1][0])}
-        top = next(iter(kernels))
-        tv = agg[top]
-        ach = tv[1] / (tv[0] * 1e-3) / 1e12 if tv[1] else 0.0
-        roof = dict(bound="tensor", kernel=top, achieved=round(ach, 3), peak=pk["bf16"], unit="TFLOP/s",
-                    frac=round(ach / pk["bf16"], 5), traffic=None, peak_source=pk["src"] + " bf16 dense (burst; kernel timed alone)",
+        # The dominant kernel is the pipelined tcgen05 GEMM (gemm_tcp_kernel: every GEMM of M*N*K >= 2^20).  It is
+        # HBM-bound by design (N, K <= 512 against T*B rows): achieved = algorithmic bytes of those launches / their
+        # CUDA-event time in one eager pass (per call: the weight pre-split kernel, when there is one, is inside the
+        # bracket); the single shape with the largest share is listed with the DRAM traffic ncu measured for it
+        # (profiles/r1_gemm_tcp_ncu.json, per launch).
+        gshare = streamed["ms_per_step"] / (tot / 3)
+        ach = streamed["bytes_per_step"] / (streamed["ms_per_step"] * 1e-3) / 1e9 if streamed["ms_per_step"] else 0.0
+        top_key = next(k for k, v in gemm_shapes.items() if max(int(t) for t in k.split()[1].split("x")[::2]) >= 4096)
+        tms, tn, tby = gemm_shapes[top_key]
+        traffic = None
+        try:
+            nj = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_tcp_ncu.json")))
+            traffic = nj.get(top_key, {}).get("dram_bytes")
+        except Exception:
+            pass
+        roof = dict(bound="hbm", kernel="gemm_tcp_kernel (pipelined tcgen05 GEMM: the %d launches/step with M*N*K >= 2^20)"
+                                        % streamed["launches_per_step"],
+                    achieved=round(ach, 1), peak=pk["hbm"], unit="GB/s", frac=round(ach / pk["hbm"], 4), traffic=traffic,
+                    peak_source=pk["src"] + " HBM copy bandwidth (MEASURED_PEAKS.json)", share_of_step_kernel_time=round(gshare, 4),
+                    top_shape=dict(shape=top_key, launches=tn, bytes_per_launch=tby, us_per_launch=round(tms / tn * 1e3, 2),
+                                   achieved=round(tby / (tms / tn * 1e-3) / 1e9, 1), traffic=traffic),
                     step_gate_gemm=dict(achieved=round(gate_fl * value / max(world, 1) / 1e12, 3), peak=pk["bf16_sustained"],
-                                        frac=round(gate_fl * value / max(world, 1) / 1e12 / pk["bf16_sustained"], 5),
+                                        unit="TFLOP/s", frac=round(gate_fl * value / max(world, 1) / 1e12 / pk["bf16_sustained"], 5),
                                         note="whole step per GPU: algorithmic gate-GEMM train FLOPs/sample (%.2f M) x samples/s "
                                              "over sustained bf16 peak" % (gate_fl / 1e6)))
     line = dict(base, value=value, ms_per_step=ms / args.steps, dtype="f32",
