@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_seq_fwd_kernel(LstmBatch bt
     if (row0 + r < B) {
       c.hs[(long long)(row0 + r) * c.ld_hs + j] = 0.0f;
       c.cs[(long long)(row0 + r) * c.ld_cs + j] = 0.0f;
+      if (c.cs_dup) c.cs_dup[(long long)(row0 + r) * c.ld_cs + j] = 0.0f;
     }
   }
   __syncthreads();
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_seq_fwd_kernel(LstmBatch bt
           float* gp = c.gates + ((long long)t * B + row) * H4 + j;
           gp[0] = ig; gp[h] = fg; gp[2 * h] = gg; gp[3 * h] = og;
           c.cs[((long long)(t + 1) * B + row) * c.ld_cs + j] = cn;
+          if (c.cs_dup) c.cs_dup[((long long)(t + 1) * B + row) * c.ld_cs + j] = cn;
           c.hs[((long long)(t + 1) * B + row) * c.ld_hs + j] = hn;
           hnxt[(rbase + r) * hp + j] = hn;
         }
@@ -204,6 +206,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_seq_bwd_kernel(LstmBatch bt
           const float tc = gate_tanh(cn);
           float dc = dcs[(rbase + r) * h + j] + dh * og * (1.0f - tc * tc);
           if (c.dc_ext) dc += __ldg(c.dc_ext + tr * c.ld_dc_ext + j);
+          if (c.dc_ext2 && t < c.T - 1) dc += __ldg(c.dc_ext2 + tr * c.ld_dc_ext + j);
           const float d_o = dh * tc * og * (1.0f - og);
           const float d_i = dc * gg * ig * (1.0f - ig);
           const float d_f = dc * cp * fg * (1.0f - fg);

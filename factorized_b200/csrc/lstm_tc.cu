@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_tc_fwd_kernel(Lstm2Batch b
     if (b < B) {
       c.hs[(long long)b * c.ld_hs + j] = 0.0f;
       c.cs[(long long)b * c.ld_cs + j] = 0.0f;
+      if (c.cs_dup) c.cs_dup[(long long)b * c.ld_cs + j] = 0.0f;
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_tc_fwd_kernel(Lstm2Batch b
           hn = og * gate_tanh(cn);
           cprev[ch][k] = cn;
           c.cs[((long long)(t + 1) * B + b) * c.ld_cs + j] = cn;
+          if (c.cs_dup) c.cs_dup[((long long)(t + 1) * B + b) * c.ld_cs + j] = cn;
           c.hs[((long long)(t + 1) * B + b) * c.ld_hs + j] = hn;
         }
         const unsigned short hb = bf16_bits(hn);
@@ -332,6 +334,7 @@ __global__ void __launch_bounds__(L2_THREADS, 1) lstm_tc_bwd_kernel(Lstm2Batch b
         if (c.dh_all) dhx[i] = __ldg(c.dh_all + tr * c.ld_dh_all + j);
         if (c.dh_last && t == T - 1) dhx[i] += __ldg(c.dh_last + (long long)b * c.ld_dh_last + j);
         if (c.dc_ext) dcx[i] = __ldg(c.dc_ext + tr * c.ld_dc_ext + j);
+        if (c.dc_ext2 && t < T - 1) dcx[i] += __ldg(c.dc_ext2 + tr * c.ld_dc_ext + j);
       }
     }
     float dh[CPT];

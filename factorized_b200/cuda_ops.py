@@ -27,7 +27,8 @@ class LstmCell(C.Structure):
                 ("gx", c_f), ("bias_rest", c_f), ("W", c_f),
                 ("hs", c_f), ("ld_hs", LL), ("cs", c_f), ("ld_cs", LL), ("gates", c_f),
                 ("dh_all", c_f), ("ld_dh_all", LL), ("dh_last", c_f), ("ld_dh_last", LL),
-                ("dc_ext", c_f), ("ld_dc_ext", LL), ("dG", c_f), ("dc_scratch", c_f)]
+                ("dc_ext", c_f), ("ld_dc_ext", LL), ("dG", c_f), ("dc_scratch", c_f),
+                ("cs_dup", c_f), ("dc_ext2", c_f)]
 
 
 class MemArgs(C.Structure):
@@ -255,6 +256,11 @@ class CudaOps:
                 if (hr, hc) != ((c["T"] + 1) * c["B"], c["h"]):
                     raise MfmCudaError("lstm hs must be [(T+1)*B,h]")
                 s.hs, s.ld_hs = phs, ldhs
+                if c.get("cs_dup") is not None:
+                    p_, r_, c_, l_ = _mat(c["cs_dup"], "lstm cs_dup")
+                    if (r_, c_) != ((c["T"] + 1) * c["B"], c["h"]) or l_ != ldcs:
+                        raise MfmCudaError("lstm cs_dup must be [(T+1)*B,h] with the leading dimension of cs")
+                    s.cs_dup = p_
             else:
                 pd, dr, dc_, ldd = _mat(c["dG"], "lstm dG")
                 if (dr, dc_) != (c["T"] * c["B"], h4) or ldd != h4:
@@ -280,6 +286,11 @@ class CudaOps:
                     if (r_, c_) != (c["T"] * c["B"], c["h"]):
                         raise MfmCudaError("lstm dc_ext shape")
                     s.dc_ext, s.ld_dc_ext = p_, l_
+                if c.get("dc_ext2") is not None and c["T"] > 1:
+                    p_, r_, c_, l_ = _mat(c["dc_ext2"], "lstm dc_ext2")
+                    if c.get("dc_ext") is None or (r_, c_) != ((c["T"] - 1) * c["B"], c["h"]) or l_ != s.ld_dc_ext:
+                        raise MfmCudaError("lstm dc_ext2 must be [(T-1)*B,h] with the leading dimension of dc_ext")
+                    s.dc_ext2 = p_
         return arr
 
     def lstm_fwd(self, cells):

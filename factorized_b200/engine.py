@@ -18,6 +18,7 @@ state histories have T+1 blocks with block 0 the zero initial state.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -83,6 +84,7 @@ class Engine:
         self._side_used = False
         self._aux_stream = None
         self._aux_used = False
+        self._pool = []                  # streams for _par branches
         self.defer_mmd_join = False      # the fused trainer joins the MMD stream in losses() instead of at the end of forward
         # loss_buf: 0 disc, 1..3 mse_l/a/v, 4..7 mmd per latent (unweighted), 8 total (weighted)
 
@@ -138,7 +140,14 @@ class Engine:
 
         # (2) six recurrences in one launch: h W_hh^T + G_x[t] -> gates -> (h, c)
         Hall = buf("Hall", (T + 1) * B, H)
-        Call = buf("Call", (T + 1) * B, H)
+        # The attention reads cat(c_{t-1}, c_t) (:171-173).  The cell histories are written straight into that layout:
+        # row block i of CS2 = [ c of history block i-1 | c of history block i ]; the kernels write every c block to the
+        # right half of its own row block (cs) and to the left half of the next one (cs_dup).  cStar is then the
+        # contiguous view CS2[B : (T+1)B] -- no copy.
+        CS2 = buf("CS2", (T + 2) * B, 2 * H)
+        Call = CS2[:(T + 1) * B, H:]
+        Cdup = CS2[B:, :H]
+        self.ws_views = dict(Call=Call)
         cells = []
         for m, tag in enumerate(TAGS if full else ""):
             cells.append(dict(T=T, B=B, h=dm.z[m], gx=self.ws["GxE%d" % m], gx_steps=T, bias_rest=None,
@@ -149,7 +158,7 @@ class Engine:
             o = dm.hoff[m]
             cells.append(dict(T=T, B=B, h=dm.hm[m], gx=self.ws["GxN%d" % m], gx_steps=T, bias_rest=None,
                               W=P[self.pre + "lstm_%s.weight_hh" % tag],
-                              hs=Hall[:, o:o + dm.hm[m]], cs=Call[:, o:o + dm.hm[m]],
+                              hs=Hall[:, o:o + dm.hm[m]], cs=Call[:, o:o + dm.hm[m]], cs_dup=Cdup[:, o:o + dm.hm[m]],
                               gates=buf("gatesN%d" % m, TB, 4 * dm.hm[m])))
         ops.lstm_fwd(cells)
 
@@ -163,9 +172,8 @@ class Engine:
 
         # (4) MFN attention for all T at once (:171-176); only gamma*_fc1's memory columns are sequential
         pre = self.pre
-        cStar = buf("cStar", TB, 2 * H)
-        ops.copy2d(Call[:TB], cStar[:, :H])
-        ops.copy2d(Call[B:], cStar[:, H:])
+        cStar = CS2[B:(T + 1) * B]
+        self.ws_views["cStar"] = cStar
         H1 = buf("H1", TB, dm.a1)
         ops.gemm("nt", cStar, P[pre + "att1_fc1.weight"], H1, bias=P[pre + "att1_fc1.bias"], act=ACT_RELU,
                  drop=drop(dm.p_att1, SITE_ATT1), rng=rng)
@@ -231,54 +239,62 @@ class Engine:
                 ops.gemm("nt", gk, gk, Kgg)
                 ops.mmd_kexp(Kgg, ng, ng, dim, inv_bb, slot)
 
-        # (8) factor MLPs (:539-542) written straight into the decoder inputs cat(fy, f_m) (:544-546)
+        # (8) factor MLPs (:539-542) written straight into the decoder inputs cat(fy, f_m) (:544-546).
+        #     The four MLPs, and below the three decoders, are independent of each other: branches run side by side.
         FY = buf("FY", B, dm.fy)
         F1y = buf("F1y", B, dm.fy)
-        ops.gemm("nt", ZY, P["zy_to_fy_fc1.weight"], F1y, bias=P["zy_to_fy_fc1.bias"], act=ACT_RELU,
-                 drop=drop(dm.p_fy, SITE_FY), rng=rng)
-        ops.gemm("nt", F1y, P["zy_to_fy_fc2.weight"], FY, bias=P["zy_to_fy_fc2.bias"], act=ACT_RELU)
-        EMB = []
-        for m, tag in enumerate(TAGS):
-            nm = "z%s_to_f%s" % (tag, tag)
-            F1 = buf("F1_%d" % m, B, dm.f[m])
-            emb = buf("EMB%d" % m, B, dm.hd[m])
-            ops.gemm("nt", Z[m], P[nm + "_fc1.weight"], F1, bias=P[nm + "_fc1.bias"], act=ACT_RELU,
-                     drop=drop(dm.p_f[m], SITE_FL + m), rng=rng)
-            ops.gemm("nt", F1, P[nm + "_fc2.weight"], emb[:, dm.fy:], bias=P[nm + "_fc2.bias"], act=ACT_RELU)
-            ops.copy2d(FY, emb[:, :dm.fy])
-            EMB.append(emb)
+        EMB = [buf("EMB%d" % m, B, dm.hd[m]) for m in range(3)]
+        F1s = [buf("F1_%d" % m, B, dm.f[m]) for m in range(3)]
+
+        def mlp_y():
+            ops.gemm("nt", ZY, P["zy_to_fy_fc1.weight"], F1y, bias=P["zy_to_fy_fc1.bias"], act=ACT_RELU,
+                     drop=drop(dm.p_fy, SITE_FY), rng=rng)
+            ops.gemm("nt", F1y, P["zy_to_fy_fc2.weight"], FY, bias=P["zy_to_fy_fc2.bias"], act=ACT_RELU)
+
+        def mlp_m(m):
+            def run():
+                nm = "z%s_to_f%s" % (TAGS[m], TAGS[m])
+                ops.gemm("nt", Z[m], P[nm + "_fc1.weight"], F1s[m], bias=P[nm + "_fc1.bias"], act=ACT_RELU,
+                         drop=drop(dm.p_f[m], SITE_FL + m), rng=rng)
+                ops.gemm("nt", F1s[m], P[nm + "_fc2.weight"], EMB[m][:, dm.fy:], bias=P[nm + "_fc2.bias"], act=ACT_RELU)
+                # the decoder's merged recurrent weight depends on the parameters only: it rides along here
+                d_ = "decoder_%s.lstm" % TAGS[m]
+                hd = dm.hd[m]
+                ops.add(P[d_ + ".weight_ih"], P[d_ + ".weight_hh"], buf("Wm%d" % m, 4 * hd, hd))
+                ops.add(P[d_ + ".bias_ih"].view(1, -1), P[d_ + ".bias_hh"].view(1, -1), buf("bsumD%d" % m, 1, 4 * hd))
+            return run
+
+        self._par([mlp_y, mlp_m(0), mlp_m(1), mlp_m(2)])
 
         # (9) decoders (:72-91): step 0 eats the embedding; for t>=1 the input IS h_{t-1}, so the two
-        #     gate GEMMs collapse into one with W_ih + W_hh
-        cells = []
-        for m, tag in enumerate(TAGS):
-            d_ = "decoder_%s.lstm" % tag
-            hd = dm.hd[m]
-            G0 = buf("G0_%d" % m, B, 4 * hd)
-            ops.gemm("nt", EMB[m], P[d_ + ".weight_ih"], G0, bias=P[d_ + ".bias_ih"], bias2=P[d_ + ".bias_hh"])
-            Wm = buf("Wm%d" % m, 4 * hd, hd)
-            ops.add(P[d_ + ".weight_ih"], P[d_ + ".weight_hh"], Wm)
-            bs = buf("bsumD%d" % m, 1, 4 * hd)
-            ops.add(P[d_ + ".bias_ih"].view(1, -1), P[d_ + ".bias_hh"].view(1, -1), bs)
-            cells.append(dict(T=T, B=B, h=hd, gx=G0, gx_steps=1, bias_rest=bs.view(-1), W=Wm,
-                              hs=buf("hsD%d" % m, (T + 1) * B, hd), cs=buf("csD%d" % m, (T + 1) * B, hd),
-                              gates=buf("gatesD%d" % m, TB, 4 * hd)))
-        ops.lstm_fwd(cells)
-
-        # (10) reconstructions  x_hat = fc1(all hiddens)  (:88-90)
-        Xhat = []
-        for m, tag in enumerate(TAGS):
-            xh = buf("Xhat%d" % m, TB, dm.d[m])
-            ops.gemm("nt", self.ws["hsD%d" % m][B:], P["decoder_%s.fc1.weight" % tag], xh,
-                     bias=P["decoder_%s.fc1.bias" % tag])
-            Xhat.append(xh)
-
-        # (11) discriminative head (:552)
+        #     gate GEMMs collapse into one with W_ih + W_hh.   (10) reconstructions x_hat = fc1(all hiddens) (:88-90)
+        # (11) discriminative head (:552) -- depends on fy only, a fifth branch
+        Xhat = [buf("Xhat%d" % m, TB, dm.d[m]) for m in range(3)]
         Y1 = buf("Y1", B, dm.fy)
         Yhat = buf("Yhat", B, dm.out)
-        ops.gemm("nt", FY, P["fy_to_y_fc1.weight"], Y1, bias=P["fy_to_y_fc1.bias"], act=ACT_RELU,
-                 drop=drop(dm.p_y, SITE_Y), rng=rng)
-        ops.gemm("nt", Y1, P["fy_to_y_fc2.weight"], Yhat, bias=P["fy_to_y_fc2.bias"])
+
+        def decoder(m):
+            def run():
+                tag = TAGS[m]
+                d_ = "decoder_%s.lstm" % tag
+                hd = dm.hd[m]
+                ops.copy2d(FY, EMB[m][:, :dm.fy])
+                G0 = buf("G0_%d" % m, B, 4 * hd)
+                ops.gemm("nt", EMB[m], P[d_ + ".weight_ih"], G0, bias=P[d_ + ".bias_ih"], bias2=P[d_ + ".bias_hh"])
+                cell = dict(T=T, B=B, h=hd, gx=G0, gx_steps=1, bias_rest=self.ws["bsumD%d" % m].view(-1), W=self.ws["Wm%d" % m],
+                            hs=buf("hsD%d" % m, (T + 1) * B, hd), cs=buf("csD%d" % m, (T + 1) * B, hd),
+                            gates=buf("gatesD%d" % m, TB, 4 * hd))
+                ops.lstm_fwd([cell])
+                ops.gemm("nt", self.ws["hsD%d" % m][B:], P["decoder_%s.fc1.weight" % tag], Xhat[m],
+                         bias=P["decoder_%s.fc1.bias" % tag])
+            return run
+
+        def head():
+            ops.gemm("nt", FY, P["fy_to_y_fc1.weight"], Y1, bias=P["fy_to_y_fc1.bias"], act=ACT_RELU,
+                     drop=drop(dm.p_y, SITE_Y), rng=rng)
+            ops.gemm("nt", Y1, P["fy_to_y_fc2.weight"], Yhat, bias=P["fy_to_y_fc2.bias"])
+
+        self._par([decoder(0), decoder(1), decoder(2), head])
         if not self.defer_mmd_join:
             self._join_aux()
         return dict(x_l_hat=Xhat[0], x_a_hat=Xhat[1], x_v_hat=Xhat[2], y_hat=Yhat,
@@ -310,7 +326,23 @@ class Engine:
         return dX, dY
 
     # -- weight-gradient GEMMs run on a side stream ---------------------------------
-    def _wgrad_gemm(self, dY, A, Gout, **kw):
+    def _on_side(self, key, fn):
+        """Run fn on the side stream selected by key, ordered after everything issued so far on the current stream."""
+        if self.device.type != "cuda" or not self.use_side_stream:
+            fn()
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+        st = self._side[(key >> 8) % len(self._side)]
+        ev = torch.cuda.Event()
+        ev.record(main)
+        st.wait_event(ev)
+        with torch.cuda.stream(st):
+            fn()
+        self._side_used = True
+
+    def _wgrad_gemm(self, dY, A, Gout, stream_key=None, **kw):
         """dW += dY^T A (TN GEMM, optionally with the fused bias gradient).  Weight gradients only read stashes and
         write the flat gradient buffer, so they do not belong on the critical path of the backward chain: they are
         issued on a side stream that forks from the main stream right after dY is produced and joins before the
@@ -323,7 +355,9 @@ class Engine:
         if self._side is None:
             self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
         # independent weight gradients also overlap each other; two GEMMs into the same tensor share a stream
-        st = self._side[(Gout.data_ptr() >> 8) % len(self._side)]
+        if os.environ.get("MFM_SKIP_WGRAD"):       # timing experiment only: how much of the step is weight gradients?
+            return
+        st = self._side[((stream_key if stream_key is not None else Gout.data_ptr()) >> 8) % len(self._side)]
         ev = torch.cuda.Event()
         ev.record(main)
         st.wait_event(ev)
@@ -337,6 +371,33 @@ class Engine:
             for st in self._side:
                 main.wait_stream(st)
             self._side_used = False
+
+    # -- independent small branches run side by side -------------------------------------
+    def _par(self, thunks):
+        """Run independent branches concurrently: branch 0 stays on the current stream, the others fork onto pool
+        streams and are joined before returning.  The tails of forward and backward are dozens of batch-row-sized
+        kernels (factor MLPs, heads, decoder input projections) of a few CTAs each; serialised they cost ~10 us apiece
+        on the critical path, side by side they cost one chain.  Sequential on the CPU test double."""
+        thunks = [t for t in thunks if t is not None]
+        if self.device.type != "cuda" or not self.use_side_stream or len(thunks) <= 1:
+            for t in thunks:
+                t()
+            return
+        main = torch.cuda.current_stream(self.device)
+        while len(self._pool) < len(thunks) - 1:
+            self._pool.append(torch.cuda.Stream(device=self.device))
+        ev = torch.cuda.Event()
+        ev.record(main)
+        used = []
+        for i, t in enumerate(thunks[1:]):
+            st = self._pool[i]
+            st.wait_event(ev)
+            with torch.cuda.stream(st):
+                t()
+            used.append(st)
+        thunks[0]()
+        for st in used:
+            main.wait_stream(st)
 
     # -- the MMD statistic is off the critical path: it runs on its own stream -------
     class _Aux:
@@ -425,39 +486,13 @@ class Engine:
                 ops.zero(dmmd[k])
                 ops.mmd_combine(zk, rc[:B], rc[B:], t1, t2, mmd_scale, dmmd[k], mmd_scale_dev)
 
-        # (11') discriminative head
+        # (11') head, (10') + (9') + (8') one chain per decoder: reconstruction head, recurrence, weight gradients, embedding,
+        #       factor MLP.  The four chains touch disjoint buffers (the decoders' shares of dFY are added after the join).
         dY1 = buf("dY1", B, dm.fy)
-        lin_bwd(dYhat, ws["Y1"], "fy_to_y_fc2", dY1, mask=ws["Y1"], mask_scale=relu_scale(dm.p_y))
         dFY = buf("dFY", B, dm.fy)
-        lin_bwd(dY1, ws["FY"], "fy_to_y_fc1", dFY)
-
-        # (10') + (9') decoders
-        cells = []
-        for m, tag in enumerate(TAGS):
-            hd = dm.hd[m]
-            dHd = buf("dHd%d" % m, TB, hd)
-            lin_bwd(dXhat[m], ws["hsD%d" % m][B:], "decoder_%s.fc1" % tag, dHd)
-            cells.append(dict(T=T, B=B, h=hd, gates=ws["gatesD%d" % m], cs=ws["csD%d" % m], W=ws["Wm%d" % m],
-                              dh_all=dHd, dh_last=None, dc_ext=None, dG=buf("dGD%d" % m, TB, 4 * hd),
-                              dc_scratch=buf("dcSD%d" % m, B, hd)))
-        ops.lstm_bwd(cells)
-        dEMB = []
-        for m, tag in enumerate(TAGS):
-            d_ = "decoder_%s.lstm" % tag
-            dG = ws["dGD%d" % m]
-            hprev = ws["hsD%d" % m][:TB]                    # h_{t-1}; block 0 is the zero state
-            self._wgrad_gemm( dG, hprev, G[d_ + ".weight_hh"], accumulate=True, colsum_out=G[d_ + ".bias_hh"])
-            self._wgrad_gemm( dG, hprev, G[d_ + ".weight_ih"], accumulate=True,        # input == h_{t-1} for t >= 1 (:85)
-                     colsum_out=G[d_ + ".bias_ih"])
-            wgrad(dG[:B], ws["EMB%d" % m], d_ + ".weight_ih")  # step 0 input is the embedding (:83)
-            de = buf("dEMB%d" % m, B, dm.hd[m])
-            ops.gemm("nn", dG[:B], P[d_ + ".weight_ih"], de)
-            ops.copy2d(de[:, :dm.fy], dFY, accumulate=True)
-            dEMB.append(de)
-
-        # (8') factor MLPs;  dZ[k] receives the decoder-side gradient of each latent
         dZ = [buf("dZ%d" % m, B, dm.z[m]) for m in range(3)]
         dZY = buf("dZY", B, dm.zy)
+        dEMB = [buf("dEMB%d" % m, B, dm.hd[m]) for m in range(3)]
 
         def mlp2_bwd(df, f, F1, zin, nm, p, dz):
             dpre = buf("dpre_" + nm, f.shape[0], f.shape[1])
@@ -466,10 +501,38 @@ class Engine:
             lin_bwd(dpre, F1, nm + "_fc2", dF1, mask=F1, mask_scale=relu_scale(p))
             lin_bwd(dF1, zin, nm + "_fc1", dz)
 
+        def head_bwd():
+            lin_bwd(dYhat, ws["Y1"], "fy_to_y_fc2", dY1, mask=ws["Y1"], mask_scale=relu_scale(dm.p_y))
+            lin_bwd(dY1, ws["FY"], "fy_to_y_fc1", dFY)
+
+        def decoder_bwd(m):
+            def run():
+                tag = TAGS[m]
+                hd = dm.hd[m]
+                d_ = "decoder_%s.lstm" % tag
+                dHd = buf("dHd%d" % m, TB, hd)
+                lin_bwd(dXhat[m], ws["hsD%d" % m][B:], "decoder_%s.fc1" % tag, dHd)
+                dG = buf("dGD%d" % m, TB, 4 * hd)
+                ops.lstm_bwd([dict(T=T, B=B, h=hd, gates=ws["gatesD%d" % m], cs=ws["csD%d" % m], W=ws["Wm%d" % m],
+                                   dh_all=dHd, dh_last=None, dc_ext=None, dG=dG, dc_scratch=buf("dcSD%d" % m, B, hd))])
+                hprev = ws["hsD%d" % m][:TB]                    # h_{t-1}; block 0 is the zero state
+                # for t >= 1 the input IS h_{t-1} (:85): dW_ih and dW_hh share the product dG^T h_prev (and the bias
+                # gradients are the same column sums), so it is computed once and added to the second gradient; step 0's
+                # input is the embedding (:83).  All three updates of dW_ih stay on one side stream (keyed by its pointer).
+                key = G[d_ + ".weight_ih"].data_ptr()
+                self._wgrad_gemm(dG, hprev, G[d_ + ".weight_hh"], accumulate=True, colsum_out=G[d_ + ".bias_hh"], stream_key=key)
+                self._on_side(key, lambda: (ops.copy2d(G[d_ + ".weight_hh"], G[d_ + ".weight_ih"], accumulate=True),
+                                            ops.copy2d(G[d_ + ".bias_hh"].view(1, -1), G[d_ + ".bias_ih"].view(1, -1), accumulate=True)))
+                self._wgrad_gemm(dG[:B], ws["EMB%d" % m], G[d_ + ".weight_ih"], accumulate=True, stream_key=key)
+                ops.gemm("nn", dG[:B], P[d_ + ".weight_ih"], dEMB[m])
+                mlp2_bwd(dEMB[m][:, dm.fy:], ws["EMB%d" % m][:, dm.fy:], ws["F1_%d" % m], ws["Z%d" % m],
+                         "z%s_to_f%s" % (tag, tag), dm.p_f[m], dZ[m])
+            return run
+
+        self._par([decoder_bwd(0), decoder_bwd(1), decoder_bwd(2), head_bwd])
+        for m in range(3):
+            ops.copy2d(dEMB[m][:, :dm.fy], dFY, accumulate=True)
         mlp2_bwd(dFY, ws["FY"], ws["F1y"], ws["ZY"], "zy_to_fy", dm.p_fy, dZY)
-        for m, tag in enumerate(TAGS):
-            mlp2_bwd(dEMB[m][:, dm.fy:], ws["EMB%d" % m][:, dm.fy:], ws["F1_%d" % m], ws["Z%d" % m],
-                     "z%s_to_f%s" % (tag, tag), dm.p_f[m], dZ[m])
 
         self._join_aux()
         dlat = dZ + [dZY]
@@ -479,7 +542,7 @@ class Engine:
         # (6') last_to_zy_fc1 over cat(h_T, mem_T)
         Wzy = P["last_to_zy_fc1.weight"]
         Gzy = G["last_to_zy_fc1.weight"]
-        Hall, Call, mems = ws["Hall"], ws["Call"], ws["mems"]
+        Hall, mems = ws["Hall"], ws["mems"]
         self._wgrad_gemm( dZY, Hall[TB:], Gzy[:, :H], accumulate=True)
         self._wgrad_gemm( dZY, mems[TB:], Gzy[:, H:], accumulate=True)
         bgrad(dZY, "last_to_zy_fc1.bias")
@@ -504,7 +567,7 @@ class Engine:
         dm, ops, buf, ws = self.dm, self.ops, self.buf, self.ws
         T, B, H, mem = dm.T, dm.B, dm.H, dm.mem
         TB = T * B
-        Hall, Call, mems = ws["Hall"], ws["Call"], ws["mems"]
+        Hall, Call, mems = ws["Hall"], self.ws_views["Call"], ws["mems"]
 
         # (5') memory recurrence, reversed
         pre = self.pre
@@ -523,7 +586,7 @@ class Engine:
             dmem_last=dmemT, dU1=dU1, dU2=dU2, dP1=dP1, dP2=dP2, dPc=dPc))
         self._wgrad_gemm( dP1, ws["U1"], G[pre + "gamma1_fc2.weight"], accumulate=True, colsum_out=G[pre + "gamma1_fc2.bias"])
         self._wgrad_gemm( dP2, ws["U2"], G[pre + "gamma2_fc2.weight"], accumulate=True, colsum_out=G[pre + "gamma2_fc2.bias"])
-        Attended, cStar, Att = ws["Attended"], ws["cStar"], ws["Att"]
+        Attended, cStar, Att = ws["Attended"], self.ws_views["cStar"], ws["Att"]
         dAtt = buf("dAttended", TB, 2 * H)
         for (dU, nm) in ((dU1, "gamma1_fc1"), (dU2, "gamma2_fc1")):
             Gw = G[pre + nm + ".weight"]
@@ -544,7 +607,9 @@ class Engine:
         dH1 = buf("dH1", TB, dm.a1)
         lin_bwd(dL, ws["H1"], pre + "att1_fc2", dH1, mask=ws["H1"], mask_scale=relu_scale(dm.p_att1))
         lin_bwd(dH1, cStar, pre + "att1_fc1", dcStar, accumulate=True)
-        # c_t enters cStar twice: as "new" at step t and as "prev" at step t+1
+        # c_t enters cStar twice: as "new" at step t and as "prev" at step t+1.  (The recurrence kernel can add the two
+        # halves itself -- dc_ext2 -- but reading the 2H-wide gradient inside the latency-bound backward recurrence
+        # measured slower than this one compact gather pass.)
         dCext = buf("dCext", TB, H)                          # row block t = grad wrt c of cell step t
         ops.copy2d(dcStar[:, H:], dCext)
         if T > 1:

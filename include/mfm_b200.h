@@ -98,6 +98,12 @@ typedef struct mfm_lstm_cell {
   float* dG;                /* [T*B, 4h] contiguous: dL/d(pre-activation gates)                      */
   float* dc_scratch;        /* [B, h] contiguous workspace (carried dc) for the tensor-core backward;
                                NULL selects the CUDA-core kernel                                      */
+  /* The MFN attention reads cat(c_{t-1}, c_t) (mfm_model.py:171-173).  Instead of copying the cell history into
+   * that layout, the forward kernel writes every c block a second time (cs_dup, leading dimension ld_cs) and the
+   * backward kernel adds a second external cell gradient: dc_t += dc_ext2[t] for t < T-1 (ld_dc_ext), i.e. the
+   * "previous c" half of the next step's concatenation.  Both may be NULL. */
+  float* cs_dup;            /* forward only:  [(T+1)*B, h], receives the same blocks as cs           */
+  const float* dc_ext2;     /* backward only: [(T-1)*B, h]                                            */
 } mfm_lstm_cell;
 #define MFM_MAX_CELLS 8
 /* all cells of one call run concurrently (blockIdx.y = cell) */

@@ -84,6 +84,9 @@ class EmuOps:
             hs, cs, gates, W = c["hs"], c["cs"], c["gates"], c["W"]
             hs[:B] = 0
             cs[:B] = 0
+            dup = c.get("cs_dup")
+            if dup is not None:
+                dup[:B] = 0
             for t in range(T):
                 hp, cp = hs[t * B:(t + 1) * B], cs[t * B:(t + 1) * B]
                 pre = hp @ W.t()
@@ -100,6 +103,8 @@ class EmuOps:
                 gates[t * B:(t + 1) * B] = torch.cat([i, f, g, o], 1)
                 hs[(t + 1) * B:(t + 2) * B] = hn
                 cs[(t + 1) * B:(t + 2) * B] = cn
+                if dup is not None:
+                    dup[(t + 1) * B:(t + 2) * B] = cn
 
     def lstm_bwd(self, cells):
         self.launches += 1
@@ -121,6 +126,8 @@ class EmuOps:
                 dc = dc + dh * o * (1 - tc * tc)
                 if c["dc_ext"] is not None:
                     dc = dc + c["dc_ext"][r]
+                if c.get("dc_ext2") is not None and t < T - 1:
+                    dc = dc + c["dc_ext2"][r]
                 d_o = dh * tc * o * (1 - o)
                 d_i = dc * g * i * (1 - i)
                 d_f = dc * cprev * f * (1 - f)

@@ -124,6 +124,34 @@ def test_lstm_fwd_bwd(ops, T, B, h, gx_steps, ld_extra):
         assert rel_l2(cbg["dG"], cb["dG"]) < 1e-4, (variant, T, B, h, rel_l2(cbg["dG"], cb["dG"]))
 
 
+@pytest.mark.parametrize("T,B,h", [(5, 40, 24), (3, 33, 88), (1, 8, 16)])
+def test_lstm_duplicate_cell_history_and_second_cell_gradient(ops, T, B, h):
+    """cs_dup (forward): every c block is written twice, here into the cat(c_{t-1}, c_t) layout the MFN attention reads;
+    dc_ext2 (backward): the second external cell gradient, added for t < T-1."""
+    c = _lstm_case(T, B, h, T, seed=3 * T + B + h)
+    cg = _to_dev({k: v for k, v in c.items() if k not in ("hs", "cs")})
+    cg["hs"] = torch.zeros((T + 1) * B, h).cuda()
+    CS2 = torch.full(((T + 2) * B, 2 * h), 7.0).cuda()
+    cg["cs"], cg["cs_dup"] = CS2[:(T + 1) * B, h:], CS2[B:, :h]
+    EmuOps().lstm_fwd([c])
+    ops.lstm_fwd([cg])
+    torch.cuda.synchronize()
+    assert rel_l2(cg["cs"], c["cs"]) < 1e-4 and rel_l2(cg["cs_dup"], c["cs"]) < 1e-4
+    cstar = CS2[B:(T + 1) * B].cpu()                              # row block t = [c_{t-1} | c_t]
+    assert rel_l2(cstar[:, :h], c["cs"][:T * B]) < 1e-4 and rel_l2(cstar[:, h:], c["cs"][B:]) < 1e-4
+    dcs = g(T * B, 2 * h, seed=21)                                  # gradient of that concatenation
+    cb = dict(T=T, B=B, h=h, gates=c["gates"], cs=c["cs"], W=c["W"], dh_all=None, dh_last=g(B, h, seed=12),
+              dc_ext=dcs[:, h:], dc_ext2=(dcs[B:, :h] if T > 1 else None), dG=torch.zeros(T * B, 4 * h),
+              dc_scratch=torch.zeros(B, h))
+    dcs_dev = dcs.cuda()
+    cbg = _to_dev({k: v for k, v in cb.items() if k not in ("dc_ext", "dc_ext2")})
+    cbg["dc_ext"], cbg["dc_ext2"] = dcs_dev[:, h:], (dcs_dev[B:, :h] if T > 1 else None)
+    EmuOps().lstm_bwd([cb])
+    ops.lstm_bwd([cbg])
+    torch.cuda.synchronize()
+    assert rel_l2(cbg["dG"], cb["dG"]) < 1e-4
+
+
 def test_lstm_multi_cell_launch(ops):
     cells = [_lstm_case(6, 40, h, gs, seed=h) for h, gs in ((32, 6), (8, 6), (80, 6), (24, 1))]
     dev = [_to_dev(c) for c in cells]
