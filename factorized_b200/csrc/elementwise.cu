@@ -61,13 +61,18 @@ __global__ void __launch_bounds__(256) mse_kernel(int M, int N, const float* __r
                                                    float grad_scale, float* __restrict__ slot,
                                                    float* __restrict__ dxh, long long lddx) {
   __shared__ float red[32];
-  const long long total = (long long)M * N;
   float s = 0.0f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int m = (int)(i / N), n = (int)(i - (long long)m * N);
-    const float r = xh[(long long)m * ldxh + n] - __ldg(x + (long long)m * ldx + n);
-    s = fmaf(r, r, s);
-    if (dxh) dxh[(long long)m * lddx + n] = grad_scale * r;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // one warp per row: coalesced, no index division
+  for (long long m = (long long)blockIdx.x * 8 + ty; m < M; m += (long long)gridDim.x * 8) {
+    const float* xr = xh + m * ldxh;
+    const float* tr = x + m * ldx;
+    float* dr = dxh ? dxh + m * lddx : nullptr;
+#pragma unroll 4
+    for (int n = tx; n < N; n += 32) {
+      const float r = xr[n] - __ldg(tr + n);
+      s = fmaf(r, r, s);
+      if (dr) dr[n] = grad_scale * r;
+    }
   }
   const float tot = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(slot, tot * loss_scale);
@@ -197,7 +202,7 @@ extern "C" int mfm_mse_fwd_bwd(int M, int N, const float* xhat, long long ldxh, 
                                float loss_scale, float grad_scale, float* slot, float* dxhat, long long lddx,
                                void* stream) {
   MFM_REQUIRE(M > 0 && N > 0 && xhat && x && slot);
-  mse_kernel<<<grid_for((long long)M * N, 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(M, N, xhat, ldxh, x, ldx, loss_scale,
+  mse_kernel<<<((M + 7) / 8 < 148 * 8 ? (M + 7) / 8 : 148 * 8), 256, 0, (cudaStream_t)stream>>>(M, N, xhat, ldxh, x, ldx, loss_scale,
                                                                                        grad_scale, slot, dxhat, lddx);
   MFM_LAUNCH_CHECK();
   return MFM_OK;

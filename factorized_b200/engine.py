@@ -118,25 +118,27 @@ class Engine:
         X2 = x.view(TB, dm.D)
         # (0) split x into per-modality matrices whose rows start 16 B aligned (leading dimension padded to a
         #     multiple of 4 floats): the reference layout concatenates the modalities on the last axis (:523-525), row
-        #     pitch 4*D bytes (1300 B on MOSI), which the cp.async-staged GEMM cannot stream.  One pass over x; the
+        #     pitch 4*D bytes (1300 B on MOSI), which TMA cannot describe.  One pass over x; the
         #     nine GEMM reads and three MSE reads of x that follow use the aligned copies.
-        xs = []
-        for m in range(3):
-            xp = buf("Xp%d" % m, TB, (dm.d[m] + 3) // 4 * 4)
-            ops.copy2d(X2[:, dm.off[m]:dm.off[m] + dm.d[m]], xp[:, :dm.d[m]])
-            xs.append(xp[:, :dm.d[m]])
+        full = not self.mfn_only
+        xs = [buf("Xp%d" % m, TB, (dm.d[m] + 3) // 4 * 4)[:, :dm.d[m]] for m in range(3)]
         self.xs = xs
         drop = (lambda p, site: (p, site) if (train and p > 0.0) else None)
 
-        # (1) hoisted input projections  G_x = X W_ih^T + b_ih + b_hh   (encoders :56, MFN :167-169)
-        full = not self.mfn_only
-        for m, tag in enumerate(TAGS):
-            e, n = "encoder_%s.lstm" % tag, self.pre + "lstm_%s" % tag
-            if full:
-                ops.gemm("nt", xs[m], P[e + ".weight_ih"], buf("GxE%d" % m, TB, 4 * dm.z[m]),
-                         bias=P[e + ".bias_ih"], bias2=P[e + ".bias_hh"])
-            ops.gemm("nt", xs[m], P[n + ".weight_ih"], buf("GxN%d" % m, TB, 4 * dm.hm[m]),
-                     bias=P[n + ".bias_ih"], bias2=P[n + ".bias_hh"])
+        # (1) hoisted input projections  G_x = X W_ih^T + b_ih + b_hh   (encoders :56, MFN :167-169); one branch per modality
+        def project(m):
+            def run():
+                tag = TAGS[m]
+                e, n = "encoder_%s.lstm" % tag, self.pre + "lstm_%s" % tag
+                ops.copy2d(X2[:, dm.off[m]:dm.off[m] + dm.d[m]], xs[m])
+                if full:
+                    ops.gemm("nt", xs[m], P[e + ".weight_ih"], buf("GxE%d" % m, TB, 4 * dm.z[m]),
+                             bias=P[e + ".bias_ih"], bias2=P[e + ".bias_hh"])
+                ops.gemm("nt", xs[m], P[n + ".weight_ih"], buf("GxN%d" % m, TB, 4 * dm.hm[m]),
+                         bias=P[n + ".bias_ih"], bias2=P[n + ".bias_hh"])
+            return run
+
+        self._par([project(0), project(1), project(2)])
 
         # (2) six recurrences in one launch: h W_hh^T + G_x[t] -> gates -> (h, c)
         Hall = buf("Hall", (T + 1) * B, H)
@@ -182,15 +184,19 @@ class Engine:
         Attended = buf("Attended", TB, 2 * H)
         ops.softmax_gate_fwd(Att, cStar, Attended)
         H2 = buf("H2", TB, dm.a2)
-        ops.gemm("nt", Attended, P[pre + "att2_fc1.weight"], H2, bias=P[pre + "att2_fc1.bias"], act=ACT_RELU,
-                 drop=drop(dm.p_att2, SITE_ATT2), rng=rng)
         cHat = buf("cHat", TB, mem)
-        ops.gemm("nt", H2, P[pre + "att2_fc2.weight"], cHat, bias=P[pre + "att2_fc2.bias"], act=ACT_TANH)
         G1pre = buf("G1pre", TB, dm.g1)
         G2pre = buf("G2pre", TB, dm.g2)
         Wg1, Wg2 = P[pre + "gamma1_fc1.weight"], P[pre + "gamma2_fc1.weight"]
-        ops.gemm("nt", Attended, Wg1[:, :2 * H], G1pre, bias=P[pre + "gamma1_fc1.bias"])
-        ops.gemm("nt", Attended, Wg2[:, :2 * H], G2pre, bias=P[pre + "gamma2_fc1.bias"])
+
+        def att2():
+            ops.gemm("nt", Attended, P[pre + "att2_fc1.weight"], H2, bias=P[pre + "att2_fc1.bias"], act=ACT_RELU,
+                     drop=drop(dm.p_att2, SITE_ATT2), rng=rng)
+            ops.gemm("nt", H2, P[pre + "att2_fc2.weight"], cHat, bias=P[pre + "att2_fc2.bias"], act=ACT_TANH)
+
+        self._par([att2,
+                   lambda: ops.gemm("nt", Attended, Wg1[:, :2 * H], G1pre, bias=P[pre + "gamma1_fc1.bias"]),
+                   lambda: ops.gemm("nt", Attended, Wg2[:, :2 * H], G2pre, bias=P[pre + "gamma2_fc1.bias"])])
 
         # (5) the memory recurrence (:177-180), T steps in one kernel
         mems = buf("mems", (T + 1) * B, mem)
@@ -309,19 +315,23 @@ class Engine:
         TB = dm.T * dm.B
         self._join_aux()                 # loss_buf[4:8] (MMD parts) come from the auxiliary stream
         ops.zero(self.loss_buf[0:4])
-        dX = []
-        for m in range(3):
-            n = float(TB * dm.d[m])
-            dxh = buf("dXhat%d" % m, TB, dm.d[m])
-            ops.mse_fwd_bwd(self.ws["Xhat%d" % m], self.xs[m], 1.0 / n, 2.0 * dm.lda[m] / n,
-                            self.loss_buf[1 + m:2 + m], dxh)
-            dX.append(dxh)
+        dX = [buf("dXhat%d" % m, TB, dm.d[m]) for m in range(3)]
         dY = buf("dYhat", dm.B, dm.out)
-        if dm.head == "l1":
-            y2 = y.view(dm.B, dm.out)
-            ops.l1_fwd_bwd(self.ws["Yhat"], y2, 1.0 / (dm.B * dm.out), self.loss_buf[0:1], dY)
-        else:
-            ops.ce_fwd_bwd(self.ws["Yhat"], y, 1.0 / dm.B, self.loss_buf[0:1], dY)
+
+        def mse(m):
+            def run():
+                n = float(TB * dm.d[m])
+                ops.mse_fwd_bwd(self.ws["Xhat%d" % m], self.xs[m], 1.0 / n, 2.0 * dm.lda[m] / n,
+                                self.loss_buf[1 + m:2 + m], dX[m])
+            return run
+
+        def disc():
+            if dm.head == "l1":
+                ops.l1_fwd_bwd(self.ws["Yhat"], y.view(dm.B, dm.out), 1.0 / (dm.B * dm.out), self.loss_buf[0:1], dY)
+            else:
+                ops.ce_fwd_bwd(self.ws["Yhat"], y, 1.0 / dm.B, self.loss_buf[0:1], dY)
+
+        self._par([mse(0), mse(1), mse(2), disc])
         ops.loss_total(self.loss_buf, dm.lda[0], dm.lda[1], dm.lda[2], dm.lda_mmd)
         return dX, dY
 
@@ -552,9 +562,10 @@ class Engine:
         ops.gemm("nn", dZY, Wzy[:, H:], dmemT)
 
         enc_cells = []
+        dhE = [buf("dhE%d" % m, B, dm.z[m]) for m in range(3)]
+        self._par([(lambda m=m: lin_bwd(dZ[m], ws["hsE%d" % m][TB:], "encoder_%s.fc1" % TAGS[m], dhE[m])) for m in range(3)])
         for m, tag in enumerate(TAGS):                       # (3') encoder heads
-            dhl = buf("dhE%d" % m, B, dm.z[m])
-            lin_bwd(dZ[m], ws["hsE%d" % m][TB:], "encoder_%s.fc1" % tag, dhl)
+            dhl = dhE[m]
             enc_cells.append(dict(T=T, B=B, h=dm.z[m], gates=ws["gatesE%d" % m], cs=ws["csE%d" % m],
                                   W=P["encoder_%s.lstm.weight_hh" % tag], dh_all=None, dh_last=dhl, dc_ext=None,
                                   dG=buf("dGE%d" % m, TB, 4 * dm.z[m]), dc_scratch=buf("dcSE%d" % m, B, dm.z[m])))
