@@ -1,19 +1,33 @@
 // Small data-movement, reduction, loss-head and optimizer kernels of the MFM step.
 #include "common.cuh"
 
-// one warp per row (blockDim = 32 x 8 rows), lanes stride the columns: 128 B coalesced segments, no index division
+// one warp per row (blockDim = 32 x 8 rows); a lane moves 4 consecutive columns per iteration (16 B, vector access on
+// whichever side is 16 B aligned: the x split reads rows of pitch 1300 B and writes aligned ones), no index division
 __global__ void __launch_bounds__(256) copy2d_kernel(int M, int N, const float* __restrict__ src, long long lds,
                                                       float* __restrict__ dst, long long ldd, int accumulate) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const bool vs = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((lds & 3) == 0);
+  const bool vd = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((ldd & 3) == 0);
+  const int N4 = N & ~3;
   for (long long m = (long long)blockIdx.x * 8 + ty; m < M; m += (long long)gridDim.x * 8) {
     const float* sp = src + m * lds;
     float* dp = dst + m * ldd;
-    if (accumulate) {
-      for (int n = tx; n < N; n += 32) dp[n] += __ldg(sp + n);
-    } else {
-#pragma unroll 4
-      for (int n = tx; n < N; n += 32) dp[n] = __ldg(sp + n);
+#pragma unroll 2
+    for (int n = 4 * tx; n < N4; n += 128) {
+      float4 v;
+      if (vs) v = __ldg(reinterpret_cast<const float4*>(sp + n));
+      else { v.x = __ldg(sp + n); v.y = __ldg(sp + n + 1); v.z = __ldg(sp + n + 2); v.w = __ldg(sp + n + 3); }
+      if (vd) {
+        float4* d4 = reinterpret_cast<float4*>(dp + n);
+        if (accumulate) { const float4 o = *d4; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        *d4 = v;
+      } else if (accumulate) {
+        dp[n] += v.x; dp[n + 1] += v.y; dp[n + 2] += v.z; dp[n + 3] += v.w;
+      } else {
+        dp[n] = v.x; dp[n + 1] = v.y; dp[n + 2] = v.z; dp[n + 3] = v.w;
+      }
     }
+    for (int n = N4 + tx; n < N; n += 32) dp[n] = accumulate ? dp[n] + __ldg(sp + n) : __ldg(sp + n);
   }
 }
 
@@ -246,6 +260,19 @@ extern "C" int mfm_randn(long long n, float* out, const long long* rng, int site
 extern "C" int mfm_rng_tick(long long* rng, void* stream) {
   MFM_REQUIRE(rng);
   rng_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rng);
+  MFM_LAUNCH_CHECK();
+  return MFM_OK;
+}
+
+// ---- debug: device-side timeline marks (scripts/step_timeline.py; there is no nsys in the image) -----------------------
+__global__ void stamp_kernel(long long* buf, int slot) {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  buf[slot] = t;
+}
+extern "C" int mfm_debug_stamp(long long* buf, int slot, void* stream) {
+  MFM_REQUIRE(buf && slot >= 0);
+  stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(buf, slot);
   MFM_LAUNCH_CHECK();
   return MFM_OK;
 }

@@ -54,6 +54,7 @@ _SIGS = {
     "mfm_gemm_ws": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_f, LL, c_f, LL, c_f, LL, c_f, c_f, C.c_int, C.c_int,
                               c_f, LL, C.c_float, C.c_float, C.c_int, c_f, c_f, c_f, LL, c_f]),
     "mfm_debug_set_gemm_trace": (C.c_int, [c_f, LL]),
+    "mfm_debug_stamp": (C.c_int, [c_f, C.c_int, c_f]),
     "mfm_lstm_seq_fwd": (C.c_int, [C.POINTER(LstmCell), C.c_int, c_f]),
     "mfm_lstm_seq_bwd": (C.c_int, [C.POINTER(LstmCell), C.c_int, c_f]),
     "mfm_mfn_mem_fwd": (C.c_int, [C.POINTER(MemArgs), c_f]),
@@ -213,6 +214,10 @@ class CudaOps:
                                     float(p), int(site), prng,
                                     None if colsum_out is None else _vec(colsum_out, "colsum_out", M),
                                     ws, ws_bytes, _stream()), "mfm_gemm_ws")
+
+    def stamp(self, buf: torch.Tensor, slot: int):
+        """Debug: write the device clock to buf[slot] (int64) when the current stream gets here."""
+        _check(self.lib.mfm_debug_stamp(buf.data_ptr(), int(slot), _stream()), "mfm_debug_stamp")
 
     def _gemm_workspace(self, device, nbytes: int) -> int:
         """One scratch buffer per (device, stream): calls on a stream are ordered, so the next call may reuse it."""

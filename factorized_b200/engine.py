@@ -85,8 +85,18 @@ class Engine:
         self._aux_stream = None
         self._aux_used = False
         self._pool = []                  # streams for _par branches
+        self._z_ready = None             # event: encoder latents written (they are produced on the auxiliary stream)
+        self.stamps, self.stamp_names = None, []      # debug timeline (mark)
         self.defer_mmd_join = False      # the fused trainer joins the MMD stream in losses() instead of at the end of forward
         # loss_buf: 0 disc, 1..3 mse_l/a/v, 4..7 mmd per latent (unweighted), 8 total (weighted)
+
+    # -- debug timeline ---------------------------------------------------------------
+    def mark(self, name: str):
+        """Milestone on the current stream (only when a stamp buffer is attached: scripts/step_timeline.py)."""
+        if self.stamps is not None:
+            if name not in self.stamp_names:
+                self.stamp_names.append(name)
+            self.ops.stamp(self.stamps, self.stamp_names.index(name))
 
     # -- workspace -----------------------------------------------------------------
     def buf(self, name: str, *shape) -> torch.Tensor:
@@ -138,7 +148,9 @@ class Engine:
                          bias=P[n + ".bias_ih"], bias2=P[n + ".bias_hh"])
             return run
 
+        self.mark("fwd:start")
         self._par([project(0), project(1), project(2)])
+        self.mark("fwd:projections")
 
         # (2) six recurrences in one launch: h W_hh^T + G_x[t] -> gates -> (h, c)
         Hall = buf("Hall", (T + 1) * B, H)
@@ -163,14 +175,20 @@ class Engine:
                               hs=Hall[:, o:o + dm.hm[m]], cs=Call[:, o:o + dm.hm[m]], cs_dup=Cdup[:, o:o + dm.hm[m]],
                               gates=buf("gatesN%d" % m, TB, 4 * dm.hm[m])))
         ops.lstm_fwd(cells)
+        self.mark("fwd:lstm enc+mfn")
 
-        # (3) z_m = fc1(h_T), no activation (:60-61)
-        Z = []
-        for m, tag in enumerate(TAGS if full else ""):
-            zt = buf("Z%d" % m, B, dm.z[m])
-            ops.gemm("nt", self.ws["hsE%d" % m][TB:], P["encoder_%s.fc1.weight" % tag], zt,
-                     bias=P["encoder_%s.fc1.bias" % tag])
-            Z.append(zt)
+        # (3) z_m = fc1(h_T), no activation (:60-61), and (7) the MMD of the three encoder latents: nothing on the MFN
+        #     path needs them, so they leave the main stream here and overlap the attention / memory chain
+        Z = [buf("Z%d" % m, B, dm.z[m]) for m in range(3)] if full else []
+        if full:
+            with self._aux():
+                for m, tag in enumerate(TAGS):
+                    ops.gemm("nt", self.ws["hsE%d" % m][TB:], P["encoder_%s.fc1.weight" % tag], Z[m],
+                             bias=P["encoder_%s.fc1.bias" % tag])
+                self._z_ready = self._aux_event()
+                ops.zero(self.loss_buf[4:8])
+                for k in range(3):
+                    self._mmd(k, Z[k])
 
         # (4) MFN attention for all T at once (:171-176); only gamma*_fc1's memory columns are sequential
         pre = self.pre
@@ -183,6 +201,7 @@ class Engine:
         ops.gemm("nt", H1, P[pre + "att1_fc2.weight"], Att, bias=P[pre + "att1_fc2.bias"])
         Attended = buf("Attended", TB, 2 * H)
         ops.softmax_gate_fwd(Att, cStar, Attended)
+        self.mark("fwd:att1+gate")
         H2 = buf("H2", TB, dm.a2)
         cHat = buf("cHat", TB, mem)
         G1pre = buf("G1pre", TB, dm.g1)
@@ -198,6 +217,7 @@ class Engine:
                    lambda: ops.gemm("nt", Attended, Wg1[:, :2 * H], G1pre, bias=P[pre + "gamma1_fc1.bias"]),
                    lambda: ops.gemm("nt", Attended, Wg2[:, :2 * H], G2pre, bias=P[pre + "gamma2_fc1.bias"])])
 
+        self.mark("fwd:att2+gamma")
         # (5) the memory recurrence (:177-180), T steps in one kernel
         mems = buf("mems", (T + 1) * B, mem)
         ops.mfn_mem_fwd(dict(
@@ -209,6 +229,7 @@ class Engine:
             Gam1=buf("Gam1", TB, mem), Gam2=buf("Gam2", TB, mem),
             drop1=drop(dm.p_g1, SITE_G1), drop2=drop(dm.p_g2, SITE_G2), rng=rng))
 
+        self.mark("fwd:mem recurrence")
         if self.mfn_only:                                     # MFN.forward returns cat(h_T^l,h_T^a,h_T^v,mem_T) (:194-198)
             last = buf("mfn_last", B, H + mem)
             ops.copy2d(Hall[TB:], last[:, :H])
@@ -221,29 +242,12 @@ class Engine:
         ops.gemm("nt", Hall[TB:], Wzy[:, :H], ZY, bias=P["last_to_zy_fc1.bias"])
         ops.gemm("nt", mems[TB:], Wzy[:, H:], ZY, accumulate=True)
 
-        # (7) MMD of each latent against its Gaussian sample (:25-34, :536)
-        #     pair matrices S = X Y^T on the tensor cores, K = exp(-(|x|^2+|y|^2-2S)/dim^2) in place; K(z,z) and
-        #     K(g,z) stay resident for the backward pass (no [B,B,dim] tensor, no recompute)
-        #     Nothing downstream of the latents waits for it, so it runs on the auxiliary stream, concurrently with the
-        #     factor MLPs and the decoders.
-        lat = Z + [ZY]
-        Kgg = buf("Kgg", B, B)
-        inv_bb = 1.0 / (float(B) * float(B))
-        bufs = [(buf("mmd_nz%d" % k, B), buf("mmd_ng%d" % k, B), buf("Kzz%d" % k, B, B), buf("Kgz%d" % k, B, B)) for k in range(4)]
+        # (7) MMD of z_y (the encoder latents went out in step 3); same auxiliary stream, off the critical path
         with self._aux():
-            ops.zero(self.loss_buf[4:8])
-            for k in range(4):
-                zk, gk, dim = lat[k], self.noise[k], lat[k].shape[1]
-                nz, ng, Kzz, Kgz = bufs[k]
-                ops.rownorm2(zk, nz)
-                ops.rownorm2(gk, ng)
-                slot = self.loss_buf[4 + k:5 + k]
-                ops.gemm("nt", zk, zk, Kzz)
-                ops.mmd_kexp(Kzz, nz, nz, dim, inv_bb, slot)
-                ops.gemm("nt", gk, zk, Kgz)                   # rows index the Gaussian sample, columns the latent
-                ops.mmd_kexp(Kgz, ng, nz, dim, -2.0 * inv_bb, slot)
-                ops.gemm("nt", gk, gk, Kgg)
-                ops.mmd_kexp(Kgg, ng, ng, dim, inv_bb, slot)
+            self._mmd(3, ZY)
+        if self._z_ready is not None:                      # the factor MLPs read Z, produced on the auxiliary stream
+            torch.cuda.current_stream(self.device).wait_event(self._z_ready)
+            self._z_ready = None
 
         # (8) factor MLPs (:539-542) written straight into the decoder inputs cat(fy, f_m) (:544-546).
         #     The four MLPs, and below the three decoders, are independent of each other: branches run side by side.
@@ -270,7 +274,9 @@ class Engine:
                 ops.add(P[d_ + ".bias_ih"].view(1, -1), P[d_ + ".bias_hh"].view(1, -1), buf("bsumD%d" % m, 1, 4 * hd))
             return run
 
+        self.mark("fwd:zy")
         self._par([mlp_y, mlp_m(0), mlp_m(1), mlp_m(2)])
+        self.mark("fwd:factor MLPs")
 
         # (9) decoders (:72-91): step 0 eats the embedding; for t>=1 the input IS h_{t-1}, so the two
         #     gate GEMMs collapse into one with W_ih + W_hh.   (10) reconstructions x_hat = fc1(all hiddens) (:88-90)
@@ -301,6 +307,7 @@ class Engine:
             ops.gemm("nt", Y1, P["fy_to_y_fc2.weight"], Yhat, bias=P["fy_to_y_fc2.bias"])
 
         self._par([decoder(0), decoder(1), decoder(2), head])
+        self.mark("fwd:decoders+head")
         if not self.defer_mmd_join:
             self._join_aux()
         return dict(x_l_hat=Xhat[0], x_a_hat=Xhat[1], x_v_hat=Xhat[2], y_hat=Yhat,
@@ -313,7 +320,11 @@ class Engine:
         loss_buf[0..3] = disc, mse_l, mse_a, mse_v (means); loss_buf[8] = total."""
         dm, ops, buf = self.dm, self.ops, self.buf
         TB = dm.T * dm.B
-        self._join_aux()                 # loss_buf[4:8] (MMD parts) come from the auxiliary stream
+        # loss_buf[4:8] (MMD parts) come from the auxiliary stream.  Only the scalar total needs their VALUES (no
+        # gradient does), so the fused trainer does not wait for the MMD here: backward() sums the total after it has
+        # joined the auxiliary stream anyway (the loss gradients do not depend on it).
+        if not self.defer_mmd_join:
+            self._join_aux()
         ops.zero(self.loss_buf[0:4])
         dX = [buf("dXhat%d" % m, TB, dm.d[m]) for m in range(3)]
         dY = buf("dYhat", dm.B, dm.out)
@@ -331,8 +342,11 @@ class Engine:
             else:
                 ops.ce_fwd_bwd(self.ws["Yhat"], y, 1.0 / dm.B, self.loss_buf[0:1], dY)
 
+        self.mark("loss:join mmd")
         self._par([mse(0), mse(1), mse(2), disc])
-        ops.loss_total(self.loss_buf, dm.lda[0], dm.lda[1], dm.lda[2], dm.lda_mmd)
+        self.mark("loss:heads")
+        if not self.defer_mmd_join:
+            ops.loss_total(self.loss_buf, dm.lda[0], dm.lda[1], dm.lda[2], dm.lda_mmd)
         return dX, dY
 
     # -- weight-gradient GEMMs run on a side stream ---------------------------------
@@ -438,6 +452,42 @@ class Engine:
     def _aux(self):
         return Engine._Aux(self)
 
+    def _aux_event(self):
+        """Event at the current point of the auxiliary stream (None on the CPU test double)."""
+        if self.device.type != "cuda" or not self.use_side_stream:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self._aux_stream)
+        return ev
+
+    def _mmd(self, k, zk):
+        """loss_MMD of latent k against its Gaussian sample (:25-34, :536) on the current (auxiliary) stream.
+        Pair matrices S = X Y^T on the tensor cores, K = exp(-(|x|^2+|y|^2-2S)/dim^2) in place; K(z,z) and K(g,z) stay
+        resident (no [B,B,dim] tensor).  Everything of the gradient that does not depend on dLoss/dMMD follows at once:
+        d/dz = (2c/B^2) [ (rowsum Kzz - colsum Kgz) * z - Kzz Z + Kgz^T G ], c = -2/dim^2 -- the column sums and the two
+        products; backward() only combines them.  So neither direction of the MMD sits on the step's critical path."""
+        ops, buf, B = self.ops, self.buf, self.dm.B
+        gk, dim = self.noise[k], zk.shape[1]
+        nz, ng = buf("mmd_nz%d" % k, B), buf("mmd_ng%d" % k, B)
+        Kzz, Kgz, Kgg = buf("Kzz%d" % k, B, B), buf("Kgz%d" % k, B, B), buf("Kgg", B, B)
+        inv_bb = 1.0 / (float(B) * float(B))
+        slot = self.loss_buf[4 + k:5 + k]
+        ops.rownorm2(zk, nz)
+        ops.rownorm2(gk, ng)
+        ops.gemm("nt", zk, zk, Kzz)
+        ops.mmd_kexp(Kzz, nz, nz, dim, inv_bb, slot)
+        ops.gemm("nt", gk, zk, Kgz)                   # rows index the Gaussian sample, columns the latent
+        ops.mmd_kexp(Kgz, ng, nz, dim, -2.0 * inv_bb, slot)
+        ops.gemm("nt", gk, gk, Kgg)
+        ops.mmd_kexp(Kgg, ng, ng, dim, inv_bb, slot)
+        rc, t12 = buf("mmd_rc%d" % k, 2 * B), buf("mmd_t12_%d" % k, 2 * B, dim)
+        ops.zero(rc)
+        ops.colsum(Kzz, rc[:B])                          # K(z,z) is symmetric: column sums == row sums
+        ops.colsum(Kgz, rc[B:])
+        ops.zero(t12)                                    # accumulate form lets the GEMM split K = B over CTAs
+        ops.gemm("nn", Kzz, zk, t12[:B], accumulate=True)
+        ops.gemm("tn", Kgz, gk, t12[B:], accumulate=True)
+
     def _join_aux(self):
         if self._aux_stream is not None and self._aux_used:
             torch.cuda.current_stream(self.device).wait_stream(self._aux_stream)
@@ -475,26 +525,15 @@ class Engine:
             self._join_side()
             return
 
-        # (7') MMD: gradient flows through K(z,z) and K(g,z) only and depends on nothing upstream but its scale, so
-        #      it starts now on the auxiliary stream and is added to dZ after the factor MLPs have produced dZ.
-        #      d/dz = (2c/B^2) [ (rowsum Kzz - colsum Kgz) * z - Kzz Z + Kgz^T G ],  c = -2/dim^2
+        # (7') MMD: the column sums and products were formed right after the forward kernels (_mmd); what is left is one
+        #      combine per latent, scaled by dLoss/dMMD = ``mmd_scale`` x ``mmd_scale_dev``
         lat = [ws["Z0"], ws["Z1"], ws["Z2"], ws["ZY"]]
         dmmd = [buf("dZmmd%d" % k, B, lat[k].shape[1]) for k in range(4)]
-        mbufs = [(buf("mmd_rc%d" % k, 2 * B), buf("mmd_t12_%d" % k, 2 * B, lat[k].shape[1])) for k in range(4)]
         with self._aux():
             for k in range(4):
-                zk, gk, dim = lat[k], self.noise[k], lat[k].shape[1]
-                Kzz, Kgz = ws["Kzz%d" % k], ws["Kgz%d" % k]
-                rc, t12 = mbufs[k]
-                ops.zero(rc)
-                ops.colsum(Kzz, rc[:B])                          # K(z,z) is symmetric: column sums == row sums
-                ops.colsum(Kgz, rc[B:])
-                t1, t2 = t12[:B], t12[B:]
-                ops.zero(t12)                                    # accumulate form lets the GEMM split K = B over CTAs
-                ops.gemm("nn", Kzz, zk, t1, accumulate=True)
-                ops.gemm("tn", Kgz, gk, t2, accumulate=True)
+                rc, t12 = ws["mmd_rc%d" % k], ws["mmd_t12_%d" % k]
                 ops.zero(dmmd[k])
-                ops.mmd_combine(zk, rc[:B], rc[B:], t1, t2, mmd_scale, dmmd[k], mmd_scale_dev)
+                ops.mmd_combine(lat[k], rc[:B], rc[B:], t12[:B], t12[B:], mmd_scale, dmmd[k], mmd_scale_dev)
 
         # (11') head, (10') + (9') + (8') one chain per decoder: reconstruction head, recurrence, weight gradients, embedding,
         #       factor MLP.  The four chains touch disjoint buffers (the decoders' shares of dFY are added after the join).
@@ -539,12 +578,18 @@ class Engine:
                          "z%s_to_f%s" % (tag, tag), dm.p_f[m], dZ[m])
             return run
 
+        self.mark("bwd:start")
         self._par([decoder_bwd(0), decoder_bwd(1), decoder_bwd(2), head_bwd])
+        self.mark("bwd:decoder chains")
         for m in range(3):
             ops.copy2d(dEMB[m][:, :dm.fy], dFY, accumulate=True)
         mlp2_bwd(dFY, ws["FY"], ws["F1y"], ws["ZY"], "zy_to_fy", dm.p_fy, dZY)
 
+        self.mark("bwd:mlp y")
         self._join_aux()
+        self.mark("bwd:join mmd")
+        if self.defer_mmd_join:              # fused trainer: the total (loss_buf[8]) is summed now that the MMD parts exist
+            ops.loss_total(self.loss_buf, dm.lda[0], dm.lda[1], dm.lda[2], dm.lda_mmd)
         dlat = dZ + [dZY]
         for k in range(4):
             ops.copy2d(dmmd[k], dlat[k], accumulate=True)
@@ -570,7 +615,9 @@ class Engine:
                                   W=P["encoder_%s.lstm.weight_hh" % tag], dh_all=None, dh_last=dhl, dc_ext=None,
                                   dG=buf("dGE%d" % m, TB, 4 * dm.z[m]), dc_scratch=buf("dcSE%d" % m, B, dm.z[m])))
         self._backward_mfn(P, G, dHlast, dmemT, enc_cells, wgrad, bgrad, lin_bwd, relu_scale)
+        self.mark("bwd:lstm enc+mfn")
         self._join_side()
+        self.mark("bwd:join wgrads")
 
     def _backward_mfn(self, P, G, dHlast, dmemT, enc_cells, wgrad, bgrad, lin_bwd, relu_scale):
         """Adjoint of steps (5),(4),(2),(1): memory recurrence, attention MLPs, then the MFN cells together
@@ -595,6 +642,7 @@ class Engine:
             W12=P[pre + "gamma1_fc2.weight"], W22=P[pre + "gamma2_fc2.weight"],
             scale1=relu_scale(dm.p_g1), scale2=relu_scale(dm.p_g2),
             dmem_last=dmemT, dU1=dU1, dU2=dU2, dP1=dP1, dP2=dP2, dPc=dPc))
+        self.mark("bwd:mem recurrence")
         self._wgrad_gemm( dP1, ws["U1"], G[pre + "gamma1_fc2.weight"], accumulate=True, colsum_out=G[pre + "gamma1_fc2.bias"])
         self._wgrad_gemm( dP2, ws["U2"], G[pre + "gamma2_fc2.weight"], accumulate=True, colsum_out=G[pre + "gamma2_fc2.bias"])
         Attended, cStar, Att = ws["Attended"], self.ws_views["cStar"], ws["Att"]
@@ -614,6 +662,7 @@ class Engine:
         ops.gemm("nn", dUcat, Wcat, dAtt)
         dL = buf("dL", TB, 2 * H)
         dcStar = buf("dcStar", TB, 2 * H)
+        self.mark("bwd:att2+dAtt")
         ops.softmax_gate_bwd(dAtt, Att, cStar, dL, dcStar)
         dH1 = buf("dH1", TB, dm.a1)
         lin_bwd(dL, ws["H1"], pre + "att1_fc2", dH1, mask=ws["H1"], mask_scale=relu_scale(dm.p_att1))
@@ -626,6 +675,7 @@ class Engine:
         if T > 1:
             ops.copy2d(dcStar[B:, :H], dCext[:TB - B], accumulate=True)
 
+        self.mark("bwd:att1+dCext")
         # (2') the recurrences reversed, one launch
         cells = list(enc_cells)
         for m, tag in enumerate(TAGS):

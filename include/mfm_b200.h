@@ -72,6 +72,9 @@ int mfm_gemm(int mode, int M, int N, int K,
 /* Debug aid (scripts/gemm_trace.py): while a device buffer is registered, every pipelined-GEMM CTA records clock stamps of
  * its producer / converter / MMA roles into it (4 + 6*32 int64 words per CTA).  NULL disables.  Not for production use. */
 int mfm_debug_set_gemm_trace(void* device_buf, long long bytes);
+/* Debug aid (scripts/step_timeline.py): a one-thread kernel that writes %globaltimer (ns) to buf[slot] when the stream
+ * reaches it -- milestones of a CUDA-graph replay, with all cross-stream overlap included. */
+int mfm_debug_stamp(long long* buf, int slot, void* stream);
 int mfm_gemm_ws(int mode, int M, int N, int K,
                 const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
                 const float* bias, const float* bias2, int act, int accumulate,
