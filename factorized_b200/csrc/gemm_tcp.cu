@@ -3,33 +3,42 @@
 // The step's time-parallel GEMMs are [T*B, <=512] activations against small weights: they are bound by streaming the
 // activation operand from HBM.  gemm_tc.cu keeps one K chunk of prefetch in registers and runs all its threads in
 // lock step (load -> convert -> fence -> barrier -> MMA), so every chunk exposes the whole latency chain.  Here the
-// links of that chain are different warps connected by mbarriers over a ring of 3 stages, and the transport is TMA:
+// links of that chain are different warps connected by mbarriers over ONE ring of 4..7 stages (BK = 16), the
+// transport is TMA, and the A operand never touches shared memory again after it has been split:
 //
-//   warp 8 (one thread)  PRODUCER    waits pfree[s]; cp.async.bulk.tensor.2d: the raw fp32 box of A for chunk c -> stage s
+//   warp 8 (one thread)  PRODUCER    waits done[s]; cp.async.bulk.tensor.2d: the raw fp32 box of A for chunk c -> stage s
 //                                    (the tensor map describes the operand as it lies in HBM, any 16 B-aligned view; M/N/K
 //                                    tails are zero-filled by the TMA unit), and B either the same way or -- when the
 //                                    caller supplied a workspace (weights: NT / NN) -- as ONE bulk copy of the chunk's
 //                                    pre-split bf16 image, already in MMA layout.  Completion: complete_tx on full[s].
-//   warps 0..7           CONVERTERS  wait full[s]; read 32 B items of the raw boxes, split fp32 -> bf16 hi + lo, store both
-//                                    planes in the tcgen05 no-swizzle canonical layout, fence.proxy.async; one arrive per
-//                                    warp on conv[s].  Warps run ahead independently (no CTA-wide barrier in the loop).
-//   warp 9 (one thread)  MMA         wait conv[s]; tcgen05.mma hi*hi + lo*hi + hi*lo (M=128, N=BN, K=16) into the fp32 TMEM
-//                                    accumulator; tcgen05.commit -> pfree[s] hands the stage back to the producer.
+//   warps 0..7           CONVERTERS  wait full[s]; thread (row, 8-k slab) reads its 32 B of the raw A box, splits fp32 ->
+//                                    bf16 hi + lo and stores both with tcgen05.st into the stage's 16 tensor-memory columns
+//                                    (TMEM lane = tile row); a raw B box is split into shared-memory planes in the tcgen05
+//                                    no-swizzle canonical layout (+ fence.proxy.async).  One arrive per warp on conv[s];
+//                                    warps run ahead independently (no CTA-wide barrier in the loop).
+//   warp 9 (one thread)  MMA         wait conv[s]; tcgen05.mma in the TS form -- A from tensor memory, B from shared memory --
+//                                    hi*hi + lo*hi + hi*lo (M=128, N=BN, K=16) into the fp32 TMEM accumulator; one
+//                                    tcgen05.commit -> done[s] hands the stage (shared memory and TMEM columns) back.
 //   warps 0..7           EPILOGUE    after the last commit: tc_epilogue.cuh (TMEM -> transposed through the idle ring ->
 //                                    512 B coalesced stores with bias / activation / dropout / mask / split-K reduction).
 //
 // Pre-split B (gemm_prep_kernel): a weight is the same for all T*B/128 row tiles, so splitting it inside every CTA is
 // T*B/128-fold redundant and costs as much as splitting A.  One small kernel writes, per (N tile, K chunk), the image
-// [hi plane | lo plane] exactly as the MMA wants it in shared memory; with B out of the converters' way a tile can be 256
-// columns wide (A is staged and split once per 256 output columns instead of once per 128).
+// [hi plane | lo plane] exactly as the MMA wants it in shared memory; a stage is then 8 KB of raw A + the image.
+// Why TS: with both operands split into shared-memory planes the shared-memory pipe saturated (TMA write + converter read
+// + plane write + 3 x MMA operand reads = 57 KB per chunk, ~119 of 128 B/cycle with two CTAs per SM).
 //
-// Two CTAs of 320 threads are resident per SM (<= 100 KB each, no static shared memory), so one CTA's epilogue stores
-// overlap the other's loads.  (Three CTAs with four converter warps each were measured slower.)  Raw layouts:
-//   K-major operand  [rows, K]:  one box [rows][16] fp32, 64 B TMA swizzle (16 B chunk ^= (row/2)%4): the two 16 B halves
-//                                of an item (r, slab) are read conflict-free -> plane byte slab*LBO + r*16, LBO = rows*16+64
-//   MN-major operand [K, cols]:  boxes of [16][32 cols], 128 B TMA swizzle (chunk ^= k%8), so the eight k rows of a core
-//                                matrix come from eight different bank groups -> plane byte (k/8)*LBO + (c/8)*128 + (k%8)*16
-// Requirements (else the caller falls back to gemm_tc.cu): A and B 16 B aligned, leading dimensions multiples of 4.
+// Two CTAs of 320 threads are resident per SM (<= 110 KB and 256 TMEM columns each, no static shared memory), so one
+// CTA's epilogue stores overlap the other's loads.  Measured alternatives that lost: three CTAs with four converter warps,
+// 16 B cp.async transport (L1-bypassing LDGSTS fetches every sector twice and writes one wavefront per lane), separate raw /
+// plane rings, two converter groups on alternate chunks.  Raw layouts:
+//   K-major operand  [rows, K]:  one box [rows][16] fp32, 64 B TMA swizzle (16 B chunk ^= (row/2)%4): a warp reads the
+//                                first / second 16 B half of 32 consecutive rows conflict-free
+//   MN-major operand [K, cols]:  boxes of [16][32 cols], 128 B TMA swizzle (chunk ^= k%8): a warp reads one k row of its
+//                                32 columns (A), or the eight k rows of a core matrix from eight bank groups (B)
+//   B planes: K-major byte slab*LBO + r*16 (LBO = rows*16+64), MN-major byte (k/8)*LBO + (c/8)*128 + (k%8)*16
+// Requirements (else the caller falls back to gemm_tc.cu): A 16 B aligned with a leading dimension that is a multiple
+// of 4; the same for a raw B (a pre-split B may have any alignment).
 #include <cuda.h>
 #include <cstdlib>
 #include "tc_epilogue.cuh"

@@ -448,11 +448,17 @@ int lstm_tc_fwd_launch(const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* re
   *nrest = 0;
   size_t smem32 = 0, smem8 = 0;
   int gx32 = 0, gx8 = 0;
+  // one CTA per SM: when 32-row tiles of the whole call would leave more than half of the SMs idle (a single decoder
+  // cell at batch 2048 is 64 tiles), 16-row tiles double the CTAs and shorten every step of the recurrence
+  long long tiles32 = 0;
+  for (int i = 0; i < ncells; ++i) tiles32 += (cells[i].B + 31) / 32;
+  const bool narrow = tiles32 <= 74;
   for (int i = 0; i < ncells; ++i) {
     const mfm_lstm_cell& c = cells[i];
     int nb = 0, cc = 0;
     if (c.h >= 1 && c.h <= 128) {
-      if (fwd_smem(c.h, 32, 32) <= (size_t)lim) { nb = 32; cc = 32; }
+      if (narrow && fwd_smem(c.h, 16, 8) <= (size_t)lim) { nb = 16; cc = 8; }
+      else if (fwd_smem(c.h, 32, 32) <= (size_t)lim) { nb = 32; cc = 32; }
       else if (fwd_smem(c.h, 32, 8) <= (size_t)lim) { nb = 32; cc = 8; }
       else if (fwd_smem(c.h, 16, 8) <= (size_t)lim) { nb = 16; cc = 8; }
     }
@@ -501,7 +507,7 @@ int lstm_tc_bwd_launch(const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* re
   for (int i = 0; i < ncells; ++i) {
     const mfm_lstm_cell& c = cells[i];
     int nb = 0;
-    if (c.h >= 1 && c.h <= 128) {
+    if (c.h >= 1 && c.h <= 128) {             // (16-row tiles for under-occupied launches, as in forward, measured slower here)
       if (bwd_smem(c.h, 32) <= (size_t)lim) nb = 32;
       else if (bwd_smem(c.h, 16) <= (size_t)lim) nb = 16;
     }

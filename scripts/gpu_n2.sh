@@ -1,4 +1,6 @@
 #!/bin/bash
+# 2-GPU weak-scaling check of the bench contract (one rank per GPU over NCCL)
 mkdir -p gpurun_out
-NCCL_DEBUG=WARN timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
-echo "bench n2 exit $?"; tail -c 1500 gpurun_out/bench_n2.json | cut -c1-1500; tail -5 gpurun_out/bench_n2.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+  bench.py --gpus 2 --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+echo "n2 exit $?"; cut -c1-700 gpurun_out/bench_n2.json; tail -3 gpurun_out/bench_n2.err
