@@ -15,6 +15,9 @@ int gemm_tc_launch(int passes, int mode, int M, int N, int K, const float* A, lo
                    float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
                    const float* mask, long long ldmask, float mask_scale, float drop_p, int drop_site,
                    const long long* rng, float* colsum_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int gemm_tcp_launch_tn_pair(int passes, int M, int K, const float* A, long long lda, int N1, const float* B1, long long ldb1,
+                            float* C1, long long ldc1, float* colsum1, int N2, const float* B2, long long ldb2, float* C2,
+                            long long ldc2, cudaStream_t st);
 static long long g_tc_min_work = 1LL << 20;   // M*N*K below this stays on the CUDA-core kernel
 
 extern "C" int mfm_set_gemm_path(int path) {
@@ -56,4 +59,20 @@ extern "C" int mfm_gemm_ws(int mode, int M, int N, int K, const float* A, long l
   }
   return gemm_simt_launch(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale,
                           drop_p, drop_site, rng, (cudaStream_t)stream);
+}
+
+extern "C" int mfm_gemm_tn_pair(int M, int K, const float* A, long long lda, int N1, const float* B1, long long ldb1,
+                                float* C1, long long ldc1, float* colsum1, int N2, const float* B2, long long ldb2,
+                                float* C2, long long ldc2, void* stream) {
+  MFM_REQUIRE(M > 0 && K > 0 && N1 > 0 && N2 > 0 && A && B1 && B2 && C1 && C2);
+  if (g_gemm_path != MFM_PATH_SIMT_FP32 && (long long)M * (N1 + N2) * K >= g_tc_min_work) {
+    const int rc = gemm_tcp_launch_tn_pair(g_gemm_path == MFM_PATH_TC_BF16X3 ? 3 : 1, M, K, A, lda, N1, B1, ldb1, C1, ldc1, colsum1,
+                                           N2, B2, ldb2, C2, ldc2, (cudaStream_t)stream);
+    if (rc != MFM_ERR_UNSUPPORTED) return rc;
+  }
+  int rc = mfm_gemm(MFM_GEMM_TN, M, N1, K, A, lda, B1, ldb1, C1, ldc1, nullptr, nullptr, MFM_ACT_NONE, 1, nullptr, 0, 1.0f, 0.0f, 0,
+                    nullptr, colsum1, stream);
+  if (rc) return rc;
+  return mfm_gemm(MFM_GEMM_TN, M, N2, K, A, lda, B2, ldb2, C2, ldc2, nullptr, nullptr, MFM_ACT_NONE, 1, nullptr, 0, 1.0f, 0.0f, 0,
+                  nullptr, nullptr, stream);
 }

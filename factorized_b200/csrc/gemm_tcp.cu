@@ -166,6 +166,8 @@ __device__ __forceinline__ void convert_a_tmem(const unsigned char* st, uint32_t
 
 struct TcpArgs {
   TcArgs t;
+  TcArgs t2;                     // pair form (TN): N tiles >= ntiles1 multiply the same A by a second B into a second C
+  int ntiles1;                   // 0 = plain GEMM
   const unsigned char* bimg;     // BPRE: images [N tile][K chunk][hi plane | lo plane]
   int nchunks_total;             // BPRE: K chunks per N tile in bimg
   int bar_off;                   // byte offset of the mbarrier block inside the dynamic shared buffer
@@ -176,18 +178,22 @@ struct TcpArgs {
 
 template <int MODE, bool BPRE>
 __global__ void __launch_bounds__(P_THREADS, 2) gemm_tcp_kernel(const TcpArgs pa, const __grid_constant__ CUtensorMap tmA,
-                                                                const __grid_constant__ CUtensorMap tmB) {
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const __grid_constant__ CUtensorMap tmB2) {
   constexpr bool A_MN = (MODE == MFM_GEMM_TN);
   constexpr bool B_MN = (MODE != MFM_GEMM_NT);
   extern __shared__ __align__(1024) unsigned char smem[];
-  const TcArgs& ta = pa.t;
-  const GemmArgs& a = ta.g;
-  const int BN = ta.BN, S = pa.nstages;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned bx, by, bz;
   asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bx));
   asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(by));
   asm volatile("mov.u32 %0, %%ctaid.z;" : "=r"(bz));
+  const bool second = MODE == MFM_GEMM_TN && pa.ntiles1 > 0 && (int)bx >= pa.ntiles1;      // CTA-uniform
+  const TcArgs& ta = second ? pa.t2 : pa.t;
+  const CUtensorMap* const tmBsel = second ? &tmB2 : &tmB;
+  if (second) bx -= (unsigned)pa.ntiles1;
+  const GemmArgs& a = ta.g;
+  const int BN = ta.BN, S = pa.nstages;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = by * P_BM, n0 = bx * BN;
   const int kbeg = bz * a.kchunk;
   const int kend = min(a.K, kbeg + a.kchunk);
@@ -235,6 +241,7 @@ __global__ void __launch_bounds__(P_THREADS, 2) gemm_tcp_kernel(const TcpArgs pa
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     tr[0] = gtimer(); tr[1] = smid; tr[2] = nchunks;
+    (void)bx;
   }
 #define TRACE(cc, slot) do { if (tr && (cc) < P_TRACE_CHUNKS) tr[4 + 6 * (cc) + (slot)] = clock64() - t0; } while (0)
 
@@ -292,9 +299,9 @@ __global__ void __launch_bounds__(P_THREADS, 2) gemm_tcp_kernel(const TcpArgs pa
         if (BPRE) {
           bulk_load(sa + offB, img + (size_t)c * (2 * plB), (uint32_t)(2 * plB), fb);
         } else if (B_MN) {
-          for (int j = 0; j < BNb / 32; ++j) tma_load_2d(sb + j * (P_BK * 128), &tmB, n0 + 32 * j, k0, fb);
+          for (int j = 0; j < BNb / 32; ++j) tma_load_2d(sb + j * (P_BK * 128), tmBsel, n0 + 32 * j, k0, fb);
         } else {
-          tma_load_2d(sb, &tmB, k0, n0, fb);
+          tma_load_2d(sb, tmBsel, k0, n0, fb);
         }
         TRACE(c, 0);
         if (++s == S) { s = 0; ph ^= 1u; }
@@ -471,8 +478,11 @@ static int tcp_launch_one(const TcpArgs& pa, dim3 grid, cudaStream_t st) {
   if (grp < 0) { const char* e = getenv("MFM_TCP_G"); grp = e ? atoi(e) : 2; }
   pb.group = grp < 1 ? 1 : (grp > rc.S / 2 ? (rc.S / 2 > 0 ? rc.S / 2 : 1) : grp);
   pb.bar_off = (int)rc.bytes;
-  pb.t.tmem_cols = rc.tmem_cols;
-  gemm_tcp_kernel<MODE, BPRE><<<grid, P_THREADS, (size_t)pb.bar_off + P_BAR_BYTES, st>>>(pb, tmA, tmB);
+  pb.t.tmem_cols = pb.t2.tmem_cols = rc.tmem_cols;
+  CUtensorMap tmB2 = tmB;
+  if (MODE == MFM_GEMM_TN && pa.ntiles1 > 0 && !make_map(&tmB2, pa.t2.g.B, pa.t2.g.ldb, pa.t2.g.N, pa.t2.g.K, 32, P_BK))
+    return MFM_ERR_UNSUPPORTED;
+  gemm_tcp_kernel<MODE, BPRE><<<grid, P_THREADS, (size_t)pb.bar_off + P_BAR_BYTES, st>>>(pb, tmA, tmB, tmB2);
   MFM_LAUNCH_CHECK();
   return MFM_OK;
 }
@@ -503,6 +513,8 @@ int gemm_tcp_launch(int passes, int mode, int M, int N, int K, const float* A, l
   pa.bimg = nullptr;
   pa.nchunks_total = 0;
   pa.trace = nullptr;
+  pa.ntiles1 = 0;
+  pa.t2 = pa.t;
   const bool plain = !bias && !bias2 && act == MFM_ACT_NONE && !mask && drop_p <= 0.0f && accumulate;
   const bool splitk = plain && K >= 2048;
   // pre-split B: weights (NT / NN) against many row tiles, caller-provided workspace, no split-K
@@ -553,4 +565,44 @@ int gemm_tcp_launch(int passes, int mode, int M, int N, int K, const float* A, l
     case MFM_GEMM_TN: return tcp_launch_one<MFM_GEMM_TN, false>(pa, grid, st);
   }
   return MFM_ERR_ARG;
+}
+
+// C1[M,N1] += A^T B1 (+ colsum1[m] += sum_k A[k,m]) and C2[M,N2] += A^T B2 in ONE launch: the two weight gradients of a
+// cell (dW_ih = dG^T x, dW_hh = dG^T h_prev) share their big operand, which is then streamed from HBM once -- the N
+// tiles of the second product run next to those of the first and find A's chunks in L2.
+int gemm_tcp_launch_tn_pair(int passes, int M, int K, const float* A, long long lda, int N1, const float* B1, long long ldb1,
+                            float* C1, long long ldc1, float* colsum1, int N2, const float* B2, long long ldb2, float* C2,
+                            long long ldc2, cudaStream_t st) {
+  auto ok16 = [](const float* p, long long ld) { return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((ld & 3) == 0); };
+  if (!gemm_tcp_eligible(MFM_GEMM_TN, M, N1, K, A, lda, B1, ldb1) || !ok16(B1, ldb1) || !ok16(B2, ldb2)) return MFM_ERR_UNSUPPORTED;
+  TcpArgs pa;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("MFM_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+  const int n1 = N1 + (colsum1 ? 1 : 0);
+  const int nmax = n1 > N2 ? n1 : N2;
+  const int n16 = round_up(nmax, 16);
+  const int nt = (n16 + P_MAXBN_RAW - 1) / P_MAXBN_RAW;
+  const int BN = round_up((n16 + nt - 1) / nt, 16);
+  const int tiles1 = (n1 + BN - 1) / BN, tiles2 = (N2 + BN - 1) / BN;
+  pa.t.g = GemmArgs{M, N1, K, A, lda, B1, ldb1, C1, ldc1, nullptr, nullptr, MFM_ACT_NONE, 1, nullptr, 0, 1.0f, 0.0f, 0, nullptr,
+                    K, 0, colsum1};
+  pa.t.passes = passes; pa.t.dbg = dbg; pa.t.BN = BN; pa.t.tmem_cols = 0;
+  pa.t2 = pa.t;
+  pa.t2.g.N = N2; pa.t2.g.B = B2; pa.t2.g.ldb = ldb2; pa.t2.g.C = C2; pa.t2.g.ldc = ldc2; pa.t2.g.colsum_out = nullptr;
+  pa.bimg = nullptr; pa.nchunks_total = 0; pa.trace = nullptr;
+  pa.ntiles1 = tiles1;
+  dim3 grid(tiles1 + tiles2, (M + P_BM - 1) / P_BM, 1);
+  if (K >= 2048) {
+    long long tiles = (long long)grid.x * grid.y;
+    int splits = (int)((2 * 148 + tiles - 1) / tiles);
+    int maxs = K / 256;
+    if (splits > maxs) splits = maxs;
+    if (splits > 1) {
+      int kc = round_up((K + splits - 1) / splits, 32);
+      pa.t.g.kchunk = pa.t2.g.kchunk = kc;
+      pa.t.g.atomic = pa.t2.g.atomic = 1;
+      grid.z = (K + kc - 1) / kc;
+    }
+  }
+  return tcp_launch_one<MFM_GEMM_TN, false>(pa, grid, st);
 }

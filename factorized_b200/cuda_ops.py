@@ -53,6 +53,7 @@ _SIGS = {
                            c_f, LL, C.c_float, C.c_float, C.c_int, c_f, c_f, c_f]),
     "mfm_gemm_ws": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_f, LL, c_f, LL, c_f, LL, c_f, c_f, C.c_int, C.c_int,
                               c_f, LL, C.c_float, C.c_float, C.c_int, c_f, c_f, c_f, LL, c_f]),
+    "mfm_gemm_tn_pair": (C.c_int, [C.c_int, C.c_int, c_f, LL, C.c_int, c_f, LL, c_f, LL, c_f, C.c_int, c_f, LL, c_f, LL, c_f]),
     "mfm_debug_set_gemm_trace": (C.c_int, [c_f, LL]),
     "mfm_debug_stamp": (C.c_int, [c_f, C.c_int, c_f]),
     "mfm_lstm_seq_fwd": (C.c_int, [C.POINTER(LstmCell), C.c_int, c_f]),
@@ -214,6 +215,19 @@ class CudaOps:
                                     float(p), int(site), prng,
                                     None if colsum_out is None else _vec(colsum_out, "colsum_out", M),
                                     ws, ws_bytes, _stream()), "mfm_gemm_ws")
+
+    def gemm_tn_pair(self, dY, A1, C1, colsum1, A2, C2):
+        """C1 += dY^T A1 (colsum1 += column sums of dY, may be None) and C2 += dY^T A2 in one launch."""
+        pa, K, M, lda = _mat(dY, "gemm_tn_pair dY")
+        p1, k1, N1, ld1 = _mat(A1, "gemm_tn_pair A1")
+        p2, k2, N2, ld2 = _mat(A2, "gemm_tn_pair A2")
+        c1, m1, n1, lc1 = _mat(C1, "gemm_tn_pair C1")
+        c2, m2, n2, lc2 = _mat(C2, "gemm_tn_pair C2")
+        if (k1, k2, m1, m2, n1, n2) != (K, K, M, M, N1, N2):
+            raise MfmCudaError("gemm_tn_pair: shapes do not agree")
+        _check(self.lib.mfm_gemm_tn_pair(M, K, pa, lda, N1, p1, ld1, c1, lc1,
+                                         None if colsum1 is None else _vec(colsum1, "colsum1", M),
+                                         N2, p2, ld2, c2, lc2, _stream()), "mfm_gemm_tn_pair")
 
     def stamp(self, buf: torch.Tensor, slot: int):
         """Debug: write the device clock to buf[slot] (int64) when the current stream gets here."""

@@ -366,6 +366,19 @@ class Engine:
             fn()
         self._side_used = True
 
+    def _wgrad_pair(self, dY, A1, G1, b1, A2, G2, b2=None):
+        """dW1 += dY^T A1, dW2 += dY^T A2 and the bias gradient(s) = column sums of dY, in one launch on a side stream: the
+        two weight gradients of a cell share dY, which is then read from HBM once.  b2 (same sums) is copied from b1."""
+        ops = self.ops
+
+        def run():
+            ops.gemm_tn_pair(dY, A1, G1, b1, A2, G2)
+            if b2 is not None:
+                ops.copy2d(b1.view(1, -1), b2.view(1, -1), accumulate=True)
+        if os.environ.get("MFM_SKIP_WGRAD"):
+            return
+        self._on_side(G1.data_ptr(), run)
+
     def _wgrad_gemm(self, dY, A, Gout, stream_key=None, **kw):
         """dW += dY^T A (TN GEMM, optionally with the fused bias gradient).  Weight gradients only read stashes and
         write the flat gradient buffer, so they do not belong on the critical path of the backward chain: they are
@@ -647,10 +660,9 @@ class Engine:
         self._wgrad_gemm( dP2, ws["U2"], G[pre + "gamma2_fc2.weight"], accumulate=True, colsum_out=G[pre + "gamma2_fc2.bias"])
         Attended, cStar, Att = ws["Attended"], self.ws_views["cStar"], ws["Att"]
         dAtt = buf("dAttended", TB, 2 * H)
-        for (dU, nm) in ((dU1, "gamma1_fc1"), (dU2, "gamma2_fc1")):
+        for (dU, nm) in ((dU1, "gamma1_fc1"), (dU2, "gamma2_fc1")):     # the two column blocks of gamma*_fc1 share dU
             Gw = G[pre + nm + ".weight"]
-            self._wgrad_gemm( dU, Attended, Gw[:, :2 * H], accumulate=True, colsum_out=G[pre + nm + ".bias"])
-            self._wgrad_gemm( dU, mems[:TB], Gw[:, 2 * H:], accumulate=True)
+            self._wgrad_pair(dU, Attended, Gw[:, :2 * H], G[pre + nm + ".bias"], mems[:TB], Gw[:, 2 * H:])
 
         # (4') attention MLPs, time-parallel
         lin_bwd(dPc, ws["H2"], pre + "att2_fc2", dH2, mask=ws["H2"], mask_scale=relu_scale(dm.p_att2))
@@ -691,7 +703,6 @@ class Engine:
             jobs = [(pre + "lstm_%s" % tag, "dGN%d" % m, Hall[:TB, dm.hoff[m]:dm.hoff[m] + dm.hm[m]])]
             if enc_cells:
                 jobs.append(("encoder_%s.lstm" % tag, "dGE%d" % m, ws["hsE%d" % m][:TB]))
-            for (nm, dGn, hs) in jobs:
-                dG = ws[dGn]
-                self._wgrad_gemm( dG, self.xs[m], G[nm + ".weight_ih"], accumulate=True, colsum_out=G[nm + ".bias_ih"])
-                self._wgrad_gemm( dG, hs, G[nm + ".weight_hh"], accumulate=True, colsum_out=G[nm + ".bias_hh"])
+            for (nm, dGn, hs) in jobs:              # dW_ih = dG^T x and dW_hh = dG^T h_prev share dG; b_ih and b_hh share its sums
+                self._wgrad_pair(ws[dGn], self.xs[m], G[nm + ".weight_ih"], G[nm + ".bias_ih"], hs, G[nm + ".weight_hh"],
+                                 G[nm + ".bias_hh"])

@@ -82,6 +82,14 @@ int mfm_gemm_ws(int mode, int M, int N, int K,
                 float drop_p, int drop_site, const long long* rng, float* colsum_out,
                 void* ws, long long ws_bytes, void* stream);
 
+/* Two weight gradients that share dY -- dW_ih = dG^T x and dW_hh = dG^T h_prev of one LSTM cell (autograd adjoint of
+ * mfm_model.py:56,167-169), or the two column blocks of gamma*_fc1 (:178-179) -- in one launch:
+ *   C1[M,N1] += A^T B1,  colsum1[m] += sum_k A[k,m] (may be NULL),  C2[M,N2] += A^T B2,   A = dY [K, M].
+ * dY is streamed from HBM once instead of twice. */
+int mfm_gemm_tn_pair(int M, int K, const float* A, long long lda,
+                     int N1, const float* B1, long long ldb1, float* C1, long long ldc1, float* colsum1,
+                     int N2, const float* B2, long long ldb2, float* C2, long long ldc2, void* stream);
+
 /* One LSTM cell unrolled over T steps inside the kernel (encoderLSTM.forward mfm_model.py:47-62,
  * decoderLSTM.forward :72-91, the three cells of MFN.forward :167-169).
  * pre_t = h_{t-1} W^T + (t < gx_steps ? gx[t] : bias_rest);  gates i,f,g,o (torch LSTMCell order);

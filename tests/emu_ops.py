@@ -76,6 +76,10 @@ class EmuOps:
         else:
             C.copy_(v)
 
+    def gemm_tn_pair(self, dY, A1, C1, colsum1, A2, C2):
+        self.gemm("tn", dY, A1, C1, accumulate=True, colsum_out=colsum1)
+        self.gemm("tn", dY, A2, C2, accumulate=True)
+
     # ---- LSTM recurrences ----
     def lstm_fwd(self, cells):
         self.launches += 1

@@ -116,3 +116,19 @@ def test_tc_gemm_fused_bias_gradient(tc_ops, K, M, N):
     EmuOps().gemm("tn", dY.double(), X.double(), w_cpu, accumulate=True, colsum_out=b_cpu)
     tc_ops.gemm("tn", dY.cuda(), X.cuda(), w_gpu, accumulate=True, colsum_out=b_gpu)
     assert rel_l2(w_gpu, w_cpu) < 5e-5 and rel_l2(b_gpu, b_cpu) < 5e-5, (rel_l2(w_gpu, w_cpu), rel_l2(b_gpu, b_cpu))
+
+
+@pytest.mark.parametrize("K,M,N1,N2", [(40960, 352, 300, 88), (4096, 32, 5, 8), (700, 128, 400, 64), (5000, 96, 20, 80),
+                                        (300, 16, 16, 16)])
+def test_tc_gemm_tn_pair(tc_ops, K, M, N1, N2):
+    """Two weight gradients that share dY in one launch: C1 += dY^T X1 (+ bias gradient), C2 += dY^T X2."""
+    ld1 = (N1 + 3) // 4 * 4                                    # x slices live in 16 B-aligned padded buffers
+    dY, X1p, X2 = g(K, M, seed=1), g(K, ld1, seed=2), g(K, N2, seed=3)
+    X1 = X1p[:, :N1]
+    w1_cpu, w2_cpu, b_cpu = torch.ones(M, N1).double(), torch.ones(M, N2).double(), torch.ones(M).double()
+    w1_gpu, w2_gpu, b_gpu = torch.ones(M, N1).cuda(), torch.ones(M, N2).cuda(), torch.ones(M).cuda()
+    EmuOps().gemm_tn_pair(dY.double(), X1.double(), w1_cpu, b_cpu, X2.double(), w2_cpu)
+    tc_ops.gemm_tn_pair(dY.cuda(), X1p.cuda()[:, :N1], w1_gpu, b_gpu, X2.cuda(), w2_gpu)
+    torch.cuda.synchronize()
+    e = (rel_l2(w1_gpu, w1_cpu), rel_l2(w2_gpu, w2_cpu), rel_l2(b_gpu, b_cpu))
+    assert max(e) < 5e-5, e
