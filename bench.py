@@ -144,6 +144,13 @@ def profile_primitives(trainer, reps=3):
                 streamed = C.shape[0] * C.shape[1] * Kd >= (1 << 20)   # the tcgen05 path (mfm_set_gemm_tc_min_work default)
                 shapes.append(("%s %dx%dx%d%s" % (a[0], C.shape[0], C.shape[1], Kd, " acc" if k.get("accumulate") else ""),
                                e0, e1, by, streamed))
+            elif name == "gemm_tn_pair":                      # C1 += dY^T A1 (+ column sums), C2 += dY^T A2: dY read once
+                dY, A1, C1, _cs, A2, C2 = a[:6]
+                fl = 2.0 * dY.shape[1] * (A1.shape[1] + A2.shape[1]) * dY.shape[0]
+                by = 4.0 * (dY.numel() + A1.numel() + A2.numel() + 2 * (C1.numel() + C2.numel()))
+                tag = "gemm_tn"
+                shapes.append(("tn-pair %dx(%d+%d)x%d acc" % (dY.shape[1], A1.shape[1], A2.shape[1], dY.shape[0]), e0, e1, by,
+                               fl / 2 >= (1 << 20)))
             elif name in ("lstm_fwd", "lstm_bwd"):
                 fl = sum(2.0 * c["T"] * c["B"] * 4 * c["h"] * c["h"] for c in a[0])
                 tag = name + ("_dec" if (a[0][0].get("gx_steps", 0) == 1 or a[0][0].get("dh_all") is not None) else "_enc_mfn")
@@ -156,7 +163,7 @@ def profile_primitives(trainer, reps=3):
             rec.append((tag, e0, e1, fl, by))
             return r
         return inner
-    names = ["gemm", "lstm_fwd", "lstm_bwd", "mfn_mem_fwd", "mfn_mem_bwd", "softmax_gate_fwd", "softmax_gate_bwd", "mmd_fwd",
+    names = ["gemm", "gemm_tn_pair", "lstm_fwd", "lstm_bwd", "mfn_mem_fwd", "mfn_mem_bwd", "softmax_gate_fwd", "softmax_gate_bwd", "mmd_fwd",
              "mmd_bwd", "copy2d", "add", "zero", "colsum", "relu_bwd", "mse_fwd_bwd", "l1_fwd_bwd", "ce_fwd_bwd",
              "loss_total", "adam", "randn", "rng_tick", "rownorm2", "mmd_kexp", "mmd_combine"]
     orig = {n: getattr(ops, n) for n in names}
@@ -322,7 +329,8 @@ def main():
         # (profiles/r1_gemm_tcp_ncu.json, per launch).
         gshare = streamed["ms_per_step"] / (tot / 3)
         ach = streamed["bytes_per_step"] / (streamed["ms_per_step"] * 1e-3) / 1e9 if streamed["ms_per_step"] else 0.0
-        top_key = next(k for k, v in gemm_shapes.items() if max(int(t) for t in k.split()[1].split("x")[::2]) >= 4096)
+        top_key = next(k for k, v in gemm_shapes.items() if not k.startswith("tn-pair") and
+                       max(int(t) for t in k.split()[1].split("x")[::2]) >= 4096)
         tms, tn, tby = gemm_shapes[top_key]
         traffic = None
         try:

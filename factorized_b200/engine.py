@@ -87,6 +87,9 @@ class Engine:
         self._pool = []                  # streams for _par branches
         self._z_ready = None             # event: encoder latents written (they are produced on the auxiliary stream)
         self.stamps, self.stamp_names = None, []      # debug timeline (mark)
+        # two launches for the last backward recurrence (heavy cells first, their weight gradients start early): measured
+        # SLOWER (3.67 vs 3.56 ms/step: the gradient GEMMs delay the second launch), kept as an experiment switch
+        self.split_last_recurrence = os.environ.get("MFM_SPLIT_LAST", "0") == "1"
         self.defer_mmd_join = False      # the fused trainer joins the MMD stream in losses() instead of at the end of forward
         # loss_buf: 0 disc, 1..3 mse_l/a/v, 4..7 mmd per latent (unweighted), 8 total (weighted)
 
@@ -688,21 +691,25 @@ class Engine:
             ops.copy2d(dcStar[B:, :H], dCext[:TB - B], accumulate=True)
 
         self.mark("bwd:att1+dCext")
-        # (2') the recurrences reversed, one launch
-        cells = list(enc_cells)
+        # (2') the recurrences reversed and (1') the weight gradients of the 6 input-side cells, all T at once
+        #      (dW_ih = dG^T x and dW_hh = dG^T h_prev share dG; b_ih and b_hh share its column sums).
+        #      One launch for all cells (optionally two, heavy cells first -- see split_last_recurrence).
+        todo = []                                            # (cell, weight-gradient job)
         for m, tag in enumerate(TAGS):
             o = dm.hoff[m]
-            cells.append(dict(T=T, B=B, h=dm.hm[m], gates=ws["gatesN%d" % m], cs=Call[:, o:o + dm.hm[m]],
-                              W=P[pre + "lstm_%s.weight_hh" % tag], dh_all=None,
-                              dh_last=dHlast[:, o:o + dm.hm[m]], dc_ext=dCext[:, o:o + dm.hm[m]],
-                              dG=buf("dGN%d" % m, TB, 4 * dm.hm[m]), dc_scratch=buf("dcSN%d" % m, B, dm.hm[m])))
-        ops.lstm_bwd(cells)
-
-        # (1') weight gradients of the 6 input-side cells, all T at once
-        for m, tag in enumerate(TAGS):
-            jobs = [(pre + "lstm_%s" % tag, "dGN%d" % m, Hall[:TB, dm.hoff[m]:dm.hoff[m] + dm.hm[m]])]
-            if enc_cells:
-                jobs.append(("encoder_%s.lstm" % tag, "dGE%d" % m, ws["hsE%d" % m][:TB]))
-            for (nm, dGn, hs) in jobs:              # dW_ih = dG^T x and dW_hh = dG^T h_prev share dG; b_ih and b_hh share its sums
+            cell = dict(T=T, B=B, h=dm.hm[m], gates=ws["gatesN%d" % m], cs=Call[:, o:o + dm.hm[m]],
+                        W=P[pre + "lstm_%s.weight_hh" % tag], dh_all=None,
+                        dh_last=dHlast[:, o:o + dm.hm[m]], dc_ext=dCext[:, o:o + dm.hm[m]],
+                        dG=buf("dGN%d" % m, TB, 4 * dm.hm[m]), dc_scratch=buf("dcSN%d" % m, B, dm.hm[m]))
+            todo.append((cell, (pre + "lstm_%s" % tag, "dGN%d" % m, m, Hall[:TB, o:o + dm.hm[m]])))
+        for m, c in enumerate(enc_cells):
+            todo.append((c, ("encoder_%s.lstm" % TAGS[m], "dGE%d" % m, m, ws["hsE%d" % m][:TB])))
+        todo.sort(key=lambda cj: -cj[0]["h"])
+        half = (len(todo) + 1) // 2 if (self.split_last_recurrence and len(todo) > 3) else len(todo)
+        for part in (todo[:half], todo[half:]):
+            if not part:
+                continue
+            ops.lstm_bwd([c for c, _ in part])
+            for _, (nm, dGn, m, hs) in part:
                 self._wgrad_pair(ws[dGn], self.xs[m], G[nm + ".weight_ih"], G[nm + ".bias_ih"], hs, G[nm + ".weight_hh"],
                                  G[nm + ".bias_hh"])
