@@ -378,8 +378,6 @@ class Engine:
             ops.gemm_tn_pair(dY, A1, G1, b1, A2, G2)
             if b2 is not None:
                 ops.copy2d(b1.view(1, -1), b2.view(1, -1), accumulate=True)
-        if os.environ.get("MFM_SKIP_WGRAD"):
-            return
         self._on_side(G1.data_ptr(), run)
 
     def _wgrad_gemm(self, dY, A, Gout, stream_key=None, **kw):
@@ -395,8 +393,6 @@ class Engine:
         if self._side is None:
             self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
         # independent weight gradients also overlap each other; two GEMMs into the same tensor share a stream
-        if os.environ.get("MFM_SKIP_WGRAD"):       # timing experiment only: how much of the step is weight gradients?
-            return
         st = self._side[((stream_key if stream_key is not None else Gout.data_ptr()) >> 8) % len(self._side)]
         ev = torch.cuda.Event()
         ev.record(main)
