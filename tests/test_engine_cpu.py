@@ -82,3 +82,26 @@ def test_engine_dropout_masks_replay():
     assert abs(float(eng.loss_buf[8]) - losses["total"]) < 1e-4 * abs(losses["total"])
     bad = [(k, rel_l2(G[k], Go[k])) for k in P if Go[k] is not None and rel_l2(G[k], Go[k]) > 3e-4]
     assert not bad, bad
+
+
+def test_engine_schedule_variants_agree():
+    """The trainer's variant of the schedule (MMD joined only in backward, total summed there) and the experiment switch
+    that splits the last backward recurrence into two launches give the same losses and gradients as the default."""
+    g, configs, P, x, y, noise, T, n = tiny_case("l1", 1)
+    ref_eng, _, Gref = run_engine(configs, P, x, y, noise, T, n, "l1")
+    for variant in ("defer_mmd_join", "split_last_recurrence"):
+        eng = Engine(configs, T, n, "cpu", EmuOps(), head="l1")
+        setattr(eng, variant, True)
+        eng.forward(OrderedDict(P), x.contiguous(), noise)
+        dX, dY = eng.losses(y)
+        G = OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+        eng.backward(OrderedDict(P), G, dX, dY, eng.dm.lda_mmd)
+        assert abs(float(eng.loss_buf[8]) - float(ref_eng.loss_buf[8])) < 1e-6 * abs(float(ref_eng.loss_buf[8])), variant
+        bad = [(k, rel_l2(G[k], Gref[k])) for k in P if float(Gref[k].abs().max()) > 0 and rel_l2(G[k], Gref[k]) > 1e-6]
+        assert not bad, (variant, bad)
+
+
+def test_engine_timeline_marks_are_inert_without_a_buffer():
+    g, configs, P, x, y, noise, T, n = tiny_case("l1", 1)
+    eng, out, G = run_engine(configs, P, x, y, noise, T, n, "l1")
+    assert eng.stamps is None and eng.stamp_names == []
