@@ -1,5 +1,6 @@
 """Parity of the CUDA path (through the C ABI) against the golden vectors of the unmodified reference and
 against the oracle on the same seeded inputs.  Tolerance: 1e-3 relative (BASELINE.json north_star), fp32."""
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -292,3 +293,51 @@ def test_standalone_modules_vs_oracle():
         elif not rel_l2(p.grad, gr) < TOL:
             bad[k] = rel_l2(p.grad, gr)
     assert not bad, bad
+
+
+def test_train_mfm_entry_point(tmp_path):
+    """The drop-in for the reference's train_mfm (mfm_mosi.py:386-503) against the oracle's restatement of the same loop:
+    shuffle once with numpy's global RNG (:387-389), time-major batches, the tail dropped (:423), Adam at the default lr
+    (:403), the epoch's mean discriminative loss (:442-443), whole-set validation L1 (:449-455), save-best / reload /
+    predict / score.  Dropout is off in this configuration, so the only difference is the MMD noise stream (device RNG
+    here, CPU generator there), which perturbs the trajectory far below the tolerance."""
+    import factorized_b200 as F
+    rs = np.random.RandomState(0)
+    configs = O.tiny_configs()
+    configs[0].update(batchsize=16, num_epochs=2)
+    T, D, bs = 5, sum(configs[0]["input_dims"]), 16
+
+    def make(n):
+        X = rs.randn(n, T, D).astype(np.float32)
+        return X, (2.0 * X[:, :, 0].mean(1)).astype(np.float32)
+    Xtr, ytr = make(bs * 12 + 5)                       # 5 samples fall off the last batch, like the reference
+    Xva, yva = make(40)
+    Xte, yte = make(48)
+    np.random.seed(11)
+    torch.manual_seed(123)
+    out = F.train_mfm(Xtr, ytr, Xva, yva, Xte, yte, configs, verbose=False, save_dir=str(tmp_path))
+
+    # the oracle's statement of the same two epochs
+    np.random.seed(11)
+    p = np.random.permutation(Xtr.shape[0])
+    Xs, ys = torch.from_numpy(np.ascontiguousarray(np.swapaxes(Xtr[p], 0, 1))), torch.from_numpy(ytr[p])
+    Xv = torch.from_numpy(np.ascontiguousarray(np.swapaxes(Xva, 0, 1)))
+    P, state, hist = O.init_params(configs, 123), {}, []
+    for ep in range(2):
+        acc = 0.0
+        for b in range(Xs.shape[1] // bs):
+            noise = O.draw_mmd_noise(configs, bs, 1000 * ep + b)
+            P, losses, _, _ = O.train_step(P, Xs[:, b * bs:(b + 1) * bs].contiguous(), ys[b * bs:(b + 1) * bs], configs, noise, state)
+            acc += losses["disc"]
+        vo = O.mfm_forward(Xv, P, configs, O.draw_mmd_noise(configs, Xv.shape[1], 5))
+        hist.append((acc / (Xs.shape[1] // bs), float(torch.nn.functional.l1_loss(vo["y_hat"].squeeze(1), torch.from_numpy(yva)))))
+
+    assert len(out["history"]) == 2 and os.path.exists(out["checkpoint"])
+    for (ep, tl, vl), (otl, ovl) in zip(out["history"], hist):
+        assert abs(tl - otl) < 1e-3 * abs(otl), (ep, tl, otl)
+        assert abs(vl - ovl) < 1e-3 * abs(ovl), (ep, vl, ovl)
+    assert out["predictions"].shape == (48,) and np.isfinite(out["predictions"]).all()
+    assert set(out["scores"]) == {"mae", "corr", "mult_acc", "binary_acc"}
+    assert abs(out["best_valid"] - min(h[2] for h in out["history"])) < 1e-7
+    reloaded = torch.load(out["checkpoint"], weights_only=False)       # whole-module pickle, as the reference saves it
+    assert sorted(reloaded.state_dict()) == sorted(out["model"].state_dict())
