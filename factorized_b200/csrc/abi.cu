@@ -1,7 +1,44 @@
 // C-ABI glue: library version, launch counter, GEMM path selection and dispatch.
+#include <mutex>
+#include <set>
+#include <utility>
 #include "common.cuh"
 
 unsigned long long g_mfm_launches = 0;
+
+// ---- per-device caches ----------------------------------------------------------------------------------------------
+static std::mutex g_dev_mu;
+static MfmDevInfo g_dev[64];
+static bool g_dev_ok[64];
+static std::set<std::pair<int, const void*>> g_attr_done;
+
+const MfmDevInfo& mfm_dev_info() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (!g_dev_ok[dev]) {
+    MfmDevInfo d;
+    if (cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) d.sms = 148;
+    if (cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) d.smem_optin = 48 * 1024;
+    (void)cudaGetLastError();
+    g_dev[dev] = d;
+    g_dev_ok[dev] = true;
+  }
+  return g_dev[dev];
+}
+
+int mfm_func_smem(const void* func, int bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  const auto key = std::make_pair(dev, func);
+  if (g_attr_done.count(key)) return 0;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return (int)e;
+  g_attr_done.insert(key);
+  return 0;
+}
 static int g_gemm_path = MFM_PATH_TC_BF16X3;   // tensor cores, split-bf16 operands; MFM_PATH_SIMT_FP32 is the exact-fp32 alternative
 
 int gemm_simt_launch(int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,

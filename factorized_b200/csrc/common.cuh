@@ -10,6 +10,14 @@
 
 extern unsigned long long g_mfm_launches;   // host-side counter, see abi.cu
 
+// Per-device facts and one-time kernel attributes (abi.cu).  The opt-in shared-memory limit and the SM count belong to
+// the CURRENT device, and cudaFuncSetAttribute applies per device: both are cached per (device[, kernel]) behind a
+// mutex, so a process that drives several GPUs -- or calls from autograd's backward thread -- stays correct.
+struct MfmDevInfo { int sms; int smem_optin; };
+const MfmDevInfo& mfm_dev_info();
+int mfm_func_smem(const void* func, int bytes);      // 0 or a cudaError_t
+template <typename F> static inline int mfm_func_smem_t(F* f, int bytes) { return mfm_func_smem(reinterpret_cast<const void*>(f), bytes); }
+
 #define MFM_LAUNCH_CHECK()                                   \
   do {                                                       \
     ++g_mfm_launches;                                        \
@@ -54,13 +62,21 @@ __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return h;
 }
+// Stream key of (seed, step, site): every input goes through its own mixing round, so consecutive steps (or sites) give
+// unrelated keys -- NOT seed + step*C, which made the step-s+1 stream the step-s stream shifted by one element.
+__host__ __device__ __forceinline__ uint32_t site_key(uint32_t seed, uint32_t step, uint32_t site) {
+  return fmix32(fmix32(seed ^ fmix32(step + 0x9E3779B9u)) + site * 0x7F4A7C15u);
+}
 __device__ __forceinline__ uint32_t site_seed(const long long* rng, int site) {
-  uint32_t seed = (uint32_t)rng[0], step = (uint32_t)rng[1];
-  return seed + step * 0x9E3779B1u + (uint32_t)site * 0x7F4A7C15u;
+  return site_key((uint32_t)rng[0], (uint32_t)rng[1], (uint32_t)site);
+}
+// Counter -> 32 random bits under a stream key: two rounds, the key enters both (a one-round hash(idx*C + key) of two keys
+// is the same sequence at two offsets).
+__host__ __device__ __forceinline__ uint32_t rng_bits(uint32_t sseed, uint32_t idx) {
+  return fmix32(fmix32(idx + sseed) ^ sseed);
 }
 __device__ __forceinline__ bool drop_keep(uint32_t sseed, uint32_t idx, float p) {
-  uint32_t h = fmix32(idx * 0x9E3779B1u + sseed);
-  float u = (float)(h >> 8) * (1.0f / 16777216.0f);
+  float u = (float)(rng_bits(sseed, idx) >> 8) * (1.0f / 16777216.0f);
   return u >= p;
 }
 

@@ -158,15 +158,16 @@ __global__ void rng_tick_kernel(long long* rng) { rng[1] += 1; }
 __global__ void randn_kernel(long long n, float* __restrict__ out, const long long* __restrict__ rng, int site) {
   const uint32_t ss = site_seed(rng, site);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const uint32_t h1 = fmix32((uint32_t)(2 * i) * 0x9E3779B1u + ss);
-    const uint32_t h2 = fmix32((uint32_t)(2 * i + 1) * 0x9E3779B1u + ss);
+    const uint32_t h1 = rng_bits(ss, (uint32_t)(2 * i));
+    const uint32_t h2 = rng_bits(ss, (uint32_t)(2 * i + 1));
     const float u1 = ((float)(h1 >> 8) + 1.0f) * (1.0f / 16777216.0f);     // (0,1]
     const float u2 = (float)(h2 >> 8) * (1.0f / 16777216.0f);              // [0,1)
     out[i] = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
   }
 }
 
-static inline int grid_for(long long n, int threads = 256, int cap = 148 * 8) {
+static inline int grid_for(long long n, int threads = 256, int cap = 0) {
+  if (cap <= 0) cap = mfm_dev_info().sms * 8;
   long long b = (n + threads - 1) / threads;
   if (b < 1) b = 1;
   if (b > cap) b = cap;
@@ -176,7 +177,7 @@ static inline int grid_for(long long n, int threads = 256, int cap = 148 * 8) {
 extern "C" int mfm_copy2d(int M, int N, const float* src, long long lds, float* dst, long long ldd, int accumulate,
                           void* stream) {
   MFM_REQUIRE(M > 0 && N > 0 && src && dst);
-  const int blocks = (M + 7) / 8 < 148 * 16 ? (M + 7) / 8 : 148 * 16;
+  const int blocks = (M + 7) / 8 < mfm_dev_info().sms * 16 ? (M + 7) / 8 : mfm_dev_info().sms * 16;
   copy2d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(M, N, src, lds, dst, ldd, accumulate);
   MFM_LAUNCH_CHECK();
   return MFM_OK;
@@ -196,7 +197,7 @@ extern "C" int mfm_zero(long long n, float* p, void* stream) {
 extern "C" int mfm_colsum(int M, int N, const float* A, long long lda, float* out, void* stream) {
   MFM_REQUIRE(M > 0 && N > 0 && A && out);
   const int strips = (N + 31) / 32;
-  int chunks = (2 * 148 + strips - 1) / strips;
+  int chunks = (2 * mfm_dev_info().sms + strips - 1) / strips;
   int maxc = (M + 63) / 64;
   if (chunks > maxc) chunks = maxc;
   if (chunks < 1) chunks = 1;
@@ -216,7 +217,7 @@ extern "C" int mfm_mse_fwd_bwd(int M, int N, const float* xhat, long long ldxh, 
                                float loss_scale, float grad_scale, float* slot, float* dxhat, long long lddx,
                                void* stream) {
   MFM_REQUIRE(M > 0 && N > 0 && xhat && x && slot);
-  mse_kernel<<<((M + 7) / 8 < 148 * 8 ? (M + 7) / 8 : 148 * 8), 256, 0, (cudaStream_t)stream>>>(M, N, xhat, ldxh, x, ldx, loss_scale,
+  mse_kernel<<<((M + 7) / 8 < mfm_dev_info().sms * 8 ? (M + 7) / 8 : mfm_dev_info().sms * 8), 256, 0, (cudaStream_t)stream>>>(M, N, xhat, ldxh, x, ldx, loss_scale,
                                                                                        grad_scale, slot, dxhat, lddx);
   MFM_LAUNCH_CHECK();
   return MFM_OK;

@@ -102,7 +102,7 @@ int gemm_simt_launch(int mode, int M, int N, int K, const float* A, long long ld
   const bool plain = !bias && !bias2 && act == MFM_ACT_NONE && !mask && drop_p <= 0.0f && accumulate;
   if (plain && K >= 1024) {
     long long tiles = (long long)grid.x * grid.y;
-    int splits = (int)((2 * 148 + tiles - 1) / tiles);
+    int splits = (int)((2 * mfm_dev_info().sms + tiles - 1) / tiles);
     int maxs = K / 256;
     if (splits > maxs) splits = maxs;
     if (splits > 1) {

@@ -261,7 +261,7 @@ int gemm_tc_launch(int passes, int mode, int M, int N, int K, const float* A, lo
   const bool plain = !bias && !bias2 && act == MFM_ACT_NONE && !mask && drop_p <= 0.0f && accumulate;
   if (plain && K >= 2048) {
     long long tiles = (long long)grid.x * grid.y;
-    int splits = (int)((2 * 148 + tiles - 1) / tiles);
+    int splits = (int)((2 * mfm_dev_info().sms + tiles - 1) / tiles);
     int maxs = K / 256;
     if (splits > maxs) splits = maxs;
     if (splits > 1) {
@@ -272,14 +272,12 @@ int gemm_tc_launch(int passes, int mode, int M, int N, int K, const float* A, lo
     }
   }
   const size_t smem = (size_t)TC_STAGES * (2 * TC_A_PLANE + 2 * 4 * (ta.BN * 16 + 32)) + 128;
-  static bool attr[3] = {false, false, false};
-  if (!attr[mode]) {
-    cudaError_t e = cudaSuccess;
-    if (mode == MFM_GEMM_NT) e = cudaFuncSetAttribute(gemm_tc_kernel<MFM_GEMM_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-    if (mode == MFM_GEMM_NN) e = cudaFuncSetAttribute(gemm_tc_kernel<MFM_GEMM_NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-    if (mode == MFM_GEMM_TN) e = cudaFuncSetAttribute(gemm_tc_kernel<MFM_GEMM_TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr[mode] = true;
+  {
+    int e = 0;
+    if (mode == MFM_GEMM_NT) e = mfm_func_smem_t(gemm_tc_kernel<MFM_GEMM_NT>, 110 * 1024);
+    if (mode == MFM_GEMM_NN) e = mfm_func_smem_t(gemm_tc_kernel<MFM_GEMM_NN>, 110 * 1024);
+    if (mode == MFM_GEMM_TN) e = mfm_func_smem_t(gemm_tc_kernel<MFM_GEMM_TN>, 110 * 1024);
+    if (e) return e;
   }
   switch (mode) {
     case MFM_GEMM_NT: gemm_tc_kernel<MFM_GEMM_NT><<<grid, TC_THREADS, smem, st>>>(ta); break;

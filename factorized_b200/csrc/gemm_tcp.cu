@@ -463,13 +463,7 @@ static int tcp_launch_one(const TcpArgs& pa, dim3 grid, cudaStream_t st) {
   if (BPRE) tmB = tmA;
   else ok = ok && (B_MN ? make_map(&tmB, g.B, g.ldb, g.N, g.K, 32, P_BK) : make_map(&tmB, g.B, g.ldb, g.K, g.N, P_BK, pa.t.BN));
   if (!ok) return MFM_ERR_UNSUPPORTED;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcp_kernel<MODE, BPRE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(P_RING_BUDGET + P_BAR_BYTES));
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
+  if (int e = mfm_func_smem_t(gemm_tcp_kernel<MODE, BPRE>, (int)(P_RING_BUDGET + P_BAR_BYTES))) return e;
   TcpArgs pb = pa;
   pb.trace = ((long long)grid.x * grid.y * grid.z * P_TRACE_WORDS <= g_trace_words) ? g_trace : nullptr;
   const RingCfg rc = tcp_ring(pa.t.BN, B_MN, BPRE);
@@ -540,7 +534,7 @@ int gemm_tcp_launch(int passes, int mode, int M, int N, int K, const float* A, l
   if (splitk) {                                   // split-K weight gradients: one split per resident CTA slot
     long long tiles = (long long)grid.x * grid.y;
     const int occ = 2;   // __launch_bounds__(P_THREADS, 2), ring budget 99 KB
-    int splits = (int)((occ * 148 + tiles - 1) / tiles);
+    int splits = (int)((occ * mfm_dev_info().sms + tiles - 1) / tiles);
     int maxs = K / 256;
     if (splits > maxs) splits = maxs;
     if (splits > 1) {
@@ -594,7 +588,7 @@ int gemm_tcp_launch_tn_pair(int passes, int M, int K, const float* A, long long 
   dim3 grid(tiles1 + tiles2, (M + P_BM - 1) / P_BM, 1);
   if (K >= 2048) {
     long long tiles = (long long)grid.x * grid.y;
-    int splits = (int)((2 * 148 + tiles - 1) / tiles);
+    int splits = (int)((2 * mfm_dev_info().sms + tiles - 1) / tiles);
     int maxs = K / 256;
     if (splits > maxs) splits = maxs;
     if (splits > 1) {

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_seq_fwd_kernel(LstmBatch bt
           for (int r = 0; r < LSTM_R; ++r) {
             const int row = row0 + rbase + r;
             if (row < B) {
-              const float* gp = c.gx + ((long long)t * B + row) * H4 + j;
+              const float* gp = c.gx + ((long long)t * B + row) * (c.ld_gx ? c.ld_gx : (long long)H4) + j;
 #pragma unroll
               for (int g = 0; g < 4; ++g) acc[r][g] = __ldg(gp + g * h);
             } else {
@@ -262,17 +262,10 @@ static int lstm_validate(const mfm_lstm_cell* cells, int n, bool bwd) {
   return MFM_OK;
 }
 
-static int smem_optin_limit() {
-  static int lim = -1;
-  if (lim < 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) lim = 48 * 1024;
-  }
-  return lim;
-}
+static int smem_optin_limit() { return mfm_dev_info().smem_optin; }
 
 int lstm_tc_fwd_launch(const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* rest, int* nrest, cudaStream_t st);
+void ws_count_fallback(bool bwd, int ncells);
 
 extern "C" int mfm_lstm_seq_fwd(const mfm_lstm_cell* cells, int ncells, void* stream) {
   int rc = lstm_validate(cells, ncells, false);
@@ -301,12 +294,8 @@ extern "C" int mfm_lstm_seq_fwd(const mfm_lstm_cell* cells, int ncells, void* st
     int tiles = (cells[i].B + RT - 1) / RT;
     if (tiles > gx) gx = tiles;
   }
-  static size_t attr_set = 0;
-  if (smem > attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bt.smem_limit);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = bt.smem_limit;
-  }
+  if (int e = mfm_func_smem_t(lstm_seq_fwd_kernel, bt.smem_limit)) return e;
+  ws_count_fallback(false, ncells);
   lstm_seq_fwd_kernel<<<dim3(gx, ncells), LSTM_THREADS, smem, (cudaStream_t)stream>>>(bt);
   MFM_LAUNCH_CHECK();
   return MFM_OK;
@@ -341,12 +330,8 @@ extern "C" int mfm_lstm_seq_bwd(const mfm_lstm_cell* cells, int ncells, void* st
     int tiles = (cells[i].B + RT - 1) / RT;
     if (tiles > gx) gx = tiles;
   }
-  static size_t attr_set = 0;
-  if (smem > attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bt.smem_limit);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = bt.smem_limit;
-  }
+  if (int e = mfm_func_smem_t(lstm_seq_bwd_kernel, bt.smem_limit)) return e;
+  ws_count_fallback(true, ncells);
   lstm_seq_bwd_kernel<<<dim3(gx, ncells), LSTM_THREADS, smem, (cudaStream_t)stream>>>(bt);
   MFM_LAUNCH_CHECK();
   return MFM_OK;

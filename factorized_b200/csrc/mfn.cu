@@ -274,15 +274,7 @@ __global__ void __launch_bounds__(MEM_THREADS, 1) mfn_mem_bwd_kernel(mfm_mem_arg
   }
 }
 
-static int mem_smem_limit() {
-  static int lim = -1;
-  if (lim < 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) lim = 48 * 1024;
-  }
-  return lim;
-}
+static int mem_smem_limit() { return mfm_dev_info().smem_optin; }
 
 static int mem_validate(const mfm_mem_args* a, bool bwd) {
   if (!a || a->T <= 0 || a->B <= 0 || a->mem <= 0 || a->mem > 512 || a->g1 <= 0 || a->g2 <= 0) return MFM_ERR_ARG;
@@ -304,12 +296,7 @@ extern "C" int mfm_mfn_mem_fwd(const mfm_mem_args* a, void* stream) {
   const int wsm = full <= (size_t)lim;
   const size_t smem = wsm ? full : base;
   if (smem > (size_t)lim) return MFM_ERR_UNSUPPORTED;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(mfn_mem_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
+  if (int e = mfm_func_smem_t(mfn_mem_fwd_kernel, lim)) return e;
   mfn_mem_fwd_kernel<<<(a->B + MEM_RT - 1) / MEM_RT, MEM_THREADS, smem, (cudaStream_t)stream>>>(*a, wsm);
   MFM_LAUNCH_CHECK();
   return MFM_OK;
@@ -325,12 +312,7 @@ extern "C" int mfm_mfn_mem_bwd(const mfm_mem_args* a, void* stream) {
   const int wsm = full <= (size_t)lim;
   const size_t smem = wsm ? full : base;
   if (smem > (size_t)lim) return MFM_ERR_UNSUPPORTED;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(mfn_mem_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
+  if (int e = mfm_func_smem_t(mfn_mem_bwd_kernel, lim)) return e;
   mfn_mem_bwd_kernel<<<(a->B + MEM_RT - 1) / MEM_RT, MEM_THREADS, smem, (cudaStream_t)stream>>>(*a, wsm);
   MFM_LAUNCH_CHECK();
   return MFM_OK;

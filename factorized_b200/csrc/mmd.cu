@@ -132,12 +132,7 @@ extern "C" int mfm_mmd_fwd(int B, int dim, const float* z, long long ldz, const 
   if (e != cudaSuccess) return (int)e;
   const int dimp = dim | 1;
   const size_t smem = (size_t)(2 * MMD_RI + MMD_TJ) * dimp * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    e = cudaFuncSetAttribute(mmd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
+  if (int ea = mfm_func_smem_t(mmd_fwd_kernel, 128 * 1024)) return ea;
   mmd_fwd_kernel<<<(B + MMD_RI - 1) / MMD_RI, MMD_THREADS, smem, st>>>(B, dim, z, ldz, g, ldg, out);
   MFM_LAUNCH_CHECK();
   return MFM_OK;
@@ -148,12 +143,7 @@ extern "C" int mfm_mmd_bwd(int B, int dim, const float* z, long long ldz, const 
   MFM_REQUIRE(B > 0 && dim > 0 && dim <= MMD_MAXDIM && z && g && dz);
   const int dimp = dim | 1;
   const size_t smem = ((size_t)(MMD_RI + MMD_TJ) * dimp + MMD_RI * MMD_TJ) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(mmd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
+  if (int ea = mfm_func_smem_t(mmd_bwd_kernel, 128 * 1024)) return ea;
   const float c = -2.0f / ((float)dim * (float)dim);
   const float coef = scale * 2.0f * c / ((float)B * (float)B);
   mmd_bwd_kernel<<<(B + MMD_RI - 1) / MMD_RI, MMD_THREADS, smem, (cudaStream_t)stream>>>(B, dim, z, ldz, g, ldg, coef,
@@ -224,7 +214,7 @@ extern "C" int mfm_mmd_kexp(int M, int N, float* S, const float* nx, const float
                             void* stream) {
   MFM_REQUIRE(M > 0 && N > 0 && dim > 0 && S && nx && ny && slot);
   long long blocks = ((long long)M * N + 256 * 8 - 1) / (256 * 8);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > mfm_dev_info().sms * 8) blocks = mfm_dev_info().sms * 8;
   if (blocks < 1) blocks = 1;
   mmd_kexp_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(M, N, S, nx, ny, 1.0f / ((float)dim * (float)dim), weight, slot);
   MFM_LAUNCH_CHECK();
@@ -237,7 +227,7 @@ extern "C" int mfm_mmd_combine(int B, int dim, const float* z, long long ldz, co
   const float c = -2.0f / ((float)dim * (float)dim);
   const float coef = scale * 2.0f * c / ((float)B * (float)B);
   long long blocks = ((long long)B * dim + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > mfm_dev_info().sms * 8) blocks = mfm_dev_info().sms * 8;
   mmd_combine_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(B, dim, z, ldz, rs, cs, t1, t2, coef, scale_dev, dz, lddz);
   MFM_LAUNCH_CHECK();
   return MFM_OK;

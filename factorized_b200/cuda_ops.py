@@ -28,7 +28,7 @@ class LstmCell(C.Structure):
                 ("hs", c_f), ("ld_hs", LL), ("cs", c_f), ("ld_cs", LL), ("gates", c_f),
                 ("dh_all", c_f), ("ld_dh_all", LL), ("dh_last", c_f), ("ld_dh_last", LL),
                 ("dc_ext", c_f), ("ld_dc_ext", LL), ("dG", c_f), ("dc_scratch", c_f),
-                ("cs_dup", c_f), ("dc_ext2", c_f)]
+                ("cs_dup", c_f), ("dc_ext2", c_f), ("ld_gx", LL)]
 
 
 class MemArgs(C.Structure):
@@ -58,6 +58,10 @@ _SIGS = {
     "mfm_debug_stamp": (C.c_int, [c_f, C.c_int, c_f]),
     "mfm_lstm_seq_fwd": (C.c_int, [C.POINTER(LstmCell), C.c_int, c_f]),
     "mfm_lstm_seq_bwd": (C.c_int, [C.POINTER(LstmCell), C.c_int, c_f]),
+    "mfm_debug_lstm_force_nb": (C.c_int, [C.c_int]),
+    "mfm_debug_lstm_force_chains": (C.c_int, [C.c_int]),
+    "mfm_debug_set_lstm_trace": (C.c_int, [c_f]),
+    "mfm_debug_lstm_variant_count": (C.c_ulonglong, [C.c_int]),
     "mfm_mfn_mem_fwd": (C.c_int, [C.POINTER(MemArgs), c_f]),
     "mfm_mfn_mem_bwd": (C.c_int, [C.POINTER(MemArgs), c_f]),
     "mfm_softmax_gate_fwd": (C.c_int, [C.c_int, C.c_int, c_f, c_f, c_f, c_f]),
@@ -265,9 +269,9 @@ class CudaOps:
             if not bwd:
                 s.gx_steps = c["gx_steps"]
                 pgx, xr, xc, ldx = _mat(c["gx"], "lstm gx")
-                if (xr, xc) != (c["gx_steps"] * c["B"], h4) or ldx != h4:
-                    raise MfmCudaError("lstm gx must be contiguous [gx_steps*B,4h]")
-                s.gx = pgx
+                if (xr, xc) != (c["gx_steps"] * c["B"], h4):
+                    raise MfmCudaError("lstm gx must be [gx_steps*B,4h]")
+                s.gx, s.ld_gx = pgx, ldx
                 s.bias_rest = _vec(c.get("bias_rest"), "lstm bias_rest", h4)
                 if c["gx_steps"] < c["T"] and s.bias_rest is None:
                     raise MfmCudaError("lstm: bias_rest required when gx_steps < T")

@@ -86,7 +86,10 @@ class MFMTrainer:
         else:
             self.y = torch.zeros(B * dm.out, dtype=torch.float32, device=dev)
         self.noise = [torch.zeros(B, k, dtype=torch.float32, device=dev) for k in (dm.z[0], dm.z[1], dm.z[2], dm.zy)]
-        self.rng = torch.tensor([int(seed), 0], dtype=torch.int64, device=dev)
+        # every rank draws its own dropout masks and MMD Gaussian samples (independent shards, like independent
+        # reference processes): the rank is folded into the stream seed here, not left to the caller
+        rank = torch.distributed.get_rank(process_group) if self.world > 1 else 0
+        self.rng = torch.tensor([(int(seed) + rank * 0x9E3779B1) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=dev)
         self.adam_state = torch.tensor([lr, 0.0, 0.0, 0.0], dtype=torch.float32, device=dev)
         self.use_graph = use_graph
         self._copy_stream = None
@@ -222,8 +225,14 @@ def train_mfm(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, head:
     sched_opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=lr)   # carrier for ReduceLROnPlateau only
     scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(sched_opt, "min")   # :417
     ydt = np.int64 if head == "ce" else np.float32
-    Xpin = torch.from_numpy(Xt).pin_memory()
-    ypin = torch.from_numpy(np.asarray(y_train, dtype=ydt)).pin_memory()
+    # Pinned staging, one CONTIGUOUS [T,bs,D] block per batch: a strided slice Xt[:, b*bs:(b+1)*bs] of the time-major array
+    # is not a legal source for one async H2D copy (torch would stage it through pageable memory and block)
+    ytr = np.asarray(y_train, dtype=ydt)
+    Xpin = torch.empty((max(num_batches, 1), T, bs, Xt.shape[2]), dtype=torch.float32).pin_memory()
+    ypin = torch.empty((max(num_batches, 1), bs) + tuple(ytr.shape[1:]), dtype=torch.from_numpy(ytr[:1]).dtype).pin_memory()
+    for b in range(num_batches):
+        Xpin[b].copy_(torch.from_numpy(Xt[:, b * bs:(b + 1) * bs]))
+        ypin[b].copy_(torch.from_numpy(ytr[b * bs:(b + 1) * bs]))
 
     def evaluate(X, y):                                              # :445-455
         model.eval()
@@ -252,7 +261,7 @@ def train_mfm(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, head:
         model.train()
         acc = torch.zeros((), dtype=torch.float32, device=dev)
         for b in range(num_batches):
-            lb = trainer.step(Xpin[:, b * bs:(b + 1) * bs], ypin[b * bs:(b + 1) * bs])
+            lb = trainer.step(Xpin[b], ypin[b])
             acc += lb[0]                                             # device-side; the reference syncs here (:442)
         train_loss = float(acc) / max(num_batches, 1)
         valid_loss = evaluate(Xv, y_valid)

@@ -115,11 +115,22 @@ typedef struct mfm_lstm_cell {
    * "previous c" half of the next step's concatenation.  Both may be NULL. */
   float* cs_dup;            /* forward only:  [(T+1)*B, h], receives the same blocks as cs           */
   const float* dc_ext2;     /* backward only: [(T-1)*B, h]                                            */
+  long long ld_gx;          /* row pitch of gx in floats (0 = 4h): lets the hoisted projections of the two cells that
+                               read the same modality (encoder + MFN cell) be column blocks of ONE GEMM's output  */
 } mfm_lstm_cell;
 #define MFM_MAX_CELLS 8
 /* all cells of one call run concurrently (blockIdx.y = cell) */
 int mfm_lstm_seq_fwd(const mfm_lstm_cell* cells, int ncells, void* stream);
 int mfm_lstm_seq_bwd(const mfm_lstm_cell* cells, int ncells, void* stream);
+/* Test hooks for the recurrence kernels (tests/test_gpu_primitives.py): force the narrow (16-row) chains where they are
+ * legal (nb = 16; 0 = automatic), and read how many cells each variant has served since load --
+ * 0 fwd 32-row chains, 1 fwd 16-row chains, 2 bwd 32-row, 3 bwd 16-row, 4 / 5 fwd / bwd CUDA-core kernel (h > 128, exact-fp32 path). */
+int mfm_debug_lstm_force_nb(int nb);
+int mfm_debug_lstm_force_chains(int n);        /* chains (batch sub-tiles) per CTA: 1, 2, or 0 = by occupancy */
+/* Debug aid (scripts/lstm_trace.py): while a device buffer of 16*32*4 int64 is registered, CTA 0 of every forward
+ * recurrence launch records clock stamps per warp and step (wait start, wait done, epilogue done, MMA issue done). */
+int mfm_debug_set_lstm_trace(void* device_buf);
+unsigned long long mfm_debug_lstm_variant_count(int variant);
 
 /* The MFN memory recurrence, mfm_model.py:177-180, T steps in one kernel:
  * u_k = dropout(relu(Gkpre[t] + mem W_km^T));  gamma_k = sig(u_k W_k2^T + b_k2);

@@ -215,7 +215,9 @@ def relu(x: Tensor, branches, key: str, t: Optional[int] = None) -> Tensor:
         return torch.relu(x)
     m = branches[key] if t is None else branches[key][t]
     m = m.to(x.dtype)
-    bad = ((x > 0).to(x.dtype) != m) & (x.abs() > 1e-3)
+    own = (x > 0).to(x.dtype)
+    m = torch.where(m < 0, own, m)              # -1 = "not observed" (the unit was dropped): the oracle decides itself
+    bad = (own != m) & (x.abs() > 1e-3)
     if bool(bad.any()):
         RELU_REPLAY_VIOLATIONS.append("%s[t=%s]: %d branch decisions differ with |x| > 1e-3" % (key, t, int(bad.sum())))
     return x * m
@@ -262,7 +264,7 @@ def mfn_encoder(x: Tensor, P, configs, train=False, masks=None, branches=None) -
         hsz = P[pre + "lstm_%s.weight_hh" % tag].shape[1]
         hcs.append([x.new_zeros(n, hsz), x.new_zeros(n, hsz)])
     mem = x.new_zeros(n, config["memsize"])
-    mk = (lambda k, t: None if masks is None else masks[k][t])
+    mk = (lambda k, t: None if (masks is None or masks.get(k) is None) else masks[k][t])
     for t in range(T):
         prev_cs = torch.cat([hc[1] for hc in hcs], 1)                       # :163-165,171
         for m, tag in enumerate("lav"):

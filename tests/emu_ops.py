@@ -22,15 +22,31 @@ def _fmix32(h):
     return h
 
 
+def _fmix32_int(h):
+    h &= M32
+    h ^= h >> 16
+    h = (h * 0x85EBCA6B) & M32
+    h ^= h >> 13
+    h = (h * 0xC2B2AE35) & M32
+    h ^= h >> 16
+    return h
+
+
 def site_seed(rng, site):
+    """csrc/common.cuh::site_key -- every input passes its own mixing round (consecutive steps give unrelated keys)."""
     seed, step = int(rng[0]) & M32, int(rng[1]) & M32
-    return (seed + step * 0x9E3779B1 + site * 0x7F4A7C15) & M32
+    return _fmix32_int(_fmix32_int(seed ^ _fmix32_int((step + 0x9E3779B9) & M32)) + ((site * 0x7F4A7C15) & M32))
+
+
+def rng_bits(sseed, idx):
+    """csrc/common.cuh::rng_bits -- counter -> 32 bits, two rounds, the key enters both."""
+    return _fmix32(_fmix32(((idx & M32) + sseed) & M32) ^ sseed)
 
 
 def keep_mask(rng, site, p, rows, cols, row0=0):
     """keep[m,n] = u(idx) >= p with idx = (row0+m)*cols + n (32-bit wrap)."""
     idx = (torch.arange(rows, dtype=torch.int64).view(-1, 1) + row0) * cols + torch.arange(cols, dtype=torch.int64).view(1, -1)
-    h = _fmix32(((idx & M32) * 0x9E3779B1 + site_seed(rng, site)) & M32)
+    h = rng_bits(site_seed(rng, site), idx)
     u = (h >> 8).to(torch.float32) * (1.0 / 16777216.0)
     return (u >= p).to(torch.float32)
 
@@ -311,8 +327,8 @@ class EmuOps:
         n = out.numel()
         i = torch.arange(n, dtype=torch.int64)
         ss = site_seed(rng, site)
-        h1 = _fmix32((((2 * i) & M32) * 0x9E3779B1 + ss) & M32)
-        h2 = _fmix32((((2 * i + 1) & M32) * 0x9E3779B1 + ss) & M32)
+        h1 = rng_bits(ss, 2 * i)
+        h2 = rng_bits(ss, 2 * i + 1)
         u1 = ((h1 >> 8).to(torch.float32) + 1.0) * (1.0 / 16777216.0)
         u2 = (h2 >> 8).to(torch.float32) * (1.0 / 16777216.0)
         out.view(-1).copy_(torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(2.0 * torch.pi * u2))

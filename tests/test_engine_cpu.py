@@ -105,3 +105,16 @@ def test_engine_timeline_marks_are_inert_without_a_buffer():
     g, configs, P, x, y, noise, T, n = tiny_case("l1", 1)
     eng, out, G = run_engine(configs, P, x, y, noise, T, n, "l1")
     assert eng.stamps is None and eng.stamp_names == []
+
+
+def test_rng_streams_of_consecutive_steps_are_unrelated():
+    """with key = seed + step*C the step-(s+1) mask was the step-s mask shifted by one element.  The stream key
+    now passes every input through its own mixing round; masks of consecutive steps / sites agree only by chance."""
+    from emu_ops import keep_mask
+    m = [keep_mask(torch.tensor([123, s]), 3, 0.5, 64, 128) for s in range(4)]
+    for s in range(3):
+        for shift in (0, 1, 2):
+            a, b = m[s].view(-1)[shift:4096 + shift], m[s + 1].view(-1)[:4096]
+            assert abs(float((a == b).float().mean()) - 0.5) < 0.05, (s, shift)
+    a, b = keep_mask(torch.tensor([123, 5]), 3, 0.5, 64, 128), keep_mask(torch.tensor([123, 5]), 4, 0.5, 64, 128)
+    assert abs(float((a == b).float().mean()) - 0.5) < 0.05

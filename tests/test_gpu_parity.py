@@ -145,8 +145,10 @@ def test_mosi_b32_golden_digest(gemm_path):
 @pytest.mark.parametrize("name,input_dims,T,n,head,od", [
     ("mosi_b256", (300, 5, 20), 20, 256, "l1", 1),          # BASELINE configs[1]
     ("mosei_b64", (300, 74, 35), 50, 64, "l1", 1),          # configs[2] shapes, one rank's shard
+    ("mosei_b512", (300, 74, 35), 50, 512, "l1", 1),        # configs[2] at its full batch on one GPU
     ("iemocap_b256", (300, 74, 35), 20, 256, "ce", 4),      # configs[3]
     ("pom_b96", (300, 43, 43), 100, 96, "l1", 16),          # configs[4] shapes (ragged batch)
+    ("pom_b1024", (300, 43, 43), 100, 1024, "l1", 16),      # configs[4] at its full per-GPU batch
 ])
 def test_full_step_vs_oracle(gemm_path, name, input_dims, T, n, head, od):
     configs = O.best_acc_configs(input_dims=input_dims, output_dim=od, dropout=False)
@@ -238,6 +240,89 @@ def test_trainer_graph_replay_trains():
         assert tr.launches_per_step > 50
     assert res[0][-1] < res[0][0]
     assert np.allclose(res[0], res[1], rtol=2e-3), res
+
+
+def _train_masks_and_branches(eng, rng_cpu):
+    """Dropout keep-masks of the CUDA step, regenerated on the CPU from the step's RNG state with the emulator's
+    statement of the hash (so the device RNG itself is under test), and the ReLU branches read back from the CUDA
+    stashes: a kept unit's branch is (output > 0); a dropped unit's branch was not observed (-1: the oracle decides)."""
+    from factorized_b200 import engine as E
+    from emu_ops import keep_mask
+    ws, dm = eng.ws, eng.dm
+    T, n = dm.T, dm.B
+    masks, br = {}, {}
+
+    def site(key, bkey, p, site_id, buf, rows, shape3=None):
+        out = buf.detach().cpu()
+        taken = (out > 0).float()
+        if p > 0.0:
+            k = keep_mask(rng_cpu, site_id, p, rows, out.shape[1])
+            taken = torch.where(k > 0, taken, torch.full_like(taken, -1.0))
+            masks[key] = k.view(shape3) if shape3 else k
+        br[bkey] = taken.view(shape3) if shape3 else taken
+    site("att1", "att1", dm.p_att1, E.SITE_ATT1, ws["H1"], T * n, (T, n, -1))
+    site("att2", "att2", dm.p_att2, E.SITE_ATT2, ws["H2"], T * n, (T, n, -1))
+    site("gamma1", "gamma1", dm.p_g1, E.SITE_G1, ws["U1"], T * n, (T, n, -1))
+    site("gamma2", "gamma2", dm.p_g2, E.SITE_G2, ws["U2"], T * n, (T, n, -1))
+    site("fy", "fy1", dm.p_fy, E.SITE_FY, ws["F1y"], n)
+    site("y", "y1", dm.p_y, E.SITE_Y, ws["Y1"], n)
+    for m, tag in enumerate("lav"):
+        site("f" + tag, "f%s1" % tag, dm.p_f[m], E.SITE_FL + m, ws["F1_%d" % m], n)
+        br["f" + tag] = (ws["EMB%d" % m][:, dm.fy:] > 0).float().cpu()
+    br["fy"] = (ws["FY"] > 0).float().cpu()
+    return masks, br
+
+
+@pytest.mark.parametrize("name,input_dims,T,n,head,od,use_graph", [
+    ("mosi_b256_eager", (300, 5, 20), 20, 256, "l1", 1, False),
+    ("mosi_b256_graph", (300, 5, 20), 20, 256, "l1", 1, True),
+    ("mosi_b2048_graph", (300, 5, 20), 20, 2048, "l1", 1, True),       # the configuration bench.py measures
+    ("iemocap_b256_graph", (300, 74, 35), 20, 256, "ce", 4, True),
+])
+def test_train_mode_fused_step_vs_oracle(name, input_dims, T, n, head, od, use_graph):
+    """The MEASURED configuration against the oracle: MFMTrainer.step in train mode (all nine dropouts active, device
+    RNG for masks and MMD noise, CUDA graph), two consecutive steps.  The step's masks / noise / ReLU branches are
+    replayed in oracle.train_step (mfm_mosi.py:427-441); losses, latents, every gradient and the post-Adam parameters
+    must agree to 1e-3."""
+    import factorized_b200 as F
+    from factorized_b200.train import MFMTrainer
+    configs = O.best_acc_configs(input_dims=input_dims, output_dim=od, dropout=True)
+    torch.manual_seed(123)
+    model = F.MFM(*configs).cuda().train()
+    P = OrderedDict((k, v.detach().cpu().clone()) for k, v in model.state_dict().items())
+    tr = MFMTrainer(model, T, n, head=head, use_graph=use_graph, seed=4242)
+    state, report = {}, {}
+    for step in (1, 2):
+        x, y = O.synthetic_batch(configs, T, n, 1000 + step, head)
+        lb = tr.step(x.cuda(), y.cuda())
+        torch.cuda.synchronize()
+        rng = tr.rng.cpu()
+        assert int(rng[1]) == step
+        masks, br = _train_masks_and_branches(tr.eng, rng)
+        noise = [t.detach().cpu().clone() for t in tr.noise]
+        del O.RELU_REPLAY_VIOLATIONS[:]
+        newP, losses, Go, outo = O.train_step(P, x, y, configs, noise, state, head=head, train=True, masks=masks, branches=br)
+        assert not O.RELU_REPLAY_VIOLATIONS, O.RELU_REPLAY_VIOLATIONS[:5]
+        lbc = lb.cpu()
+        tag = "s%d." % step
+        for i, k in ((0, "disc"), (1, "mse_l"), (2, "mse_a"), (3, "mse_v"), (8, "total")):
+            report[tag + "loss." + k] = abs(float(lbc[i]) - losses[k]) / abs(losses[k])
+        report[tag + "loss.mmd"] = abs(float(lbc[4:8].sum()) * configs[0]["lda_mmd"] - losses["mmd"]) / abs(losses["mmd"])
+        ws = tr.eng.ws
+        for k, b in (("zl", "Z0"), ("za", "Z1"), ("zv", "Z2"), ("zy", "ZY"), ("y_hat", "Yhat")):
+            report[tag + k] = rel_l2(ws[b], outo[k])
+        for k, go in Go.items():
+            if go is not None:
+                report[tag + "grad." + k] = rel_l2(tr.G[k], go)
+        sd = model.state_dict()
+        num = sum(float((sd[k].cpu().double() - newP[k].double()).pow(2).sum()) for k in P if Go[k] is not None)
+        den = sum(float((newP[k].double() - P[k].double()).pow(2).sum()) for k in P if Go[k] is not None)
+        report[tag + "adam.delta"] = (num / den) ** 0.5
+        P = newP
+    bad = {k: v for k, v in report.items() if not (v < (5e-3 if k.endswith("adam.delta") else TOL))}
+    worst = max((k for k in report if not k.endswith("adam.delta")), key=report.get)
+    print("%s: worst %s = %.3g, adam.delta %.3g / %.3g" % (name, worst, report[worst], report["s1.adam.delta"], report["s2.adam.delta"]))
+    assert not bad, bad
 
 
 def test_standalone_modules_vs_oracle():

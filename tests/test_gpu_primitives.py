@@ -91,8 +91,44 @@ def _dev_view(c_cpu, key, base_cpu, base_gpu):
     return None
 
 
+def _variant_counts(ops):
+    return [int(ops.lib.mfm_debug_lstm_variant_count(i)) for i in range(6)]
+
+
+@pytest.mark.parametrize("chains", [1, 2])
+def test_lstm_one_and_two_chains_per_cta(ops, chains):
+    """Both CTA shapes of the recurrence kernels (one / two batch sub-tiles per CTA) on the same cells."""
+    cells = [_lstm_case(5, 150, h, gs, seed=h) for h, gs in ((88, 5), (24, 1), (64, 5), (104, 1))]
+    cbs = [dict(T=5, B=150, h=c["h"], gates=c["gates"], cs=c["cs"], W=c["W"], dh_all=g(5 * 150, c["h"], seed=3), dh_last=None,
+                dc_ext=g(5 * 150, c["h"], seed=4), dG=torch.zeros(5 * 150, 4 * c["h"]), dc_scratch=torch.zeros(150, c["h"]))
+           for c in cells]
+    EmuOps().lstm_fwd(cells)
+    EmuOps().lstm_bwd(cbs)
+    dev, dbs = [_to_dev(c) for c in cells], [_to_dev(c) for c in cbs]
+    assert ops.lib.mfm_debug_lstm_force_chains(chains) == 0
+    try:
+        n0 = [int(ops.lib.mfm_debug_lstm_variant_count(i)) for i in (6, 7)]
+        ops.lstm_fwd(dev)
+        ops.lstm_bwd(dbs)
+        torch.cuda.synchronize()
+        n1 = [int(ops.lib.mfm_debug_lstm_variant_count(i)) for i in (6, 7)]
+    finally:
+        ops.lib.mfm_debug_lstm_force_chains(0)
+    assert [a - b for a, b in zip(n1, n0)] == ([2, 0] if chains == 1 else [0, 2])
+    for c, d in zip(cells, dev):
+        assert rel_l2(d["hs"], c["hs"]) < 1e-4 and rel_l2(d["gates"], c["gates"]) < 1e-4, c["h"]
+    for c, d in zip(cbs, dbs):
+        assert rel_l2(d["dG"], c["dG"]) < 1e-4, c["h"]
+
+
+# (T, B, h, gx_steps, ld_extra): every layout of the recurrence kernels -- replicated unit rows (h <= 32: x4, <= 64: x2),
+# three and four lane quadrants, 16-row chains (h = 104 backward), the CUDA-core kernel (h > 128) -- on ragged batches,
+# plus the production sizes: many CTAs of full 64-row tiles with a ragged last one (B = 2405), decoder-like gx_steps = 1
 @pytest.mark.parametrize("T,B,h,gx_steps,ld_extra", [(3, 5, 6, 3, 0), (4, 19, 32, 4, 3), (5, 33, 104, 1, 0), (2, 9, 8, 2, 0),
-                                                     (3, 17, 128, 3, 0), (2, 6, 300, 1, 0), (20, 70, 88, 20, 112)])
+                                                     (3, 17, 128, 3, 0), (2, 6, 300, 1, 0), (20, 70, 88, 20, 112),
+                                                     (3, 100, 64, 3, 0), (3, 70, 48, 3, 5), (2, 45, 96, 2, 0), (4, 77, 80, 4, 0),
+                                                     (3, 130, 24, 1, 0), (2, 67, 108, 2, 0),
+                                                     (4, 2405, 88, 4, 0), (3, 2048, 104, 1, 0), (3, 2100, 32, 3, 0)])
 def test_lstm_fwd_bwd(ops, T, B, h, gx_steps, ld_extra):
     c = _lstm_case(T, B, h, gx_steps, seed=T + B + h, ld_extra=ld_extra)
     # device copies that preserve the strided views
@@ -152,15 +188,77 @@ def test_lstm_duplicate_cell_history_and_second_cell_gradient(ops, T, B, h):
     assert rel_l2(cbg["dG"], cb["dG"]) < 1e-4
 
 
-def test_lstm_multi_cell_launch(ops):
-    cells = [_lstm_case(6, 40, h, gs, seed=h) for h, gs in ((32, 6), (8, 6), (80, 6), (24, 1))]
+@pytest.mark.parametrize("B,hs", [(40, ((32, 6), (8, 6), (80, 6), (24, 1))),
+                                  (448, ((32, 6), (8, 6), (80, 6), (88, 6), (64, 6), (48, 6)))])     # the step's 6-cell launch
+def test_lstm_multi_cell_launch(ops, B, hs):
+    cells = [_lstm_case(6, B, h, gs, seed=h) for h, gs in hs]
     dev = [_to_dev(c) for c in cells]
     EmuOps().lstm_fwd(cells)
+    before = _variant_counts(ops)
     ops.lstm_fwd(dev)
     torch.cuda.synchronize()
+    after = _variant_counts(ops)
+    assert after[0] - before[0] == len(cells), (before, after)       # every cell ran on the 32-row tensor-core chains
     for c, d in zip(cells, dev):
         for k in ("hs", "cs", "gates"):
             assert rel_l2(d[k], c[k]) < 1e-4, (k, c["h"], rel_l2(d[k], c[k]))
+    # backward of all cells in one launch, on the emulator's forward state
+    cbs = []
+    for c in cells:
+        T, h = c["T"], c["h"]
+        cbs.append(dict(T=T, B=B, h=h, gates=c["gates"], cs=c["cs"], W=c["W"], dh_all=g(T * B, h, seed=21 + h),
+                        dh_last=g(B, h, seed=22 + h), dc_ext=g(T * B, h, seed=23 + h), dG=torch.zeros(T * B, 4 * h),
+                        dc_scratch=torch.zeros(B, h)))
+    dbs = [_to_dev(c) for c in cbs]
+    EmuOps().lstm_bwd(cbs)
+    ops.lstm_bwd(dbs)
+    torch.cuda.synchronize()
+    for c, d in zip(cbs, dbs):
+        assert rel_l2(d["dG"], c["dG"]) < 1e-4, (c["h"], rel_l2(d["dG"], c["dG"]))
+
+
+def test_lstm_variants_are_the_ones_intended(ops):
+    """The per-variant launch counters of the ABI: which kernel served a cell is asserted, not assumed."""
+    def run(h, B, force=0):
+        c = _lstm_case(3, B, h, 3, seed=5)
+        cb = dict(T=3, B=B, h=h, gates=c["gates"], cs=c["cs"], W=c["W"], dh_all=g(3 * B, h, seed=1), dh_last=None, dc_ext=None,
+                  dG=torch.zeros(3 * B, 4 * h), dc_scratch=torch.zeros(B, h))
+        EmuOps().lstm_fwd([c])
+        EmuOps().lstm_bwd([cb])
+        assert ops.lib.mfm_debug_lstm_force_nb(force) == 0
+        assert ops.lib.mfm_debug_lstm_force_chains(2) == 0        # two chains per CTA: the shared-memory plan of the full step
+        try:
+            before = _variant_counts(ops)
+            cg, cbg = _to_dev(c), _to_dev(cb)
+            ops.lstm_fwd([cg])
+            ops.lstm_bwd([cbg])
+            torch.cuda.synchronize()
+            after = _variant_counts(ops)
+        finally:
+            ops.lib.mfm_debug_lstm_force_nb(0)
+            ops.lib.mfm_debug_lstm_force_chains(0)
+        assert rel_l2(cg["hs"], c["hs"]) < 1e-4 and rel_l2(cg["gates"], c["gates"]) < 1e-4
+        assert rel_l2(cbg["dG"], cb["dG"]) < 1e-4
+        return [a - b for a, b in zip(after, before)]
+    assert run(88, 300) == [1, 0, 1, 0, 0, 0]                 # 32-row chains both ways
+    assert run(88, 300, force=16) == [0, 1, 0, 1, 0, 0]       # 16-row chains forced
+    assert run(104, 300) == [1, 0, 0, 1, 0, 0]                # backward of h = 104 only fits with 16-row chains
+    assert run(48, 300, force=16) == [1, 0, 1, 0, 0, 0]       # replicated layouts have no 16-row form
+    assert run(200, 50) == [0, 0, 0, 0, 1, 1]                 # h > 128: CUDA-core kernels
+
+
+def test_lstm_gx_leading_dimension(ops):
+    """gx as a column block of a wider matrix (ld_gx): two cells fed by ONE input-projection GEMM."""
+    T, B = 4, 37
+    c1, c2 = _lstm_case(T, B, 32, T, seed=1), _lstm_case(T, B, 88, T, seed=2)
+    wide = torch.cat([c1["gx"], c2["gx"]], 1).cuda()
+    d1, d2 = _to_dev(c1), _to_dev(c2)
+    d1["gx"], d2["gx"] = wide[:, :128], wide[:, 128:]
+    EmuOps().lstm_fwd([c1, c2])
+    ops.lstm_fwd([d1, d2])
+    torch.cuda.synchronize()
+    for c, d in ((c1, d1), (c2, d2)):
+        assert rel_l2(d["hs"], c["hs"]) < 1e-4 and rel_l2(d["gates"], c["gates"]) < 1e-4
 
 
 @pytest.mark.parametrize("T,B,mem,g1,g2,drop", [(3, 5, 9, 12, 13, False), (4, 21, 64, 128, 128, True), (2, 7, 300, 256, 32, False),
@@ -335,6 +433,15 @@ def test_randn_and_rng(ops):
     assert abs(float(out_g.mean())) < 0.02 and abs(float(out_g.std()) - 1.0) < 0.02
     k = keep_mask(rg.cpu(), 7, 0.3, 100, 50)
     assert abs(float(k.mean()) - 0.7) < 0.03
+    # consecutive steps draw unrelated samples (the first RNG produced the step-s sample shifted by one element at step s+2)
+    ops.rng_tick(rg)
+    ops.rng_tick(rg)
+    out2 = torch.zeros(100000).cuda()
+    ops.randn(out2, rg, 20)
+    a, b = out_g.cpu(), out2.cpu()
+    for shift in (0, 1, 2):
+        cc = float(torch.corrcoef(torch.stack([a[shift:50000 + shift], b[:50000]]))[0, 1])
+        assert abs(cc) < 0.02, (shift, cc)
 
 
 def test_bad_arguments_fail_loudly(ops):
