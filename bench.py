@@ -165,7 +165,7 @@ def profile_primitives(trainer, reps=3):
         return inner
     names = ["gemm", "gemm_tn_pair", "lstm_fwd", "lstm_bwd", "mfn_mem_fwd", "mfn_mem_bwd", "softmax_gate_fwd", "softmax_gate_bwd", "mmd_fwd",
              "mmd_bwd", "copy2d", "add", "zero", "colsum", "relu_bwd", "mse_fwd_bwd", "l1_fwd_bwd", "ce_fwd_bwd",
-             "loss_total", "adam", "randn", "rng_tick", "rownorm2", "mmd_kexp", "mmd_combine"]
+             "loss_total", "adam", "randn", "rng_tick", "rownorm2", "mmd_kexp", "mmd_kexp64", "mmd_fold", "mmd_combine"]
     orig = {n: getattr(ops, n) for n in names}
     agg = {}
     side = trainer.eng.use_side_stream

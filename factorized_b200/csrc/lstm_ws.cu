@@ -1,15 +1,24 @@
 // LSTM recurrences on the tensor cores, warp-specialised (mfm_model.py:56,83,85,167-169 and their adjoint).
 //
-// A recurrence step is a strict chain: gate GEMM -> TMEM -> activations -> h_t -> next gate GEMM.  One chain cannot
-// keep an SM busy (the first version of these kernels ran one chain per SM and spent 3/4 of every step waiting), so a CTA
-// runs up to two independent chains -- batch sub-tiles of the same cell that share the resident weight image: while
-// chain A's warps run their activations, chain B's gate GEMM executes, and the loads / SFU / stores of both overlap.
+// A recurrence step is a strict chain: gate GEMM -> TMEM -> activations -> h_t -> next gate GEMM.  One chain cannot keep
+// an SM busy, so a CTA owns TWO chains -- batch sub-tiles A and B of the same cell, sharing the resident weight image --
+// and alternates: all sixteen compute warps run the cell update of A while the tensor core runs the gate GEMM of B, then
+// swap.  What the timeline of the earlier versions showed (scripts/lstm_trace.py) and this layout answers:
+//   * a warp that issues tcgen05.mma blocks for the whole GEMM (the MMA queue is shallow: ~90 cycles per instruction
+//     when two issuers compete), so the issue loop belongs to a warp that has no other work: warp 16, alone in a fifth
+//     warpgroup that gives its registers away (setmaxnreg: 24 there, 112 for the compute warps);
+//   * two chains that each own half of the warps drift into lock step and their GEMMs are never hidden; with all
+//     compute warps on one chain at a time the alternation is enforced by construction;
+//   * consecutive MMAs into one accumulator serialise at the pipeline latency: the four gates (forward) / four partial
+//     sums over K (backward) are separate accumulators and every pass goes to all of them in turn;
+//   * the cell update is issue-bound: addresses are (64-bit running base of the step) + (32-bit column offset), rows
+//     beyond B and lanes beyond h are clamped onto valid elements and only their stores are predicated (no divergent
+//     branch in the loop), two logistic values share one reciprocal, and the warp index is made provably uniform.
 //
-//   warps 8c .. 8c+7       chain c.   wait done[c]; tcgen05.ld; cell update; stash; h_t -> shared memory (split bf16,
-//                          K-major B operand); fence.proxy.async; count in on arrive[c] (acq_rel).  The LAST warp to count in
-//                          issues the chain's next gate GEMM (one thread): tcgen05.mma hi*hi + lo*hi + hi*lo over K,
-//                          tcgen05.commit -> done[c].  (A 17th, MMA-only warp would put five warps on one scheduler
-//                          and cap every thread at 96 registers.)
+//   warp 16 (one thread)   per step and chain: wait ready[c] (h_{t-1} / dG_t of the chain is in shared memory);
+//                          tcgen05.mma hi*hi + lo*hi + hi*lo over K; tcgen05.commit -> done[c].
+//   warps 0..15            per step, chain A then chain B: wait done[c]; tcgen05.ld; cell update; stash; h_t -> shared
+//                          memory (split bf16, K-major B operand); fence.proxy.async; arrive ready[c].
 //
 // The gate GEMM is issued TRANSPOSED, one MMA tile PER GATE:   D_g[unit j, batch b] = W_g[j, :] . h_{t-1}[b, :]
 //   A = W_g (split-bf16, resident in shared memory, K-major = W's own layout), M = 128 rows = hidden units;
@@ -18,28 +27,36 @@
 // g*NB + b): the cell update needs no exchange between threads, and because lane = unit, the 32 lanes of a warp touch
 // 32 consecutive floats of the row-major stashes (G_x, gates, c, h, dG): one 128 B line per access.
 // Small cells would leave most of the 128 lanes idle, so the unit rows of the A tile are REPLICATED (h <= 32: 4 copies,
-// h <= 64: 2): every lane quadrant then holds every unit and the quadrants split the batch columns instead.  Eight
-// warps serve a chain: warp k reads quadrant k%4 and the column half k/4.
+// h <= 64: 2): every lane quadrant then holds every unit and the quadrants split the batch columns instead (such cells
+// take 64-row chains).  Warp w reads lane quadrant w%4 and the column part w/4.
 //
 // Backward:  dh^T[unit j, batch b] = sum_k' W^T[j, k'] dG[b, k'],  k' = 4*unit + gate (unit-major, so the four gate
 // gradients a thread produces are 8 contiguous bytes of the B operand); same roles, same replication; the carried dc
-// stays in registers.  Cells that do not fit on chip (h > ~108 forward, h > 128 backward) run on lstm_seq.cu.
+// stays in registers.  Cells that do not fit on chip (h > ~108 forward, h > ~104 backward) run on lstm_seq.cu.
 #include <cstdlib>
 #include "tc_common.cuh"
 
-// Timing experiments and the clock-stamp trace are compiled in only with -DWS_DEBUG=1 (scripts/lstm_trace.py): their
-// lane-divergent branches inside the step loop cost the production kernel uniform registers.
+// -DWS_DEBUG=1 compiles a clock-stamp trace of CTA 0 into the forward kernel (scripts/lstm_trace.py); off in production:
+// its lane-divergent stores inside the step loop cost uniform registers
 #ifndef WS_DEBUG
 #define WS_DEBUG 0
 #endif
+#if WS_DEBUG
+__device__ long long g_ws_trace_buf[17 * 32 * 8];          // [warp 0..16][step 32][8 stamps]
+#define WS_STAMP(w, t, k) do { if (blockIdx.x == 0 && lane == 0 && (t) < 32) g_ws_trace_buf[((w) * 32 + (t)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define WS_STAMP(w, t, k) do { } while (0)
+#endif
 
-#define WS_CWARPS 8
+#define WS_CW 16                          // compute warps
+#define WS_THREADS ((WS_CW + 4) * 32)     // + the issuer's warpgroup (setmaxnreg works on warpgroups)
 #define WS_MAXCHAIN 2
 
 struct WsCell {
   mfm_lstm_cell c;
-  int nb;        // batch rows per chain = UMMA N (32 or 16)
-  int nsub;      // ceil(h / 32): lane quadrants one copy of the units occupies
+  int nb;        // batch rows per chain = UMMA N (16, 32 or 64)
+  int nsub;      // lane quadrants one copy of the units occupies: max(2, ceil(h / 32))
+  int nact;      // compute warps that own units (the rest idle): arrivals per chain and step
   int gs;        // forward: rows per gate block of the W image (128 when replicated, else h rounded up to 8)
   int kp;        // MMA K: forward h rounded up to 16; backward 4 * (h rounded up to 8)
   int lboA, lboB;
@@ -48,14 +65,11 @@ struct WsCell {
 struct WsBatch {
   WsCell c[MFM_MAX_CELLS];
   int n;
-  long long* trace;   // debug (mfm_debug_set_lstm_trace): clock stamps of CTA 0, [warp 16][step 32][4]
-  int dbg;       // timing experiments (env MFM_WS_DBG; results are WRONG when set): 1 no stash stores, 2 no G_x loads,
-                 // 4 relaxed count-in, 8 no proxy fence, 16 no MMAs (commit only)
 };
 
-// wait on an mbarrier phase.  The suspend-time hint keeps the warp parked until the phase completes instead of
-// re-polling (the first version re-polled ~200 times per step: a third of all issued instructions); bounded: a barrier
-// that never completes traps instead of hanging the GPU
+// wait on an mbarrier phase.  The suspend-time hint parks the warp until the phase completes instead of re-polling (the
+// first version re-polled ~200 times per step: a third of all issued instructions); bounded: a barrier that never
+// completes traps instead of hanging the GPU
 __device__ __forceinline__ void ws_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   for (int spin = 0; spin < (1 << 24); ++spin) {
@@ -70,20 +84,12 @@ __device__ __forceinline__ void ws_wait(uint32_t bar, uint32_t parity) {
   }
   __trap();
 }
+__device__ __forceinline__ void ws_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
 static unsigned long long g_ws_counts[8];     // launches per variant, see mfm_debug_lstm_variant_count
 
-// counts a warp in; true for the last of `n` (the counter only grows: arrivals of step s are [s*n, (s+1)*n))
-__device__ __forceinline__ bool ws_count_in(unsigned int* cnt, unsigned int n) {
-  unsigned int old;
-  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
-  return (old + 1u) % n == 0u;
-}
-__device__ __forceinline__ bool ws_count_in_relaxed(unsigned int* cnt, unsigned int n) {
-  unsigned int old;
-  asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
-  return (old + 1u) % n == 0u;
-}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float v[4]) {
   uint32_t r[4];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
@@ -93,27 +99,19 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float v[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float v[2]) {
+  uint32_t r[2];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+  v[0] = __uint_as_float(r[0]);
+  v[1] = __uint_as_float(r[1]);
+}
 __device__ __forceinline__ unsigned short bf16_bits(float x) {
   __nv_bfloat16 b = __float2bfloat16_rn(x);
   return *reinterpret_cast<unsigned short*>(&b);
 }
-// sigmoid and tanh through one path: tanh(x) = 2*sigmoid(2x) - 1  ->  a * rcp(1 + ex2(k * x)) + b
-__device__ __forceinline__ float act_sig(float x) {
-  x = fminf(fmaxf(x, -30.0f), 30.0f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
-  return rcp_fast(1.0f + e);
-}
-__device__ __forceinline__ float act_tanh(float x) {
-  x = fminf(fmaxf(x, -15.0f), 15.0f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -2.8853900817779268f));
-  return fmaf(2.0f, rcp_fast(1.0f + e), -1.0f);
-}
-
 // 1 + 2^a with the exponent clamped from above (2^28: products of two such terms stay finite); no lower clamp is needed:
 // ex2 underflows to 0 and the logistic saturates correctly.  Two logistic values then share ONE reciprocal:
-//   1/(1+ea) = (1+eb) * rcp((1+ea)(1+eb)),   1/(1+eb) = (1+ea) * rcp(...)         (MUFU is the scarce pipe: 8 lanes/clk/SM...)
+//   1/(1+ea) = (1+eb) * rcp((1+ea)(1+eb)),   1/(1+eb) = (1+ea) * rcp(...)     (the SFU takes 8 cycles per warp instruction)
 __device__ __forceinline__ float one_plus_ex2(float a) {
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(a, 28.0f)));
@@ -123,30 +121,30 @@ __device__ __forceinline__ float one_plus_ex2(float a) {
 __device__ __forceinline__ void st_if(float* p, float v, int ok) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"(ok));
 }
-// which units and batch columns of its chain a compute warp owns
+
+// which units and batch columns of a chain a compute warp owns
 struct WsRole {
   int q;        // TMEM lane quadrant (= warp % 4)
   int j;        // hidden unit of this lane
-  bool on;      // lane has a unit (warp-level activity is `warp_on`)
-  bool warp_on;
+  bool on;      // lane has a unit
+  bool warp_on; // warp has work
   int col0;     // first batch column of this warp inside the chain's NB
-  int nsg;      // groups of 4 columns: 1, 2 or 4
+  int ncol;     // its columns: 2, 4 or 8
 };
-__device__ __forceinline__ WsRole ws_role(int k, int lane, int h, int nsub, int nb) {
+__device__ __forceinline__ WsRole ws_role(int w, int lane, int h, int nsub, int nb) {
   WsRole r;
-  r.q = k & 3;
-  const int half = k >> 2;
-  if (nsub <= 2) {                         // replicated: quadrant = (copy, sub-block); copies and halves split the columns
-    const int sub = r.q % nsub, rep = r.q / nsub, R = 4 / nsub;
-    const int ncol = nb / (2 * R);
+  r.q = w & 3;
+  const int part = w >> 2;
+  if (nsub == 2) {                         // two copies: quadrant = (copy, sub-block); copies and parts split the columns
+    const int sub = r.q & 1, rep = r.q >> 1;
+    r.ncol = nb >> 3;
     r.j = sub * 32 + lane;
-    r.col0 = (rep * 2 + half) * ncol;
-    r.nsg = ncol >> 2;
-    r.warp_on = true;
+    r.col0 = (rep * 4 + part) * r.ncol;
+    r.warp_on = sub * 32 < h;              // h <= 32: the second sub-block is empty
   } else {
     r.j = r.q * 32 + lane;
-    r.col0 = half * (nb >> 1);
-    r.nsg = nb >> 3;
+    r.ncol = nb >> 2;
+    r.col0 = part * r.ncol;
     r.warp_on = r.q < nsub;
   }
   r.on = r.warp_on && r.j < h;
@@ -159,22 +157,18 @@ __device__ __forceinline__ const WsCell& ws_find(const WsBatch& bt, int bx) {
   return bt.c[ci];
 }
 
+#define WS_REG_COMPUTE() asm volatile("setmaxnreg.inc.sync.aligned.u32 112;")
+#define WS_REG_ISSUER() asm volatile("setmaxnreg.dec.sync.aligned.u32 24;")
+
 // ----------------------------------------------------------------------------------------------------------------
 // forward
 // ----------------------------------------------------------------------------------------------------------------
-// Addressing: every per-element address is  (running 64-bit base of the step) + (32-bit column offset) * 4 -- one
-// IMAD.WIDE per access; rows beyond B and lanes beyond h are CLAMPED onto valid elements and only their stores are
-// predicated, so the loop body has no divergent branches (each one cost a BSSY region that re-materialised every
-// descriptor; together with recomputed 64-bit indices the first version issued ~195 instructions per (unit, column)).
-template <int NCHAIN>
-__global__ void __launch_bounds__(NCHAIN * WS_CWARPS * 32, 1) lstm_ws_fwd_kernel(const __grid_constant__ WsBatch bt) {
-  constexpr int NTHREADS = NCHAIN * WS_CWARPS * 32;
+template <int NCH>
+__global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_fwd_kernel(const __grid_constant__ WsBatch bt) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long bar_done[WS_MAXCHAIN];
-  __shared__ unsigned int arrive_cnt[WS_MAXCHAIN];
+  __shared__ __align__(8) unsigned long long bar_done[WS_MAXCHAIN], bar_ready[WS_MAXCHAIN];
   __shared__ uint32_t tmem_holder;
   const WsCell& wc = ws_find(bt, (int)blockIdx.x);
-  const int dbg = WS_DEBUG ? bt.dbg : 0;
   const int h = wc.c.h, B = wc.c.B, T = wc.c.T, H4 = 4 * h, gx_steps = wc.c.gx_steps;
   const int NB = wc.nb, KP = wc.kp, GS = wc.gs, nsub = wc.nsub;
   const int slabs = KP >> 3;
@@ -192,16 +186,15 @@ __global__ void __launch_bounds__(NCHAIN * WS_CWARPS * 32, 1) lstm_ws_fwd_kernel
   unsigned char* Hbase = Wlo + slabs * lboA;                 // per chain: [hi plane | lo plane]
   const int chainH = 2 * slabs * lboH;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: role branches become uniform branches
-  const int row0 = ((int)blockIdx.x - wc.cta0) * (NCHAIN * NB);
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: role branches stay uniform
+  const int row0 = ((int)blockIdx.x - wc.cta0) * (NCH * NB);
   int tmem_cols = 32;
-  while (tmem_cols < NCHAIN * 4 * NB) tmem_cols <<= 1;
+  while (tmem_cols < NCH * 4 * NB) tmem_cols <<= 1;
 
-  const unsigned int nact = (nsub == 3) ? 6u : 8u;           // warps with work per chain
   if (tid == 0) {
-    for (int i = 0; i < NCHAIN; ++i) {
-      mbar_init(smem_u32(&bar_done[i]), 1);
-      arrive_cnt[i] = 0u;
+    for (int i = 0; i < NCH; ++i) {
+      mbar_init(smem_u32(&bar_done[i]), 4);                    // one commit per issuing warp
+      mbar_init(smem_u32(&bar_ready[i]), wc.nact);             // compute warps that own units
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -216,18 +209,18 @@ __global__ void __launch_bounds__(NCHAIN * WS_CWARPS * 32, 1) lstm_ws_fwd_kernel
     const bool vecW = ((reinterpret_cast<uintptr_t>(Wg) & 15) == 0) && ((h & 3) == 0);
     const int span = nsub <= 2 ? 32 * nsub : GS;             // rows of one copy
     const int rows = 4 * GS;
-    for (int idx = tid; idx < rows * slabs; idx += NTHREADS) {
+    for (int idx = tid; idx < rows * slabs; idx += WS_THREADS) {
       const int slab = idx % slabs, r = idx / slabs;
       const int g = r / GS, j = (r - g * GS) % span;
       float v[8];
       load8(Wg, h, j < h ? g * h + j : H4, H4, slab * 8, h, vecW, v);
       split_store(v, Whi + slab * lboA + r * 16, Wlo + slab * lboA + r * 16, true);
     }
-    for (int idx = tid * 16; idx < NCHAIN * chainH; idx += NTHREADS * 16)
+    for (int idx = tid * 16; idx < NCH * chainH; idx += WS_THREADS * 16)
       *reinterpret_cast<uint4*>(Hbase + idx) = make_uint4(0, 0, 0, 0);     // h_{-1} = 0, K padding = 0
   }
   // block 0 of the histories is the zero initial state
-  for (int idx = tid; idx < NCHAIN * NB * h; idx += NTHREADS) {
+  for (int idx = tid; idx < NCH * NB * h; idx += WS_THREADS) {
     const int b = row0 + idx / h, j = idx % h;
     if (b < B) {
       hs_base[(long long)b * ldhs + j] = 0.0f;
@@ -241,155 +234,179 @@ __global__ void __launch_bounds__(NCHAIN * WS_CWARPS * 32, 1) lstm_ws_fwd_kernel
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_holder;
 
-  // the chain's gate GEMM for the next step, issued by one thread (the last warp of the chain to count in)
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  auto issue = [&](int ch) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint64_t dAh0 = make_smem_desc(smem_u32(Whi), lboA, 128), dAl0 = make_smem_desc(smem_u32(Wlo), lboA, 128);
-    const uint32_t hb = smem_u32(Hbase + ch * chainH);
-    const uint64_t dBh0 = make_smem_desc(hb, lboH, 128), dBl0 = make_smem_desc(hb + slabs * lboH, lboH, 128);
-    const int ksteps = KP >> 4;
-    const uint64_t astep = (uint64_t)((2 * lboA) >> 4), bstep = (uint64_t)((2 * lboH) >> 4);
-    // Consecutive MMAs into the SAME accumulator serialise at the full pipeline latency (~90 cycles each, measured), so the
-    // four gates -- independent accumulators -- are interleaved: every pass of every k-step goes to all gates in turn.
-    const uint32_t d0 = tmem_base + (uint32_t)(ch * 4 * NB);
-    const uint64_t gstep = (uint64_t)((GS * 16) >> 4);
-    uint64_t ao = 0, bo = 0;
-    if (!(dbg & 16)) {
+  if (warp >= WS_CW) {
+    // ================================ MMA issue (warps 16..19: one thread and one gate each) + L2 prefetch of G_x =========
+    WS_REG_ISSUER();
+    {
+      // One issuing thread sustains only one tcgen05.mma per ~60 cycles (descriptor arithmetic + the instruction's own
+      // latency; the trace showed the tensor core waiting for the issuer, not the other way round), and MMAs into one
+      // accumulator serialise anyway: the four warps of this warpgroup issue ONE GATE each, concurrently.
+      const int g = warp - WS_CW;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint64_t gofs = (uint64_t)((g * GS * 16) >> 4);
+      const uint64_t dAh0 = make_smem_desc(smem_u32(Whi), lboA, 128) + gofs, dAl0 = make_smem_desc(smem_u32(Wlo), lboA, 128) + gofs;
+      const int ksteps = KP >> 4;
+      const uint64_t astep = (uint64_t)((2 * lboA) >> 4), bstep = (uint64_t)((2 * lboH) >> 4);
+      // The cell update's G_x reads are the long pole of a step (ncu: 90 % of the active warp samples waited on them, one
+      // column group of register prefetch does not cover HBM latency under load).  These warps are idle between GEMMs, so
+      // they pull the G_x rows of the chain's NEXT step into L2 a whole step ahead: one bulk prefetch per batch row and gate.
+      const bool pf_ok = ((reinterpret_cast<uintptr_t>(gx_base) & 15) == 0) && ((ldgx & 3) == 0) && ((h & 3) == 0);
+      for (int t = 0; t < T; ++t) {                            // step 0 multiplies the zero state like every other step
 #pragma unroll 1
-      for (int kk = 0; kk < ksteps; ++kk, ao += astep, bo += bstep) {
-        const uint32_t acc = kk > 0 ? 1u : 0u;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) umma_bf16(d0 + (uint32_t)(g * NB), dAh0 + ao + g * gstep, dBh0 + bo, idesc, acc);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) umma_bf16(d0 + (uint32_t)(g * NB), dAl0 + ao + g * gstep, dBh0 + bo, idesc, 1u);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) umma_bf16(d0 + (uint32_t)(g * NB), dAh0 + ao + g * gstep, dBl0 + bo, idesc, 1u);
-      }
-    }
-    umma_commit(smem_u32(&bar_done[ch]));
-  };
-
-  const int ch = warp / WS_CWARPS;
-  const WsRole ro = ws_role(warp % WS_CWARPS, lane, h, nsub, NB);
-  if (ro.warp_on) {
-    const bool on = ro.on;
-    const int jc = on ? ro.j : 0;                              // lanes without a unit shadow unit 0 (stores predicated)
-    const int crow0 = row0 + ch * NB + ro.col0;                // global batch row of this warp's first column
-    const int bvalid = B - crow0;                              // columns of this warp that are real rows (may be <= 0)
-    const int rbase = bvalid > 0 ? crow0 : B - 1;              // rows beyond B shadow the last valid row
-    const int cmax = bvalid > 0 ? bvalid - 1 : 0;
-    const uint32_t tl = tmem_base + ((uint32_t)(ro.q * 32) << 16) + (uint32_t)(ch * 4 * NB + ro.col0);
-    unsigned char* const Hhi = Hbase + ch * chainH + (ro.j >> 3) * lboH + (ro.j & 7) * 2 + ro.col0 * 16;
-    unsigned char* const Hlo = Hhi + slabs * lboH;
-    const uint32_t bar = smem_u32(&bar_done[ch]);
-    long long* const tr = (WS_DEBUG && bt.trace && blockIdx.x == 0 && lane == 0) ? bt.trace : nullptr;
-    // running bases of the current step (element (first column, gate g, unit jc)); advanced by a constant every step
-    const float* gxp[4];
-    float* gtp[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      gxp[g] = gx_base + (long long)rbase * ldgx + g * h + jc;
-      gtp[g] = gates_base + (long long)rbase * H4 + g * h + jc;
-    }
-    float* csp = cs_base + (long long)(B + rbase) * ldcs + jc;
-    float* cdp = csd_base ? csd_base + (long long)(B + rbase) * ldcs + jc : nullptr;
-    float* hsp = hs_base + (long long)(B + rbase) * ldhs + jc;
-    int ldx = ldgx;                                            // column pitch / step stride of the gx source: switch to the
-    unsigned gx_step = (unsigned)B * (unsigned)ldgx;           // constant bias row (pitch 0) after gx_steps steps (decoder)
-    const unsigned gt_step = (unsigned)B * (unsigned)H4;
-    const unsigned cs_step = (unsigned)B * (unsigned)ldcs, hs_step = (unsigned)B * (unsigned)ldhs;
-    float cst[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) cst[i] = 0.0f;
-    const int nsg = ro.nsg;
-    // step 0 multiplies the zero initial state like every other step (D = 0 exactly): no special case in the loop
-    if (warp % WS_CWARPS == 0 && lane == 0) issue(ch);
-
-    for (int t = 0; t < T; ++t) {
-      if (t == gx_steps) {                                     // warp-uniform, once
-#pragma unroll
-        for (int g = 0; g < 4; ++g) gxp[g] = bias_rest + g * h + jc;
-        ldx = 0;
-        gx_step = 0u;
-      }
-      float gx[2][4][4];
-      auto load_gx = [&](int sg, float (&dst)[4][4]) {
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const unsigned o = (unsigned)(min(sg * 4 + cc, cmax) * ldx);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) dst[g][cc] = (dbg & 2) ? 0.1f : __ldg(gxp[g] + o);
-        }
-      };
-      load_gx(0, gx[0]);                                       // first column group: in flight across the MMA wait
-      if (tr && t < 32) tr[(warp * 32 + t) * 4 + 0] = clock64();
-      if (dbg & 32) mbar_wait(bar, (uint32_t)(t & 1)); else ws_wait(bar, (uint32_t)(t & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (tr && t < 32) tr[(warp * 32 + t) * 4 + 1] = clock64();
-#pragma unroll
-      for (int sg = 0; sg < 4; ++sg) {
-        if (sg < nsg) {                                        // warp-uniform
-          float acc[4][4];
-          if (dbg & 64) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-#pragma unroll
-              for (int cc = 0; cc < 4; ++cc) acc[g][cc] = 0.0f;
-          } else {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) tmem_ld4(tl + (uint32_t)(g * NB + sg * 4), acc[g]);
+        for (int ch = 0; ch < NCH; ++ch) {
+          if (lane == 0) {
+            if (t > 0) ws_wait(smem_u32(&bar_ready[ch]), (uint32_t)((t - 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (g == 0) WS_STAMP(16, t, ch * 2);
+            const uint32_t hb = smem_u32(Hbase + ch * chainH);
+            const uint64_t dBh0 = make_smem_desc(hb, lboH, 128), dBl0 = make_smem_desc(hb + slabs * lboH, lboH, 128);
+            const uint32_t dcol = tmem_base + (uint32_t)((ch * 4 + g) * NB);
+            uint64_t ao = 0, bo = 0;
+#pragma unroll 1
+            for (int kk = 0; kk < ksteps; ++kk, ao += astep, bo += bstep) {
+              umma_bf16(dcol, dAh0 + ao, dBh0 + bo, idesc, kk > 0 ? 1u : 0u);
+              umma_bf16(dcol, dAl0 + ao, dBh0 + bo, idesc, 1u);
+              umma_bf16(dcol, dAh0 + ao, dBl0 + bo, idesc, 1u);
+            }
+            umma_commit(smem_u32(&bar_done[ch]));
+            if (g == 0) WS_STAMP(16, t, ch * 2 + 1);
           }
-          if (sg + 1 < nsg) load_gx(sg + 1, gx[(sg + 1) & 1]);  // next group's G_x travels while this one is computed
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const int col = sg * 4 + cc;
-            const int ci = min(col, cmax);
-            const int ok = (on && col < bvalid && !(dbg & 1)) ? 1 : 0;
-            constexpr float kS = -1.4426950408889634f, kT = -2.8853900817779268f;
-            const float di = one_plus_ex2((acc[0][cc] + gx[sg & 1][0][cc]) * kS), df = one_plus_ex2((acc[1][cc] + gx[sg & 1][1][cc]) * kS);
-            const float dg = one_plus_ex2((acc[2][cc] + gx[sg & 1][2][cc]) * kT), dq = one_plus_ex2((acc[3][cc] + gx[sg & 1][3][cc]) * kS);
-            const float rif = rcp_fast(di * df), rgo = rcp_fast(dg * dq);
-            const float ig = rif * df, fg = rif * di, og = rgo * dg;
-            const float gg = fmaf(2.0f, rgo * dq, -1.0f);      // tanh(x) = 2 * logistic(2x) - 1
-            const float cn = fmaf(fg, cst[col], ig * gg);
-            float hn = og * fmaf(2.0f, rcp_fast(one_plus_ex2(cn * kT)), -1.0f);
-            hn = (col < bvalid) ? hn : 0.0f;                   // rows beyond B feed zeros to the next gate GEMM
-            cst[col] = cn;
-            const unsigned o4 = (unsigned)(ci * H4), oc = (unsigned)(ci * ldcs), oh = (unsigned)(ci * ldhs);
-            st_if(gtp[0] + o4, ig, ok); st_if(gtp[1] + o4, fg, ok); st_if(gtp[2] + o4, gg, ok); st_if(gtp[3] + o4, og, ok);
-            st_if(csp + oc, cn, ok);
-            st_if(hsp + oh, hn, ok);
-            if (cdp) st_if(cdp + oc, cn, ok);
-            if (on && !(dbg & 128)) {                          // h_t as the next step's B operand
-              const unsigned short hb = bf16_bits(hn);
-              const float hr = hn - __uint_as_float((uint32_t)hb << 16);
-              *reinterpret_cast<unsigned short*>(Hhi + col * 16) = hb;
-              *reinterpret_cast<unsigned short*>(Hlo + col * 16) = bf16_bits(hr);
+          __syncwarp();
+          if (pf_ok && t + 1 < gx_steps) {
+            for (int r = lane; r < NB; r += 32) {
+              const int b = row0 + ch * NB + r;
+              if (b < B) {
+                const float* src = gx_base + ((long long)(t + 1) * B + b) * ldgx + g * h;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(h * 4)) : "memory");
+              }
             }
           }
         }
       }
+    }
+  } else {
+    // ================================ cell update (warps 0..15) ================================
+    WS_REG_COMPUTE();
+    const WsRole ro = ws_role(warp, lane, h, nsub, NB);
+    if (ro.warp_on) {
+      const bool on = ro.on;
+      const int jc = on ? ro.j : 0;                            // lanes without a unit shadow unit 0 (stores predicated)
+      const int crow0 = row0 + ro.col0;                        // global batch row of this warp's first column in chain 0
+      const int bvalid = B - crow0;                            // CTA-relative columns below this are real rows
+      const int rbase = bvalid > 0 ? crow0 : B - 1;            // rows beyond B shadow the last valid row
+      const int cmax = bvalid > 0 ? bvalid - 1 : 0;
+      const uint32_t tl = tmem_base + ((uint32_t)(ro.q * 32) << 16) + (uint32_t)ro.col0;
+      unsigned char* const Hhi = Hbase + (ro.j >> 3) * lboH + (ro.j & 7) * 2 + ro.col0 * 16;
+      const int planeH = slabs * lboH;
+      // running bases of the current step (element (first column of chain 0, gate g, unit jc)); + constant every step
+      const float* gxp[4];
+      float* gtp[4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) { gxp[g] += gx_step; gtp[g] += gt_step; }
-      csp += cs_step;
-      if (cdp) cdp += cs_step;
-      hsp += hs_step;
-      if (t + 1 < T) {
-        if (!(dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (tr && t < 32) tr[(warp * 32 + t) * 4 + 2] = clock64();
-        if (lane == 0 && ((dbg & 4) ? ws_count_in_relaxed(&arrive_cnt[ch], nact) : ws_count_in(&arrive_cnt[ch], nact))) {
-          issue(ch);
-          if (tr && t < 32) tr[(warp * 32 + t) * 4 + 3] = clock64();
+      for (int g = 0; g < 4; ++g) {
+        gxp[g] = gx_base + (long long)rbase * ldgx + g * h + jc;
+        gtp[g] = gates_base + (long long)rbase * H4 + g * h + jc;
+      }
+      float* csp = cs_base + (long long)(B + rbase) * ldcs + jc;
+      float* cdp = csd_base ? csd_base + (long long)(B + rbase) * ldcs + jc : nullptr;
+      float* hsp = hs_base + (long long)(B + rbase) * ldhs + jc;
+      int ldx = ldgx;                                          // column pitch / step stride of the gx source: switches to the
+      unsigned gx_step = (unsigned)B * (unsigned)ldgx;         // constant bias row (pitch 0) after gx_steps steps (decoder)
+      const unsigned gt_step = (unsigned)B * (unsigned)H4;
+      const unsigned cs_step = (unsigned)B * (unsigned)ldcs, hs_step = (unsigned)B * (unsigned)ldhs;
+      float cst[NCH][8];
+#pragma unroll
+      for (int a = 0; a < NCH; ++a)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cst[a][i] = 0.0f;
+      // every warp owns 8 columns per chain = two groups of 4: the group count is static, so the double-buffered G_x
+      // registers are indexed statically (a run-time parity put the buffers in local memory)
+
+      float gx[2][4][4];
+      for (int t = 0; t < T; ++t) {
+        if (t == gx_steps) {                                   // warp-uniform, once
+#pragma unroll
+          for (int g = 0; g < 4; ++g) gxp[g] = bias_rest + g * h + jc;
+          ldx = 0;
+          gx_step = 0u;
         }
-        __syncwarp();
+        // G_x groups are double-buffered in processing order (group k of a step lives in gx[k & 1]) and always loaded one
+        // group ahead -- across the chain switch and across the step boundary: since the gate GEMM is hidden behind the
+        // other chain's cell update, nothing else would cover the load latency of a step's first group
+        auto load_gx = [&](int ch, int sg, unsigned step_off, float (&dst)[4][4]) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const unsigned o = (unsigned)(min(ch * NB + sg * 4 + cc, cmax) * ldx) + step_off;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) dst[g][cc] = __ldg(gxp[g] + o);
+          }
+        };
+        if (t == 0 || t == gx_steps) load_gx(0, 0, 0u, gx[0]);  // (the source switched: reload)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          WS_STAMP(warp, t, ch * 3);
+          ws_wait(smem_u32(&bar_done[ch]), (uint32_t)(t & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          WS_STAMP(warp, t, ch * 3 + 1);
+#pragma unroll
+          for (int sg = 0; sg < 2; ++sg) {
+            {
+              constexpr int nsg = 2;
+              const int cur = sg;                              // parity of this group in processing order
+              float acc[4][4];
+              if (ch == 0 && sg == 0) WS_STAMP(warp, t, 6);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) tmem_ld4(tl + (uint32_t)((ch * 4 + g) * NB + sg * 4), acc[g]);
+              // the next group's G_x (same chain, or the first group of the other chain) travels while this one is computed
+              if (sg + 1 < nsg) load_gx(ch, sg + 1, 0u, gx[cur ^ 1]);
+              else if (ch + 1 < NCH) load_gx(ch + 1, 0, 0u, gx[cur ^ 1]);
+              else if (t + 1 < T && t + 1 != gx_steps) load_gx(0, 0, gx_step, gx[cur ^ 1]);     // next step's first group
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              if (ch == 0 && sg == 0) WS_STAMP(warp, t, 7);
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) {
+                const int col = sg * 4 + cc, gcol = ch * NB + col;      // column inside the chain / inside the CTA
+                const int ci = min(gcol, cmax);
+                const int ok = (on && gcol < bvalid) ? 1 : 0;
+                constexpr float kS = -1.4426950408889634f, kT = -2.8853900817779268f;
+                const float di = one_plus_ex2((acc[0][cc] + gx[cur][0][cc]) * kS), df = one_plus_ex2((acc[1][cc] + gx[cur][1][cc]) * kS);
+                const float dg = one_plus_ex2((acc[2][cc] + gx[cur][2][cc]) * kT), dq = one_plus_ex2((acc[3][cc] + gx[cur][3][cc]) * kS);
+                const float rif = rcp_fast(di * df), rgo = rcp_fast(dg * dq);
+                const float ig = rif * df, fg = rif * di, og = rgo * dg;
+                const float gg = fmaf(2.0f, rgo * dq, -1.0f);  // tanh(x) = 2 * logistic(2x) - 1
+                const float cn = fmaf(fg, cst[ch][col], ig * gg);
+                float hn = og * fmaf(2.0f, rcp_fast(one_plus_ex2(cn * kT)), -1.0f);
+                hn = (gcol < bvalid) ? hn : 0.0f;              // rows beyond B feed zeros to the next gate GEMM
+                cst[ch][col] = cn;
+                const unsigned o4 = (unsigned)(ci * H4), oc = (unsigned)(ci * ldcs), oh = (unsigned)(ci * ldhs);
+                st_if(gtp[0] + o4, ig, ok); st_if(gtp[1] + o4, fg, ok); st_if(gtp[2] + o4, gg, ok); st_if(gtp[3] + o4, og, ok);
+                st_if(csp + oc, cn, ok);
+                st_if(hsp + oh, hn, ok);
+                if (cdp) st_if(cdp + oc, cn, ok);
+                if (on) {                                      // h_t as the next step's B operand
+                  const unsigned short hb = bf16_bits(hn);
+                  const float hr = hn - __uint_as_float((uint32_t)hb << 16);
+                  unsigned char* hp = Hhi + ch * chainH + col * 16;
+                  *reinterpret_cast<unsigned short*>(hp) = hb;
+                  *reinterpret_cast<unsigned short*>(hp + planeH) = bf16_bits(hr);
+                }
+              }
+            }
+          }
+          WS_STAMP(warp, t, ch * 3 + 2);
+          if (t + 1 < T) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) ws_arrive(smem_u32(&bar_ready[ch]));
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { gxp[g] += gx_step; gtp[g] += gt_step; }
+        csp += cs_step;
+        if (cdp) cdp += cs_step;
+        hsp += hs_step;
       }
     }
-  } else if (T > 0 && (warp % WS_CWARPS) == 0 && lane == 0) {
-    issue(ch);                                                 // (never: warp 0 of a chain always has work)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -401,19 +418,10 @@ __global__ void __launch_bounds__(NCHAIN * WS_CWARPS * 32, 1) lstm_ws_fwd_kernel
 // ----------------------------------------------------------------------------------------------------------------
 // backward
 // ----------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float v[2]) {
-  uint32_t r[2];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
-  v[0] = __uint_as_float(r[0]);
-  v[1] = __uint_as_float(r[1]);
-}
-
-template <int NCHAIN>
-__global__ void __launch_bounds__(NCHAIN * WS_CWARPS * 32, 1) lstm_ws_bwd_kernel(const __grid_constant__ WsBatch bt) {
-  constexpr int NTHREADS = NCHAIN * WS_CWARPS * 32;
+template <int NCH>
+__global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_bwd_kernel(const __grid_constant__ WsBatch bt) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long bar_done[WS_MAXCHAIN];
-  __shared__ unsigned int arrive_cnt[WS_MAXCHAIN];
+  __shared__ __align__(8) unsigned long long bar_done[WS_MAXCHAIN], bar_ready[WS_MAXCHAIN];
   __shared__ uint32_t tmem_holder;
   const WsCell& wc = ws_find(bt, (int)blockIdx.x);
   const int h = wc.c.h, B = wc.c.B, T = wc.c.T, H4 = 4 * h;
@@ -435,15 +443,17 @@ __global__ void __launch_bounds__(NCHAIN * WS_CWARPS * 32, 1) lstm_ws_bwd_kernel
   unsigned char* Bbase = Alo + slabs * lboA;                // per chain: dG tile [hi | lo]
   const int chainB = 2 * slabs * lboB;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: role branches become uniform branches
-  const int row0 = ((int)blockIdx.x - wc.cta0) * (NCHAIN * NB);
-  const int tmem_cols = NCHAIN * NB < 32 ? 32 : NCHAIN * NB;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int row0 = ((int)blockIdx.x - wc.cta0) * (NCH * NB);
+  const int ksteps = KP >> 4;
+  const int nacc = ksteps < 4 ? ksteps : 4;                 // partial sums over K: independent accumulators
+  int tmem_cols = 32;
+  while (tmem_cols < NCH * 4 * NB) tmem_cols <<= 1;
 
-  const unsigned int nact = (nsub == 3) ? 6u : 8u;
   if (tid == 0) {
-    for (int i = 0; i < NCHAIN; ++i) {
-      mbar_init(smem_u32(&bar_done[i]), 1);
-      arrive_cnt[i] = 0u;
+    for (int i = 0; i < NCH; ++i) {
+      mbar_init(smem_u32(&bar_done[i]), 4);                   // one commit per issuing warp
+      mbar_init(smem_u32(&bar_ready[i]), wc.nact);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -457,7 +467,7 @@ __global__ void __launch_bounds__(NCHAIN * WS_CWARPS * 32, 1) lstm_ws_bwd_kernel
   {
     const int span = nsub <= 2 ? 32 * nsub : h;
     const int rows = nsub <= 2 ? 128 : h;
-    for (int idx = tid; idx < rows * slabs; idx += NTHREADS) {
+    for (int idx = tid; idx < rows * slabs; idx += WS_THREADS) {
       const int r = idx % rows, slab = idx / rows;
       const int j = r % span;
       float v[8];
@@ -468,7 +478,7 @@ __global__ void __launch_bounds__(NCHAIN * WS_CWARPS * 32, 1) lstm_ws_bwd_kernel
       }
       split_store(v, Ahi + slab * lboA + r * 16, Alo + slab * lboA + r * 16, true);
     }
-    for (int idx = tid * 16; idx < NCHAIN * chainB; idx += NTHREADS * 16)
+    for (int idx = tid * 16; idx < NCH * chainB; idx += WS_THREADS * 16)
       *reinterpret_cast<uint4*>(Bbase + idx) = make_uint4(0, 0, 0, 0);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -477,140 +487,154 @@ __global__ void __launch_bounds__(NCHAIN * WS_CWARPS * 32, 1) lstm_ws_bwd_kernel
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_holder;
 
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  auto issue = [&](int ch) {                                // dG of the step just finished -> dh of the step before
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint64_t dAh0 = make_smem_desc(smem_u32(Ahi), lboA, 128), dAl0 = make_smem_desc(smem_u32(Alo), lboA, 128);
-    const uint32_t bb = smem_u32(Bbase + ch * chainB);
-    const uint64_t dBh0 = make_smem_desc(bb, lboB, 128), dBl0 = make_smem_desc(bb + slabs * lboB, lboB, 128);
-    const uint32_t dcol = tmem_base + (uint32_t)(ch * NB);
-    const int ksteps = KP >> 4;
-    const uint64_t astep = (uint64_t)((2 * lboA) >> 4), bstep = (uint64_t)((2 * lboB) >> 4);
-    uint64_t ao = 0, bo = 0;
+  if (warp >= WS_CW) {
+    WS_REG_ISSUER();
+    if (lane == 0) {
+      // the four warps of this warpgroup issue one partial sum over K each (k-steps a, a+4, a+8, ...), concurrently
+      const int a = warp - WS_CW;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint64_t dAh0 = make_smem_desc(smem_u32(Ahi), lboA, 128), dAl0 = make_smem_desc(smem_u32(Alo), lboA, 128);
+      const uint64_t astep = (uint64_t)((2 * lboA) >> 4), bstep = (uint64_t)((2 * lboB) >> 4);
+      for (int n = 0; n < T; ++n) {                         // n-th product: dG of step T-n (zero for n = 0) -> dh of step T-1-n
 #pragma unroll 1
-    for (int kk = 0; kk < ksteps; ++kk, ao += astep, bo += bstep) {
-      umma_bf16(dcol, dAh0 + ao, dBh0 + bo, idesc, kk > 0 ? 1u : 0u);
-      umma_bf16(dcol, dAl0 + ao, dBh0 + bo, idesc, 1u);
-      umma_bf16(dcol, dAh0 + ao, dBl0 + bo, idesc, 1u);
-    }
-    umma_commit(smem_u32(&bar_done[ch]));
-  };
-
-  const int ch = warp / WS_CWARPS;
-  const WsRole ro = ws_role(warp % WS_CWARPS, lane, h, nsub, NB);
-  if (ro.warp_on) {
-    const bool on = ro.on;
-    const int jc = on ? ro.j : 0;
-    const int crow0 = row0 + ch * NB + ro.col0;
-    const int bvalid = B - crow0;
-    const int rbase = bvalid > 0 ? crow0 : B - 1;
-    const int cmax = bvalid > 0 ? bvalid - 1 : 0;
-    const uint32_t tl = tmem_base + ((uint32_t)(ro.q * 32) << 16) + (uint32_t)(ch * NB + ro.col0);
-    const bool jb = ro.j < hp8;                               // lanes of the K padding keep writing zeros
-    unsigned char* const Bhi = Bbase + ch * chainB + (ro.j >> 1) * lboB + (ro.j & 1) * 8 + ro.col0 * 16;
-    unsigned char* const Blo = Bhi + slabs * lboB;
-    const uint32_t bar = smem_u32(&bar_done[ch]);
-    // running bases of the current step (t = T-1 first), moved back by a constant every step
-    const long long tb0 = (long long)(T - 1) * B + rbase;
-    const float* gtp[4];
-    float* dgp[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      gtp[g] = gates_base + tb0 * H4 + g * h + jc;
-      dgp[g] = dG_base + tb0 * H4 + g * h + jc;
-    }
-    const float* cpp = cs_base + tb0 * ldcs + jc;             // c_{t-1}; c_t is one block further
-    const float* dhp = dha_base ? dha_base + tb0 * lddh + jc : nullptr;
-    const float* dcp = dce_base ? dce_base + tb0 * lddc + jc : nullptr;
-    const float* dc2p = dce2_base ? dce2_base + tb0 * lddc + jc : nullptr;
-    const float* dhlp = dhl_base ? dhl_base + (long long)rbase * lddhl + jc : nullptr;
-    const unsigned gt_step = (unsigned)B * (unsigned)H4, cs_step = (unsigned)B * (unsigned)ldcs;
-    const unsigned dh_step = (unsigned)B * (unsigned)lddh, dc_step = (unsigned)B * (unsigned)lddc;
-    float dc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) dc[i] = 0.0f;
-    const int nsg = 2 * ro.nsg;                               // groups of TWO columns here (register budget)
-    // the last step multiplies a zero dG like every other step (dh_rec = 0 exactly): no special case in the loop
-    if (warp % WS_CWARPS == 0 && lane == 0) issue(ch);
-
-    for (int t = T - 1; t >= 0; --t) {
-      struct In { float ig, fg, gg, og, cp, cn, dhx, dcx; };
-      In buf[2][2];
-      const bool last = t == T - 1;
-      auto load_in = [&](int sg, In (&d)[2]) {
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int ci = min(sg * 2 + cc, cmax);
-          const unsigned o4 = (unsigned)(ci * H4), oc = (unsigned)(ci * ldcs);
-          In v;
-          v.ig = gtp[0][o4]; v.fg = gtp[1][o4]; v.gg = gtp[2][o4]; v.og = gtp[3][o4];
-          v.cp = cpp[oc];
-          v.cn = cpp[oc + cs_step];
-          v.dhx = dhp ? __ldg(dhp + (unsigned)(ci * lddh)) : 0.0f;
-          if (last && dhlp) v.dhx += __ldg(dhlp + (unsigned)(ci * lddhl));
-          v.dcx = dcp ? __ldg(dcp + (unsigned)(ci * lddc)) : 0.0f;
-          if (!last && dc2p) v.dcx += __ldg(dc2p + (unsigned)(ci * lddc));
-          d[cc] = v;
-        }
-      };
-      load_in(0, buf[0]);
-      ws_wait(bar, (uint32_t)((T - 1 - t) & 1));              // dh_rec of this step = product T-1-t
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int sg = 0; sg < 8; ++sg) {
-        if (sg < nsg) {
-          float dh[2];
-          tmem_ld2(tl + (uint32_t)(sg * 2), dh);
-          if (sg + 1 < nsg) load_in(sg + 1, buf[(sg + 1) & 1]);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int col = sg * 2 + cc;
-            const int ci = min(col, cmax);
-            const bool ok = on && col < bvalid;
-            const In& v = buf[sg & 1][cc];
-            const float dht = dh[cc] + v.dhx;
-            const float tc = act_tanh(v.cn);
-            const float dci = dc[col] + dht * v.og * (1.0f - tc * tc) + v.dcx;
-            float d_i = dci * v.gg * v.ig * (1.0f - v.ig);
-            float d_f = dci * v.cp * v.fg * (1.0f - v.fg);
-            float d_g = dci * v.ig * (1.0f - v.gg * v.gg);
-            float d_o = dht * tc * v.og * (1.0f - v.og);
-            dc[col] = dci * v.fg;
-            const unsigned o4 = (unsigned)(ci * H4);
-            if (ok) {
-              dgp[0][o4] = d_i; dgp[1][o4] = d_f; dgp[2][o4] = d_g; dgp[3][o4] = d_o;
-            } else {
-              d_i = d_f = d_g = d_o = 0.0f;
-            }
-            if (jb && t > 0) {                                 // B operand: row = batch column, k' = 4j..4j+3 (8 contiguous bytes)
-              const float v4[4] = {d_i, d_f, d_g, d_o};
-              unsigned short hb[4], lb[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                hb[e] = bf16_bits(v4[e]);
-                lb[e] = bf16_bits(v4[e] - __uint_as_float((uint32_t)hb[e] << 16));
-              }
-              *reinterpret_cast<uint2*>(Bhi + col * 16) =
-                  make_uint2((uint32_t)hb[0] | ((uint32_t)hb[1] << 16), (uint32_t)hb[2] | ((uint32_t)hb[3] << 16));
-              *reinterpret_cast<uint2*>(Blo + col * 16) =
-                  make_uint2((uint32_t)lb[0] | ((uint32_t)lb[1] << 16), (uint32_t)lb[2] | ((uint32_t)lb[3] << 16));
-            }
+        for (int ch = 0; ch < NCH; ++ch) {
+          if (n > 0) ws_wait(smem_u32(&bar_ready[ch]), (uint32_t)((n - 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t bb = smem_u32(Bbase + ch * chainB);
+          const uint64_t dBh0 = make_smem_desc(bb, lboB, 128), dBl0 = make_smem_desc(bb + slabs * lboB, lboB, 128);
+          const uint32_t dcol = tmem_base + (uint32_t)((ch * 4 + a) * NB);
+#pragma unroll 1
+          for (int kk = a; kk < ksteps; kk += 4) {
+            umma_bf16(dcol, dAh0 + kk * astep, dBh0 + kk * bstep, idesc, kk > a ? 1u : 0u);
+            umma_bf16(dcol, dAl0 + kk * astep, dBh0 + kk * bstep, idesc, 1u);
+            umma_bf16(dcol, dAh0 + kk * astep, dBl0 + kk * bstep, idesc, 1u);
           }
+          umma_commit(smem_u32(&bar_done[ch]));             // (a warp with no k-step still arrives)
         }
       }
+    }
+  } else {
+    WS_REG_COMPUTE();
+    const WsRole ro = ws_role(warp, lane, h, nsub, NB);
+    if (ro.warp_on) {
+      const bool on = ro.on;
+      const int jc = on ? ro.j : 0;
+      const int crow0 = row0 + ro.col0;
+      const int bvalid = B - crow0;
+      const int rbase = bvalid > 0 ? crow0 : B - 1;
+      const int cmax = bvalid > 0 ? bvalid - 1 : 0;
+      const uint32_t tl = tmem_base + ((uint32_t)(ro.q * 32) << 16) + (uint32_t)ro.col0;
+      const bool jb = ro.j < hp8;                             // lanes of the K padding keep writing zeros
+      unsigned char* const Bhi = Bbase + (ro.j >> 1) * lboB + (ro.j & 1) * 8 + ro.col0 * 16;
+      const int planeB = slabs * lboB;
+      // running bases of the current step (t = T-1 first), moved back by a constant every step
+      const long long tb0 = (long long)(T - 1) * B + rbase;
+      const float* gtp[4];
+      float* dgp[4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) { gtp[g] -= gt_step; dgp[g] -= gt_step; }
-      cpp -= cs_step;
-      if (dhp) dhp -= dh_step;
-      if (dcp) dcp -= dc_step;
-      if (dc2p) dc2p -= dc_step;
-      if (t > 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0 && ws_count_in(&arrive_cnt[ch], nact)) issue(ch);
-        __syncwarp();
+      for (int g = 0; g < 4; ++g) {
+        gtp[g] = gates_base + tb0 * H4 + g * h + jc;
+        dgp[g] = dG_base + tb0 * H4 + g * h + jc;
+      }
+      const float* cpp = cs_base + tb0 * ldcs + jc;           // c_{t-1}; c_t is one block further
+      const float* dhp = dha_base ? dha_base + tb0 * lddh + jc : nullptr;
+      const float* dcp = dce_base ? dce_base + tb0 * lddc + jc : nullptr;
+      const float* dc2p = dce2_base ? dce2_base + tb0 * lddc + jc : nullptr;
+      const float* dhlp = dhl_base ? dhl_base + (long long)rbase * lddhl + jc : nullptr;
+      const unsigned gt_step = (unsigned)B * (unsigned)H4, cs_step = (unsigned)B * (unsigned)ldcs;
+      const unsigned dh_step = (unsigned)B * (unsigned)lddh, dc_step = (unsigned)B * (unsigned)lddc;
+      float dc[NCH][8];
+#pragma unroll
+      for (int a = 0; a < NCH; ++a)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dc[a][i] = 0.0f;
+      const int nsg = ro.ncol >> 1;                           // groups of TWO columns per chain: 2 or 4 (even: static parity)
+
+      for (int t = T - 1; t >= 0; --t) {
+        struct In { float ig, fg, gg, og, cp, cn, dhx, dcx; };
+        In buf[2][2];                                         // groups double-buffered in processing order
+        const bool last = t == T - 1;
+        auto load_in = [&](int ch, int sg, In (&d)[2]) {
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int ci = min(ch * NB + sg * 2 + cc, cmax);
+            const unsigned o4 = (unsigned)(ci * H4), oc = (unsigned)(ci * ldcs);
+            In v;
+            v.ig = gtp[0][o4]; v.fg = gtp[1][o4]; v.gg = gtp[2][o4]; v.og = gtp[3][o4];
+            v.cp = cpp[oc];
+            v.cn = cpp[oc + cs_step];
+            v.dhx = dhp ? __ldg(dhp + (unsigned)(ci * lddh)) : 0.0f;
+            if (last && dhlp) v.dhx += __ldg(dhlp + (unsigned)(ci * lddhl));
+            v.dcx = dcp ? __ldg(dcp + (unsigned)(ci * lddc)) : 0.0f;
+            if (!last && dc2p) v.dcx += __ldg(dc2p + (unsigned)(ci * lddc));
+            d[cc] = v;
+          }
+        };
+        load_in(0, 0, buf[0]);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          ws_wait(smem_u32(&bar_done[ch]), (uint32_t)((T - 1 - t) & 1));     // dh_rec of this step = product T-1-t
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int sg = 0; sg < 4; ++sg) {
+            if (sg < nsg) {
+              const int cur = sg & 1;
+              float dh[4][2];
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                if (a < nacc) tmem_ld2(tl + (uint32_t)((ch * 4 + a) * NB + sg * 2), dh[a]);
+                else dh[a][0] = dh[a][1] = 0.0f;
+              }
+              if (sg + 1 < nsg) load_in(ch, sg + 1, buf[cur ^ 1]);
+              else if (ch + 1 < NCH) load_in(ch + 1, 0, buf[cur ^ 1]);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc) {
+                const int col = sg * 2 + cc, gcol = ch * NB + col;
+                const int ci = min(gcol, cmax);
+                const int ok = (on && gcol < bvalid) ? 1 : 0;
+                const In& v = buf[cur][cc];
+                const float dht = (dh[0][cc] + dh[1][cc]) + (dh[2][cc] + dh[3][cc]) + v.dhx;
+                const float tc = fmaf(2.0f, rcp_fast(one_plus_ex2(v.cn * -2.8853900817779268f)), -1.0f);
+                const float dci = dc[ch][col] + dht * v.og * (1.0f - tc * tc) + v.dcx;
+                float d_i = dci * v.gg * v.ig * (1.0f - v.ig);
+                float d_f = dci * v.cp * v.fg * (1.0f - v.fg);
+                float d_g = dci * v.ig * (1.0f - v.gg * v.gg);
+                float d_o = dht * tc * v.og * (1.0f - v.og);
+                dc[ch][col] = dci * v.fg;
+                const unsigned o4 = (unsigned)(ci * H4);
+                st_if(dgp[0] + o4, d_i, ok); st_if(dgp[1] + o4, d_f, ok); st_if(dgp[2] + o4, d_g, ok); st_if(dgp[3] + o4, d_o, ok);
+                if (!ok) d_i = d_f = d_g = d_o = 0.0f;
+                if (jb && t > 0) {                             // B operand: row = batch column, k' = 4j..4j+3 (8 contiguous bytes)
+                  const float v4[4] = {d_i, d_f, d_g, d_o};
+                  unsigned short hb[4], lb[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    hb[e] = bf16_bits(v4[e]);
+                    lb[e] = bf16_bits(v4[e] - __uint_as_float((uint32_t)hb[e] << 16));
+                  }
+                  unsigned char* bp = Bhi + ch * chainB + col * 16;
+                  *reinterpret_cast<uint2*>(bp) =
+                      make_uint2((uint32_t)hb[0] | ((uint32_t)hb[1] << 16), (uint32_t)hb[2] | ((uint32_t)hb[3] << 16));
+                  *reinterpret_cast<uint2*>(bp + planeB) =
+                      make_uint2((uint32_t)lb[0] | ((uint32_t)lb[1] << 16), (uint32_t)lb[2] | ((uint32_t)lb[3] << 16));
+                }
+              }
+            }
+          }
+          if (t > 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) ws_arrive(smem_u32(&bar_ready[ch]));
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { gtp[g] -= gt_step; dgp[g] -= gt_step; }
+        cpp -= cs_step;
+        if (dhp) dhp -= dh_step;
+        if (dcp) dcp -= dc_step;
+        if (dc2p) dc2p -= dc_step;
       }
     }
   }
@@ -627,11 +651,6 @@ __global__ void __launch_bounds__(NCHAIN * WS_CWARPS * 32, 1) lstm_ws_bwd_kernel
 static inline int ru(int x, int m) { return (x + m - 1) / m * m; }
 static int ws_smem_limit() { return mfm_dev_info().smem_optin - 1024; }     // the opt-in limit covers static + dynamic
 
-static long long* g_ws_trace = nullptr;
-extern "C" int mfm_debug_set_lstm_trace(void* buf) {
-  g_ws_trace = static_cast<long long*>(buf);
-  return MFM_OK;
-}
 static int g_ws_force_nb = 0;      // tests: 16 forces the narrow chains where they are legal (nsub >= 3)
 static int g_ws_force_chains = 0;  // tests: 1 or 2 chains per CTA (0 = by occupancy)
 extern "C" int mfm_debug_lstm_force_nb(int nb) {
@@ -644,8 +663,19 @@ extern "C" int mfm_debug_lstm_force_chains(int n) {
   g_ws_force_chains = n;
   return MFM_OK;
 }
-// variant ids: 0 fwd NB=32, 1 fwd NB=16, 2 bwd NB=32, 3 bwd NB=16, 4 fwd CUDA-core fallback, 5 bwd CUDA-core fallback,
-// 6 launches with one chain per CTA, 7 launches with two
+// copies the clock-stamp trace of the last forward launch to `host` (17*32*8 int64); only in -DWS_DEBUG=1 builds
+extern "C" int mfm_debug_set_lstm_trace(void* host) {
+#if WS_DEBUG
+  if (!host) return MFM_ERR_ARG;
+  cudaError_t e = cudaMemcpyFromSymbol(host, g_ws_trace_buf, sizeof(long long) * 17 * 32 * 8);
+  return e == cudaSuccess ? MFM_OK : (int)e;
+#else
+  (void)host;
+  return MFM_ERR_UNSUPPORTED;
+#endif
+}
+// variant ids: 0 fwd wide chains (32 / 64 rows), 1 fwd 16-row chains, 2 bwd wide, 3 bwd 16-row, 4 fwd CUDA-core fallback,
+// 5 bwd CUDA-core fallback, 6 launches with one chain per CTA, 7 launches with two
 extern "C" unsigned long long mfm_debug_lstm_variant_count(int variant) {
   return (variant >= 0 && variant < 8) ? g_ws_counts[variant] : 0ull;
 }
@@ -653,11 +683,15 @@ void ws_count_fallback(bool bwd, int ncells) { g_ws_counts[bwd ? 5 : 4] += (unsi
 
 // shared-memory plan of one cell; returns bytes, 0 if it does not fit
 static size_t ws_plan(bool bwd, int h, int nb, int nchain, int limit, WsCell& lc) {
-  const int nsub = (h + 31) / 32;
-  if (nsub > 4) return 0;
-  if (nb == 16 && nsub <= 2) return 0;                      // the replicated layouts split 32 columns over 8 warps
+  const int nsub0 = (h + 31) / 32;
+  if (nsub0 > 4) return 0;
+  const int nsub = nsub0 < 2 ? 2 : nsub0;                   // layout: h <= 32 uses the two-copy layout with an empty sub-block
+  const int R = nsub == 2 ? 2 : 1;
+  const int ncol = nb / (4 * R);                            // columns per warp and chain: 8 (forward), 8 or 4 (backward)
+  if (ncol * 4 * R != nb || !(ncol == 8 || (bwd && ncol == 4))) return 0;
   lc.nb = nb;
   lc.nsub = nsub;
+  lc.nact = nsub0 == 1 ? 8 : nsub0 == 3 ? 12 : 16;
   for (int pad = 32; pad >= 0; pad -= 32) {
     int rowsA, slabs;
     if (!bwd) {
@@ -692,9 +726,10 @@ static int ws_plan_all(bool bwd, const mfm_lstm_cell* cells, int ncells, int nch
     WsCell lc;
     size_t s = 0;
     if (c.h >= 1 && c.h <= 128) {
-      if (g_ws_force_nb != 16) s = ws_plan(bwd, c.h, 32, nchain, lim, lc);
-      if (!s) s = ws_plan(bwd, c.h, 16, nchain, lim, lc);
-      if (!s && g_ws_force_nb == 16) s = ws_plan(bwd, c.h, 32, nchain, lim, lc);
+      // widest chains first (64 rows for the replicated layouts, 32 otherwise); 16 rows when shared memory demands it
+      static const int order[3] = {64, 32, 16}, narrow_first[3] = {16, 32, 64};
+      const int* cand = g_ws_force_nb == 16 ? narrow_first : order;
+      for (int k = 0; k < 3 && !s; ++k) s = ws_plan(bwd, c.h, cand[k], nchain, lim, lc);
     }
     if (!s) { rest[(*nrest)++] = c; continue; }
     lc.c = c;
@@ -719,14 +754,10 @@ static int ws_plan_all(bool bwd, const mfm_lstm_cell* cells, int ncells, int nch
 static int ws_launch(bool bwd, const mfm_lstm_cell* cells, int ncells, mfm_lstm_cell* rest, int* nrest, cudaStream_t st) {
   const int lim = ws_smem_limit();
   WsBatch bt;
-  {
-    const char* e = getenv("MFM_WS_DBG");
-    bt.dbg = e ? atoi(e) : 0;
-    bt.trace = g_ws_trace;
-  }
   size_t smem = 0;
-  // two chains per CTA overlap each other's latency; when that leaves most SMs without a CTA (a single decoder cell,
+  // two chains per CTA hide each other's gate GEMM; when that leaves most SMs without a CTA (a single decoder cell,
   // small batches), one chain per CTA spreads the chains over twice as many SMs instead
+  if (const char* e = getenv("MFM_WS_CHAINS")) g_ws_force_chains = atoi(e) == 1 ? 1 : atoi(e) == 2 ? 2 : 0;
   int nchain = g_ws_force_chains ? g_ws_force_chains : 2;
   int total = ws_plan_all(bwd, cells, ncells, nchain, lim, bt, smem, rest, nrest);
   if (!g_ws_force_chains && bt.n && total * 3 < mfm_dev_info().sms * 2) {
@@ -738,11 +769,11 @@ static int ws_launch(bool bwd, const mfm_lstm_cell* cells, int ncells, mfm_lstm_
   g_ws_counts[nchain == 1 ? 6 : 7] += 1;
   int e = 0;
   if (bwd) {
-    if (nchain == 1) { if (!(e = mfm_func_smem_t(lstm_ws_bwd_kernel<1>, lim))) lstm_ws_bwd_kernel<1><<<total, WS_CWARPS * 32, smem, st>>>(bt); }
-    else             { if (!(e = mfm_func_smem_t(lstm_ws_bwd_kernel<2>, lim))) lstm_ws_bwd_kernel<2><<<total, 2 * WS_CWARPS * 32, smem, st>>>(bt); }
+    if (nchain == 1) { if (!(e = mfm_func_smem_t(lstm_ws_bwd_kernel<1>, lim))) lstm_ws_bwd_kernel<1><<<total, WS_THREADS, smem, st>>>(bt); }
+    else             { if (!(e = mfm_func_smem_t(lstm_ws_bwd_kernel<2>, lim))) lstm_ws_bwd_kernel<2><<<total, WS_THREADS, smem, st>>>(bt); }
   } else {
-    if (nchain == 1) { if (!(e = mfm_func_smem_t(lstm_ws_fwd_kernel<1>, lim))) lstm_ws_fwd_kernel<1><<<total, WS_CWARPS * 32, smem, st>>>(bt); }
-    else             { if (!(e = mfm_func_smem_t(lstm_ws_fwd_kernel<2>, lim))) lstm_ws_fwd_kernel<2><<<total, 2 * WS_CWARPS * 32, smem, st>>>(bt); }
+    if (nchain == 1) { if (!(e = mfm_func_smem_t(lstm_ws_fwd_kernel<1>, lim))) lstm_ws_fwd_kernel<1><<<total, WS_THREADS, smem, st>>>(bt); }
+    else             { if (!(e = mfm_func_smem_t(lstm_ws_fwd_kernel<2>, lim))) lstm_ws_fwd_kernel<2><<<total, WS_THREADS, smem, st>>>(bt); }
   }
   if (e) return e;
   MFM_LAUNCH_CHECK();

@@ -172,21 +172,38 @@ __global__ void __launch_bounds__(256) rownorm2_kernel(int B, int dim, const flo
   if (lane == 0) out[row] = s;
 }
 
+// The MMD is a difference of three O(1) means that cancel to O(1/B): the means need ~1e-7 absolute accuracy for the
+// loss term to hold 1e-3 relative at batch 2048.  Thousands of fp32 atomicAdds into one O(1) slot lose that (each rounds
+// at 3e-8), so the sums are carried in double: per thread, per block, and in the accumulator (slot64); a float slot is
+// supported for the stand-alone API and gets one add per block of the already weighted double sum.
 __global__ void __launch_bounds__(256) mmd_kexp_kernel(int M, int N, float* __restrict__ S, const float* __restrict__ nx,
-                                                        const float* __restrict__ ny, float inv_d2, float weight,
-                                                        float* __restrict__ slot) {
-  __shared__ float red[32];
+                                                        const float* __restrict__ ny, float inv_d2, double weight,
+                                                        float* __restrict__ slot, double* __restrict__ slot64) {
+  __shared__ double red[8];
   const long long total = (long long)M * N;
-  float acc = 0.0f;
+  double acc = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(i / N), n = (int)(i - (long long)m * N);
     const float d2 = fmaxf(__ldg(nx + m) + __ldg(ny + n) - 2.0f * S[i], 0.0f);
     const float k = expf(-d2 * inv_d2);
     S[i] = k;
-    acc += k;
+    acc += (double)k;
   }
-  const float tot = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(slot, tot * weight);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    if (slot64) atomicAdd(slot64, tot * weight);
+    else atomicAdd(slot, (float)(tot * weight));
+  }
+}
+// slots[i] = (float)acc[i]: the double accumulators of the training schedule folded into the fp32 loss buffer
+__global__ void mmd_fold_kernel(int n, const double* __restrict__ acc, float* __restrict__ slots) {
+  const int i = threadIdx.x;
+  if (i < n) slots[i] = (float)acc[i];
 }
 
 // dz += coef * sdev * ((rs - cs) * z - t1 + t2)
@@ -210,13 +227,28 @@ extern "C" int mfm_rownorm2(int B, int dim, const float* x, long long ld, float*
   MFM_LAUNCH_CHECK();
   return MFM_OK;
 }
-extern "C" int mfm_mmd_kexp(int M, int N, float* S, const float* nx, const float* ny, int dim, float weight, float* slot,
-                            void* stream) {
-  MFM_REQUIRE(M > 0 && N > 0 && dim > 0 && S && nx && ny && slot);
+static int mmd_kexp_launch(int M, int N, float* S, const float* nx, const float* ny, int dim, double weight, float* slot,
+                           double* slot64, void* stream) {
+  MFM_REQUIRE(M > 0 && N > 0 && dim > 0 && S && nx && ny && (slot || slot64));
   long long blocks = ((long long)M * N + 256 * 8 - 1) / (256 * 8);
   if (blocks > mfm_dev_info().sms * 8) blocks = mfm_dev_info().sms * 8;
   if (blocks < 1) blocks = 1;
-  mmd_kexp_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(M, N, S, nx, ny, 1.0f / ((float)dim * (float)dim), weight, slot);
+  mmd_kexp_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(M, N, S, nx, ny, 1.0f / ((float)dim * (float)dim), weight, slot,
+                                                                  slot64);
+  MFM_LAUNCH_CHECK();
+  return MFM_OK;
+}
+extern "C" int mfm_mmd_kexp(int M, int N, float* S, const float* nx, const float* ny, int dim, float weight, float* slot,
+                            void* stream) {
+  return mmd_kexp_launch(M, N, S, nx, ny, dim, (double)weight, slot, nullptr, stream);
+}
+extern "C" int mfm_mmd_kexp64(int M, int N, float* S, const float* nx, const float* ny, int dim, double weight, double* slot64,
+                              void* stream) {
+  return mmd_kexp_launch(M, N, S, nx, ny, dim, weight, nullptr, slot64, stream);
+}
+extern "C" int mfm_mmd_fold(int n, const double* acc, float* slots, void* stream) {
+  MFM_REQUIRE(n > 0 && n <= 32 && acc && slots);
+  mmd_fold_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(n, acc, slots);
   MFM_LAUNCH_CHECK();
   return MFM_OK;
 }

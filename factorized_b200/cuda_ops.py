@@ -71,6 +71,8 @@ _SIGS = {
     "mfm_randn": (C.c_int, [LL, c_f, c_f, C.c_int, c_f]),
     "mfm_rownorm2": (C.c_int, [C.c_int, C.c_int, c_f, LL, c_f, c_f]),
     "mfm_mmd_kexp": (C.c_int, [C.c_int, C.c_int, c_f, c_f, c_f, C.c_int, C.c_float, c_f, c_f]),
+    "mfm_mmd_kexp64": (C.c_int, [C.c_int, C.c_int, c_f, c_f, c_f, C.c_int, C.c_double, c_f, c_f]),
+    "mfm_mmd_fold": (C.c_int, [C.c_int, c_f, c_f, c_f]),
     "mfm_mmd_combine": (C.c_int, [C.c_int, C.c_int, c_f, LL, c_f, c_f, c_f, c_f, C.c_float, c_f, c_f, LL, c_f]),
     "mfm_copy2d": (C.c_int, [C.c_int, C.c_int, c_f, LL, c_f, LL, C.c_int, c_f]),
     "mfm_add": (C.c_int, [LL, c_f, c_f, c_f, c_f]),
@@ -423,6 +425,21 @@ class CudaOps:
             raise MfmCudaError("mmd_kexp: S must be contiguous")
         _check(self.lib.mfm_mmd_kexp(M, N, ps, _vec(nx, "nx", M), _vec(ny, "ny", N), int(dim), float(weight),
                                      _vec(slot, "slot", 1), _stream()), "mfm_mmd_kexp")
+
+    def mmd_kexp64(self, S, nx, ny, dim, weight, acc):
+        """mmd_kexp with a float64 accumulator element (acc: 1-element float64 CUDA tensor view)."""
+        ps, M, N, ld = _mat(S, "mmd_kexp S")
+        if ld != N:
+            raise MfmCudaError("mmd_kexp: S must be contiguous")
+        if not acc.is_cuda or acc.dtype != torch.float64 or acc.numel() != 1:
+            raise MfmCudaError("mmd_kexp64: acc must be one CUDA float64 element")
+        _check(self.lib.mfm_mmd_kexp64(M, N, ps, _vec(nx, "nx", M), _vec(ny, "ny", N), int(dim), float(weight),
+                                       acc.data_ptr(), _stream()), "mfm_mmd_kexp64")
+
+    def mmd_fold(self, acc, slots):
+        if not acc.is_cuda or acc.dtype != torch.float64 or not acc.is_contiguous() or acc.numel() != slots.numel():
+            raise MfmCudaError("mmd_fold: acc must be a contiguous CUDA float64 vector as long as slots")
+        _check(self.lib.mfm_mmd_fold(acc.numel(), acc.data_ptr(), _vec(slots, "slots", acc.numel()), _stream()), "mfm_mmd_fold")
 
     def mmd_combine(self, z, rs, cs, t1, t2, scale, dz, scale_dev=None):
         pz, B, dim, ldz = _mat(z, "mmd_combine z")

@@ -79,6 +79,7 @@ class Engine:
         self.ws: Dict[str, torch.Tensor] = {}
         self.train = False
         self.loss_buf = torch.zeros(16, dtype=torch.float32, device=self.device)
+        self.mmd_acc = torch.zeros(4, dtype=torch.float64, device=self.device)     # the four MMD terms, summed in double
         self.use_side_stream = True
         self._side = None
         self._side_used = False
@@ -189,7 +190,7 @@ class Engine:
                     ops.gemm("nt", self.ws["hsE%d" % m][TB:], P["encoder_%s.fc1.weight" % tag], Z[m],
                              bias=P["encoder_%s.fc1.bias" % tag])
                 self._z_ready = self._aux_event()
-                ops.zero(self.loss_buf[4:8])
+                ops.zero(self.mmd_acc.view(torch.float32))
                 for k in range(3):
                     self._mmd(k, Z[k])
 
@@ -248,6 +249,7 @@ class Engine:
         # (7) MMD of z_y (the encoder latents went out in step 3); same auxiliary stream, off the critical path
         with self._aux():
             self._mmd(3, ZY)
+            ops.mmd_fold(self.mmd_acc, self.loss_buf[4:8])
         if self._z_ready is not None:                      # the factor MLPs read Z, produced on the auxiliary stream
             torch.cuda.current_stream(self.device).wait_event(self._z_ready)
             self._z_ready = None
@@ -483,15 +485,15 @@ class Engine:
         nz, ng = buf("mmd_nz%d" % k, B), buf("mmd_ng%d" % k, B)
         Kzz, Kgz, Kgg = buf("Kzz%d" % k, B, B), buf("Kgz%d" % k, B, B), buf("Kgg", B, B)
         inv_bb = 1.0 / (float(B) * float(B))
-        slot = self.loss_buf[4 + k:5 + k]
+        slot = self.mmd_acc[k:k + 1]                   # double: the three means cancel to O(1/B)
         ops.rownorm2(zk, nz)
         ops.rownorm2(gk, ng)
         ops.gemm("nt", zk, zk, Kzz)
-        ops.mmd_kexp(Kzz, nz, nz, dim, inv_bb, slot)
+        ops.mmd_kexp64(Kzz, nz, nz, dim, inv_bb, slot)
         ops.gemm("nt", gk, zk, Kgz)                   # rows index the Gaussian sample, columns the latent
-        ops.mmd_kexp(Kgz, ng, nz, dim, -2.0 * inv_bb, slot)
+        ops.mmd_kexp64(Kgz, ng, nz, dim, -2.0 * inv_bb, slot)
         ops.gemm("nt", gk, gk, Kgg)
-        ops.mmd_kexp(Kgg, ng, ng, dim, inv_bb, slot)
+        ops.mmd_kexp64(Kgg, ng, ng, dim, inv_bb, slot)
         rc, t12 = buf("mmd_rc%d" % k, 2 * B), buf("mmd_t12_%d" % k, 2 * B, dim)
         ops.zero(rc)
         ops.colsum(Kzz, rc[:B])                          # K(z,z) is symmetric: column sums == row sums

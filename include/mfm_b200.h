@@ -178,6 +178,11 @@ int mfm_mmd_bwd(int B, int dim, const float* z, long long ldz, const float* g, l
  *                    with rs = row sums of K(z,z), cs = column sums of K(g,z), t1 = K(z,z) Z, t2 = K(g,z)^T G */
 int mfm_rownorm2(int B, int dim, const float* x, long long ld, float* out, void* stream);
 int mfm_mmd_kexp(int M, int N, float* S, const float* nx, const float* ny, int dim, float weight, float* slot, void* stream);
+/* The same with a DOUBLE accumulator, and the fold of n such accumulators into fp32 slots.  The MMD is a difference of
+ * three O(1) means that cancel to O(1/B); thousands of fp32 atomic adds into one slot do not hold the loss term to 1e-3
+ * relative at batch 2048, the double accumulator does (the training schedule uses this pair). */
+int mfm_mmd_kexp64(int M, int N, float* S, const float* nx, const float* ny, int dim, double weight, double* slot64, void* stream);
+int mfm_mmd_fold(int n, const double* acc, float* slots, void* stream);
 int mfm_mmd_combine(int B, int dim, const float* z, long long ldz, const float* rs, const float* cs, const float* t1,
                     const float* t2, float scale, const float* scale_dev, float* dz, long long lddz, void* stream);
 /* out[i] ~ N(0,1), counter-based (Box-Muller over the library's hash RNG keyed by rng=[seed,step] and site):

@@ -247,6 +247,16 @@ class EmuOps:
         S.copy_(torch.exp(-d2 / float(dim * dim)))
         slot[0] += weight * S.sum()
 
+    def mmd_kexp64(self, S, nx, ny, dim, weight, acc):
+        self.launches += 1
+        d2 = (nx.view(-1, 1) + ny.view(1, -1) - 2.0 * S).clamp_min(0.0)
+        S.copy_(torch.exp(-d2 / float(dim * dim)))
+        acc[0] += weight * S.double().sum()
+
+    def mmd_fold(self, acc, slots):
+        self.launches += 1
+        slots.copy_(acc.to(slots.dtype))
+
     def mmd_combine(self, z, rs, cs, t1, t2, scale, dz, scale_dev=None):
         self.launches += 1
         if scale_dev is not None:

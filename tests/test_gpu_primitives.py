@@ -241,9 +241,9 @@ def test_lstm_variants_are_the_ones_intended(ops):
         assert rel_l2(cbg["dG"], cb["dG"]) < 1e-4
         return [a - b for a, b in zip(after, before)]
     assert run(88, 300) == [1, 0, 1, 0, 0, 0]                 # 32-row chains both ways
-    assert run(88, 300, force=16) == [0, 1, 0, 1, 0, 0]       # 16-row chains forced
+    assert run(88, 300, force=16) == [1, 0, 0, 1, 0, 0]       # 16-row chains forced (backward only: forward has no such form)
     assert run(104, 300) == [1, 0, 0, 1, 0, 0]                # backward of h = 104 only fits with 16-row chains
-    assert run(48, 300, force=16) == [1, 0, 1, 0, 0, 0]       # replicated layouts have no 16-row form
+    assert run(48, 300, force=16) == [1, 0, 1, 0, 0, 0]       # two-copy layouts have no 16-row form
     assert run(200, 50) == [0, 0, 0, 0, 1, 1]                 # h > 128: CUDA-core kernels
 
 
