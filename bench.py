@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- MFM train samples/sec on synthetic CMU-MOSI shapes (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B_per_gpu] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config mosi|mosei|iemocap|pom] [--batch B] [--scaling weak|strong]
+                  [--impl ours|reference]
 
 One "step" = one MFM training step (forward, L1 + sum(lambda*MSE) + lambda*MMD, backward, [all-reduce], Adam) on one
 synthetic batch [T=20, B, D=325] per GPU, best_acc hyper-parameters (mfm_mosi.py:1239-1286), dropout ACTIVE
@@ -19,8 +20,6 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GATE_TRAIN_FLOPS_PER_SAMPLE = {20: 40.55e6}     # SURVEY.md section 8d (MOSI T=20, reference formulation, x3 for training)
-T_STEPS, B_DEFAULT = 20, 2048
 
 
 def gate_train_flops_per_sample(configs, T):
@@ -91,7 +90,7 @@ class ClockSampler:
                     samples=len(sm))
 
 
-def cpu_reference_leg(configs, T, B, steps, warmup):
+def cpu_reference_leg(configs, T, B, steps, warmup, head="l1"):
     """The reference's own CPU path for this workload, timed on this box's host cores: the oracle port of
     MFM + the 25-line train step (forward, loss, backward, Adam) in torch fp32 on all host threads.
     (/root/reference cannot travel to the GPU box; the oracle is pinned to it by tests/golden.)"""
@@ -99,13 +98,13 @@ def cpu_reference_leg(configs, T, B, steps, warmup):
     from oracle import mfm_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     P = O.init_params(configs, 123)
-    x, y = O.synthetic_batch(configs, T, B, 1234)
+    x, y = O.synthetic_batch(configs, T, B, 1234, head)
     state = {}
     times = []
     for i in range(warmup + steps):
         noise = O.draw_mmd_noise(configs, B, 999 + i)
         t0 = time.perf_counter()
-        P, losses, _, _ = O.train_step(P, x, y, configs, noise, state, train=True)
+        P, losses, _, _ = O.train_step(P, x, y, configs, noise, state, head=head, train=True)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -212,39 +211,112 @@ def profile_primitives(trainer, reps=3):
     return agg
 
 
+def parity_check(trainer, configs, T, B, head):
+    """One fixed-seed TRAIN-MODE step of the measured trainer against the oracle (the CPU restatement of the reference,
+    oracle/): the step's dropout masks / MMD noise / ReLU branches are replayed in oracle.train_step
+    (mfm_mosi.py:427-441) starting from the trainer's current parameters and Adam state.  Returns the worst relative
+    error over losses, latents and all gradients.  Rank 0, outside the timed region; the oracle is the checker only."""
+    import torch
+    from collections import OrderedDict
+    from oracle import mfm_oracle as O
+    from oracle.rng_replay import train_masks_and_branches
+    model = trainer.model
+    P = OrderedDict((k, v.detach().cpu().clone()) for k, v in model.state_dict().items())
+    x, y = O.synthetic_batch(configs, T, B, 4321, head)
+    lb = trainer.step(x.to(trainer.dev), y.to(trainer.dev))
+    torch.cuda.synchronize()
+    masks, br = train_masks_and_branches(trainer.eng, trainer.rng.cpu())
+    noise = [t.detach().cpu().clone() for t in trainer.noise]
+    del O.RELU_REPLAY_VIOLATIONS[:]
+    _, losses, Go, outo = O.train_step(P, x, y, configs, noise, {}, head=head, train=True, masks=masks, branches=br)
+    rel = lambda a, b: float((a.detach().cpu().double() - b.double()).norm() / (b.double().norm() + 1e-30))
+    lbc = lb.cpu()
+    rep = {}
+    for i, k in ((0, "disc"), (1, "mse_l"), (2, "mse_a"), (3, "mse_v"), (8, "total")):
+        rep["loss." + k] = abs(float(lbc[i]) - losses[k]) / abs(losses[k])
+    rep["loss.mmd"] = abs(float(lbc[4:8].sum()) * configs[0]["lda_mmd"] - losses["mmd"]) / abs(losses["mmd"])
+    ws = trainer.eng.ws
+    for k, b in (("zl", "Z0"), ("za", "Z1"), ("zv", "Z2"), ("zy", "ZY"), ("y_hat", "Yhat")):
+        rep[k] = rel(ws[b], outo[k])
+    for k, go in Go.items():
+        if go is not None:
+            rep["grad." + k] = rel(trainer.G[k], go)
+    worst = max(rep, key=rep.get)
+    top = sorted(rep, key=rep.get, reverse=True)[:6]
+    return dict(worst_rel=rep[worst], worst=worst, n_compared=len(rep), top={k: float("%.3g" % rep[k]) for k in top}, relu_replay_violations=len(O.RELU_REPLAY_VIOLATIONS),
+                tolerance=1e-3, passed=bool(rep[worst] < 1e-3 and not O.RELU_REPLAY_VIOLATIONS),
+                config="train mode (9 dropouts, device RNG), batch %d, T=%d, %s head, CUDA graph; masks / noise / ReLU "
+                       "branches replayed in oracle.train_step" % (B, T, head))
+
+
+def top_gemm_shape(dm):
+    """The streamed GEMM shape with the most algorithmic bytes per launch in the step: the attention products over
+    [T*B, 2H] (att1_fc2: [T*B,a1] x [2H,a1]^T -> [T*B,2H]).  Chosen from the dimensions, NOT from a timing, so the ncu
+    DRAM traffic recorded for it (profiles/r2_gemm_tcp_ncu.json) can be looked up deterministically."""
+    M, N, K = dm.T * dm.B, 2 * dm.H, dm.a1
+    return "nt %dx%dx%d" % (M, N, K), 4.0 * (M * K + N * K + M * N)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=B_DEFAULT, help="batch per GPU")
+    ap.add_argument("--config", default="mosi", choices=["mosi", "mosei", "iemocap", "pom"],
+                    help="BASELINE.json workload (default: the headline, MOSI shapes batch 2048 per GPU)")
+    ap.add_argument("--batch", type=int, default=0, help="batch (per GPU for weak scaling, global for strong); 0 = the workload's own")
+    ap.add_argument("--scaling", default="", choices=["", "weak", "strong"],
+                    help="weak: the batch is per GPU; strong: the batch is global and split over the ranks")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    T, B = T_STEPS, args.batch
 
-    from oracle import mfm_oracle as O          # configs + (rank 0 only) the CPU baseline leg; never on the GPU path
-    configs = O.best_acc_configs(dropout=True)
+    from factorized_b200.configs import WORKLOADS, best_acc_configs
+    wl = WORKLOADS[args.config]
+    T, head = wl["T"], wl["head"]
+    scaling = args.scaling or ("strong" if wl["batch_is"] == "global" else "weak")
+    batch = args.batch or wl["batch"]
+    if scaling == "strong":
+        if batch % max(world, 1):
+            raise SystemExit("strong scaling: global batch %d is not divisible by %d ranks" % (batch, world))
+        B, global_batch = batch // max(world, 1), batch
+    else:
+        B, global_batch = batch, batch * max(world, 1)
+    configs = best_acc_configs(input_dims=wl["input_dims"], output_dim=wl["out"], dropout=True)
     gate_fl = gate_train_flops_per_sample(configs, T)
-    workload = "synthetic CMU-MOSI shapes: text 300 / audio 5 / visual 20, T=20, batch %d per GPU, best_acc hyper-parameters " \
-               "(mfm_mosi.py:1239-1286), fp32, dropout active, L1 head" % B
-    base = dict(metric="MFM train samples/sec (MOSI seq_len=20)", unit="samples/s", n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, higher_is_better=True, scaling="weak", vs_baseline=None, data="synthetic",
-                config=dict(workload=workload, batch_per_gpu=B, global_batch=B * max(world, 1), seq_len=T,
+    workload = "%s; batch %d per GPU (global %d, %s scaling), best_acc hyper-parameters (mfm_mosi.py:1239-1286), fp32 storage, " \
+               "dropout active, %s head" % (wl["desc"], B, global_batch, scaling, "L1" if head == "l1" else "cross-entropy")
+    metric = "MFM train samples/sec (MOSI seq_len=20)" if args.config == "mosi" else "MFM train samples/sec (%s shapes, seq_len=%d)" % (args.config, T)
+    D = sum(wl["input_dims"])
+    in_mb = T * B * D * 4 / 2 ** 20
+    base = dict(metric=metric, unit="samples/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, higher_is_better=True, scaling=scaling, vs_baseline=None, data="synthetic",
+                config=dict(workload=workload, name=args.config, batch_per_gpu=B, global_batch=global_batch, seq_len=T,
                             parallelism="dp%d" % max(world, 1),
-                            l2="4 distinct input batches rotate (213 MB) and the step streams a ~1.8 GB workspace, both > 126 MB L2; no explicit flush"))
+                            l2="4 distinct input batches rotate (%.0f MB) and the step streams its whole stash workspace (see "
+                               "workspace_mb), together > 126 MB L2; no explicit flush" % (4 * in_mb)))
+    DTYPE = "f32 (fp32 storage; contractions as bf16x3 split tcgen05 MMA with f32 accumulate, ~2^-16)"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 3))
-        cb, sec = cpu_reference_leg(configs, T, B, steps, min(args.warmup, 1))
+        steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
+        from oracle import ref_runner
+        if ref_runner.available():           # the UNMODIFIED reference model (oracle/_ref, built by oracle/build_ref.py)
+            sec, threads = ref_runner.time_train_steps(configs, T, B, steps, warm, head)
+            cb = dict(value=B / sec, unit="samples/s", cores=threads, kind="reference",
+                      sample="%d warm-up + %d timed steps of batch %d (T=%d): the unmodified reference MFM (oracle/_ref, "
+                             ".cuda() neutralised) under the py3 restatement of mfm_mosi.py:427-441, torch fp32, %.2f s/step"
+                             % (warm, steps, B, T, sec))
+        else:
+            cb, sec = cpu_reference_leg(configs, T, B, steps, warm, head)
         line = dict(base, impl="reference", value=cb["value"], ms_per_step=sec * 1e3, dtype="f32", cpu_baseline=cb,
-                    steps=steps, warmup=min(args.warmup, 1),
+                    steps=steps, warmup=warm,
                     e2e=dict(value=cb["value"], unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                     gpu_launches=0, n_gpus=args.gpus)
         print(json.dumps(line))
@@ -259,12 +331,16 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
     torch.manual_seed(123)
     model = F.MFM(*configs).to(dev).train()
-    trainer = MFMTrainer(model, T, B, head="l1", use_graph=not args.no_graph, seed=123 + rank)
-    D = trainer.eng.dm.D
+    trainer = MFMTrainer(model, T, B, head=head, use_graph=not args.no_graph, seed=123)
     gen = torch.Generator().manual_seed(1234 + rank)
     NB = 4
+
+    def make_y():
+        if head == "ce":
+            return torch.randint(0, wl["out"], (B,), generator=gen)
+        return torch.randn(B * wl["out"], generator=gen)
     xs_host = [torch.randn(T, B, D, generator=gen).pin_memory() for _ in range(NB)]
-    ys_host = [torch.randn(B, generator=gen).pin_memory() for _ in range(NB)]
+    ys_host = [make_y().pin_memory() for _ in range(NB)]
     xs_dev = [t.to(dev) for t in xs_host]
     ys_dev = [t.to(dev) for t in ys_host]
 
@@ -305,14 +381,28 @@ def main():
         f1.record()
         barrier()
         ms_e2e = max_over_ranks(f0.elapsed_time(f1))
+        if ms + ms_e2e < 1500.0:             # short timed regions: keep the sampler up until it has seen the GPU under load
+            t_end = time.time() + 1.2
+            while time.time() < t_end:
+                trainer.step_device()
+            torch.cuda.synchronize()
     clocks = cs.summary()
     final_loss = float(loss_host[-1][8])
     value = world * B * args.steps / (ms * 1e-3)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
     pk = peaks()
 
+    # ---- replicas must hold identical parameters after the same number of steps (the all-reduce keeps them in sync) -----
+    replicas = None
+    if world > 1:
+        chk = trainer.flat_p.double().sum().view(1)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        torch.distributed.all_gather(allc, chk)
+        vals = [float(v) for v in allc]
+        replicas = dict(param_checksums_equal=bool(max(vals) - min(vals) <= 1e-9 * max(1.0, abs(vals[0]))), checksum=vals[0])
+
     # ---- dominant kernel + roofline (rank 0, outside the timed region) --------------------------------------------------
-    roof, kernels = None, None
+    roof, kernels, parity = None, None, None
     if rank == 0:
         agg = profile_primitives(trainer)
         gemm_shapes = agg.pop("_gemm_shapes")
@@ -325,43 +415,71 @@ def main():
         # The dominant kernel is the pipelined tcgen05 GEMM (gemm_tcp_kernel: every GEMM of M*N*K >= 2^20).  It is
         # HBM-bound by design (N, K <= 512 against T*B rows): achieved = algorithmic bytes of those launches / their
         # CUDA-event time in one eager pass (per call: the weight pre-split kernel, when there is one, is inside the
-        # bracket); the single shape with the largest share is listed with the DRAM traffic ncu measured for it
-        # (profiles/r1_gemm_tcp_ncu.json, per launch).
+        # bracket).  `traffic` = DRAM bytes per launch that ncu --set full measured for the largest streamed shape of this
+        # workload (chosen from the dimensions, not from a timing; profiles/r2_gemm_tcp_ncu.json).
         gshare = streamed["ms_per_step"] / (tot / 3)
         ach = streamed["bytes_per_step"] / (streamed["ms_per_step"] * 1e-3) / 1e9 if streamed["ms_per_step"] else 0.0
-        top_key = next(k for k, v in gemm_shapes.items() if not k.startswith("tn-pair") and
-                       max(int(t) for t in k.split()[1].split("x")[::2]) >= 4096)
-        tms, tn, tby = gemm_shapes[top_key]
-        traffic = None
+        top_key, top_bytes = top_gemm_shape(trainer.eng.dm)
+        tms, tn, tby = gemm_shapes.get(top_key, (None, None, top_bytes))
+        traffic, traffic_src = None, "profiles/r2_gemm_tcp_ncu.json has no entry for '%s' (run scripts/gemm_prof.py under ncu)" % top_key
         try:
-            nj = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_tcp_ncu.json")))
-            traffic = nj.get(top_key, {}).get("dram_bytes")
-        except Exception:
-            pass
+            nj = json.load(open(os.path.join(ROOT, "profiles", "r2_gemm_tcp_ncu.json")))
+            if top_key in nj:
+                traffic, traffic_src = nj[top_key]["dram_bytes"], "ncu --set full, profiles/r2_gemm_tcp_ncu.json"
+        except Exception as ex:
+            traffic_src = "profiles/r2_gemm_tcp_ncu.json unreadable: %s" % type(ex).__name__
+        # the recurrence kernels on the TENSOR roof: recurrent gate-GEMM FLOPs of the launches (2*4h*h per
+        # row and step; the input-projection half of the gate GEMM is hoisted into the streamed GEMMs above) / their time
+        lstm = {}
+        for k in ("lstm_fwd_enc_mfn", "lstm_bwd_enc_mfn", "lstm_fwd_dec", "lstm_bwd_dec"):
+            if k in kernels and kernels[k]["tflops"]:
+                lstm[k] = dict(us_per_step=round(kernels[k]["ms_per_step"] * 1e3, 1), tflops=kernels[k]["tflops"],
+                               frac_of_bf16_peak=round(kernels[k]["tflops"] / pk["bf16"], 5))
         roof = dict(bound="hbm", kernel="gemm_tcp_kernel (pipelined tcgen05 GEMM: the %d launches/step with M*N*K >= 2^20)"
                                         % streamed["launches_per_step"],
                     achieved=round(ach, 1), peak=pk["hbm"], unit="GB/s", frac=round(ach / pk["hbm"], 4), traffic=traffic,
+                    traffic_source=traffic_src,
                     peak_source=pk["src"] + " HBM copy bandwidth (MEASURED_PEAKS.json)", share_of_step_kernel_time=round(gshare, 4),
-                    top_shape=dict(shape=top_key, launches=tn, bytes_per_launch=tby, us_per_launch=round(tms / tn * 1e3, 2),
-                                   achieved=round(tby / (tms / tn * 1e-3) / 1e9, 1), traffic=traffic),
-                    step_gate_gemm=dict(achieved=round(gate_fl * value / max(world, 1) / 1e12, 3), peak=pk["bf16_sustained"],
-                                        unit="TFLOP/s", frac=round(gate_fl * value / max(world, 1) / 1e12 / pk["bf16_sustained"], 5),
+                    top_shape=dict(shape=top_key, launches=tn, bytes_per_launch=tby,
+                                   us_per_launch=(round(tms / tn * 1e3, 2) if tms else None),
+                                   achieved=(round(tby / (tms / tn * 1e-3) / 1e9, 1) if tms else None), traffic=traffic),
+                    lstm_tensor=dict(bound="tensor", peak=pk["bf16"], unit="TFLOP/s", kernels=lstm,
+                                     note="recurrent gate-GEMM FLOPs (2*4h*h per row-step, reference formulation) of the "
+                                          "recurrence launches / CUDA-event time, against the measured burst bf16 peak; the "
+                                          "kernels are bound by the per-step dependency chain (DESIGN.md section 4.2), ncu "
+                                          "counters in profiles/r2_lstm_ws_ncu.md"),
+                    step_gate_gemm=dict(achieved=round(gate_fl * value / max(world, 1) / 1e12, 3), peak=pk["bf16"],
+                                        unit="TFLOP/s", frac=round(gate_fl * value / max(world, 1) / 1e12 / pk["bf16"], 5),
+                                        frac_of_sustained=round(gate_fl * value / max(world, 1) / 1e12 / pk["bf16_sustained"], 5),
                                         note="whole step per GPU: algorithmic gate-GEMM train FLOPs/sample (%.2f M) x samples/s "
-                                             "over sustained bf16 peak" % (gate_fl / 1e6)))
-    line = dict(base, value=value, ms_per_step=ms / args.steps, dtype="f32",
-                e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=(T * B * D + B) * 4 * world,
+                                             "over the measured burst bf16 peak (clocks held at max, no power cap)" % (gate_fl / 1e6)))
+        if not args.no_parity_check:
+            try:
+                parity = parity_check(trainer, configs, T, B, head)
+            except Exception as ex:          # a host without the memory for the oracle's [B,B,dim] MMD tensors
+                parity = dict(passed=None, error="%s: %s" % (type(ex).__name__, str(ex)[:200]))
+    line = dict(base, value=value, ms_per_step=ms / args.steps, dtype=DTYPE,
+                e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=(T * B * D + B * (1 if head == "ce" else wl["out"])) * 4 * world,
                          d2h_bytes_per_step=64 * world, ms_per_step=ms_e2e / args.steps),
                 gpu_launches=trainer.launches_per_step * args.steps, launches_per_step=trainer.launches_per_step,
                 cuda_graph=not args.no_graph, clocks=clocks, roofline=roof, kernels=kernels, final_loss=final_loss,
+                parity_check=parity, replicas=replicas,
                 workspace_mb=round(trainer.eng.workspace_bytes() / 2 ** 20, 1))
     if rank == 0 and os.environ.get("MFM_BENCH_GEMM_SHAPES"):
         line["gemm_shapes_ms"] = gemm_shapes
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
+            from oracle import ref_runner
             try:
-                cb, _ = cpu_reference_leg(configs, T, B, 2, 1)
+                if ref_runner.available():
+                    sec, threads = ref_runner.time_train_steps(configs, T, B, 2, 1, head)
+                    cb = dict(value=B / sec, unit="samples/s", cores=threads, kind="reference",
+                              sample="1 warm-up + 2 timed steps of batch %d (T=%d): the unmodified reference MFM (oracle/_ref) under "
+                                     "the py3 restatement of mfm_mosi.py:427-441, torch fp32, %.2f s/step" % (B, T, sec))
+                else:
+                    cb, _ = cpu_reference_leg(configs, T, B, 2, 1, head)
             except Exception as ex:   # e.g. host OOM on the reference's [B,B,dim] MMD tensors
-                cb, _ = cpu_reference_leg(configs, T, 256, 3, 1)
+                cb, _ = cpu_reference_leg(configs, T, 256, 3, 1, head)
                 cb["sample"] += " (batch %d failed on this host: %s)" % (B, type(ex).__name__)
             line["cpu_baseline"] = cb
         print(json.dumps(line))

@@ -2,7 +2,7 @@
 #include <mutex>
 #include <set>
 #include <utility>
-#include "common.cuh"
+#include "gemm_args.cuh"
 
 unsigned long long g_mfm_launches = 0;
 
@@ -96,6 +96,19 @@ extern "C" int mfm_gemm_ws(int mode, int M, int N, int K, const float* A, long l
   }
   return gemm_simt_launch(mode, M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale,
                           drop_p, drop_site, rng, (cudaStream_t)stream);
+}
+
+thread_local GemmMse g_pending_mse = {nullptr, 0, 0.0f, 0.0f, nullptr, nullptr, 0};
+
+extern "C" int mfm_gemm_mse(int M, int N, int K, const float* A, long long lda, const float* B, long long ldb, const float* bias,
+                            const float* x, long long ldx, float loss_scale, float grad_scale, float* slot,
+                            float* dxhat, long long lddx, float* xhat, long long ldxhat, void* ws, long long ws_bytes, void* stream) {
+  MFM_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && x && slot && dxhat);
+  g_pending_mse = GemmMse{x, ldx, loss_scale, grad_scale, slot, xhat, ldxhat};
+  const int rc = mfm_gemm_ws(MFM_GEMM_NT, M, N, K, A, lda, B, ldb, dxhat, lddx, bias, nullptr, MFM_ACT_NONE, 0, nullptr, 0, 1.0f, 0.0f, 0,
+                             nullptr, nullptr, ws, ws_bytes, stream);
+  (void)take_pending_mse();          // (an argument error returned before any launcher consumed it)
+  return rc;
 }
 
 extern "C" int mfm_gemm_tn_pair(int M, int K, const float* A, long long lda, int N1, const float* B1, long long ldb1,

@@ -106,6 +106,34 @@ __global__ void __launch_bounds__(256) l1_kernel(long long n, const float* __res
   if (threadIdx.x == 0) atomicAdd(slot, tot * scale);
 }
 
+// loss_KLD (mfm_model.py:36-38): slot += -0.5 * sum(1 + logvar - mu^2 - exp(logvar))  (a sum over all elements)
+__global__ void __launch_bounds__(256) kld_fwd_kernel(int M, int N, const float* __restrict__ mu, long long ldm,
+                                                       const float* __restrict__ lv, long long ldl, float* __restrict__ slot) {
+  __shared__ float red[32];
+  float s = 0.0f;
+  const long long n = (long long)M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / N), c = (int)(i - (long long)r * N);
+    const float m = mu[(long long)r * ldm + c], l = lv[(long long)r * ldl + c];
+    s += 1.0f + l - m * m - expf(l);
+  }
+  const float tot = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(slot, -0.5f * tot);
+}
+// its gradient: dmu += s * mu;  dlogvar = s * 0.5 * (exp(logvar) - 1);  s = scale * (scale_dev ? *scale_dev : 1)
+__global__ void __launch_bounds__(256) kld_bwd_kernel(int M, int N, const float* __restrict__ mu, long long ldm,
+                                                       const float* __restrict__ lv, long long ldl, float scale,
+                                                       const float* __restrict__ scale_dev, float* __restrict__ dmu, long long lddm,
+                                                       float* __restrict__ dlv, long long lddl) {
+  const float sc = scale * (scale_dev ? __ldg(scale_dev) : 1.0f);
+  const long long n = (long long)M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / N), c = (int)(i - (long long)r * N);
+    dmu[(long long)r * lddm + c] += sc * mu[(long long)r * ldm + c];
+    dlv[(long long)r * lddl + c] = sc * 0.5f * (expf(lv[(long long)r * ldl + c]) - 1.0f);
+  }
+}
+
 // nn.CrossEntropyLoss (mfm_mosi_acc.py:450): one thread per sample, C is tiny (2..4 classes)
 __global__ void __launch_bounds__(256) ce_kernel(int B, int C, const float* __restrict__ yh, const long long* __restrict__ y,
                                                   float scale, float* __restrict__ slot, float* __restrict__ dy) {
@@ -219,6 +247,21 @@ extern "C" int mfm_mse_fwd_bwd(int M, int N, const float* xhat, long long ldxh, 
   MFM_REQUIRE(M > 0 && N > 0 && xhat && x && slot);
   mse_kernel<<<((M + 7) / 8 < mfm_dev_info().sms * 8 ? (M + 7) / 8 : mfm_dev_info().sms * 8), 256, 0, (cudaStream_t)stream>>>(M, N, xhat, ldxh, x, ldx, loss_scale,
                                                                                        grad_scale, slot, dxhat, lddx);
+  MFM_LAUNCH_CHECK();
+  return MFM_OK;
+}
+extern "C" int mfm_kld_fwd(int M, int N, const float* mu, long long ldmu, const float* logvar, long long ldlv, float* slot,
+                           void* stream) {
+  MFM_REQUIRE(M > 0 && N > 0 && mu && logvar && slot);
+  kld_fwd_kernel<<<grid_for((long long)M * N, 256, 64), 256, 0, (cudaStream_t)stream>>>(M, N, mu, ldmu, logvar, ldlv, slot);
+  MFM_LAUNCH_CHECK();
+  return MFM_OK;
+}
+extern "C" int mfm_kld_bwd(int M, int N, const float* mu, long long ldmu, const float* logvar, long long ldlv, float scale,
+                           const float* scale_dev, float* dmu, long long lddmu, float* dlogvar, long long lddlv, void* stream) {
+  MFM_REQUIRE(M > 0 && N > 0 && mu && logvar && dmu && dlogvar);
+  kld_bwd_kernel<<<grid_for((long long)M * N, 256, 64), 256, 0, (cudaStream_t)stream>>>(M, N, mu, ldmu, logvar, ldlv, scale, scale_dev,
+                                                                                      dmu, lddmu, dlogvar, lddlv);
   MFM_LAUNCH_CHECK();
   return MFM_OK;
 }

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs a) {
   const bool do_drop = a.drop_p > 0.0f;
   if (do_drop) sseed = site_seed(a.rng, a.drop_site);
   const float keep_scale = do_drop ? 1.0f / (1.0f - a.drop_p) : 1.0f;
+  float sq = 0.0f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty * 4 + i;
@@ -86,8 +87,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs a) {
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= a.N) continue;
-      gemm_epilogue_store(a, m, n, acc[i][j], do_drop, sseed, keep_scale);
+      gemm_epilogue_store(a, m, n, acc[i][j], do_drop, sseed, keep_scale, &sq);
     }
+  }
+  if (a.mse.x) {                                       // fused MSE head: one atomic per warp
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) atomicAdd(a.mse.slot, a.mse.loss_scale * sq);
   }
 }
 
@@ -97,6 +102,7 @@ int gemm_simt_launch(int mode, int M, int N, int K, const float* A, long long ld
                      const long long* rng, cudaStream_t st) {
   GemmArgs a{M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale,
              drop_p, drop_site, rng, K, 0, nullptr};
+  a.mse = g_pending_mse;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, 1);
   // split K over CTAs for the weight-gradient shape (tiny M,N; K = T*B rows), plain sums only
   const bool plain = !bias && !bias2 && act == MFM_ACT_NONE && !mask && drop_p <= 0.0f && accumulate;

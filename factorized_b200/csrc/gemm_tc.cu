@@ -246,6 +246,7 @@ int gemm_tc_launch(int passes, int mode, int M, int N, int K, const float* A, lo
   TcArgs ta;
   ta.g = GemmArgs{M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale,
                   drop_p, drop_site, rng, K, 0, colsum_out};
+  ta.g.mse = g_pending_mse;          // (cleared by mfm_gemm_mse after the call)
   ta.passes = passes;
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("MFM_TC_DEBUG"); dbg = e ? atoi(e) : 0; }

@@ -489,27 +489,51 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_bwd_kernel(const __grid
 
   if (warp >= WS_CW) {
     WS_REG_ISSUER();
-    if (lane == 0) {
-      // the four warps of this warpgroup issue one partial sum over K each (k-steps a, a+4, a+8, ...), concurrently
+    {
+      // the four warps of this warpgroup issue one partial sum over K each (k-steps a, a+4, a+8, ...), concurrently, and
+      // between GEMMs pull the rows the cell update of the chain's NEXT step (t-1) reads into L2: gates (warp a = gate a),
+      // cell history, external gradients
       const int a = warp - WS_CW;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t dAh0 = make_smem_desc(smem_u32(Ahi), lboA, 128), dAl0 = make_smem_desc(smem_u32(Alo), lboA, 128);
       const uint64_t astep = (uint64_t)((2 * lboA) >> 4), bstep = (uint64_t)((2 * lboB) >> 4);
+      const bool pf_g = ((reinterpret_cast<uintptr_t>(gates_base) & 15) == 0) && ((h & 3) == 0);
+      auto pf_row = [&](const float* base, int ld, long long row) {
+        if (base && ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((ld & 3) == 0) && ((h & 3) == 0))
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + row * ld), "r"((uint32_t)(h * 4)) : "memory");
+      };
       for (int n = 0; n < T; ++n) {                         // n-th product: dG of step T-n (zero for n = 0) -> dh of step T-1-n
 #pragma unroll 1
         for (int ch = 0; ch < NCH; ++ch) {
-          if (n > 0) ws_wait(smem_u32(&bar_ready[ch]), (uint32_t)((n - 1) & 1));
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t bb = smem_u32(Bbase + ch * chainB);
-          const uint64_t dBh0 = make_smem_desc(bb, lboB, 128), dBl0 = make_smem_desc(bb + slabs * lboB, lboB, 128);
-          const uint32_t dcol = tmem_base + (uint32_t)((ch * 4 + a) * NB);
+          if (lane == 0) {
+            if (n > 0) ws_wait(smem_u32(&bar_ready[ch]), (uint32_t)((n - 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t bb = smem_u32(Bbase + ch * chainB);
+            const uint64_t dBh0 = make_smem_desc(bb, lboB, 128), dBl0 = make_smem_desc(bb + slabs * lboB, lboB, 128);
+            const uint32_t dcol = tmem_base + (uint32_t)((ch * 4 + a) * NB);
 #pragma unroll 1
-          for (int kk = a; kk < ksteps; kk += 4) {
-            umma_bf16(dcol, dAh0 + kk * astep, dBh0 + kk * bstep, idesc, kk > a ? 1u : 0u);
-            umma_bf16(dcol, dAl0 + kk * astep, dBh0 + kk * bstep, idesc, 1u);
-            umma_bf16(dcol, dAh0 + kk * astep, dBl0 + kk * bstep, idesc, 1u);
+            for (int kk = a; kk < ksteps; kk += 4) {
+              umma_bf16(dcol, dAh0 + kk * astep, dBh0 + kk * bstep, idesc, kk > a ? 1u : 0u);
+              umma_bf16(dcol, dAl0 + kk * astep, dBh0 + kk * bstep, idesc, 1u);
+              umma_bf16(dcol, dAh0 + kk * astep, dBl0 + kk * bstep, idesc, 1u);
+            }
+            umma_commit(smem_u32(&bar_done[ch]));           // (a warp with no k-step still arrives)
           }
-          umma_commit(smem_u32(&bar_done[ch]));             // (a warp with no k-step still arrives)
+          __syncwarp();
+          const int tn = T - 2 - n;                         // the step whose inputs to fetch: the one after the step being multiplied for
+          if (tn >= 0) {
+            for (int r = lane; r < NB; r += 32) {
+              const int b = row0 + ch * NB + r;
+              if (b < B) {
+                const long long tr = (long long)tn * B + b;
+                if (pf_g) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gates_base + tr * H4 + a * h), "r"((uint32_t)(h * 4)) : "memory");
+                if (a == 0) pf_row(cs_base, ldcs, tr);
+                if (a == 1) pf_row(dha_base, lddh, tr);
+                if (a == 2) pf_row(dce_base, lddc, tr);
+                if (a == 3) pf_row(dce2_base, lddc, tr);
+              }
+            }
+          }
         }
       }
     }
@@ -552,7 +576,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_bwd_kernel(const __grid
 
       for (int t = T - 1; t >= 0; --t) {
         struct In { float ig, fg, gg, og, cp, cn, dhx, dcx; };
-        In buf[2][2];                                         // groups double-buffered in processing order
+        In buf[2];                                            // (single-buffered: the issuer warps keep the next step's rows in L2)
         const bool last = t == T - 1;
         auto load_in = [&](int ch, int sg, In (&d)[2]) {
 #pragma unroll
@@ -570,30 +594,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_bwd_kernel(const __grid
             d[cc] = v;
           }
         };
-        load_in(0, 0, buf[0]);
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
+          load_in(ch, 0, buf);                                // first group: in flight across the MMA wait
           ws_wait(smem_u32(&bar_done[ch]), (uint32_t)((T - 1 - t) & 1));     // dh_rec of this step = product T-1-t
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
           for (int sg = 0; sg < 4; ++sg) {
             if (sg < nsg) {
-              const int cur = sg & 1;
               float dh[4][2];
 #pragma unroll
               for (int a = 0; a < 4; ++a) {
                 if (a < nacc) tmem_ld2(tl + (uint32_t)((ch * 4 + a) * NB + sg * 2), dh[a]);
                 else dh[a][0] = dh[a][1] = 0.0f;
               }
-              if (sg + 1 < nsg) load_in(ch, sg + 1, buf[cur ^ 1]);
-              else if (ch + 1 < NCH) load_in(ch + 1, 0, buf[cur ^ 1]);
+              if (sg > 0) load_in(ch, sg, buf);
               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
               for (int cc = 0; cc < 2; ++cc) {
                 const int col = sg * 2 + cc, gcol = ch * NB + col;
                 const int ci = min(gcol, cmax);
                 const int ok = (on && gcol < bvalid) ? 1 : 0;
-                const In& v = buf[cur][cc];
+                const In& v = buf[cc];
                 const float dht = (dh[0][cc] + dh[1][cc]) + (dh[2][cc] + dh[3][cc]) + v.dhx;
                 const float tc = fmaf(2.0f, rcp_fast(one_plus_ex2(v.cn * -2.8853900817779268f)), -1.0f);
                 const float dci = dc[ch][col] + dht * v.og * (1.0f - tc * tc) + v.dcx;

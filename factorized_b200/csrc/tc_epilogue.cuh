@@ -44,7 +44,12 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base
   const int e_M = a.M, e_N = a.N, e_act = a.act;
   const bool e_atomic = a.atomic != 0, e_acc = a.accumulate != 0, e_simple = !a.mask && !do_drop;
   const bool mask_vec = !a.mask || (((reinterpret_cast<uintptr_t>(a.mask) & 15) == 0) && ((a.ldmask & 3) == 0));
-  const bool e_vec = !e_atomic && ones_col < 0 && mask_vec && ((reinterpret_cast<uintptr_t>(e_C) & 15) == 0) &&
+  const GemmMse& ms = a.mse;
+  const bool e_mse = ms.x != nullptr;
+  const bool mse_vec = !e_mse || (((reinterpret_cast<uintptr_t>(ms.x) & 15) == 0) && ((ms.ldx & 3) == 0) &&
+                                  (!ms.xhat || (((reinterpret_cast<uintptr_t>(ms.xhat) & 15) == 0) && ((ms.ldxhat & 3) == 0))));
+  float sq = 0.0f;                                  // this lane's share of sum (x_hat - x)^2
+  const bool e_vec = !e_atomic && ones_col < 0 && mask_vec && mse_vec && ((reinterpret_cast<uintptr_t>(e_C) & 15) == 0) &&
                      ((e_ldc & 3) == 0) && ((n0 & 3) == 0);
   const int quad = warp & 3, half = warp >> 2;
   const int cbeg = half * (BN / nhalves), cend = cbeg + (BN / nhalves);
@@ -91,6 +96,20 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base
           if (rr < nrows) {
             float4 t = *reinterpret_cast<const float4*>(scratch + rr * TC_EPI_LD + cg * 4);
             t = act4(t, b[0], b[1], b[2], b[3], e_act);
+            if (e_mse) {                                      // fused reconstruction head: residual, its square, its gradient
+              const float* xp = ms.x + (long long)(mbase + rr) * ms.ldx + n;
+              float4 xv;
+              if (full4) xv = __ldg(reinterpret_cast<const float4*>(xp));
+              else { xv.x = __ldg(xp); xv.y = n + 1 < e_N ? __ldg(xp + 1) : t.y; xv.z = n + 2 < e_N ? __ldg(xp + 2) : t.z; xv.w = t.w; }
+              if (ms.xhat) {
+                float* hp = ms.xhat + (long long)(mbase + rr) * ms.ldxhat + n;
+                if (full4) *reinterpret_cast<float4*>(hp) = t;
+                else { hp[0] = t.x; if (n + 1 < e_N) hp[1] = t.y; if (n + 2 < e_N) hp[2] = t.z; }
+              }
+              t.x -= xv.x; t.y -= xv.y; t.z -= xv.z; t.w -= xv.w;        // columns beyond N: x := x_hat, residual 0
+              sq = fmaf(t.x, t.x, fmaf(t.y, t.y, fmaf(t.z, t.z, fmaf(t.w, t.w, sq))));
+              t.x *= ms.grad_scale; t.y *= ms.grad_scale; t.z *= ms.grad_scale; t.w *= ms.grad_scale;
+            }
             if (!e_simple) {                                  // dropout and / or ReLU mask, four columns at a time
               const int m = mbase + rr;
               if (do_drop) {
@@ -141,7 +160,13 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base
             const float bsum = (a.bias ? __ldg(a.bias + n) : 0.0f) + (a.bias2 ? __ldg(a.bias2 + n) : 0.0f);
 #pragma unroll 4
             for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) {
-              const float t = apply_act(sp[rr * TC_EPI_LD] + bsum, e_act);
+              float t = apply_act(sp[rr * TC_EPI_LD] + bsum, e_act);
+              if (e_mse) {
+                if (ms.xhat) ms.xhat[(long long)(mbase + rr) * ms.ldxhat + n] = t;
+                t -= __ldg(ms.x + (long long)(mbase + rr) * ms.ldx + n);
+                sq = fmaf(t, t, sq);
+                t *= ms.grad_scale;
+              }
               cp[0] = e_acc ? t + cp[0] : t;
             }
           } else {                                            // dropout and/or ReLU-mask epilogues
@@ -160,5 +185,9 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base
       }
     }
     __syncwarp();
+  }
+  if (e_mse) {                                      // one atomic per warp
+    sq = warp_sum(sq);
+    if (lane == 0) atomicAdd(ms.slot, sq * ms.loss_scale);
   }
 }

@@ -53,6 +53,8 @@ _SIGS = {
                            c_f, LL, C.c_float, C.c_float, C.c_int, c_f, c_f, c_f]),
     "mfm_gemm_ws": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_f, LL, c_f, LL, c_f, LL, c_f, c_f, C.c_int, C.c_int,
                               c_f, LL, C.c_float, C.c_float, C.c_int, c_f, c_f, c_f, LL, c_f]),
+    "mfm_gemm_mse": (C.c_int, [C.c_int, C.c_int, C.c_int, c_f, LL, c_f, LL, c_f, c_f, LL, C.c_float, C.c_float, c_f, c_f, LL, c_f, LL,
+                               c_f, LL, c_f]),
     "mfm_gemm_tn_pair": (C.c_int, [C.c_int, C.c_int, c_f, LL, C.c_int, c_f, LL, c_f, LL, c_f, C.c_int, c_f, LL, c_f, LL, c_f]),
     "mfm_debug_set_gemm_trace": (C.c_int, [c_f, LL]),
     "mfm_debug_stamp": (C.c_int, [c_f, C.c_int, c_f]),
@@ -82,6 +84,8 @@ _SIGS = {
     "mfm_mse_fwd_bwd": (C.c_int, [C.c_int, C.c_int, c_f, LL, c_f, LL, C.c_float, C.c_float, c_f, c_f, LL, c_f]),
     "mfm_l1_fwd_bwd": (C.c_int, [LL, c_f, c_f, C.c_float, c_f, c_f, c_f]),
     "mfm_ce_fwd_bwd": (C.c_int, [C.c_int, C.c_int, c_f, c_f, C.c_float, c_f, c_f, c_f]),
+    "mfm_kld_fwd": (C.c_int, [C.c_int, C.c_int, c_f, LL, c_f, LL, c_f, c_f]),
+    "mfm_kld_bwd": (C.c_int, [C.c_int, C.c_int, c_f, LL, c_f, LL, C.c_float, c_f, c_f, LL, c_f, LL, c_f]),
     "mfm_loss_total": (C.c_int, [c_f, C.c_float, C.c_float, C.c_float, C.c_float, c_f]),
     "mfm_adam_step": (C.c_int, [LL, c_f, c_f, c_f, c_f, c_f, C.c_float, C.c_double, C.c_double, C.c_double, c_f]),
     "mfm_rng_tick": (C.c_int, [c_f, c_f]),
@@ -221,6 +225,27 @@ class CudaOps:
                                     float(p), int(site), prng,
                                     None if colsum_out is None else _vec(colsum_out, "colsum_out", M),
                                     ws, ws_bytes, _stream()), "mfm_gemm_ws")
+
+    def gemm_mse(self, A, W, bias, x, loss_scale, grad_scale, slot, dxhat, xhat=None):
+        """x_hat = A W^T + bias fused with the MSE head: slot += loss_scale * sum (x_hat - x)^2, dxhat = grad_scale * (x_hat - x);
+        x_hat is written only when `xhat` is given."""
+        pa, M, K, lda = _mat(A, "gemm_mse A")
+        pw, N, K2, ldw = _mat(W, "gemm_mse W")
+        px, mx, nx, ldx = _mat(x, "gemm_mse x")
+        pd, md, nd, ldd = _mat(dxhat, "gemm_mse dxhat")
+        if K2 != K or (mx, nx) != (M, N) or (md, nd) != (M, N):
+            raise MfmCudaError("gemm_mse: shapes A%s W%s x%s dxhat%s do not agree" % (tuple(A.shape), tuple(W.shape), tuple(x.shape), tuple(dxhat.shape)))
+        ph, ldh = None, 0
+        if xhat is not None:
+            ph, mh, nh, ldh = _mat(xhat, "gemm_mse xhat")
+            if (mh, nh) != (M, N):
+                raise MfmCudaError("gemm_mse xhat shape")
+        ws, ws_bytes = None, 0
+        if M >= 4096:
+            ws_bytes = 8 * (N + 64) * (K + 16)
+            ws = self._gemm_workspace(dxhat.device, ws_bytes)
+        _check(self.lib.mfm_gemm_mse(M, N, K, pa, lda, pw, ldw, _vec(bias, "bias", N), px, ldx, float(loss_scale), float(grad_scale),
+                                     _vec(slot, "mse slot", 1), pd, ldd, ph, ldh, ws, ws_bytes, _stream()), "mfm_gemm_mse")
 
     def gemm_tn_pair(self, dY, A1, C1, colsum1, A2, C2):
         """C1 += dY^T A1 (colsum1 += column sums of dY, may be None) and C2 += dY^T A2 in one launch."""
@@ -512,6 +537,23 @@ class CudaOps:
             raise MfmCudaError("ce: contiguous logits and CUDA int64 labels [B] required")
         _check(self.lib.mfm_ce_fwd_bwd(B, Cn, p, y.data_ptr(), float(scale), _vec(slot, "ce slot", 1), dy.data_ptr(),
                                        _stream()), "mfm_ce_fwd_bwd")
+
+    def kld_fwd(self, mu, logvar, slot):
+        pm, M, N, ldm = _mat(mu, "kld mu")
+        pl, M2, N2, ldl = _mat(logvar, "kld logvar")
+        if (M, N) != (M2, N2):
+            raise MfmCudaError("kld shapes")
+        _check(self.lib.mfm_kld_fwd(M, N, pm, ldm, pl, ldl, _vec(slot, "kld slot", 1), _stream()), "mfm_kld_fwd")
+
+    def kld_bwd(self, mu, logvar, scale, dmu, dlogvar, scale_dev=None):
+        pm, M, N, ldm = _mat(mu, "kld mu")
+        pl, M2, N2, ldl = _mat(logvar, "kld logvar")
+        pdm, M3, N3, lddm = _mat(dmu, "kld dmu")
+        pdl, M4, N4, lddl = _mat(dlogvar, "kld dlogvar")
+        if not ((M, N) == (M2, N2) == (M3, N3) == (M4, N4)):
+            raise MfmCudaError("kld shapes")
+        psd = None if scale_dev is None else scale_dev.data_ptr()
+        _check(self.lib.mfm_kld_bwd(M, N, pm, ldm, pl, ldl, float(scale), psd, pdm, lddm, pdl, lddl, _stream()), "mfm_kld_bwd")
 
     def loss_total(self, lb, l0, l1, l2, lmmd):
         _check(self.lib.mfm_loss_total(lb.data_ptr(), float(l0), float(l1), float(l2), float(lmmd), _stream()),

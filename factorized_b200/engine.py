@@ -70,8 +70,13 @@ class Engine:
     """One (T, B) instance of the schedule with its HBM workspace."""
 
     def __init__(self, configs, T: int, B: int, device, ops, head: str = "l1", mfn_only: bool = False,
-                 mfn_prefix: str = "mfn_encoder."):
+                 mfn_prefix: str = "mfn_encoder.", variant: str = "mfm"):
         self.dm = Dims(configs, T, B, head)
+        if variant not in ("mfm", "kl"):
+            raise ValueError(variant)
+        # "kl": MFM_KL (mfm_model.py:662-764) -- the encoder outputs pass one more Linear to the means (the latents z) and
+        # another to the log-variances, and the regulariser is loss_KLD instead of loss_MMD; everything else is MFM
+        self.kl = variant == "kl"
         self.mfn_only = bool(mfn_only)          # standalone MFN module: only steps (1,2,4,5) on the MFN cells
         self.pre = mfn_prefix
         self.device = torch.device(device)
@@ -92,6 +97,9 @@ class Engine:
         # SLOWER (3.67 vs 3.56 ms/step: the gradient GEMMs delay the second launch), kept as an experiment switch
         self.split_last_recurrence = os.environ.get("MFM_SPLIT_LAST", "0") == "1"
         self.defer_mmd_join = False      # the fused trainer joins the MMD stream in losses() instead of at the end of forward
+        # Fused trainer: the decoders' reconstruction head (fc1, mfm_model.py:88-90) produces the MSE terms and their
+        # gradients in its GEMM epilogue (mfm_gemm_mse); x_hat never touches HBM and losses() launches no MSE kernel.
+        self.fuse_mse = False
         # loss_buf: 0 disc, 1..3 mse_l/a/v, 4..7 mmd per latent (unweighted), 8 total (weighted)
 
     # -- debug timeline ---------------------------------------------------------------
@@ -153,6 +161,8 @@ class Engine:
             return run
 
         self.mark("fwd:start")
+        if self.fuse_mse and full:
+            ops.zero(self.loss_buf[0:4])                       # the decoder heads accumulate the MSE terms during forward
         self._par([project(0), project(1), project(2)])
         self.mark("fwd:projections")
 
@@ -186,13 +196,22 @@ class Engine:
         Z = [buf("Z%d" % m, B, dm.z[m]) for m in range(3)] if full else []
         if full:
             with self._aux():
+                if self.kl:
+                    ops.zero(self.loss_buf[4:8])
                 for m, tag in enumerate(TAGS):
-                    ops.gemm("nt", self.ws["hsE%d" % m][TB:], P["encoder_%s.fc1.weight" % tag], Z[m],
+                    zlast = buf("Zlast%d" % m, B, dm.z[m]) if self.kl else Z[m]
+                    ops.gemm("nt", self.ws["hsE%d" % m][TB:], P["encoder_%s.fc1.weight" % tag], zlast,
                              bias=P["encoder_%s.fc1.bias" % tag])
+                    if self.kl:                                   # means and log-variances (mfm_model.py:735-740), KL term (:746)
+                        lv = buf("LV%d" % m, B, dm.z[m])
+                        ops.gemm("nt", zlast, P["last_to_z%s_fc1.weight" % tag], Z[m], bias=P["last_to_z%s_fc1.bias" % tag])
+                        ops.gemm("nt", zlast, P["last_to_logvarz%s_fc1.weight" % tag], lv, bias=P["last_to_logvarz%s_fc1.bias" % tag])
+                        ops.kld_fwd(Z[m], lv, self.loss_buf[4 + m:5 + m])
                 self._z_ready = self._aux_event()
-                ops.zero(self.mmd_acc.view(torch.float32))
-                for k in range(3):
-                    self._mmd(k, Z[k])
+                if not self.kl:
+                    ops.zero(self.mmd_acc.view(torch.float32))
+                    for k in range(3):
+                        self._mmd(k, Z[k])
 
         # (4) MFN attention for all T at once (:171-176); only gamma*_fc1's memory columns are sequential
         pre = self.pre
@@ -248,8 +267,15 @@ class Engine:
 
         # (7) MMD of z_y (the encoder latents went out in step 3); same auxiliary stream, off the critical path
         with self._aux():
-            self._mmd(3, ZY)
-            ops.mmd_fold(self.mmd_acc, self.loss_buf[4:8])
+            if self.kl:                                           # log-variance of z_y and its KL term (mfm_model.py:744,746)
+                Wlv = P["last_to_logvarzy_fc1.weight"]
+                LVY = buf("LVY", B, dm.zy)
+                ops.gemm("nt", Hall[TB:], Wlv[:, :H], LVY, bias=P["last_to_logvarzy_fc1.bias"])
+                ops.gemm("nt", mems[TB:], Wlv[:, H:], LVY, accumulate=True)
+                ops.kld_fwd(ZY, LVY, self.loss_buf[7:8])
+            else:
+                self._mmd(3, ZY)
+                ops.mmd_fold(self.mmd_acc, self.loss_buf[4:8])
         if self._z_ready is not None:                      # the factor MLPs read Z, produced on the auxiliary stream
             torch.cuda.current_stream(self.device).wait_event(self._z_ready)
             self._z_ready = None
@@ -286,7 +312,8 @@ class Engine:
         # (9) decoders (:72-91): step 0 eats the embedding; for t>=1 the input IS h_{t-1}, so the two
         #     gate GEMMs collapse into one with W_ih + W_hh.   (10) reconstructions x_hat = fc1(all hiddens) (:88-90)
         # (11) discriminative head (:552) -- depends on fy only, a fifth branch
-        Xhat = [buf("Xhat%d" % m, TB, dm.d[m]) for m in range(3)]
+        Xhat = [None] * 3 if self.fuse_mse else [buf("Xhat%d" % m, TB, dm.d[m]) for m in range(3)]
+        dXf = [buf("dXhat%d" % m, TB, dm.d[m]) for m in range(3)] if self.fuse_mse else None
         Y1 = buf("Y1", B, dm.fy)
         Yhat = buf("Yhat", B, dm.out)
 
@@ -302,8 +329,13 @@ class Engine:
                             hs=buf("hsD%d" % m, (T + 1) * B, hd), cs=buf("csD%d" % m, (T + 1) * B, hd),
                             gates=buf("gatesD%d" % m, TB, 4 * hd))
                 ops.lstm_fwd([cell])
-                ops.gemm("nt", self.ws["hsD%d" % m][B:], P["decoder_%s.fc1.weight" % tag], Xhat[m],
-                         bias=P["decoder_%s.fc1.bias" % tag])
+                if self.fuse_mse:
+                    n = float(TB * dm.d[m])
+                    ops.gemm_mse(self.ws["hsD%d" % m][B:], P["decoder_%s.fc1.weight" % tag], P["decoder_%s.fc1.bias" % tag],
+                                 xs[m], 1.0 / n, 2.0 * dm.lda[m] / n, self.loss_buf[1 + m:2 + m], dXf[m])
+                else:
+                    ops.gemm("nt", self.ws["hsD%d" % m][B:], P["decoder_%s.fc1.weight" % tag], Xhat[m],
+                             bias=P["decoder_%s.fc1.bias" % tag])
             return run
 
         def head():
@@ -330,11 +362,14 @@ class Engine:
         # joined the auxiliary stream anyway (the loss gradients do not depend on it).
         if not self.defer_mmd_join:
             self._join_aux()
-        ops.zero(self.loss_buf[0:4])
+        if not self.fuse_mse:
+            ops.zero(self.loss_buf[0:4])
         dX = [buf("dXhat%d" % m, TB, dm.d[m]) for m in range(3)]
         dY = buf("dYhat", dm.B, dm.out)
 
         def mse(m):
+            if self.fuse_mse:                      # already done by the decoder heads' GEMM epilogue
+                return None
             def run():
                 n = float(TB * dm.d[m])
                 ops.mse_fwd_bwd(self.ws["Xhat%d" % m], self.xs[m], 1.0 / n, 2.0 * dm.lda[m] / n,
@@ -543,11 +578,15 @@ class Engine:
         #      combine per latent, scaled by dLoss/dMMD = ``mmd_scale`` x ``mmd_scale_dev``
         lat = [ws["Z0"], ws["Z1"], ws["Z2"], ws["ZY"]]
         dmmd = [buf("dZmmd%d" % k, B, lat[k].shape[1]) for k in range(4)]
+        dLV = [buf("dLV%d" % k, B, lat[k].shape[1]) for k in range(4)] if self.kl else None
         with self._aux():
             for k in range(4):
-                rc, t12 = ws["mmd_rc%d" % k], ws["mmd_t12_%d" % k]
                 ops.zero(dmmd[k])
-                ops.mmd_combine(lat[k], rc[:B], rc[B:], t12[:B], t12[B:], mmd_scale, dmmd[k], mmd_scale_dev)
+                if self.kl:                                       # d KLD / d mu and / d logvar, scaled by dLoss/dKLD
+                    ops.kld_bwd(lat[k], ws["LV%d" % k] if k < 3 else ws["LVY"], mmd_scale, dmmd[k], dLV[k], mmd_scale_dev)
+                else:
+                    rc, t12 = ws["mmd_rc%d" % k], ws["mmd_t12_%d" % k]
+                    ops.mmd_combine(lat[k], rc[:B], rc[B:], t12[:B], t12[B:], mmd_scale, dmmd[k], mmd_scale_dev)
 
         # (11') head, (10') + (9') + (8') one chain per decoder: reconstruction head, recurrence, weight gradients, embedding,
         #       factor MLP.  The four chains touch disjoint buffers (the decoders' shares of dFY are added after the join).
@@ -619,10 +658,28 @@ class Engine:
         dmemT = buf("dmemT", B, mem)
         ops.gemm("nn", dZY, Wzy[:, :H], dHlast)
         ops.gemm("nn", dZY, Wzy[:, H:], dmemT)
+        if self.kl:                                               # the log-variance head of z_y reads the same cat(h_T, mem_T)
+            Wlv, Glv = P["last_to_logvarzy_fc1.weight"], G["last_to_logvarzy_fc1.weight"]
+            self._wgrad_gemm(dLV[3], Hall[TB:], Glv[:, :H], accumulate=True)
+            self._wgrad_gemm(dLV[3], mems[TB:], Glv[:, H:], accumulate=True)
+            bgrad(dLV[3], "last_to_logvarzy_fc1.bias")
+            ops.gemm("nn", dLV[3], Wlv[:, :H], dHlast, accumulate=True)
+            ops.gemm("nn", dLV[3], Wlv[:, H:], dmemT, accumulate=True)
 
         enc_cells = []
         dhE = [buf("dhE%d" % m, B, dm.z[m]) for m in range(3)]
-        self._par([(lambda m=m: lin_bwd(dZ[m], ws["hsE%d" % m][TB:], "encoder_%s.fc1" % TAGS[m], dhE[m])) for m in range(3)])
+
+        def enc_head_bwd(m):
+            def run():
+                tag = TAGS[m]
+                dzl = dZ[m]
+                if self.kl:                                       # z = last_to_z_fc1(zlast), logvar = last_to_logvarz_fc1(zlast)
+                    dzl = buf("dZlast%d" % m, B, dm.z[m])
+                    lin_bwd(dZ[m], ws["Zlast%d" % m], "last_to_z%s_fc1" % tag, dzl)
+                    lin_bwd(dLV[m], ws["Zlast%d" % m], "last_to_logvarz%s_fc1" % tag, dzl, accumulate=True)
+                lin_bwd(dzl, ws["hsE%d" % m][TB:], "encoder_%s.fc1" % tag, dhE[m])
+            return run
+        self._par([enc_head_bwd(m) for m in range(3)])
         for m, tag in enumerate(TAGS):                       # (3') encoder heads
             dhl = dhE[m]
             enc_cells.append(dict(T=T, B=B, h=dm.z[m], gates=ws["gatesE%d" % m], cs=ws["csE%d" % m],

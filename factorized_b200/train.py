@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 from . import engine as E
-from .mfm_model import MFM, UNUSED, _ops
+from .mfm_model import MFM, MFM_KL, UNUSED, _ops
 
 SITE_NOISE = 20   # RNG sites 20..23: the four MMD Gaussian samples
 
@@ -77,8 +77,10 @@ class MFMTrainer:
                 p.data = view
                 self.P[k] = view
                 self.G[k] = self.flat_g[o:o + p.numel()].view(p.shape)
-        self.eng = E.Engine(model._cfg, T, B, dev, self.ops, head=head)
+        self.variant = getattr(model, "_variant", "mfm")
+        self.eng = E.Engine(model._cfg, T, B, dev, self.ops, head=head, variant=self.variant)
         self.eng.defer_mmd_join = True
+        self.eng.fuse_mse = True
         dm = self.eng.dm
         self.x = torch.zeros(T, B, dm.D, dtype=torch.float32, device=dev)
         if head == "ce":
@@ -110,8 +112,9 @@ class MFMTrainer:
         """forward + losses + backward into the flat gradient buffer (no communication)."""
         ops, eng = self.ops, self.eng
         ops.rng_tick(self.rng)
-        for k in range(4):                                    # loss_MMD's Gaussian samples (mfm_model.py:26)
-            ops.randn(self.noise[k], self.rng, SITE_NOISE + k)
+        if self.variant != "kl":
+            for k in range(4):                                # loss_MMD's Gaussian samples (mfm_model.py:26)
+                ops.randn(self.noise[k], self.rng, SITE_NOISE + k)
         eng.forward(self.P, self.x, self.noise, train=True, rng=self.rng)
         dX, dY = eng.losses(self.y)
         ops.zero(self.flat_g)
@@ -209,13 +212,11 @@ def train_mfm(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, head:
     """Drop-in for the reference's train_mfm (mfm_mosi.py:386-503); CE head: mfm_mosi_acc.py:396-503.
     X_* are numpy [n,T,D]; y_* [n] (or [n,out]).  Returns a dict with the trained model and scores."""
     config = configs[0]
-    if config.get("type", "mfm") == "kl":
-        raise NotImplementedError("MFM_KL is outside the accelerated path (SURVEY.md section 2, row 9)")
     p = np.random.permutation(X_train.shape[0])                     # :387-389
     X_train, y_train = np.asarray(X_train)[p], np.asarray(y_train)[p]
     Xt, Xv, Xte = _to_time_major(X_train), _to_time_major(X_valid), _to_time_major(X_test)    # :391-393
     dev = torch.device("cuda")
-    model = MFM(*configs).to(dev)                                    # :401,414
+    model = (MFM_KL if config.get("type", "mfm") == "kl" else MFM)(*configs).to(dev)      # :398-401,414
     model.mmd_noise = "cuda"
     T, total_n = Xt.shape[0], Xt.shape[1]
     bs = int(config["batchsize"])

@@ -82,6 +82,14 @@ int mfm_gemm_ws(int mode, int M, int N, int K,
                 float drop_p, int drop_site, const long long* rng, float* colsum_out,
                 void* ws, long long ws_bytes, void* stream);
 
+/* The reconstruction head fused into one GEMM (decoderLSTM.forward's fc1, mfm_model.py:88-90, with the MSE term of the
+ * train step, mfm_mosi.py:437):   x_hat = A B^T + bias;   *slot += loss_scale * sum (x_hat - x)^2;
+ * dxhat = grad_scale * (x_hat - x)  (the gradient of lambda * mean((x_hat - x)^2) when grad_scale = 2 lambda / numel).
+ * x_hat itself is written only when `xhat` is not NULL (predict()); in training it never touches HBM. */
+int mfm_gemm_mse(int M, int N, int K, const float* A, long long lda, const float* B, long long ldb, const float* bias,
+                 const float* x, long long ldx, float loss_scale, float grad_scale, float* slot,
+                 float* dxhat, long long lddx, float* xhat, long long ldxhat, void* ws, long long ws_bytes, void* stream);
+
 /* Two weight gradients that share dY -- dW_ih = dG^T x and dW_hh = dG^T h_prev of one LSTM cell (autograd adjoint of
  * mfm_model.py:56,167-169), or the two column blocks of gamma*_fc1 (:178-179) -- in one launch:
  *   C1[M,N1] += A^T B1,  colsum1[m] += sum_k A[k,m] (may be NULL),  C2[M,N2] += A^T B2,   A = dY [K, M].
@@ -201,6 +209,11 @@ int mfm_mse_fwd_bwd(int M, int N, const float* xhat, long long ldxh, const float
                     float loss_scale, float grad_scale, float* slot, float* dxhat, long long lddx, void* stream);
 int mfm_l1_fwd_bwd(long long n, const float* yhat, const float* y, float scale, float* slot, float* dy, void* stream);
 int mfm_ce_fwd_bwd(int B, int C, const float* yhat, const long long* y, float scale, float* slot, float* dy, void* stream);
+/* loss_KLD of MFM_KL / MFM_KL_EF (mfm_model.py:36-38): *slot += -0.5 * sum(1 + logvar - mu^2 - exp(logvar)) over [M,N];
+ * its gradient: dmu += s * mu, dlogvar = s * 0.5 * (exp(logvar) - 1), s = scale * (scale_dev ? *scale_dev : 1). */
+int mfm_kld_fwd(int M, int N, const float* mu, long long ldmu, const float* logvar, long long ldlv, float* slot, void* stream);
+int mfm_kld_bwd(int M, int N, const float* mu, long long ldmu, const float* logvar, long long ldlv, float scale,
+                const float* scale_dev, float* dmu, long long lddmu, float* dlogvar, long long lddlv, void* stream);
 /* lb[8] = lb[0] + l0 lb[1] + l1 lb[2] + l2 lb[3] + lmmd (lb[4]+lb[5]+lb[6]+lb[7]) */
 int mfm_loss_total(float* lb, float l0, float l1, float l2, float lmmd, void* stream);
 

@@ -37,13 +37,15 @@ def import_reference():
     return ref
 
 
-def run_reference(ref, configs, seed, T, n, head, data_seed, noise_seed):
+def run_reference(ref, configs, seed, T, n, head, data_seed, noise_seed, variant="mfm"):
     torch.manual_seed(seed)
-    model = ref.MFM(*configs).eval()              # eval(): the 9 dropouts become identity
+    model = (ref.MFM_KL if variant == "kl" else ref.MFM)(*configs).eval()              # eval(): the 9 dropouts become identity
     params0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
     x, y = O.synthetic_batch(configs, T, n, data_seed, head)
     lat = {}
     hooks = dict(zl=model.encoder_l.fc1, za=model.encoder_a.fc1, zv=model.encoder_v.fc1, zy=model.last_to_zy_fc1)
+    if variant == "kl":                              # the latents are the means: one more Linear after the encoders
+        hooks = dict(zl=model.last_to_zl_fc1, za=model.last_to_za_fc1, zv=model.last_to_zv_fc1, zy=model.last_to_zy_fc1)
     for k, m in hooks.items():
         m.register_forward_hook(lambda mod, i, o, k=k: lat.__setitem__(k, o.detach().clone()))
     opt = torch.optim.Adam(model.parameters())     # mfm_mosi.py:403
@@ -71,16 +73,16 @@ def run_reference(ref, configs, seed, T, n, head, data_seed, noise_seed):
                             mse_l=float(mse[0]), mse_a=float(mse[1]), mse_v=float(mse[2])))
 
 
-def check_oracle(r, configs, seed, n, head, noise_seed, tag):
+def check_oracle(r, configs, seed, n, head, noise_seed, tag, variant="mfm"):
     """oracle restatement vs live reference; returns the max abs diff seen."""
-    P = O.init_params(configs, seed)
+    P = O.init_params(configs, seed, variant=variant)
     worst = 0.0
     for k, v in r["params0"].items():
         dd = float((P[k] - v).abs().max())
         worst = max(worst, dd)
     assert worst == 0.0, "init_params does not reproduce the reference's init (max diff %g)" % worst
     noise = O.draw_mmd_noise(configs, n, noise_seed)
-    newP, losses, G, out = O.train_step(P, r["x"], r["y"], configs, noise, {}, head=head)
+    newP, losses, G, out = O.train_step(P, r["x"], r["y"], configs, noise, {}, head=head, variant=variant)
     def rel(a, b):
         return float((a - b).norm() / (b.norm() + 1e-30))
     errs = {}
@@ -134,6 +136,28 @@ def main():
         for k, v in r["losses"].items():
             blob["loss/" + k] = np.float64(v)
         np.savez_compressed(os.path.join(outdir, "tiny_%s_out%d.npz" % (head, od)), **blob)
+
+    # ---- (1b) MFM_KL (the variant train_mfm dispatches to for config['type'] == 'kl', mfm_mosi.py:398-399) ----
+    configs = O.tiny_configs(output_dim=1)
+    configs[0]["type"] = "kl"
+    seed, T, n, data_seed, noise_seed = 321, 4, 6, 11, 77
+    r = run_reference(ref, configs, seed, T, n, "l1", data_seed, noise_seed, variant="kl")
+    check_oracle(r, configs, seed, n, "l1", noise_seed, "tiny_kl/l1/out1", variant="kl")
+    blob = dict(meta=np.array([seed, T, n, data_seed, noise_seed, 1]), x=r["x"].numpy(), y=r["y"].numpy())
+    for k, v in r["params0"].items():
+        blob["p0/" + k] = v.numpy()
+    for k, v in r["params1"].items():
+        blob["p1/" + k] = v.numpy()
+    for k, v in r["grads"].items():
+        if v is not None:
+            blob["g/" + k] = v.numpy()
+    for k, v in r["lat"].items():
+        blob["lat/" + k] = v.numpy()
+    for k in ("x_l_hat", "x_a_hat", "x_v_hat", "y_hat"):
+        blob[k] = r[k].numpy()
+    for k, v in r["losses"].items():
+        blob["loss/" + k] = np.float64(v)
+    np.savez_compressed(os.path.join(outdir, "tiny_kl_l1_out1.npz"), **blob)
 
     # ---- (2) BASELINE configs[0]: MOSI shapes, best_acc dims, B=32, T=20 --------------
     # parameters are regenerated from the seed (2.9 MB otherwise); the fixture keeps

@@ -72,10 +72,10 @@ def tiny_configs(output_dim=1):
     return [config, nn_(10), nn_(11), nn_(12), nn_(13), nn_(6)]
 
 
-def param_shapes(configs) -> "OrderedDict[str, Tuple[int, ...]]":
+def param_shapes(configs, variant: str = "mfm") -> "OrderedDict[str, Tuple[int, ...]]":
     """state_dict names and shapes in the reference's construction order
     (mfm_model.py:491-520 for MFM; :43-44 encoderLSTM; :67-68 decoderLSTM;
-    :116-137 MFN).  90 tensors."""
+    :116-137 MFN).  90 tensors.  variant "kl": MFM_KL (mfm_model.py:683-721), 104 tensors."""
     config, nn1, nn2, g1, g2, out = configs
     d = config["input_dims"]
     hm = config["h_dims"]
@@ -117,6 +117,12 @@ def param_shapes(configs) -> "OrderedDict[str, Tuple[int, ...]]":
     lin("mfn_encoder.out_fc1", H + mem, out["shapes"])          # constructed, never used (mfm_model.py:136-137)
     lin("mfn_encoder.out_fc2", out["shapes"], config["output_dim"])
     lin("last_to_zy_fc1", H + mem, zy)
+    if variant == "kl":                                       # mfm_model.py:696-704
+        lin("last_to_logvarzy_fc1", H + mem, zy)
+        for m, tag in enumerate("lav"):
+            lin("last_to_z%s_fc1" % tag, z[m], z[m])
+        for m, tag in enumerate("lav"):
+            lin("last_to_logvarz%s_fc1" % tag, z[m], z[m])
     lin("zy_to_fy_fc1", zy, fy)
     lin("zy_to_fy_fc2", fy, fy)
     for m, tag in enumerate("lav"):
@@ -131,7 +137,7 @@ UNUSED_PARAMS = ("mfn_encoder.out_fc1.weight", "mfn_encoder.out_fc1.bias",
                  "mfn_encoder.out_fc2.weight", "mfn_encoder.out_fc2.bias")
 
 
-def init_params(configs, seed: int, dtype=torch.float32) -> "OrderedDict[str, Tensor]":
+def init_params(configs, seed: int, dtype=torch.float32, variant: str = "mfm") -> "OrderedDict[str, Tensor]":
     """Parameters as ``torch.manual_seed(seed); MFM(*configs)`` would draw them.
 
     The reference constructs nn.LSTMCell / nn.Linear in the order of
@@ -144,7 +150,7 @@ def init_params(configs, seed: int, dtype=torch.float32) -> "OrderedDict[str, Te
     import torch.nn as nn
     torch.manual_seed(seed)
     out: "OrderedDict[str, Tensor]" = OrderedDict()
-    shapes = param_shapes(configs)
+    shapes = param_shapes(configs, variant)
     names = list(shapes)
     i = 0
     while i < len(names):
@@ -342,6 +348,42 @@ def mfm_forward(x: Tensor, P, configs, noise: Sequence[Tensor], train=False, mas
                 zl=zl, za=za, zv=zv, zy=zy, fy=fy, fl=fl, fa=fa, fv=fv, mfn_last=mfn_last)
 
 
+def loss_kld(mu: Tensor, logvar: Tensor) -> Tensor:
+    """mfm_model.py:36-38: -0.5 * sum(1 + logvar - mu^2 - exp(logvar)) -- a SUM over all elements, not a mean."""
+    return -0.5 * torch.sum(1 + logvar - mu.pow(2) - logvar.exp())
+
+
+def mfm_kl_forward(x: Tensor, P, configs, train=False, masks=None, branches=None):
+    """MFM_KL.forward, mfm_model.py:723-764: the encoders' outputs pass one more Linear to the means (z) and another to
+    the log-variances; there is NO sampling (the means feed the factor MLPs); the regulariser is the KL term, returned in
+    the slot MFM uses for the MMD ("mmd" below) and weighted by lda_mmd in the train step (mfm_mosi.py:433)."""
+    config = configs[0]
+    d_l, d_a, d_v = config["input_dims"]
+    T = x.shape[0]
+    x_l, x_a, x_v = x[:, :, :d_l], x[:, :, d_l:d_l + d_a], x[:, :, d_l + d_a:]
+    lasts = [encoder_lstm(x_l, P, "encoder_l"), encoder_lstm(x_a, P, "encoder_a"), encoder_lstm(x_v, P, "encoder_v")]    # :732-734
+    zs = [linear(lasts[m], P, "last_to_z%s_fc1" % tag) for m, tag in enumerate("lav")]                                  # :735-737
+    lvs = [linear(lasts[m], P, "last_to_logvarz%s_fc1" % tag) for m, tag in enumerate("lav")]                           # :738-740
+    mfn_last = mfn_encoder(x, P, configs, train, masks, branches)                                                        # :742
+    zy = linear(mfn_last, P, "last_to_zy_fc1")
+    lvy = linear(mfn_last, P, "last_to_logvarzy_fc1")                                                                    # :743-744
+    kld = loss_kld(zs[0], lvs[0]) + loss_kld(zs[1], lvs[1]) + loss_kld(zs[2], lvs[2]) + loss_kld(zy, lvy)               # :746
+    zl, za, zv = zs
+    mk = (lambda k: None if masks is None else masks.get(k))
+    fy = factor_mlp(zy, P, "zy_to_fy", config["zy_to_fy_dropout"], train, mk("fy"), branches, "fy")
+    fl = factor_mlp(zl, P, "zl_to_fl", config["zl_to_fl_dropout"], train, mk("fl"), branches, "fl")
+    fa = factor_mlp(za, P, "za_to_fa", config["za_to_fa_dropout"], train, mk("fa"), branches, "fa")
+    fv = factor_mlp(zv, P, "zv_to_fv", config["zv_to_fv_dropout"], train, mk("fv"), branches, "fv")
+    x_l_hat = decoder_lstm(torch.cat([fy, fl], 1), T, P, "decoder_l")
+    x_a_hat = decoder_lstm(torch.cat([fy, fa], 1), T, P, "decoder_a")
+    x_v_hat = decoder_lstm(torch.cat([fy, fv], 1), T, P, "decoder_v")
+    y1 = dropout(relu(linear(fy, P, "fy_to_y_fc1"), branches, "y1"), config["fy_to_y_dropout"], train, mk("y"))
+    y_hat = linear(y1, P, "fy_to_y_fc2")
+    return dict(x_l_hat=x_l_hat, x_a_hat=x_a_hat, x_v_hat=x_v_hat, y_hat=y_hat, mmd=kld,
+                zl=zl, za=za, zv=zv, zy=zy, lvl=lvs[0], lva=lvs[1], lvv=lvs[2], lvy=lvy, fy=fy, fl=fl, fa=fa, fv=fv,
+                mfn_last=mfn_last)
+
+
 def mfm_losses(out: Dict[str, Tensor], x: Tensor, y: Tensor, configs, head: str = "l1") -> Dict[str, Tensor]:
     """Loss assembly of the train step: mfm_mosi.py:432-439 (L1 head) and
     mfm_mosi_acc.py:441-451 / mfm_moud.py:495-508 (cross-entropy head)."""
@@ -383,11 +425,15 @@ def adam_step(P, G, state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
     return P
 
 
-def train_step(P, x, y, configs, noise, state, head="l1", lr=1e-3, train=False, masks=None, branches=None):
+def train_step(P, x, y, configs, noise, state, head="l1", lr=1e-3, train=False, masks=None, branches=None, variant="mfm"):
     """One iteration of the inner loop of train_mfm (mfm_mosi.py:427-442):
-    forward, loss, backward, Adam.  Returns (new params, losses, grads, fwd)."""
+    forward, loss, backward, Adam.  Returns (new params, losses, grads, fwd).  variant "kl": the model is MFM_KL
+    (train_mfm's own dispatch, mfm_mosi.py:398-399; `noise` is unused)."""
     Pg = OrderedDict((k, v.detach().clone().requires_grad_(k not in UNUSED_PARAMS)) for k, v in P.items())
-    out = mfm_forward(x, Pg, configs, noise, train=train, masks=masks, branches=branches)
+    if variant == "kl":
+        out = mfm_kl_forward(x, Pg, configs, train=train, masks=masks, branches=branches)
+    else:
+        out = mfm_forward(x, Pg, configs, noise, train=train, masks=masks, branches=branches)
     losses = mfm_losses(out, x, y, configs, head)
     losses["total"].backward()
     G = OrderedDict((k, (None if v.grad is None else v.grad.detach().clone())) for k, v in Pg.items())

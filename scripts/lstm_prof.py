@@ -33,6 +33,10 @@ dec_b = [[bwd_cell(c[0], True)] for c in dec]
 
 
 def timed(name, fn, algo_bytes, flops, reps=5):
+    if os.environ.get("LSTM_PROF_ONCE"):          # ncu capture: one launch per shape, no timing
+        fn()
+        torch.cuda.synchronize()
+        return
     fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

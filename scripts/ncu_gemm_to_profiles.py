@@ -1,5 +1,5 @@
 """Turn the `ncu --set full` capture of scripts/gemm_prof.py (read here, no GPU needed) into the committed evidence:
-profiles/<tag>_gemm_tcp_ncu_full_extract.csv (headline metrics per launch) and profiles/r1_gemm_tcp_ncu.json (DRAM bytes
+profiles/<tag>_gemm_tcp_ncu_full_extract.csv (headline metrics per launch) and profiles/<rN>_gemm_tcp_ncu.json (DRAM bytes
 per launch, keyed by the GEMM shape string bench.py uses -- bench.py reads `traffic` from it).
 usage: ncu_gemm_to_profiles.py report.ncu-rep tag"""
 import csv, io, json, os, subprocess, sys
@@ -32,5 +32,5 @@ for k, r in zip(keys, data):
                  dram_pct=float(r[idx['gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed']]))
 with open(os.path.join(ROOT, "profiles", tag + "_gemm_tcp_ncu_full_extract.csv"), "w", newline="") as f:
     csv.writer(f).writerows(zip(*out))          # one column per launch
-json.dump(js, open(os.path.join(ROOT, "profiles", "r1_gemm_tcp_ncu.json"), "w"), indent=1)
+json.dump(js, open(os.path.join(ROOT, "profiles", tag[:2] + "_gemm_tcp_ncu.json"), "w"), indent=1)
 print(json.dumps(js, indent=1))

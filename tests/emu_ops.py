@@ -9,46 +9,7 @@ The product never imports this file.
 """
 import torch
 
-M32 = 0xFFFFFFFF
-
-
-def _fmix32(h):
-    h = h & M32
-    h = h ^ (h >> 16)
-    h = (h * 0x85EBCA6B) & M32
-    h = h ^ (h >> 13)
-    h = (h * 0xC2B2AE35) & M32
-    h = h ^ (h >> 16)
-    return h
-
-
-def _fmix32_int(h):
-    h &= M32
-    h ^= h >> 16
-    h = (h * 0x85EBCA6B) & M32
-    h ^= h >> 13
-    h = (h * 0xC2B2AE35) & M32
-    h ^= h >> 16
-    return h
-
-
-def site_seed(rng, site):
-    """csrc/common.cuh::site_key -- every input passes its own mixing round (consecutive steps give unrelated keys)."""
-    seed, step = int(rng[0]) & M32, int(rng[1]) & M32
-    return _fmix32_int(_fmix32_int(seed ^ _fmix32_int((step + 0x9E3779B9) & M32)) + ((site * 0x7F4A7C15) & M32))
-
-
-def rng_bits(sseed, idx):
-    """csrc/common.cuh::rng_bits -- counter -> 32 bits, two rounds, the key enters both."""
-    return _fmix32(_fmix32(((idx & M32) + sseed) & M32) ^ sseed)
-
-
-def keep_mask(rng, site, p, rows, cols, row0=0):
-    """keep[m,n] = u(idx) >= p with idx = (row0+m)*cols + n (32-bit wrap)."""
-    idx = (torch.arange(rows, dtype=torch.int64).view(-1, 1) + row0) * cols + torch.arange(cols, dtype=torch.int64).view(1, -1)
-    h = rng_bits(site_seed(rng, site), idx)
-    u = (h >> 8).to(torch.float32) * (1.0 / 16777216.0)
-    return (u >= p).to(torch.float32)
+from oracle.rng_replay import M32, _fmix32, site_seed, rng_bits, keep_mask   # noqa: F401  (one statement of the RNG)
 
 
 class EmuOps:
@@ -91,6 +52,15 @@ class EmuOps:
             C += v
         else:
             C.copy_(v)
+
+    def gemm_mse(self, A, W, bias, x, loss_scale, grad_scale, slot, dxhat, xhat=None):
+        self.launches += 1
+        v = A @ W.t() + bias
+        r = v - x
+        slot[0] += loss_scale * (r * r).sum()
+        dxhat.copy_(grad_scale * r)
+        if xhat is not None:
+            xhat.copy_(v)
 
     def gemm_tn_pair(self, dY, A1, C1, colsum1, A2, C2):
         self.gemm("tn", dY, A1, C1, accumulate=True, colsum_out=colsum1)
@@ -310,6 +280,17 @@ class EmuOps:
         p = torch.exp(lp)
         p.scatter_add_(1, idx, -torch.ones_like(p[:, :1]))
         dy.copy_(scale * p)
+
+    def kld_fwd(self, mu, logvar, slot):
+        self.launches += 1
+        slot[0] += -0.5 * (1 + logvar - mu * mu - torch.exp(logvar)).sum()
+
+    def kld_bwd(self, mu, logvar, scale, dmu, dlogvar, scale_dev=None):
+        self.launches += 1
+        if scale_dev is not None:
+            scale = scale * float(scale_dev)
+        dmu += scale * mu
+        dlogvar.copy_(scale * 0.5 * (torch.exp(logvar) - 1.0))
 
     def loss_total(self, lb, l0, l1, l2, lmmd):
         self.launches += 1

@@ -34,3 +34,14 @@ def tiny_case(head="l1", od=1):
     y = torch.from_numpy(g["y"].copy())
     noise = O.draw_mmd_noise(configs, n, noise_seed)
     return g, configs, P, x, y, noise, T, n
+
+
+def tiny_kl_case():
+    g = load_golden("tiny_kl_l1_out1.npz")
+    seed, T, n, data_seed, noise_seed, od_ = [int(v) for v in g["meta"]]
+    configs = O.tiny_configs(output_dim=1)
+    configs[0]["type"] = "kl"
+    P = golden_params(g)
+    x = torch.from_numpy(g["x"].copy())
+    y = torch.from_numpy(g["y"].copy())
+    return g, configs, P, x, y, T, n

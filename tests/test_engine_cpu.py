@@ -10,7 +10,7 @@ import torch
 from oracle import mfm_oracle as O
 from factorized_b200.engine import Engine
 from emu_ops import EmuOps
-from helpers import rel_l2, tiny_case
+from helpers import rel_l2, tiny_case, tiny_kl_case
 
 
 def run_engine(configs, P, x, y, noise, T, n, head, dtype=torch.float32, train=False, rng=None):
@@ -85,11 +85,12 @@ def test_engine_dropout_masks_replay():
 
 
 def test_engine_schedule_variants_agree():
-    """The trainer's variant of the schedule (MMD joined only in backward, total summed there) and the experiment switch
-    that splits the last backward recurrence into two launches give the same losses and gradients as the default."""
+    """The trainer's variants of the schedule (MMD joined only in backward, total summed there; reconstruction MSE fused
+    into the decoder heads' GEMM) and the experiment switch that splits the last backward recurrence into two launches
+    give the same losses and gradients as the default."""
     g, configs, P, x, y, noise, T, n = tiny_case("l1", 1)
     ref_eng, _, Gref = run_engine(configs, P, x, y, noise, T, n, "l1")
-    for variant in ("defer_mmd_join", "split_last_recurrence"):
+    for variant in ("defer_mmd_join", "split_last_recurrence", "fuse_mse"):
         eng = Engine(configs, T, n, "cpu", EmuOps(), head="l1")
         setattr(eng, variant, True)
         eng.forward(OrderedDict(P), x.contiguous(), noise)
@@ -118,3 +119,32 @@ def test_rng_streams_of_consecutive_steps_are_unrelated():
             assert abs(float((a == b).float().mean()) - 0.5) < 0.05, (s, shift)
     a, b = keep_mask(torch.tensor([123, 5]), 3, 0.5, 64, 128), keep_mask(torch.tensor([123, 5]), 4, 0.5, 64, 128)
     assert abs(float((a == b).float().mean()) - 0.5) < 0.05
+
+
+def test_engine_kl_variant_matches_reference_golden():
+    """MFM_KL (the variant train_mfm dispatches to for config['type'] == 'kl', mfm_mosi.py:398-399): schedule + hand-derived
+    backward against the golden vectors of the unmodified reference's MFM_KL."""
+    g, configs, P, x, y, T, n = tiny_kl_case()
+    P = OrderedDict(P)
+    eng = Engine(configs, T, n, "cpu", EmuOps(), head="l1", variant="kl")
+    out = eng.forward(P, x.contiguous(), [torch.zeros(1, 1)] * 4)
+    dX, dY = eng.losses(y)
+    G = OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    eng.backward(P, G, dX, dY, eng.dm.lda_mmd)
+    tol = 1e-4
+    for k in ("zl", "za", "zv", "zy"):
+        assert rel_l2(out[k], g["lat/" + k]) < tol, k
+    assert rel_l2(out["y_hat"], g["y_hat"]) < tol
+    lb = eng.loss_buf
+    kld_w = float(lb[4:8].sum()) * configs[0]["lda_mmd"]
+    assert abs(kld_w - float(g["loss/mmd"])) < tol * abs(float(g["loss/mmd"]))
+    assert abs(float(lb[8]) - float(g["loss/total"])) < tol * abs(float(g["loss/total"]))
+    bad = []
+    for k in P:
+        if "g/" + k in g:
+            e = rel_l2(G[k], g["g/" + k])
+            if e > 2e-4:
+                bad.append((k, e))
+        else:
+            assert float(G[k].abs().max()) == 0.0, k
+    assert not bad, bad

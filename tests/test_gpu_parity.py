@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import mfm_oracle as O
-from helpers import load_golden, rel_l2, tiny_case
+from helpers import load_golden, rel_l2, tiny_case, tiny_kl_case
 
 pytestmark = pytest.mark.gpu
 
@@ -242,35 +242,7 @@ def test_trainer_graph_replay_trains():
     assert np.allclose(res[0], res[1], rtol=2e-3), res
 
 
-def _train_masks_and_branches(eng, rng_cpu):
-    """Dropout keep-masks of the CUDA step, regenerated on the CPU from the step's RNG state with the emulator's
-    statement of the hash (so the device RNG itself is under test), and the ReLU branches read back from the CUDA
-    stashes: a kept unit's branch is (output > 0); a dropped unit's branch was not observed (-1: the oracle decides)."""
-    from factorized_b200 import engine as E
-    from emu_ops import keep_mask
-    ws, dm = eng.ws, eng.dm
-    T, n = dm.T, dm.B
-    masks, br = {}, {}
-
-    def site(key, bkey, p, site_id, buf, rows, shape3=None):
-        out = buf.detach().cpu()
-        taken = (out > 0).float()
-        if p > 0.0:
-            k = keep_mask(rng_cpu, site_id, p, rows, out.shape[1])
-            taken = torch.where(k > 0, taken, torch.full_like(taken, -1.0))
-            masks[key] = k.view(shape3) if shape3 else k
-        br[bkey] = taken.view(shape3) if shape3 else taken
-    site("att1", "att1", dm.p_att1, E.SITE_ATT1, ws["H1"], T * n, (T, n, -1))
-    site("att2", "att2", dm.p_att2, E.SITE_ATT2, ws["H2"], T * n, (T, n, -1))
-    site("gamma1", "gamma1", dm.p_g1, E.SITE_G1, ws["U1"], T * n, (T, n, -1))
-    site("gamma2", "gamma2", dm.p_g2, E.SITE_G2, ws["U2"], T * n, (T, n, -1))
-    site("fy", "fy1", dm.p_fy, E.SITE_FY, ws["F1y"], n)
-    site("y", "y1", dm.p_y, E.SITE_Y, ws["Y1"], n)
-    for m, tag in enumerate("lav"):
-        site("f" + tag, "f%s1" % tag, dm.p_f[m], E.SITE_FL + m, ws["F1_%d" % m], n)
-        br["f" + tag] = (ws["EMB%d" % m][:, dm.fy:] > 0).float().cpu()
-    br["fy"] = (ws["FY"] > 0).float().cpu()
-    return masks, br
+from oracle.rng_replay import train_masks_and_branches as _train_masks_and_branches   # noqa: E402
 
 
 @pytest.mark.parametrize("name,input_dims,T,n,head,od,use_graph", [
@@ -426,3 +398,88 @@ def test_train_mfm_entry_point(tmp_path):
     assert abs(out["best_valid"] - min(h[2] for h in out["history"])) < 1e-7
     reloaded = torch.load(out["checkpoint"], weights_only=False)       # whole-module pickle, as the reference saves it
     assert sorted(reloaded.state_dict()) == sorted(out["model"].state_dict())
+
+
+def test_mfm_kl_variant_golden_module_and_trainer(gemm_path):
+    """MFM_KL (mfm_model.py:662-764; what train_mfm builds for config['type'] == 'kl', mfm_mosi.py:398-399) on the GPU:
+    the drop-in module under torch autograd against the golden vectors of the unmodified reference, then the fused
+    trainer step against the same."""
+    import factorized_b200 as F
+    from factorized_b200.train import MFMTrainer
+    g, configs, P, x, y, T, n = tiny_kl_case()
+    torch.manual_seed(int(g["meta"][0]))
+    model = F.MFM_KL(*configs).cuda().eval()
+    sd = model.state_dict()
+    assert len(sd) == 104
+    for k, v in sd.items():
+        assert torch.equal(v.cpu(), P[k]), k                      # same construction order -> same init stream
+    xd, yd = x.cuda(), y.cuda()
+    decoded, kld, missing = model.forward(xd)
+    c = configs[0]
+    d_l, d_a, d_v = c["input_dims"]
+    Fn = torch.nn.functional
+    gen = c["lda_xl"] * Fn.mse_loss(decoded[0], xd[:, :, :d_l]) + c["lda_xa"] * Fn.mse_loss(decoded[1], xd[:, :, d_l:d_l + d_a]) \
+        + c["lda_xv"] * Fn.mse_loss(decoded[2], xd[:, :, d_l + d_a:])
+    loss = Fn.l1_loss(decoded[3].squeeze(1), yd) + gen + c["lda_mmd"] * kld + missing
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss/total"])) < TOL * abs(float(g["loss/total"]))
+    assert abs(float(kld.detach()) * c["lda_mmd"] - float(g["loss/mmd"])) < TOL * abs(float(g["loss/mmd"]))
+    for k in ("zl", "za", "zv", "zy"):
+        assert rel_l2(model.latents[k], g["lat/" + k]) < TOL
+    bad = {}
+    for k, p in model.named_parameters():
+        if "g/" + k in g:
+            e = rel_l2(p.grad, g["g/" + k])
+            if not e < TOL:
+                bad[k] = e
+        else:
+            assert p.grad is None, k
+    assert not bad, bad
+    # fused trainer
+    torch.manual_seed(int(g["meta"][0]))
+    model2 = F.MFM_KL(*configs).cuda()
+    tr = MFMTrainer(model2, T, n, head="l1", use_graph=False)
+    tr.x.copy_(xd)
+    tr.y.copy_(yd.reshape(-1))
+    tr.step_device()
+    torch.cuda.synchronize()
+    assert abs(float(tr.eng.loss_buf[8]) - float(g["loss/total"])) < TOL * abs(float(g["loss/total"]))
+    sd2 = model2.state_dict()
+    bad = {k: rel_l2(sd2[k].cpu() - P[k], g["p1/" + k] - P[k].numpy()) for k in P if "g/" + k in g}
+    bad = {k: v for k, v in bad.items() if not v < 5e-3}
+    assert not bad, bad
+
+
+def test_mfm_kl_train_mode_step_and_train_mfm_dispatch(tmp_path):
+    """MFM_KL at MOSI shapes in train mode (dropout masks replayed) against the oracle, and train_mfm's dispatch on
+    config['type'] (mfm_mosi.py:398-399)."""
+    import factorized_b200 as F
+    from factorized_b200.train import MFMTrainer
+    from oracle.rng_replay import train_masks_and_branches
+    configs = O.best_acc_configs(dropout=True)
+    configs[0]["type"] = "kl"
+    T, n = 20, 128
+    torch.manual_seed(123)
+    model = F.MFM_KL(*configs).cuda().train()
+    P = OrderedDict((k, v.detach().cpu().clone()) for k, v in model.state_dict().items())
+    tr = MFMTrainer(model, T, n, head="l1", use_graph=True, seed=99)
+    x, y = O.synthetic_batch(configs, T, n, 5)
+    lb = tr.step(x.cuda(), y.cuda())
+    torch.cuda.synchronize()
+    masks, br = train_masks_and_branches(tr.eng, tr.rng.cpu())
+    del O.RELU_REPLAY_VIOLATIONS[:]
+    newP, losses, Go, outo = O.train_step(P, x, y, configs, None, {}, head="l1", train=True, masks=masks, branches=br, variant="kl")
+    assert not O.RELU_REPLAY_VIOLATIONS
+    lbc = lb.cpu()
+    assert abs(float(lbc[8]) - losses["total"]) < TOL * abs(losses["total"])
+    assert abs(float(lbc[4:8].sum()) * configs[0]["lda_mmd"] - losses["mmd"]) < TOL * abs(losses["mmd"])
+    bad = {k: rel_l2(tr.G[k], go) for k, go in Go.items() if go is not None and not rel_l2(tr.G[k], go) < TOL}
+    assert not bad, bad
+    # train_mfm builds MFM_KL for type == 'kl'
+    rs = np.random.RandomState(0)
+    cfg = O.tiny_configs()
+    cfg[0].update(batchsize=8, num_epochs=1, type="kl")
+    D = sum(cfg[0]["input_dims"])
+    Xtr, ytr = rs.randn(40, 5, D).astype(np.float32), rs.randn(40).astype(np.float32)
+    out = F.train_mfm(Xtr, ytr, Xtr[:16], ytr[:16], Xtr[:16], ytr[:16], cfg, verbose=False, save_dir=str(tmp_path))
+    assert type(out["model"]).__name__ == "MFM_KL" and np.isfinite(out["history"][0][1])

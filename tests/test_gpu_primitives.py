@@ -72,6 +72,35 @@ def test_gemm_strided_views_and_epilogues(ops):
     assert rel_l2(o_gpu, o_cpu) < TOL
 
 
+@pytest.mark.parametrize("path", ["simt_fp32", "tcgen05_bf16x3"])
+@pytest.mark.parametrize("M,N,K,ldx,want_xhat", [(640, 300, 104, 300, False), (4500, 300, 104, 300, True), (700, 5, 24, 8, True),
+                                                   (333, 20, 24, 20, False), (64, 7, 9, 7, True)])
+def test_gemm_mse_fused_reconstruction_head(ops, path, M, N, K, ldx, want_xhat):
+    """mfm_gemm_mse: x_hat = A W^T + b with the MSE term and its gradient produced in the GEMM epilogue
+    (mfm_model.py:88-90 + mfm_mosi.py:437); x_hat is written only on request."""
+    from factorized_b200.cuda_ops import PATH_SIMT_FP32, PATH_TC_BF16X3
+    old = ops.get_gemm_path()
+    ops.set_gemm_path(PATH_SIMT_FP32 if path == "simt_fp32" else PATH_TC_BF16X3)
+    try:
+        A, W, b = g(M, K, seed=1), g(N, K, seed=2, scale=0.2), g(N, seed=3)
+        xfull = g(M, ldx, seed=4)
+        x = xfull[:, :N]
+        slot_c, slot_g = torch.tensor([0.25]), torch.tensor([0.25]).cuda()
+        d_c, d_g = torch.zeros(M, N), torch.zeros(M, N).cuda()
+        h_c = torch.zeros(M, N) if want_xhat else None
+        h_g = torch.zeros(M, N).cuda() if want_xhat else None
+        ls, gs = 1.0 / (M * N), 2.0 * 0.5 / (M * N)
+        EmuOps().gemm_mse(A, W, b, x, ls, gs, slot_c, d_c, h_c)
+        ops.gemm_mse(A.cuda(), W.cuda(), b.cuda(), xfull.cuda()[:, :N], ls, gs, slot_g, d_g, h_g)
+        torch.cuda.synchronize()
+        assert abs(float(slot_g) - float(slot_c)) < 1e-4 * abs(float(slot_c)), (float(slot_g), float(slot_c))
+        assert rel_l2(d_g, d_c) < 1e-4
+        if want_xhat:
+            assert rel_l2(h_g, h_c) < 1e-4
+    finally:
+        ops.set_gemm_path(old)
+
+
 def _lstm_case(T, B, h, gx_steps, seed, ld_extra=0):
     W = g(4 * h, h, seed=seed, scale=0.3)
     gx = g(gx_steps * B, 4 * h, seed=seed + 1)

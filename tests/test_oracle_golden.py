@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import mfm_oracle as O
-from helpers import load_golden, golden_params, rel_l2, tiny_case
+from helpers import load_golden, golden_params, rel_l2, tiny_case, tiny_kl_case
 
 TOL = 2e-5   # fp32 op-order noise between two torch formulations of the same math
 
@@ -64,3 +64,26 @@ def test_mosi_b32_digest():
         assert rel_l2(G[k], g["g/" + k]) < 1e-4, k
     dn = np.array([float((newP[k] - P[k]).double().norm()) for k in names])
     assert np.allclose(dn, g["p1_minus_p0_norms"], rtol=1e-3)
+
+
+def test_tiny_kl_full_step():
+    """MFM_KL (mfm_model.py:662-764) restated in oracle.mfm_kl_forward, against the unmodified reference's MFM_KL."""
+    g, configs, P, x, y, T, n = tiny_kl_case()
+    P2 = O.init_params(configs, int(g["meta"][0]), variant="kl")
+    assert list(P2) == list(P) and len(P) == 104
+    for k in P:
+        assert torch.equal(P[k], P2[k]), k
+    newP, losses, G, out = O.train_step(P, x, y, configs, None, {}, head="l1", variant="kl")
+    for k in ("zl", "za", "zv", "zy"):
+        assert rel_l2(out[k], g["lat/" + k]) < TOL, k
+    for k in ("x_l_hat", "x_a_hat", "x_v_hat", "y_hat"):
+        assert rel_l2(out[k], g[k]) < TOL, k
+    for k, v in losses.items():
+        assert abs(v - float(g["loss/" + k])) <= TOL * abs(float(g["loss/" + k])) + 1e-7, k
+    for k in P:
+        if "g/" + k in g:
+            assert rel_l2(G[k], g["g/" + k]) < TOL, k
+        else:
+            assert G[k] is None and k in O.UNUSED_PARAMS
+    for k in P:
+        assert rel_l2(newP[k], g["p1/" + k]) < TOL, k
