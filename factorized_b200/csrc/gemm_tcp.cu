@@ -273,8 +273,11 @@ __global__ void __launch_bounds__(P_THREADS, 2) gemm_tcp_kernel(const TcpArgs pa
     }
     if (nchunks > 0) mbar_wait(smem_u32(&accum_bar), 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0 && nchunks < 31) TRACE(31, 0);
     // every chunk has been converted and multiplied: the ring is idle and serves as the transpose scratch
-    if (!(ta.dbg & 4)) tc_epilogue(ta, tmem_base, reinterpret_cast<float*>(smem), warp, lane, m0, n0, nchunks > 0, ones_col, P_NCONV / 128);
+    if (!(ta.dbg & 4)) tc_epilogue(ta, tmem_base, reinterpret_cast<float*>(smem), warp, lane, m0, n0, nchunks > 0, ones_col, P_NCONV / 128,
+                                   (tr && nchunks < 30) ? tr + 4 + 6 * 30 : nullptr);
+    if (tid == 0 && nchunks < 31) TRACE(31, 1);
   } else if (warp == P_WPROD) {
     // ================================ PRODUCER (one thread) ================================
     if (lane == 0) {
@@ -343,9 +346,10 @@ __global__ void __launch_bounds__(P_THREADS, 2) gemm_tcp_kernel(const TcpArgs pa
     }
     if (nchunks > 0) umma_commit(smem_u32(&accum_bar));    // all MMAs complete: the accumulator is final
   }
-#undef TRACE
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (tid == 0 && nchunks < 31) TRACE(31, 2);
+#undef TRACE
   if (tr && tid == 0) tr[3] = gtimer();
   if (warp == P_WMMA) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)ta.tmem_cols)

@@ -8,21 +8,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-// bounded wait: a barrier that never completes traps instead of hanging the GPU
+// Wait on an mbarrier phase.  try_wait carries a suspend-time hint, so a waiting warp is parked by the hardware until
+// the phase completes instead of re-polling: a polling loop (the first version, with a clock64() time-out per iteration)
+// spent a third of an SM's issue slots on waiters -- slots the co-resident CTA's epilogue needed.  Bounded: a barrier
+// that never completes traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  const long long t0 = clock64();
-  while (true) {
+  for (int spin = 0; spin < (1 << 22); ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (done) break;
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (done) return;
   }
+  __trap();
 }
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {

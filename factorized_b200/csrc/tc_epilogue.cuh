@@ -22,15 +22,28 @@ struct TcArgs {
   int dbg;         // experiment switches (env MFM_TC_DEBUG): 1 skip MMA, 2 skip convert/store, 4 skip epilogue, 8 skip loads
 };
 
-__device__ __forceinline__ float4 act4(float4 v, float b0, float b1, float b2, float b3, int act) {
-  v.x = apply_act(v.x + b0, act); v.y = apply_act(v.y + b1, act);
-  v.z = apply_act(v.z + b2, act); v.w = apply_act(v.w + b3, act);
+// The activation is chosen by a COMPILE-TIME constant inside the store loops (tc_epilogue dispatches once per call): with a
+// run-time `act` the compiler if-converted the switch and evaluated tanhf AND expf for every output element of every GEMM
+// -- ~60 instructions per element, 6 000 cycles per 32x32 block, two thirds of a small-K GEMM's CTA lifetime (measured
+// with the epilogue clock stamps of scripts/gemm_trace.py).
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+  if (ACT == MFM_ACT_RELU) return fmaxf(v, 0.0f);
+  if (ACT == MFM_ACT_TANH) return tanhf(v);
+  if (ACT == MFM_ACT_SIGMOID) return sigmoidf_acc(v);
+  return v;
+}
+template <int ACT>
+__device__ __forceinline__ float4 act4(float4 v, float b0, float b1, float b2, float b3) {
+  v.x = act_t<ACT>(v.x + b0); v.y = act_t<ACT>(v.y + b1);
+  v.z = act_t<ACT>(v.z + b2); v.w = act_t<ACT>(v.w + b3);
   return v;
 }
 
 // warp, lane: indices within the epilogue warps.  scratch_all: 32*TC_EPI_LD floats of idle shared memory per warp.
-__device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base, float* scratch_all, int warp, int lane,
-                                            int m0, int n0, bool have_acc, int ones_col, int nhalves = 2) {
+template <int ACT>
+__device__ __forceinline__ void tc_epilogue_t(const TcArgs& ta, uint32_t tmem_base, float* scratch_all, int warp, int lane,
+                                              int m0, int n0, bool have_acc, int ones_col, int nhalves, long long* trs) {
   const GemmArgs& a = ta.g;
   const int BN = ta.BN;
   uint32_t sseed = 0;
@@ -41,7 +54,7 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base
   // epilogue parameters pinned in registers (the fully generic per-element form cost ~30 instructions per output)
   float* const e_C = a.C;
   const long long e_ldc = a.ldc;
-  const int e_M = a.M, e_N = a.N, e_act = a.act;
+  const int e_M = a.M, e_N = a.N;
   const bool e_atomic = a.atomic != 0, e_acc = a.accumulate != 0, e_simple = !a.mask && !do_drop;
   const bool mask_vec = !a.mask || (((reinterpret_cast<uintptr_t>(a.mask) & 15) == 0) && ((a.ldmask & 3) == 0));
   const GemmMse& ms = a.mse;
@@ -56,11 +69,14 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base
   const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
   const int mbase = m0 + quad * 32;
   const int nrows = max(0, min(32, e_M - mbase));
+  int trk = 0;
+#define EPI_STAMP() do { if (trs && warp == 0 && lane == 0 && trk < 6) trs[trk++] = clock64(); } while (0)
+  EPI_STAMP();
   for (int c0 = cbeg; c0 < cend; c0 += 32) {
     float v[32];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (c0 + 8 * q < cend) {          // warp-uniform
+      if (c0 + 8 * q < cend && !(ta.dbg & 32)) {          // warp-uniform  (dbg 32: experiment, no TMEM loads)
         uint32_t r[8];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -74,10 +90,12 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base
       }
     }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (c0 == cbeg) EPI_STAMP();
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       *reinterpret_cast<float4*>(scratch + lane * TC_EPI_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     __syncwarp();
+    if (c0 == cbeg) EPI_STAMP();
     if (!have_acc) { __syncwarp(); continue; }
     if (e_vec) {
       // lane -> (row within a group of 4, 4-column group); 8 passes cover the 32 rows
@@ -90,12 +108,28 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (n + i < e_N) b[i] = (a.bias ? __ldg(a.bias + n + i) : 0.0f) + (a.bias2 ? __ldg(a.bias2 + n + i) : 0.0f);
-#pragma unroll
+        // NOT unrolled: the body carries every fused variant (MSE head, dropout, ReLU mask, accumulate, ragged tail); eight
+        // copies of it made the epilogue ~60 KB of straight-line code per activation, far beyond the instruction cache,
+        // and the epilogue -- two thirds of a small-K GEMM's CTA lifetime -- was bound by instruction FETCH (ncu: `no_inst`
+        // on every line of it).  The plain case (bias + activation into an aligned C) has its own short loop.
+        if (e_simple && !e_mse && !e_acc && full4) {
+          const float* sp4 = scratch + rsub * TC_EPI_LD + cg * 4;
+          float* cp4 = e_C + (long long)(mbase + rsub) * e_ldc + n;
+#pragma unroll 2
+          for (int p = 0; p < 8; ++p) {
+            if (p * 4 + rsub < nrows) {
+              float4 t = *reinterpret_cast<const float4*>(sp4 + p * 4 * TC_EPI_LD);
+              t = act4<ACT>(t, b[0], b[1], b[2], b[3]);
+              *reinterpret_cast<float4*>(cp4 + (long long)(p * 4) * e_ldc) = t;
+            }
+          }
+        } else
+#pragma unroll 1
         for (int p = 0; p < 8; ++p) {
           const int rr = p * 4 + rsub;
           if (rr < nrows) {
             float4 t = *reinterpret_cast<const float4*>(scratch + rr * TC_EPI_LD + cg * 4);
-            t = act4(t, b[0], b[1], b[2], b[3], e_act);
+            t = act4<ACT>(t, b[0], b[1], b[2], b[3]);
             if (e_mse) {                                      // fused reconstruction head: residual, its square, its gradient
               const float* xp = ms.x + (long long)(mbase + rr) * ms.ldx + n;
               float4 xv;
@@ -131,6 +165,7 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base
               }
             }
             float* cp = e_C + (long long)(mbase + rr) * e_ldc + n;
+            if (ta.dbg & 16) continue;                        // experiment: no global stores
             if (full4) {
               if (e_acc) {
                 const float4 o = *reinterpret_cast<const float4*>(cp);
@@ -158,9 +193,9 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base
             for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) atomicAdd(cp, sp[rr * TC_EPI_LD]);
           } else if (e_simple) {                              // bias + activation (+ C) on an unaligned C
             const float bsum = (a.bias ? __ldg(a.bias + n) : 0.0f) + (a.bias2 ? __ldg(a.bias2 + n) : 0.0f);
-#pragma unroll 4
+#pragma unroll 1
             for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) {
-              float t = apply_act(sp[rr * TC_EPI_LD] + bsum, e_act);
+              float t = act_t<ACT>(sp[rr * TC_EPI_LD] + bsum);
               if (e_mse) {
                 if (ms.xhat) ms.xhat[(long long)(mbase + rr) * ms.ldxhat + n] = t;
                 t -= __ldg(ms.x + (long long)(mbase + rr) * ms.ldx + n);
@@ -172,9 +207,9 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base
           } else {                                            // dropout and/or ReLU-mask epilogues
             const float bsum = (a.bias ? __ldg(a.bias + n) : 0.0f) + (a.bias2 ? __ldg(a.bias2 + n) : 0.0f);
             const float* mp = a.mask ? a.mask + (long long)mbase * a.ldmask + n : nullptr;
-#pragma unroll 2
+#pragma unroll 1
             for (int rr = 0; rr < nrows; ++rr, cp += e_ldc) {
-              float t = apply_act(sp[rr * TC_EPI_LD] + bsum, e_act);
+              float t = act_t<ACT>(sp[rr * TC_EPI_LD] + bsum);
               const int m = mbase + rr;
               if (do_drop) t = drop_keep(sseed, (uint32_t)m * (uint32_t)e_N + (uint32_t)n, a.drop_p) ? t * keep_scale : 0.0f;
               if (mp) t = __ldg(mp + (long long)rr * a.ldmask) > 0.0f ? t * a.mask_scale : 0.0f;
@@ -185,9 +220,22 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base
       }
     }
     __syncwarp();
+    EPI_STAMP();
   }
+#undef EPI_STAMP
   if (e_mse) {                                      // one atomic per warp
     sq = warp_sum(sq);
     if (lane == 0) atomicAdd(ms.slot, sq * ms.loss_scale);
+  }
+}
+
+__device__ __forceinline__ void tc_epilogue(const TcArgs& ta, uint32_t tmem_base, float* scratch_all, int warp, int lane,
+                                            int m0, int n0, bool have_acc, int ones_col, int nhalves = 2,
+                                            long long* trs = nullptr) {
+  switch (ta.g.act) {                              // CTA-uniform
+    case MFM_ACT_RELU: tc_epilogue_t<MFM_ACT_RELU>(ta, tmem_base, scratch_all, warp, lane, m0, n0, have_acc, ones_col, nhalves, trs); break;
+    case MFM_ACT_TANH: tc_epilogue_t<MFM_ACT_TANH>(ta, tmem_base, scratch_all, warp, lane, m0, n0, have_acc, ones_col, nhalves, trs); break;
+    case MFM_ACT_SIGMOID: tc_epilogue_t<MFM_ACT_SIGMOID>(ta, tmem_base, scratch_all, warp, lane, m0, n0, have_acc, ones_col, nhalves, trs); break;
+    default: tc_epilogue_t<MFM_ACT_NONE>(ta, tmem_base, scratch_all, warp, lane, m0, n0, have_acc, ones_col, nhalves, trs); break;
   }
 }

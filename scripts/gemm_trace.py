@@ -49,6 +49,15 @@ for mode, M, N, K in shapes:
     for c in list(range(min(nc, 8))) + list(range(max(8, nc - 3), nc)):
         print("   %3d  %7.0f %7.0f %7.0f %7.0f %7.0f   tma-lat %6.0f  convert %5.0f  conv->mma %5.0f" % (
             c, issue[c], fullw[c], arr[c], mmaw[c], commit[c], fullw[c] - issue[c], arr[c] - fullw[c], mmaw[c] - arr[c]))
+    if nch.max() < 31:
+        ep = t[:, 4 + 6 * 31:4 + 6 * 31 + 3].astype(np.float64)[first]
+        last_commit = st[first, nc - 1, 4]
+        print("   after the last commit (cycles, median): accumulator ready +%.0f, epilogue %.0f, final barrier +%.0f" % (
+            np.median(ep[:, 0] - last_commit), np.median(ep[:, 1] - ep[:, 0]), np.median(ep[:, 2] - ep[:, 1])))
+    if nch.max() < 30:
+        e6 = t[:, 4 + 6 * 30:4 + 6 * 30 + 6].astype(np.float64)[first]
+        d = np.median(e6[:, 1:] - e6[:, :-1], axis=0)
+        print("   epilogue of warp 0 (cycles, median): first tcgen05.ld %.0f, to scratch %.0f, first block stored %.0f, block 2 %.0f, block 3 %.0f" % tuple(d))
     if nc > 4:
         per_chunk = (commit[nc - 1] - commit[2]) / (nc - 3)
         print("   steady state: %.0f cycles per chunk per CTA; epilogue+teardown %.1f us" % (
