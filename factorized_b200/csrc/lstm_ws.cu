@@ -163,8 +163,9 @@ __device__ __forceinline__ const WsCell& ws_find(const WsBatch& bt, int bx) {
 // ----------------------------------------------------------------------------------------------------------------
 // forward
 // ----------------------------------------------------------------------------------------------------------------
-template <int NCH>
+template <int NCH, int NSG>      // chains per CTA; groups of 4 batch columns per warp and chain (2: 32-/64-row chains, 1: half as wide)
 __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_fwd_kernel(const __grid_constant__ WsBatch bt) {
+  static_assert((NCH * NSG) % 2 == 0, "the G_x double buffer needs an even number of column groups per step");
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar_done[WS_MAXCHAIN], bar_ready[WS_MAXCHAIN];
   __shared__ uint32_t tmem_holder;
@@ -313,13 +314,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_fwd_kernel(const __grid
       unsigned gx_step = (unsigned)B * (unsigned)ldgx;         // constant bias row (pitch 0) after gx_steps steps (decoder)
       const unsigned gt_step = (unsigned)B * (unsigned)H4;
       const unsigned cs_step = (unsigned)B * (unsigned)ldcs, hs_step = (unsigned)B * (unsigned)ldhs;
-      float cst[NCH][8];
+      float cst[NCH][4 * NSG];
 #pragma unroll
       for (int a = 0; a < NCH; ++a)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) cst[a][i] = 0.0f;
-      // every warp owns 8 columns per chain = two groups of 4: the group count is static, so the double-buffered G_x
-      // registers are indexed statically (a run-time parity put the buffers in local memory)
+        for (int i = 0; i < 4 * NSG; ++i) cst[a][i] = 0.0f;
+      // every warp owns NSG groups of 4 columns per chain: the group count is a template parameter, so the double-buffered
+      // G_x registers are indexed statically (a run-time parity put the buffers in local memory)
 
       float gx[2][4][4];
       for (int t = 0; t < T; ++t) {
@@ -348,10 +349,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_fwd_kernel(const __grid
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           WS_STAMP(warp, t, ch * 3 + 1);
 #pragma unroll
-          for (int sg = 0; sg < 2; ++sg) {
+          for (int sg = 0; sg < NSG; ++sg) {
             {
-              constexpr int nsg = 2;
-              const int cur = sg;                              // parity of this group in processing order
+              constexpr int nsg = NSG;
+              const int cur = (ch * NSG + sg) & 1;             // parity of this group in processing order
               float acc[4][4];
               if (ch == 0 && sg == 0) WS_STAMP(warp, t, 6);
 #pragma unroll
@@ -696,7 +697,7 @@ extern "C" int mfm_debug_set_lstm_trace(void* host) {
   return MFM_ERR_UNSUPPORTED;
 #endif
 }
-// variant ids: 0 fwd wide chains (32 / 64 rows), 1 fwd 16-row chains, 2 bwd wide, 3 bwd 16-row, 4 fwd CUDA-core fallback,
+// variant ids: 0 fwd wide chains (32 / 64 rows), 1 fwd half-width chains, 2 bwd wide, 3 bwd half-width, 4 fwd CUDA-core fallback,
 // 5 bwd CUDA-core fallback, 6 launches with one chain per CTA, 7 launches with two
 extern "C" unsigned long long mfm_debug_lstm_variant_count(int variant) {
   return (variant >= 0 && variant < 8) ? g_ws_counts[variant] : 0ull;
@@ -709,8 +710,9 @@ static size_t ws_plan(bool bwd, int h, int nb, int nchain, int limit, WsCell& lc
   if (nsub0 > 4) return 0;
   const int nsub = nsub0 < 2 ? 2 : nsub0;                   // layout: h <= 32 uses the two-copy layout with an empty sub-block
   const int R = nsub == 2 ? 2 : 1;
-  const int ncol = nb / (4 * R);                            // columns per warp and chain: 8 (forward), 8 or 4 (backward)
-  if (ncol * 4 * R != nb || !(ncol == 8 || (bwd && ncol == 4))) return 0;
+  const int ncol = nb / (4 * R);                            // columns per warp and chain: 8 or 4
+  if (ncol * 4 * R != nb || !(ncol == 8 || ncol == 4)) return 0;
+  if (!bwd && nchain == 1 && ncol == 4) return 0;           // (forward keeps an even number of column groups per step)
   lc.nb = nb;
   lc.nsub = nsub;
   lc.nact = nsub0 == 1 ? 8 : nsub0 == 3 ? 12 : 16;
@@ -737,9 +739,10 @@ static size_t ws_plan(bool bwd, int h, int nb, int nchain, int limit, WsCell& lc
   return 0;
 }
 
-// plans every cell for `nchain` chains per CTA; returns the CTA count (cells that do not fit are left out)
-static int ws_plan_all(bool bwd, const mfm_lstm_cell* cells, int ncells, int nchain, int lim, WsBatch& bt, size_t& smem,
-                       mfm_lstm_cell* rest, int* nrest) {
+// plans every cell for `nchain` chains per CTA, wide (8 columns per warp and chain) or narrow (4); returns the CTA count,
+// -1 when a cell fits on chip but not in this shape (cells that fit in no shape go to `rest`)
+static int ws_plan_all(bool bwd, const mfm_lstm_cell* cells, int ncells, int nchain, bool narrow, int lim, WsBatch& bt,
+                       size_t& smem, mfm_lstm_cell* rest, int* nrest) {
   bt.n = 0;
   *nrest = 0;
   smem = 0;
@@ -747,13 +750,22 @@ static int ws_plan_all(bool bwd, const mfm_lstm_cell* cells, int ncells, int nch
     const mfm_lstm_cell& c = cells[i];
     WsCell lc;
     size_t s = 0;
+    bool any = false;
     if (c.h >= 1 && c.h <= 128) {
-      // widest chains first (64 rows for the replicated layouts, 32 otherwise); 16 rows when shared memory demands it
-      static const int order[3] = {64, 32, 16}, narrow_first[3] = {16, 32, 64};
-      const int* cand = g_ws_force_nb == 16 ? narrow_first : order;
-      for (int k = 0; k < 3 && !s; ++k) s = ws_plan(bwd, c.h, cand[k], nchain, lim, lc);
+      const int nb_wide = c.h <= 64 ? 64 : 32;              // two-copy layouts take chains twice as wide
+      const int nb = narrow ? nb_wide / 2 : nb_wide;
+      s = ws_plan(bwd, c.h, nb, nchain, lim, lc);
+      if (!s) {                                             // would any other shape hold it?  then the caller tries that shape
+        WsCell tmp;
+        for (int nc = 1; nc <= 2 && !any; ++nc)
+          for (int w = 0; w < 2 && !any; ++w) any = ws_plan(bwd, c.h, w ? nb_wide / 2 : nb_wide, nc, lim, tmp) != 0;
+      }
     }
-    if (!s) { rest[(*nrest)++] = c; continue; }
+    if (!s) {
+      if (any) return -1;
+      rest[(*nrest)++] = c;
+      continue;
+    }
     lc.c = c;
     bt.c[bt.n++] = lc;
     if (s > smem) smem = s;
@@ -777,25 +789,44 @@ static int ws_launch(bool bwd, const mfm_lstm_cell* cells, int ncells, mfm_lstm_
   const int lim = ws_smem_limit();
   WsBatch bt;
   size_t smem = 0;
-  // two chains per CTA hide each other's gate GEMM; when that leaves most SMs without a CTA (a single decoder cell,
-  // small batches), one chain per CTA spreads the chains over twice as many SMs instead
   if (const char* e = getenv("MFM_WS_CHAINS")) g_ws_force_chains = atoi(e) == 1 ? 1 : atoi(e) == 2 ? 2 : 0;
-  int nchain = g_ws_force_chains ? g_ws_force_chains : 2;
-  int total = ws_plan_all(bwd, cells, ncells, nchain, lim, bt, smem, rest, nrest);
-  if (!g_ws_force_chains && bt.n && total * 3 < mfm_dev_info().sms * 2) {
-    nchain = 1;
-    total = ws_plan_all(bwd, cells, ncells, nchain, lim, bt, smem, rest, nrest);
+  // Shapes, in order of preference: two wide chains per CTA (each hides the other's gate GEMM); when that leaves most
+  // SMs without a CTA (a single decoder cell, small batches), two chains of half the width -- twice the CTAs, the GEMMs
+  // still hidden; one wide chain per CTA when shared memory holds nothing else.
+  struct Shape { int nchain; bool narrow; };
+  Shape order[3] = {{2, false}, {2, true}, {1, false}};
+  if (g_ws_force_nb == 16) { order[0] = {2, true}; order[1] = {2, false}; }
+  if (g_ws_force_chains == 1) { order[0] = {1, false}; order[1] = {2, false}; order[2] = {2, true}; }
+  const int want = mfm_dev_info().sms * 2 / 3;
+  int pick = -1;
+  for (int k = 0; k < 3; ++k) {
+    const int t = ws_plan_all(bwd, cells, ncells, order[k].nchain, order[k].narrow, lim, bt, smem, rest, nrest);
+    if (t < 0) continue;                                    // a cell does not take this shape
+    pick = k;
+    // keep looking for a shape with more CTAs only when this one under-fills the GPU and nothing forces the choice
+    if (t >= want || g_ws_force_nb == 16 || g_ws_force_chains || order[k].narrow) break;
   }
-  if (!bt.n) return MFM_OK;
-  for (int i = 0; i < bt.n; ++i) g_ws_counts[(bwd ? 2 : 0) + (bt.c[i].nb == 16 ? 1 : 0)] += 1;
+  if (pick < 0) {                                           // (cannot happen: every on-chip cell takes the last shape or none)
+    *nrest = 0;
+    for (int i = 0; i < ncells; ++i) rest[(*nrest)++] = cells[i];
+    return MFM_OK;
+  }
+  const int nchain = order[pick].nchain;
+  const bool narrow = order[pick].narrow;
+  const int total = ws_plan_all(bwd, cells, ncells, nchain, narrow, lim, bt, smem, rest, nrest);
+  if (!bt.n) return MFM_OK;                                 // nothing fits on chip: all cells are in `rest`
+  for (int i = 0; i < bt.n; ++i) g_ws_counts[(bwd ? 2 : 0) + (narrow ? 1 : 0)] += 1;
   g_ws_counts[nchain == 1 ? 6 : 7] += 1;
   int e = 0;
   if (bwd) {
     if (nchain == 1) { if (!(e = mfm_func_smem_t(lstm_ws_bwd_kernel<1>, lim))) lstm_ws_bwd_kernel<1><<<total, WS_THREADS, smem, st>>>(bt); }
     else             { if (!(e = mfm_func_smem_t(lstm_ws_bwd_kernel<2>, lim))) lstm_ws_bwd_kernel<2><<<total, WS_THREADS, smem, st>>>(bt); }
+  } else if (nchain == 1) {
+    if (!(e = mfm_func_smem_t(lstm_ws_fwd_kernel<1, 2>, lim))) lstm_ws_fwd_kernel<1, 2><<<total, WS_THREADS, smem, st>>>(bt);
+  } else if (narrow) {
+    if (!(e = mfm_func_smem_t(lstm_ws_fwd_kernel<2, 1>, lim))) lstm_ws_fwd_kernel<2, 1><<<total, WS_THREADS, smem, st>>>(bt);
   } else {
-    if (nchain == 1) { if (!(e = mfm_func_smem_t(lstm_ws_fwd_kernel<1>, lim))) lstm_ws_fwd_kernel<1><<<total, WS_THREADS, smem, st>>>(bt); }
-    else             { if (!(e = mfm_func_smem_t(lstm_ws_fwd_kernel<2>, lim))) lstm_ws_fwd_kernel<2><<<total, WS_THREADS, smem, st>>>(bt); }
+    if (!(e = mfm_func_smem_t(lstm_ws_fwd_kernel<2, 2>, lim))) lstm_ws_fwd_kernel<2, 2><<<total, WS_THREADS, smem, st>>>(bt);
   }
   if (e) return e;
   MFM_LAUNCH_CHECK();

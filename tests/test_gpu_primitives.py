@@ -227,7 +227,7 @@ def test_lstm_multi_cell_launch(ops, B, hs):
     ops.lstm_fwd(dev)
     torch.cuda.synchronize()
     after = _variant_counts(ops)
-    assert after[0] - before[0] == len(cells), (before, after)       # every cell ran on the 32-row tensor-core chains
+    assert (after[0] + after[1]) - (before[0] + before[1]) == len(cells), (before, after)   # every cell on the tensor-core chains
     for c, d in zip(cells, dev):
         for k in ("hs", "cs", "gates"):
             assert rel_l2(d[k], c[k]) < 1e-4, (k, c["h"], rel_l2(d[k], c[k]))
@@ -269,10 +269,11 @@ def test_lstm_variants_are_the_ones_intended(ops):
         assert rel_l2(cg["hs"], c["hs"]) < 1e-4 and rel_l2(cg["gates"], c["gates"]) < 1e-4
         assert rel_l2(cbg["dG"], cb["dG"]) < 1e-4
         return [a - b for a, b in zip(after, before)]
-    assert run(88, 300) == [1, 0, 1, 0, 0, 0]                 # 32-row chains both ways
-    assert run(88, 300, force=16) == [1, 0, 0, 1, 0, 0]       # 16-row chains forced (backward only: forward has no such form)
+    assert run(88, 300) == [1, 0, 1, 0, 0, 0]                 # wide (32-row) chains both ways
+    assert run(88, 300, force=16) == [0, 1, 0, 1, 0, 0]       # half-width (16-row) chains forced
     assert run(104, 300) == [1, 0, 0, 1, 0, 0]                # backward of h = 104 only fits with 16-row chains
-    assert run(48, 300, force=16) == [1, 0, 1, 0, 0, 0]       # two-copy layouts have no 16-row form
+    assert run(48, 300, force=16) == [0, 1, 0, 1, 0, 0]       # two-copy layout: 64-row chains wide, 32-row half-width
+    assert run(24, 300) == [1, 0, 1, 0, 0, 0] and run(24, 300, force=16) == [0, 1, 0, 1, 0, 0]
     assert run(200, 50) == [0, 0, 0, 0, 1, 1]                 # h > 128: CUDA-core kernels
 
 
