@@ -180,18 +180,38 @@ __global__ void __launch_bounds__(256) mmd_kexp_kernel(int M, int N, float* __re
                                                         const float* __restrict__ ny, float inv_d2, double weight,
                                                         float* __restrict__ slot, double* __restrict__ slot64) {
   __shared__ double red[8];
-  const long long total = (long long)M * N;
+  // one warp per row at a time, lanes along the row (float4 when the row allows): no 64-bit index division per element
+  // (the first version spent most of its 26 us per 2048 x 2048 matrix on exactly that)
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const bool vec = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0) && ((reinterpret_cast<uintptr_t>(ny) & 15) == 0);
   double acc = 0.0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int m = (int)(i / N), n = (int)(i - (long long)m * N);
-    const float d2 = fmaxf(__ldg(nx + m) + __ldg(ny + n) - 2.0f * S[i], 0.0f);
-    const float k = expf(-d2 * inv_d2);
-    S[i] = k;
-    acc += (double)k;
+  for (int m = blockIdx.x * 8 + wib; m < M; m += gridDim.x * 8) {
+    const float nxm = __ldg(nx + m);
+    float* row = S + (long long)m * N;
+    float racc = 0.0f;                                        // one row's share of a lane: <= N/32 values in (0, 1]
+    if (vec) {
+      for (int n = lane * 4; n < N; n += 128) {
+        float4 s4 = *reinterpret_cast<const float4*>(row + n);
+        const float4 y4 = __ldg(reinterpret_cast<const float4*>(ny + n));
+        s4.x = expf(-fmaxf(nxm + y4.x - 2.0f * s4.x, 0.0f) * inv_d2);
+        s4.y = expf(-fmaxf(nxm + y4.y - 2.0f * s4.y, 0.0f) * inv_d2);
+        s4.z = expf(-fmaxf(nxm + y4.z - 2.0f * s4.z, 0.0f) * inv_d2);
+        s4.w = expf(-fmaxf(nxm + y4.w - 2.0f * s4.w, 0.0f) * inv_d2);
+        *reinterpret_cast<float4*>(row + n) = s4;
+        racc += (s4.x + s4.y) + (s4.z + s4.w);
+      }
+    } else {
+      for (int n = lane; n < N; n += 32) {
+        const float k = expf(-fmaxf(nxm + __ldg(ny + n) - 2.0f * row[n], 0.0f) * inv_d2);
+        row[n] = k;
+        racc += k;
+      }
+    }
+    acc += (double)racc;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  if (lane == 0) red[wib] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double tot = 0.0;
@@ -230,7 +250,7 @@ extern "C" int mfm_rownorm2(int B, int dim, const float* x, long long ld, float*
 static int mmd_kexp_launch(int M, int N, float* S, const float* nx, const float* ny, int dim, double weight, float* slot,
                            double* slot64, void* stream) {
   MFM_REQUIRE(M > 0 && N > 0 && dim > 0 && S && nx && ny && (slot || slot64));
-  long long blocks = ((long long)M * N + 256 * 8 - 1) / (256 * 8);
+  long long blocks = (M + 7) / 8;
   if (blocks > mfm_dev_info().sms * 8) blocks = mfm_dev_info().sms * 8;
   if (blocks < 1) blocks = 1;
   mmd_kexp_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(M, N, S, nx, ny, 1.0f / ((float)dim * (float)dim), weight, slot,

@@ -88,10 +88,11 @@ class Engine:
         self.use_side_stream = True
         self._side = None
         self._side_used = False
-        self._aux_stream = None
-        self._aux_used = False
+        self._aux_streams = {}           # the MMD / KL terms of the four latents run on their own streams, side by side
+        self._aux_used = set()
         self._pool = []                  # streams for _par branches
-        self._z_ready = None             # event: encoder latents written (they are produced on the auxiliary stream)
+        self._z_ready = None             # events: encoder latents written (they are produced on the auxiliary streams)
+        self._mmd_pending = False        # MMD accumulators (double) not yet folded into loss_buf[4:8]
         self.stamps, self.stamp_names = None, []      # debug timeline (mark)
         # two launches for the last backward recurrence (heavy cells first, their weight gradients start early): measured
         # SLOWER (3.67 vs 3.56 ms/step: the gradient GEMMs delay the second launch), kept as an experiment switch
@@ -195,10 +196,13 @@ class Engine:
         #     path needs them, so they leave the main stream here and overlap the attention / memory chain
         Z = [buf("Z%d" % m, B, dm.z[m]) for m in range(3)] if full else []
         if full:
-            with self._aux():
-                if self.kl:
-                    ops.zero(self.loss_buf[4:8])
-                for m, tag in enumerate(TAGS):
+            if self.kl:
+                ops.zero(self.loss_buf[4:8])
+            else:
+                ops.zero(self.mmd_acc.view(torch.float32))
+            self._z_ready = []
+            for m, tag in enumerate(TAGS):
+                with self._aux(m):
                     zlast = buf("Zlast%d" % m, B, dm.z[m]) if self.kl else Z[m]
                     ops.gemm("nt", self.ws["hsE%d" % m][TB:], P["encoder_%s.fc1.weight" % tag], zlast,
                              bias=P["encoder_%s.fc1.bias" % tag])
@@ -207,11 +211,9 @@ class Engine:
                         ops.gemm("nt", zlast, P["last_to_z%s_fc1.weight" % tag], Z[m], bias=P["last_to_z%s_fc1.bias" % tag])
                         ops.gemm("nt", zlast, P["last_to_logvarz%s_fc1.weight" % tag], lv, bias=P["last_to_logvarz%s_fc1.bias" % tag])
                         ops.kld_fwd(Z[m], lv, self.loss_buf[4 + m:5 + m])
-                self._z_ready = self._aux_event()
-                if not self.kl:
-                    ops.zero(self.mmd_acc.view(torch.float32))
-                    for k in range(3):
-                        self._mmd(k, Z[k])
+                    self._z_ready.append(self._aux_event(m))
+                    if not self.kl:
+                        self._mmd(m, Z[m])
 
         # (4) MFN attention for all T at once (:171-176); only gamma*_fc1's memory columns are sequential
         pre = self.pre
@@ -266,7 +268,7 @@ class Engine:
         ops.gemm("nt", mems[TB:], Wzy[:, H:], ZY, accumulate=True)
 
         # (7) MMD of z_y (the encoder latents went out in step 3); same auxiliary stream, off the critical path
-        with self._aux():
+        with self._aux(3):
             if self.kl:                                           # log-variance of z_y and its KL term (mfm_model.py:744,746)
                 Wlv = P["last_to_logvarzy_fc1.weight"]
                 LVY = buf("LVY", B, dm.zy)
@@ -275,10 +277,10 @@ class Engine:
                 ops.kld_fwd(ZY, LVY, self.loss_buf[7:8])
             else:
                 self._mmd(3, ZY)
-                ops.mmd_fold(self.mmd_acc, self.loss_buf[4:8])
-        if self._z_ready is not None:                      # the factor MLPs read Z, produced on the auxiliary stream
-            torch.cuda.current_stream(self.device).wait_event(self._z_ready)
-            self._z_ready = None
+        for ev in (self._z_ready or []):                   # the factor MLPs read Z, produced on the auxiliary streams
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+        self._z_ready = None
 
         # (8) factor MLPs (:539-542) written straight into the decoder inputs cat(fy, f_m) (:544-546).
         #     The four MLPs, and below the three decoders, are independent of each other: branches run side by side.
@@ -474,23 +476,24 @@ class Engine:
 
     # -- the MMD statistic is off the critical path: it runs on its own stream -------
     class _Aux:
-        """``with eng._aux():`` runs the body on the auxiliary stream, forked from the main stream at entry."""
+        """``with eng._aux(k):`` runs the body on auxiliary stream k, forked from the main stream at entry."""
 
-        def __init__(self, eng):
-            self.eng, self.ctx = eng, None
+        def __init__(self, eng, k):
+            self.eng, self.k, self.ctx = eng, k, None
 
         def __enter__(self):
             e = self.eng
             if e.device.type != "cuda" or not e.use_side_stream:
                 return self
-            if e._aux_stream is None:
-                e._aux_stream = torch.cuda.Stream(device=e.device)
+            st = e._aux_streams.get(self.k)
+            if st is None:
+                st = e._aux_streams[self.k] = torch.cuda.Stream(device=e.device)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(e.device))
-            e._aux_stream.wait_event(ev)
-            self.ctx = torch.cuda.stream(e._aux_stream)
+            st.wait_event(ev)
+            self.ctx = torch.cuda.stream(st)
             self.ctx.__enter__()
-            e._aux_used = True
+            e._aux_used.add(self.k)
             return self
 
         def __exit__(self, *a):
@@ -498,15 +501,15 @@ class Engine:
                 self.ctx.__exit__(*a)
             return False
 
-    def _aux(self):
-        return Engine._Aux(self)
+    def _aux(self, k=0):
+        return Engine._Aux(self, k)
 
-    def _aux_event(self):
-        """Event at the current point of the auxiliary stream (None on the CPU test double)."""
+    def _aux_event(self, k=0):
+        """Event at the current point of auxiliary stream k (None on the CPU test double)."""
         if self.device.type != "cuda" or not self.use_side_stream:
             return None
         ev = torch.cuda.Event()
-        ev.record(self._aux_stream)
+        ev.record(self._aux_streams[k])
         return ev
 
     def _mmd(self, k, zk):
@@ -516,9 +519,10 @@ class Engine:
         d/dz = (2c/B^2) [ (rowsum Kzz - colsum Kgz) * z - Kzz Z + Kgz^T G ], c = -2/dim^2 -- the column sums and the two
         products; backward() only combines them.  So neither direction of the MMD sits on the step's critical path."""
         ops, buf, B = self.ops, self.buf, self.dm.B
+        self._mmd_pending = True
         gk, dim = self.noise[k], zk.shape[1]
         nz, ng = buf("mmd_nz%d" % k, B), buf("mmd_ng%d" % k, B)
-        Kzz, Kgz, Kgg = buf("Kzz%d" % k, B, B), buf("Kgz%d" % k, B, B), buf("Kgg", B, B)
+        Kzz, Kgz, Kgg = buf("Kzz%d" % k, B, B), buf("Kgz%d" % k, B, B), buf("Kgg%d" % k, B, B)
         inv_bb = 1.0 / (float(B) * float(B))
         slot = self.mmd_acc[k:k + 1]                   # double: the three means cancel to O(1/B)
         ops.rownorm2(zk, nz)
@@ -538,9 +542,15 @@ class Engine:
         ops.gemm("tn", Kgz, gk, t12[B:], accumulate=True)
 
     def _join_aux(self):
-        if self._aux_stream is not None and self._aux_used:
-            torch.cuda.current_stream(self.device).wait_stream(self._aux_stream)
-            self._aux_used = False
+        """Join the auxiliary streams; the four double MMD accumulators are folded into the fp32 loss buffer here."""
+        if self._aux_used:
+            main = torch.cuda.current_stream(self.device)
+            for k in sorted(self._aux_used):
+                main.wait_stream(self._aux_streams[k])
+            self._aux_used = set()
+        if self._mmd_pending:
+            self.ops.mmd_fold(self.mmd_acc, self.loss_buf[4:8])
+            self._mmd_pending = False
 
     # -- backward ------------------------------------------------------------------
     def backward(self, P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], dXhat: Sequence[torch.Tensor],
@@ -579,8 +589,8 @@ class Engine:
         lat = [ws["Z0"], ws["Z1"], ws["Z2"], ws["ZY"]]
         dmmd = [buf("dZmmd%d" % k, B, lat[k].shape[1]) for k in range(4)]
         dLV = [buf("dLV%d" % k, B, lat[k].shape[1]) for k in range(4)] if self.kl else None
-        with self._aux():
-            for k in range(4):
+        for k in range(4):
+            with self._aux(k):
                 ops.zero(dmmd[k])
                 if self.kl:                                       # d KLD / d mu and / d logvar, scaled by dLoss/dKLD
                     ops.kld_bwd(lat[k], ws["LV%d" % k] if k < 3 else ws["LVY"], mmd_scale, dmmd[k], dLV[k], mmd_scale_dev)
