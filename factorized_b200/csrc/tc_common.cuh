@@ -14,6 +14,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 // that never completes traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+#pragma unroll 1
   for (int spin = 0; spin < (1 << 22); ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"

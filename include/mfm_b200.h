@@ -139,6 +139,11 @@ int mfm_debug_lstm_force_chains(int n);        /* chains (batch sub-tiles) per C
  * recurrence launch records clock stamps per warp and step (wait start, wait done, epilogue done, MMA issue done). */
 int mfm_debug_set_lstm_trace(void* device_buf);
 unsigned long long mfm_debug_lstm_variant_count(int variant);
+/* Launches of the persistent streaming GEMM (csrc/gemm_ps.cu) since load: the tests assert that the large-M layers run on it. */
+int mfm_debug_gemm_ps_count(void);
+/* Debug aid (scripts/gemm_ps_trace.py; library built with -DPS_DEBUG=1, else MFM_ERR_UNSUPPORTED): while a device buffer of
+ * 148 * (4 + 6*64 + 4*16) int64 is registered, every CTA of the persistent GEMM records clock stamps of its roles. */
+int mfm_debug_set_gemm_ps_trace(void* device_buf);
 
 /* The MFN memory recurrence, mfm_model.py:177-180, T steps in one kernel:
  * u_k = dropout(relu(Gkpre[t] + mem W_km^T));  gamma_k = sig(u_k W_k2^T + b_k2);
