@@ -286,9 +286,13 @@ static int mem_validate(const mfm_mem_args* a, bool bwd) {
   return MFM_OK;
 }
 
+int mem_ws_launch(const mfm_mem_args* a, bool bwd, cudaStream_t st);     // mem_ws.cu: the tensor-core form, where it applies
+
 extern "C" int mfm_mfn_mem_fwd(const mfm_mem_args* a, void* stream) {
   int rc = mem_validate(a, false);
   if (rc) return rc;
+  rc = mem_ws_launch(a, false, (cudaStream_t)stream);
+  if (rc != MFM_ERR_UNSUPPORTED) return rc;
   const int G = a->g1 + a->g2;
   size_t base = (size_t)(MEM_RT * (ru4(a->mem) + ru4(a->g1) + ru4(a->g2)) + 2 * MEM_RT * a->mem) * 4;
   size_t full = base + (size_t)(2 * a->mem * G) * 4;
@@ -305,6 +309,8 @@ extern "C" int mfm_mfn_mem_fwd(const mfm_mem_args* a, void* stream) {
 extern "C" int mfm_mfn_mem_bwd(const mfm_mem_args* a, void* stream) {
   int rc = mem_validate(a, true);
   if (rc) return rc;
+  rc = mem_ws_launch(a, true, (cudaStream_t)stream);
+  if (rc != MFM_ERR_UNSUPPORTED) return rc;
   const int G = a->g1 + a->g2;
   size_t base = (size_t)(MEM_RT * (3 * ru4(a->mem) + ru4(a->g1) + ru4(a->g2))) * 4;
   size_t full = base + (size_t)(2 * a->mem * G) * 4;

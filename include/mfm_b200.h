@@ -171,6 +171,10 @@ typedef struct mfm_mem_args {
 } mfm_mem_args;
 int mfm_mfn_mem_fwd(const mfm_mem_args* a, void* stream);
 int mfm_mfn_mem_bwd(const mfm_mem_args* a, void* stream);
+/* Test hooks: the recurrence runs on the tensor cores (csrc/mem_ws.cu) when mem <= 64 and g1, g2 <= 128, else on CUDA cores
+ * (csrc/mfn.cu); force the latter (on != 0), and read how many launches the tensor-core kernels have served since load. */
+int mfm_debug_mem_force_simt(int on);
+unsigned long long mfm_debug_mem_ws_count(int bwd);
 
 /* attention = softmax(L, dim=1) (in place); attended = attention * cstar  (mfm_model.py:174-175) */
 int mfm_softmax_gate_fwd(int M, int N, float* L, const float* cstar, float* attended, void* stream);

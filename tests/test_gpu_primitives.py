@@ -291,9 +291,24 @@ def test_lstm_gx_leading_dimension(ops):
         assert rel_l2(d["hs"], c["hs"]) < 1e-4 and rel_l2(d["gates"], c["gates"]) < 1e-4
 
 
+@pytest.mark.parametrize("simt", [False, True])
 @pytest.mark.parametrize("T,B,mem,g1,g2,drop", [(3, 5, 9, 12, 13, False), (4, 21, 64, 128, 128, True), (2, 7, 300, 256, 32, False),
-                                                (20, 64, 64, 128, 128, False)])
-def test_mfn_mem_fwd_bwd(ops, T, B, mem, g1, g2, drop):
+                                                (20, 64, 64, 128, 128, False), (1, 16, 32, 128, 40, True), (5, 161, 64, 100, 128, True),
+                                                (3, 33, 16, 16, 16, False)])
+def test_mfn_mem_fwd_bwd(ops, T, B, mem, g1, g2, drop, simt):
+    """Both forms of the recurrence: tcgen05 (csrc/mem_ws.cu; mem <= 64, g <= 128) and CUDA cores (csrc/mfn.cu)."""
+    ops.lib.mfm_debug_mem_force_simt(1 if simt else 0)
+    n0 = [ops.lib.mfm_debug_mem_ws_count(i) for i in (0, 1)]
+    try:
+        _mfn_mem_case(ops, T, B, mem, g1, g2, drop)
+    finally:
+        ops.lib.mfm_debug_mem_force_simt(0)
+    used = [ops.lib.mfm_debug_mem_ws_count(i) - n0[i] for i in (0, 1)]
+    want = 1 if (not simt and mem <= 64 and g1 <= 128 and g2 <= 128) else 0
+    assert used == [want, want], (used, want)
+
+
+def _mfn_mem_case(ops, T, B, mem, g1, g2, drop):
     TB = T * B
     Wg1, Wg2 = g(g1, 20 + mem, seed=1, scale=0.2), g(g2, 20 + mem, seed=2, scale=0.2)
     rng = torch.tensor([5, 2], dtype=torch.int64)
