@@ -460,7 +460,7 @@ class Engine:
             return
         main = torch.cuda.current_stream(self.device)
         while len(self._pool) < len(thunks) - 1:
-            self._pool.append(torch.cuda.Stream(device=self.device))
+            self._pool.append(torch.cuda.Stream(device=self.device, priority=-1))
         ev = torch.cuda.Event()
         ev.record(main)
         used = []

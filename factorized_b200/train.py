@@ -149,7 +149,9 @@ class MFMTrainer:
             # all-reduce + Adam (3 launches) stay eager on the same stream -- the collective is not captured.
             g = torch.cuda.CUDAGraph()
             n0 = self.ops.launches
-            with torch.cuda.graph(g):
+            # the capture stream (and the engine's branch pool) are HIGH priority, the weight-gradient and MMD streams normal:
+            # kernel nodes inherit it, so when SMs free up the critical chain's CTAs are placed before the background work's
+            with torch.cuda.graph(g, stream=torch.cuda.Stream(device=self.dev, priority=-1)):
                 if self.world > 1:
                     self._schedule_compute()
                 else:
