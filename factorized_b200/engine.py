@@ -88,6 +88,8 @@ class Engine:
         self.use_side_stream = True
         self._side = None
         self._side_used = False
+        self._enc_stream = None          # the encoder cells' backward runs beside the MFN backward
+        self._enc_used = False
         self._aux_streams = {}           # the MMD / KL terms of the four latents run on their own streams, side by side
         self._aux_used = set()
         self._pool = []                  # streams for _par branches
@@ -446,6 +448,9 @@ class Engine:
             for st in self._side:
                 main.wait_stream(st)
             self._side_used = False
+        if self._enc_used:
+            torch.cuda.current_stream(self.device).wait_stream(self._enc_stream)
+            self._enc_used = False
 
     # -- independent small branches run side by side -------------------------------------
     def _par(self, thunks):
@@ -695,6 +700,24 @@ class Engine:
             enc_cells.append(dict(T=T, B=B, h=dm.z[m], gates=ws["gatesE%d" % m], cs=ws["csE%d" % m],
                                   W=P["encoder_%s.lstm.weight_hh" % tag], dh_all=None, dh_last=dhl, dc_ext=None,
                                   dG=buf("dGE%d" % m, TB, 4 * dm.z[m]), dc_scratch=buf("dcSE%d" % m, B, dm.z[m])))
+        # The encoder cells hang off the latents only: their recurrence and weight gradients do not wait for the attention /
+        # memory chain.  They leave the main stream here (one launch for the three cells, then their weight gradients) and
+        # run under the MFN backward; only the three MFN cells remain in the last recurrence launch of the step.
+        if self.device.type == "cuda" and self.use_side_stream and not self.split_last_recurrence:
+            if self._enc_stream is None:
+                self._enc_stream = torch.cuda.Stream(device=self.device)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._enc_stream.wait_event(ev)
+            with torch.cuda.stream(self._enc_stream):
+                ops.lstm_bwd(enc_cells)
+                for m, c in enumerate(enc_cells):
+                    nm = "encoder_%s.lstm" % TAGS[m]
+                    ops.gemm_tn_pair(c["dG"], self.xs[m], G[nm + ".weight_ih"], G[nm + ".bias_ih"], ws["hsE%d" % m][:TB],
+                                     G[nm + ".weight_hh"])
+                    ops.copy2d(G[nm + ".bias_ih"].view(1, -1), G[nm + ".bias_hh"].view(1, -1), accumulate=True)
+            self._enc_used = True
+            enc_cells = []
         self._backward_mfn(P, G, dHlast, dmemT, enc_cells, wgrad, bgrad, lin_bwd, relu_scale)
         self.mark("bwd:lstm enc+mfn")
         self._join_side()
