@@ -25,6 +25,16 @@
 #include <cstdlib>
 #include "tc_common.cuh"
 
+// -DMW_DEBUG=1 compiles clock stamps of CTA 0 into the forward kernel (scripts/mem_trace.py)
+#ifndef MW_DEBUG
+#define MW_DEBUG 0
+#endif
+#if MW_DEBUG
+__device__ long long g_mw_trace[32 * 16];                 // [step][slot]
+#define MW_STAMP(t, k) do { if (blockIdx.x == 0 && (t) < 32) g_mw_trace[(t) * 16 + (k)] = clock64(); } while (0)
+#else
+#define MW_STAMP(t, k) do { } while (0)
+#endif
 #define MW_NB 16                      // batch rows per CTA = UMMA N
 #define MW_CW 8                       // compute warps
 #define MW_THREADS ((MW_CW + 4) * 32)
@@ -225,12 +235,16 @@ __global__ void __launch_bounds__(MW_THREADS, 1) mem_ws_fwd_kernel(const __grid_
       for (int t = 0; t < T; ++t) {
         if (t > 0) mw_wait(smem_u32(&bars[0]), (uint32_t)((t - 1) & 1));         // mem_{t-1} is in shared memory
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (q == 3) MW_STAMP(t, 0);
         mw_issue(tA, smem_u32(smem + d.offW[k]), d.KM, smem_u32(opM), kk0, idesc);
         umma_commit(smem_u32(&bars[1]));
+        if (q == 3) MW_STAMP(t, 1);
         mw_wait(smem_u32(&bars[2]), (uint32_t)(t & 1));                          // u_1, u_2 are in shared memory
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (q == 3) MW_STAMP(t, 2);
         mw_issue(tB, smem_u32(smem + d.offW[2 + k]), k ? d.K2 : d.K1, smem_u32(k ? opU2 : opU1), kk0, idesc);
         umma_commit(smem_u32(&bars[3]));
+        if (q == 3) MW_STAMP(t, 3);
       }
     }
   } else {
@@ -268,13 +282,16 @@ __global__ void __launch_bounds__(MW_THREADS, 1) mem_ws_fwd_kernel(const __grid_
       // ---- stage 1: u_k = dropout(relu(Gkpre[t] + mem W_km^T)) ----
 #pragma unroll
       for (int c = 0; c < 4; ++c) ch[c] = __ldg(a.cHat + (tb + row0 + min(c0 + c, nvalid - 1)) * mem + jc);
+      if (tid == 0) MW_STAMP(t, 4);
       mw_wait(smem_u32(&bars[1]), (uint32_t)(t & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (tid == 0) MW_STAMP(t, 5);
       {
         float acc[16], acc2[16];
         mw_ld16(tl + (uint32_t)(half * MW_NB), acc);
         if (two_a) mw_ld16(tl + (uint32_t)((2 + half) * MW_NB), acc2);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (tid == 0) MW_STAMP(t, 6);
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
           float v = gp[b] + acc[b];
@@ -287,14 +304,18 @@ __global__ void __launch_bounds__(MW_THREADS, 1) mem_ws_fwd_kernel(const __grid_
           if (u_on) mw_put(opU, planeU, b, u, b < nvalid ? v : 0.0f);
         }
       }
+      if (tid == 0) MW_STAMP(t, 7);
       MW_PUBLISH(bars[2]);
+      if (tid == 0) MW_STAMP(t, 8);
       // ---- stage 2: gamma_k = sigmoid(u_k W_k2^T + b_k2);  mem' = gamma_1 mem + gamma_2 cHat[t] ----
       if (t + 1 < T) {
 #pragma unroll
         for (int b = 0; b < 16; ++b) gp[b] = __ldg(gpre + (tb + B + row0 + min(b, nvalid - 1)) * gk + uc);
       }
+      if (tid == 0) MW_STAMP(t, 9);
       mw_wait(smem_u32(&bars[3]), (uint32_t)(t & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (tid == 0) MW_STAMP(t, 10);
       {
         float p1[4], p1b[4], p2[4], p2b[4];
         mw_ld4(tl + (uint32_t)(64 + c0), p1);
@@ -319,7 +340,9 @@ __global__ void __launch_bounds__(MW_THREADS, 1) mem_ws_fwd_kernel(const __grid_
           if (j_on) mw_put(opM, planeM, col, j, nm);
         }
       }
+      if (tid == 0) MW_STAMP(t, 11);
       if (t + 1 < T) MW_PUBLISH(bars[0]);
+      if (tid == 0) MW_STAMP(t, 12);
     }
   }
   MW_END();
@@ -465,6 +488,14 @@ __global__ void __launch_bounds__(MW_THREADS, 1) mem_ws_bwd_kernel(const __grid_
 static unsigned long long g_mw_counts[2];
 static int g_mw_off = 0;
 extern "C" int mfm_debug_mem_ws_flags(int f) { return (int)cudaMemcpyToSymbol(g_mw_dbg, &f, sizeof(int)); }
+extern "C" int mfm_debug_mem_ws_trace(long long* host32x16) {
+#if MW_DEBUG
+  return (int)cudaMemcpyFromSymbol(host32x16, g_mw_trace, sizeof(long long) * 32 * 16);
+#else
+  (void)host32x16;
+  return MFM_ERR_UNSUPPORTED;
+#endif
+}
 extern "C" int mfm_debug_mem_force_simt(int on) { g_mw_off = on; return MFM_OK; }
 extern "C" unsigned long long mfm_debug_mem_ws_count(int bwd) { return g_mw_counts[bwd ? 1 : 0]; }
 
