@@ -424,7 +424,8 @@ def main():
                            tflops=(round(v[1] / (v[0] * 1e-3) / 1e12, 3) if v[1] else None),
                            gbs=(round(v[3] / (v[0] * 1e-3) / 1e9, 1) if v[3] else None)) for k, v in
                    sorted(agg.items(), key=lambda kv: -kv[1][0])}
-        # The dominant kernel is the pipelined tcgen05 GEMM (gemm_tcp_kernel: every GEMM of M*N*K >= 2^20).  It is
+        # The dominant kernel class is the streamed tcgen05 GEMM (gemm_ps_kernel for activations x weights, gemm_tcp_kernel for
+        # the weight gradients and the masked / accumulating epilogues: every GEMM of M*N*K >= 2^20).  It is
         # HBM-bound by design (N, K <= 512 against T*B rows): achieved = algorithmic bytes of those launches / their
         # CUDA-event time in one eager pass (per call: the weight pre-split kernel, when there is one, is inside the
         # bracket).  `traffic` = DRAM bytes per launch that ncu --set full measured for the largest streamed shape of this
@@ -447,7 +448,8 @@ def main():
             if k in kernels and kernels[k]["tflops"]:
                 lstm[k] = dict(us_per_step=round(kernels[k]["ms_per_step"] * 1e3, 1), tflops=kernels[k]["tflops"],
                                frac_of_bf16_peak=round(kernels[k]["tflops"] / pk["bf16"], 5))
-        roof = dict(bound="hbm", kernel="gemm_tcp_kernel (pipelined tcgen05 GEMM: the %d launches/step with M*N*K >= 2^20)"
+        roof = dict(bound="hbm", kernel="gemm_ps_kernel + gemm_tcp_kernel (streamed tcgen05 GEMMs: the %d launches/step with "
+                                        "M*N*K >= 2^20; the top shape below runs on the persistent gemm_ps_kernel)"
                                         % streamed["launches_per_step"],
                     achieved=round(ach, 1), peak=pk["hbm"], unit="GB/s", frac=round(ach / pk["hbm"], 4), traffic=traffic,
                     traffic_source=traffic_src,
