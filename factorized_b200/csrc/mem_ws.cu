@@ -129,18 +129,14 @@ __device__ __forceinline__ void mw_build(unsigned char* hi, int K, const float* 
   }
 }
 
-__device__ int g_mw_dbg = 0;      // experiment switches (mfm_debug_mem_ws_flags): 1 = hi*hi pass only, 2 = no MMAs at all
 // one issuer's share of a GEMM: K steps kk0, kk0 + 2, ... of tile image `img` against operand `op` into its partial accumulator
 __device__ __forceinline__ void mw_issue(uint32_t tD, uint32_t img, int K, uint32_t op, int kk0, uint32_t idesc) {
   const int slabs = K >> 3, ksteps = K >> 4;
   const uint64_t dAh = make_smem_desc(img, MW_LBO, 128), dAl = make_smem_desc(img + slabs * MW_LBO, MW_LBO, 128);
   const uint64_t dBh = make_smem_desc(op, MW_LBOB, 128), dBl = make_smem_desc(op + slabs * MW_LBOB, MW_LBOB, 128);
-  const int dbg = g_mw_dbg;
-  if (dbg & 2) return;
   for (int kk = kk0; kk < ksteps; kk += 2) {
     const uint64_t ao = (uint64_t)((kk * 2 * MW_LBO) >> 4), bo = (uint64_t)((kk * 2 * MW_LBOB) >> 4);
     umma_bf16(tD, dAh + ao, dBh + bo, idesc, kk > kk0 ? 1u : 0u);
-    if (dbg & 1) continue;
     umma_bf16(tD, dAl + ao, dBh + bo, idesc, 1u);
     umma_bf16(tD, dAh + ao, dBl + bo, idesc, 1u);
   }
@@ -259,7 +255,7 @@ __global__ void __launch_bounds__(MW_THREADS, 1) mem_ws_fwd_kernel(const __grid_
     float* const Uo = half ? a.U2 : a.U1;
     unsigned char* const opU = half ? opU2 : opU1;
     const int planeU = ((half ? d.K2 : d.K1) >> 3) * MW_LBOB;
-    const bool two_a = d.KM >= 32, two_b = (half ? d.K2 : d.K1) >= 32;           // a second partial exists
+    const bool two_a = d.KM >= 32;                                               // a second partial exists
     const float dp = half ? a.drop_p2 : a.drop_p1;
     const bool dd = dp > 0.0f;
     const uint32_t ss = dd ? site_seed(a.rng, half ? a.site2 : a.site1) : 0u;
@@ -487,7 +483,6 @@ __global__ void __launch_bounds__(MW_THREADS, 1) mem_ws_bwd_kernel(const __grid_
 
 static unsigned long long g_mw_counts[2];
 static int g_mw_off = 0;
-extern "C" int mfm_debug_mem_ws_flags(int f) { return (int)cudaMemcpyToSymbol(g_mw_dbg, &f, sizeof(int)); }
 extern "C" int mfm_debug_mem_ws_trace(long long* host32x16) {
 #if MW_DEBUG
   return (int)cudaMemcpyFromSymbol(host32x16, g_mw_trace, sizeof(long long) * 32 * 16);

@@ -67,7 +67,7 @@ _SIGS = {
     "mfm_debug_gemm_ps_count": (C.c_int, []),
     "mfm_debug_set_gemm_ps_trace": (C.c_int, [c_f]),
     "mfm_debug_mem_force_simt": (C.c_int, [C.c_int]),
-    "mfm_debug_mem_ws_flags": (C.c_int, [C.c_int]),
+    "mfm_debug_mem_ws_trace": (C.c_int, [c_f]),
     "mfm_debug_mem_ws_count": (C.c_ulonglong, [C.c_int]),
     "mfm_mfn_mem_fwd": (C.c_int, [C.POINTER(MemArgs), c_f]),
     "mfm_mfn_mem_bwd": (C.c_int, [C.POINTER(MemArgs), c_f]),

@@ -175,6 +175,9 @@ int mfm_mfn_mem_bwd(const mfm_mem_args* a, void* stream);
  * (csrc/mfn.cu); force the latter (on != 0), and read how many launches the tensor-core kernels have served since load. */
 int mfm_debug_mem_force_simt(int on);
 unsigned long long mfm_debug_mem_ws_count(int bwd);
+/* Debug aid (scripts/mem_trace.py; library built with -DMW_DEBUG=1, else MFM_ERR_UNSUPPORTED): copies the clock stamps CTA 0 of the
+ * last forward launch recorded (32 steps x 16 slots, int64) to the HOST buffer. */
+int mfm_debug_mem_ws_trace(long long* host32x16);
 
 /* attention = softmax(L, dim=1) (in place); attended = attention * cstar  (mfm_model.py:174-175) */
 int mfm_softmax_gate_fwd(int M, int N, float* L, const float* cstar, float* attended, void* stream);

@@ -17,9 +17,8 @@ a = dict(T=T, B=B, mem=mem, g1=g1, g2=g2, G1pre=r(TB, g1), G2pre=r(TB, g2), cHat
 b = dict(a)
 b.update(scale1=1.0, scale2=1.0, dmem_last=r(B, mem), dU1=torch.zeros(TB, g1, device=dev), dU2=torch.zeros(TB, g2, device=dev),
          dP1=torch.zeros(TB, mem, device=dev), dP2=torch.zeros(TB, mem, device=dev), dPc=torch.zeros(TB, mem, device=dev))
-for simt, flags in ((0, 0), (0, 1), (0, 2), (1, 0)):
+for simt, flags in ((0, 0), (1, 0)):
     ops.lib.mfm_debug_mem_force_simt(simt)
-    ops.lib.mfm_debug_mem_ws_flags(flags)
     for name, fn, arg in (("fwd", ops.mfn_mem_fwd, a), ("bwd", ops.mfn_mem_bwd, b)):
         for _ in range(3):
             fn(arg)

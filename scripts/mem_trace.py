@@ -19,7 +19,6 @@ for _ in range(3):
     ops.mfn_mem_fwd(a)
 torch.cuda.synchronize()
 buf = np.zeros(32 * 16, dtype=np.int64)
-ops.lib.mfm_debug_mem_ws_trace.argtypes = [ctypes.c_void_p]
 assert ops.lib.mfm_debug_mem_ws_trace(buf.ctypes.data) == 0, "build mem_ws.cu with -DMW_DEBUG=1"
 t = buf.reshape(32, 16)[:T].astype(np.float64)
 t0 = t[0, 4]
