@@ -228,7 +228,7 @@ def parity_check(configs, T, B, head, dev, use_graph):
     from oracle.rng_replay import train_masks_and_branches
     torch.manual_seed(123)
     model = F.MFM(*configs).to(dev).train()
-    trainer = MFMTrainer(model, T, B, head=head, use_graph=use_graph, seed=2024)
+    trainer = MFMTrainer(model, T, B, head=head, use_graph=use_graph, seed=2024, distributed=False)
     for i in range(2):
         xw, yw = O.synthetic_batch(configs, T, B, 77 + i, head)
         trainer.step(xw.to(dev), yw.to(dev))

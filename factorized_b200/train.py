@@ -39,7 +39,8 @@ class MFMTrainer:
     """
 
     def __init__(self, model: MFM, T: int, B: int, head: str = "l1", lr: float = 1e-3, betas=(0.9, 0.999),
-                 eps: float = 1e-8, use_graph: bool = True, process_group=None, seed: int = 123, _test_ops=None):
+                 eps: float = 1e-8, use_graph: bool = True, process_group=None, seed: int = 123, _test_ops=None,
+                 distributed: bool = True):
         dev = next(model.parameters()).device
         if dev.type != "cuda" and _test_ops is None:
             raise RuntimeError("MFMTrainer: model must be on a CUDA device (model.to('cuda')); no CPU path exists")
@@ -52,7 +53,9 @@ class MFMTrainer:
         self.betas, self.eps = betas, eps
         self.pg = process_group
         self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        # distributed=False: a single-rank trainer inside an initialised process group (bench.py's parity check runs on rank 0
+        # only -- a collective there would wait for ranks that never call it)
+        if distributed and (process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
         pd = dict(model.named_parameters())
         self.names = [k for k in pd if k not in UNUSED]
