@@ -54,6 +54,16 @@ def _worker(rank, world, port, ret):
         d_ref, d_got = ref[k] - P[k], got[k] - P[k]
         worst = max(worst, float((d_got - d_ref).norm() / (d_ref.norm() + 1e-30)))
     ret[rank] = worst
+    # a single-rank trainer inside the initialised group (what bench.py's rank-0 parity check builds): no collective -- rank 0
+    # steps it ALONE and must not wait for rank 1 (this hung the N>1 bench runs when it inherited the world size)
+    if rank == 0:
+        torch.manual_seed(7)
+        solo = MFMTrainer(F.MFM(*configs), T, n, head="l1", _test_ops=EmuOps(), distributed=False)
+        assert solo.world == 1
+        solo.ops.randn = lambda *a, **k: None
+        solo.step(xs, ys)
+        ret["solo"] = float(solo.eng.loss_buf[8])
+    dist.barrier()
     dist.destroy_process_group()
 
 
@@ -63,6 +73,6 @@ def test_two_rank_gloo_matches_shard_averaged_oracle():
     ret = mgr.dict()
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-    assert len(ret) == world
+    assert len(ret) == world + 1 and ret["solo"] == ret["solo"]       # the single-rank step finished (and is not NaN)
     for r in range(world):
         assert ret[r] < 2e-3, dict(ret)
