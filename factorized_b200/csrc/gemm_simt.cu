@@ -109,7 +109,7 @@ int gemm_simt_launch(int mode, int M, int N, int K, const float* A, long long ld
   if (plain && K >= 1024) {
     long long tiles = (long long)grid.x * grid.y;
     int splits = (int)((2 * mfm_dev_info().sms + tiles - 1) / tiles);
-    int maxs = K / 256;
+    int maxs = K / 64;       // the K loop is not software-pipelined: a CTA pays one load latency per 16 k, so short slices win
     if (splits > maxs) splits = maxs;
     if (splits > 1) {
       int kc = (K + splits - 1) / splits;

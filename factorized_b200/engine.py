@@ -394,15 +394,16 @@ class Engine:
         return dX, dY
 
     # -- weight-gradient GEMMs run on a side stream ---------------------------------
-    def _on_side(self, key, fn):
-        """Run fn on the side stream selected by key, ordered after everything issued so far on the current stream."""
+    def _on_side(self, key, fn, index=None):
+        """Run fn on the side stream selected by key (or, explicitly, by index), ordered after everything issued so far on the
+        current stream."""
         if self.device.type != "cuda" or not self.use_side_stream:
             fn()
             return
         main = torch.cuda.current_stream(self.device)
         if self._side is None:
             self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
-        st = self._side[(key >> 8) % len(self._side)]
+        st = self._side[((key >> 8) if index is None else index) % len(self._side)]
         ev = torch.cuda.Event()
         ev.record(main)
         st.wait_event(ev)
@@ -410,7 +411,7 @@ class Engine:
             fn()
         self._side_used = True
 
-    def _wgrad_pair(self, dY, A1, G1, b1, A2, G2, b2=None):
+    def _wgrad_pair(self, dY, A1, G1, b1, A2, G2, b2=None, index=None):
         """dW1 += dY^T A1, dW2 += dY^T A2 and the bias gradient(s) = column sums of dY, in one launch on a side stream: the
         two weight gradients of a cell share dY, which is then read from HBM once.  b2 (same sums) is copied from b1."""
         ops = self.ops
@@ -419,7 +420,7 @@ class Engine:
             ops.gemm_tn_pair(dY, A1, G1, b1, A2, G2)
             if b2 is not None:
                 ops.copy2d(b1.view(1, -1), b2.view(1, -1), accumulate=True)
-        self._on_side(G1.data_ptr(), run)
+        self._on_side(G1.data_ptr(), run, index)
 
     def _wgrad_gemm(self, dY, A, Gout, stream_key=None, **kw):
         """dW += dY^T A (TN GEMM, optionally with the fused bias gradient).  Weight gradients only read stashes and
@@ -798,6 +799,7 @@ class Engine:
             if not part:
                 continue
             ops.lstm_bwd([c for c, _ in part])
-            for _, (nm, dGn, m, hs) in part:
+            # the step ends when these finish: one side stream each (the pointer hash could put two on one stream)
+            for i, (_, (nm, dGn, m, hs)) in enumerate(part):
                 self._wgrad_pair(ws[dGn], self.xs[m], G[nm + ".weight_ih"], G[nm + ".bias_ih"], hs, G[nm + ".weight_hh"],
-                                 G[nm + ".bias_hh"])
+                                 G[nm + ".bias_hh"], index=i)
