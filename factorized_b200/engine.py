@@ -95,6 +95,7 @@ class Engine:
         self._pool = []                  # streams for _par branches
         self._z_ready = None             # events: encoder latents written (they are produced on the auxiliary streams)
         self._mmd_pending = False        # MMD accumulators (double) not yet folded into loss_buf[4:8]
+        self.want_mmd = True             # False: forward-only inference skips the O(B^2) MMD (its parts read 0)
         self.stamps, self.stamp_names = None, []      # debug timeline (mark)
         # two launches for the last backward recurrence (heavy cells first, their weight gradients start early): measured
         # SLOWER (3.67 vs 3.56 ms/step: the gradient GEMMs delay the second launch), kept as an experiment switch
@@ -214,7 +215,7 @@ class Engine:
                         ops.gemm("nt", zlast, P["last_to_logvarz%s_fc1.weight" % tag], lv, bias=P["last_to_logvarz%s_fc1.bias" % tag])
                         ops.kld_fwd(Z[m], lv, self.loss_buf[4 + m:5 + m])
                     self._z_ready.append(self._aux_event(m))
-                    if not self.kl:
+                    if not self.kl and self.want_mmd:
                         self._mmd(m, Z[m])
 
         # (4) MFN attention for all T at once (:171-176); only gamma*_fc1's memory columns are sequential
@@ -278,7 +279,8 @@ class Engine:
                 ops.gemm("nt", mems[TB:], Wlv[:, H:], LVY, accumulate=True)
                 ops.kld_fwd(ZY, LVY, self.loss_buf[7:8])
             else:
-                self._mmd(3, ZY)
+                if self.want_mmd:
+                    self._mmd(3, ZY)
         for ev in (self._z_ready or []):                   # the factor MLPs read Z, produced on the auxiliary streams
             if ev is not None:
                 torch.cuda.current_stream(self.device).wait_event(ev)

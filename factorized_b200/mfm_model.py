@@ -55,7 +55,15 @@ class _MFMFunction(torch.autograd.Function):
         rng = module._rng_state(x.device)
         if module.training:
             _ops().rng_tick(rng)
-        out = eng.forward(P, x, [n0, n1, n2, n3], train=module.training, rng=rng)
+        # forward-only inference (evaluate / predict, mfm_mosi.py:445-465, call forward on the WHOLE validation / test set under
+        # no_grad and discard the MMD): with ``module.eval_skip_mmd`` set the O(n^2) statistic is not computed and reads 0
+        eng.want_mmd = not module.__dict__.get("_skip_mmd_now", False)     # (decided in MFM.forward: grad mode is off in here)
+        if not eng.want_mmd:
+            _ops().zero(eng.loss_buf[4:8])
+        try:
+            out = eng.forward(P, x, [n0, n1, n2, n3], train=module.training, rng=rng)
+        finally:
+            eng.want_mmd = True
         ctx.eng, ctx.P, ctx.gen = eng, P, eng_generation(eng, bump=True)
         dm = eng.dm
         mmd = eng.loss_buf[4:8].sum()
@@ -265,6 +273,7 @@ class MFM(nn.Module):
         noise = self.draw_mmd_noise(x.shape[1], x.device)
         pd = dict(self.named_parameters())
         params = [pd[k] for k in self._param_names]
+        self.__dict__["_skip_mmd_now"] = bool(getattr(self, "eval_skip_mmd", False) and not self.training and not torch.is_grad_enabled())
         x_l_hat, x_a_hat, x_v_hat, y_hat, mmd_loss = _MFMFunction.apply(self, x, *noise, *params)
         missing_loss = 0.0
         decoded = [x_l_hat, x_a_hat, x_v_hat, y_hat]

@@ -223,6 +223,7 @@ def train_mfm(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, head:
     dev = torch.device("cuda")
     model = (MFM_KL if config.get("type", "mfm") == "kl" else MFM)(*configs).to(dev)      # :398-401,414
     model.mmd_noise = "cuda"
+    model.eval_skip_mmd = True            # evaluate / predict discard the MMD of the whole-set forward (:448,:460)
     T, total_n = Xt.shape[0], Xt.shape[1]
     bs = int(config["batchsize"])
     num_batches = total_n // bs                                      # :423 (py2 integer division: drops the tail)

@@ -159,6 +159,35 @@ def test_full_step_vs_oracle(gemm_path, name, input_dims, T, n, head, od):
     assert not bad, bad
 
 
+def test_forward_only_inference_skips_the_mmd():
+    """evaluate() / predict() of the reference call forward on the whole set under no_grad and discard the MMD
+    (mfm_mosi.py:445-465).  With ``eval_skip_mmd`` the O(n^2) statistic is not launched: same decoded outputs and latents,
+    mmd reads 0, fewer kernels; in train mode or with grad enabled the flag changes nothing."""
+    import factorized_b200 as F
+    from factorized_b200.mfm_model import _ops
+    g, configs, P, x, y, noise, T, n = tiny_case("l1", 1)
+    torch.manual_seed(int(g["meta"][0]))
+    model = F.MFM(*configs).cuda().eval()
+    xd = x.cuda()
+    with torch.no_grad():
+        n0 = _ops().launches
+        dec_a, mmd_a, _ = model.forward(xd)
+        full = _ops().launches - n0
+        lat_a = {k: v.clone() for k, v in model.latents.items()}
+        model.eval_skip_mmd = True
+        n0 = _ops().launches
+        dec_b, mmd_b, _ = model.forward(xd)
+        lean = _ops().launches - n0
+    assert float(mmd_a) > 0.0 and float(mmd_b) == 0.0
+    assert lean < full - 30, (lean, full)
+    for a, b in zip(dec_a, dec_b):
+        assert torch.equal(a, b)
+    for k in lat_a:
+        assert torch.equal(lat_a[k], model.latents[k])
+    decoded, mmd_c, _ = model.forward(xd)                   # grad enabled: the statistic is part of the loss again
+    assert float(mmd_c) > 0.0
+
+
 def test_dropin_module_autograd_and_trainer():
     """The nn.Module boundary: MFM.forward + torch losses + loss.backward() (the reference's own loop body,
     mfm_mosi.py:430-441) against the oracle; then MFMTrainer's fused step against the same."""
