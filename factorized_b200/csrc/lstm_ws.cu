@@ -70,12 +70,19 @@ struct WsBatch {
 // wait on an mbarrier phase.  The suspend-time hint parks the warp until the phase completes instead of re-polling (the
 // first version re-polled ~200 times per step: a third of all issued instructions); bounded: a barrier that never
 // completes traps instead of hanging the GPU
+#ifndef WS_SPIN
+#define WS_SPIN 0
+#endif
 __device__ __forceinline__ void ws_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   for (int spin = 0; spin < (1 << 24); ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
+#if WS_SPIN
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+#endif
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity)
@@ -165,7 +172,6 @@ __device__ __forceinline__ const WsCell& ws_find(const WsBatch& bt, int bx) {
 // ----------------------------------------------------------------------------------------------------------------
 template <int NCH, int NSG>      // chains per CTA; groups of 4 batch columns per warp and chain (2: 32-/64-row chains, 1: half as wide)
 __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_fwd_kernel(const __grid_constant__ WsBatch bt) {
-  static_assert((NCH * NSG) % 2 == 0, "the G_x double buffer needs an even number of column groups per step");
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar_done[WS_MAXCHAIN], bar_ready[WS_MAXCHAIN];
   __shared__ uint32_t tmem_holder;
@@ -348,6 +354,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_fwd_kernel(const __grid
           ws_wait(smem_u32(&bar_done[ch]), (uint32_t)(t & 1));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           WS_STAMP(warp, t, ch * 3 + 1);
+          if ((NCH * NSG) % 2 == 1 && ch == 0 && t > 0 && t != gx_steps) {
+            // an odd number of column groups per step (one half-width chain): the prefetch of this step's first group went to
+            // the other buffer; the parities stay compile-time constants and the registers are moved instead
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) gx[0][g][cc] = gx[1][g][cc];
+          }
 #pragma unroll
           for (int sg = 0; sg < NSG; ++sg) {
             {
@@ -712,7 +726,6 @@ static size_t ws_plan(bool bwd, int h, int nb, int nchain, int limit, WsCell& lc
   const int R = nsub == 2 ? 2 : 1;
   const int ncol = nb / (4 * R);                            // columns per warp and chain: 8 or 4
   if (ncol * 4 * R != nb || !(ncol == 8 || ncol == 4)) return 0;
-  if (!bwd && nchain == 1 && ncol == 4) return 0;           // (forward keeps an even number of column groups per step)
   lc.nb = nb;
   lc.nsub = nsub;
   lc.nact = nsub0 == 1 ? 8 : nsub0 == 3 ? 12 : 16;
@@ -793,18 +806,25 @@ static int ws_launch(bool bwd, const mfm_lstm_cell* cells, int ncells, mfm_lstm_
   // Shapes, in order of preference: two wide chains per CTA (each hides the other's gate GEMM); when that leaves most
   // SMs without a CTA (a single decoder cell, small batches), two chains of half the width -- twice the CTAs, the GEMMs
   // still hidden; one wide chain per CTA when shared memory holds nothing else.
+  // When even that leaves two thirds of the SMs without a CTA (a decoder cell at batch <= 1024), ONE half-width chain per
+  // CTA: the step is bound by the MMA issue rate (~46 cycles per instruction; two chains = twice the instructions per step and
+  // CTA), so a lone decoder cell h = 104 at batch 2048 runs 149 -> 111 us backward, 111 -> 100 us forward in this shape -- but
+  // the step launches its three decoder cells side by side, 3 x 128 CTAs then queue for SMs and the step got 3 % SLOWER, so at
+  // that size the two-chain shape stays.
   struct Shape { int nchain; bool narrow; };
-  Shape order[3] = {{2, false}, {2, true}, {1, false}};
+  Shape order[4] = {{2, false}, {2, true}, {1, true}, {1, false}};
   if (g_ws_force_nb == 16) { order[0] = {2, true}; order[1] = {2, false}; }
-  if (g_ws_force_chains == 1) { order[0] = {1, false}; order[1] = {2, false}; order[2] = {2, true}; }
-  const int want = mfm_dev_info().sms * 2 / 3;
+  if (g_ws_force_chains == 1) { order[0] = {1, false}; order[1] = {2, false}; order[2] = {2, true}; order[3] = {1, true}; }
+  const int sms = mfm_dev_info().sms;
   int pick = -1;
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < 4; ++k) {
     const int t = ws_plan_all(bwd, cells, ncells, order[k].nchain, order[k].narrow, lim, bt, smem, rest, nrest);
     if (t < 0) continue;                                    // a cell does not take this shape
+    if (pick >= 0 && order[k].nchain == 1 && !order[k].narrow) break;   // (one wide chain: only when nothing else fits)
     pick = k;
     // keep looking for a shape with more CTAs only when this one under-fills the GPU and nothing forces the choice
-    if (t >= want || g_ws_force_nb == 16 || g_ws_force_chains || order[k].narrow) break;
+    const int want = order[k].nchain == 2 && order[k].narrow ? sms / 3 : sms * 2 / 3;
+    if (t >= want || g_ws_force_nb == 16 || g_ws_force_chains) break;
   }
   if (pick < 0) {                                           // (cannot happen: every on-chip cell takes the last shape or none)
     *nrest = 0;
@@ -821,6 +841,8 @@ static int ws_launch(bool bwd, const mfm_lstm_cell* cells, int ncells, mfm_lstm_
   if (bwd) {
     if (nchain == 1) { if (!(e = mfm_func_smem_t(lstm_ws_bwd_kernel<1>, lim))) lstm_ws_bwd_kernel<1><<<total, WS_THREADS, smem, st>>>(bt); }
     else             { if (!(e = mfm_func_smem_t(lstm_ws_bwd_kernel<2>, lim))) lstm_ws_bwd_kernel<2><<<total, WS_THREADS, smem, st>>>(bt); }
+  } else if (nchain == 1 && narrow) {
+    if (!(e = mfm_func_smem_t(lstm_ws_fwd_kernel<1, 1>, lim))) lstm_ws_fwd_kernel<1, 1><<<total, WS_THREADS, smem, st>>>(bt);
   } else if (nchain == 1) {
     if (!(e = mfm_func_smem_t(lstm_ws_fwd_kernel<1, 2>, lim))) lstm_ws_fwd_kernel<1, 2><<<total, WS_THREADS, smem, st>>>(bt);
   } else if (narrow) {

@@ -41,8 +41,8 @@ __device__ long long g_mw_trace[32 * 16];                 // [step][slot]
 #define MW_LBO (128 * 16)             // A images: 128 rows per K slab
 #define MW_LBOB (MW_NB * 16)          // B operands: 16 rows per K slab
 
-// The chain is strictly serial and nothing else runs on the SM: the waiters poll (test_wait) instead of parking on the barrier
-// (the parked form of tc_common.cuh wakes up later).  Bounded: a barrier that never completes traps.
+// The chain is strictly serial and nothing else runs on the SM: the waiters poll (test_wait).  (Parking on the barrier -- the
+// try_wait form of tc_common.cuh -- was measured equal in lstm_ws.cu.)  Bounded: a barrier that never completes traps.
 __device__ __forceinline__ void mw_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
 #pragma unroll 1
