@@ -1,9 +1,9 @@
 """factorized_b200 -- the MFM (Multimodal Factorization Model) training step on B200 (sm_100a).
 
-Drop-in for the hot path of pliang279/factorized: ``encoderLSTM / decoderLSTM / MFN / MFM / MFM_KL`` and
+Drop-in for the hot path of pliang279/factorized: ``encoderLSTM / decoderLSTM / MFN / MFM / MFM_KL / MFM_KL_EF`` and
 ``train_mfm``; arithmetic in hand-written CUDA behind ``include/mfm_b200.h``.  CUDA only.
 """
-from .mfm_model import encoderLSTM, decoderLSTM, MFN, MFM, MFM_KL  # noqa: F401
+from .mfm_model import encoderLSTM, decoderLSTM, MFN, MFM, MFM_KL, MFM_KL_EF  # noqa: F401
 
 
 def train_mfm(*a, **k):

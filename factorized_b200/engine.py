@@ -72,11 +72,12 @@ class Engine:
     def __init__(self, configs, T: int, B: int, device, ops, head: str = "l1", mfn_only: bool = False,
                  mfn_prefix: str = "mfn_encoder.", variant: str = "mfm"):
         self.dm = Dims(configs, T, B, head)
-        if variant not in ("mfm", "kl"):
+        if variant not in ("mfm", "kl", "kl_ef"):
             raise ValueError(variant)
         # "kl": MFM_KL (mfm_model.py:662-764) -- the encoder outputs pass one more Linear to the means (the latents z) and
         # another to the log-variances, and the regulariser is loss_KLD instead of loss_MMD; everything else is MFM
-        self.kl = variant == "kl"
+        self.kl = variant in ("kl", "kl_ef")   # KL regulariser on (mean, log-variance) heads instead of the MMD
+        self.ef = variant == "kl_ef"           # MFM_KL_EF (mfm_model.py:557-660): ONE early-fusion encoder cell instead of the MFN
         self.mfn_only = bool(mfn_only)          # standalone MFN module: only steps (1,2,4,5) on the MFN cells
         self.pre = mfn_prefix
         self.device = torch.device(device)
@@ -141,6 +142,7 @@ class Engine:
         self.x = x
         self.noise = list(noise)
         self.rng = rng
+        self.x_in = x
         X2 = x.view(TB, dm.D)
         # (0) split x into per-modality matrices whose rows start 16 B aligned (leading dimension padded to a
         #     multiple of 4 floats): the reference layout concatenates the modalities on the last axis (:523-525), row
@@ -160,14 +162,20 @@ class Engine:
                 if full:
                     ops.gemm("nt", xs[m], P[e + ".weight_ih"], buf("GxE%d" % m, TB, 4 * dm.z[m]),
                              bias=P[e + ".bias_ih"], bias2=P[e + ".bias_hh"])
-                ops.gemm("nt", xs[m], P[n + ".weight_ih"], buf("GxN%d" % m, TB, 4 * dm.hm[m]),
-                         bias=P[n + ".bias_ih"], bias2=P[n + ".bias_hh"])
+                if not self.ef:
+                    ops.gemm("nt", xs[m], P[n + ".weight_ih"], buf("GxN%d" % m, TB, 4 * dm.hm[m]),
+                             bias=P[n + ".bias_ih"], bias2=P[n + ".bias_hh"])
             return run
+
+        def project_ef():                                      # the early-fusion cell reads the whole row of x (:639)
+            ops.gemm("nt", X2, P["ef_encoder.lstm.weight_ih"], buf("GxEF", TB, 4 * hef),
+                     bias=P["ef_encoder.lstm.bias_ih"], bias2=P["ef_encoder.lstm.bias_hh"])
 
         self.mark("fwd:start")
         if self.fuse_mse and full:
             ops.zero(self.loss_buf[0:4])                       # the decoder heads accumulate the MSE terms during forward
-        self._par([project(0), project(1), project(2)])
+        hef = sum(dm.z)
+        self._par([project(0), project(1), project(2)] + ([project_ef] if self.ef else []))
         self.mark("fwd:projections")
 
         # (2) six recurrences in one launch: h W_hh^T + G_x[t] -> gates -> (h, c)
@@ -186,7 +194,11 @@ class Engine:
                               W=P["encoder_%s.lstm.weight_hh" % tag],
                               hs=buf("hsE%d" % m, (T + 1) * B, dm.z[m]), cs=buf("csE%d" % m, (T + 1) * B, dm.z[m]),
                               gates=buf("gatesE%d" % m, TB, 4 * dm.z[m])))
-        for m, tag in enumerate(TAGS):
+        if self.ef:
+            cells.append(dict(T=T, B=B, h=hef, gx=self.ws["GxEF"], gx_steps=T, bias_rest=None,
+                              W=P["ef_encoder.lstm.weight_hh"], hs=buf("hsEF", (T + 1) * B, hef),
+                              cs=buf("csEF", (T + 1) * B, hef), gates=buf("gatesEF", TB, 4 * hef)))
+        for m, tag in enumerate("" if self.ef else TAGS):
             o = dm.hoff[m]
             cells.append(dict(T=T, B=B, h=dm.hm[m], gx=self.ws["GxN%d" % m], gx_steps=T, bias_rest=None,
                               W=P[self.pre + "lstm_%s.weight_hh" % tag],
@@ -218,69 +230,12 @@ class Engine:
                     if not self.kl and self.want_mmd:
                         self._mmd(m, Z[m])
 
-        # (4) MFN attention for all T at once (:171-176); only gamma*_fc1's memory columns are sequential
-        pre = self.pre
-        cStar = CS2[B:(T + 1) * B]
-        self.ws_views["cStar"] = cStar
-        H1 = buf("H1", TB, dm.a1)
-        ops.gemm("nt", cStar, P[pre + "att1_fc1.weight"], H1, bias=P[pre + "att1_fc1.bias"], act=ACT_RELU,
-                 drop=drop(dm.p_att1, SITE_ATT1), rng=rng)
-        Att = buf("Att", TB, 2 * H)
-        ops.gemm("nt", H1, P[pre + "att1_fc2.weight"], Att, bias=P[pre + "att1_fc2.bias"])
-        Attended = buf("Attended", TB, 2 * H)
-        ops.softmax_gate_fwd(Att, cStar, Attended)
-        self.mark("fwd:att1+gate")
-        H2 = buf("H2", TB, dm.a2)
-        cHat = buf("cHat", TB, mem)
-        G1pre = buf("G1pre", TB, dm.g1)
-        G2pre = buf("G2pre", TB, dm.g2)
-        Wg1, Wg2 = P[pre + "gamma1_fc1.weight"], P[pre + "gamma2_fc1.weight"]
-
-        def att2():
-            ops.gemm("nt", Attended, P[pre + "att2_fc1.weight"], H2, bias=P[pre + "att2_fc1.bias"], act=ACT_RELU,
-                     drop=drop(dm.p_att2, SITE_ATT2), rng=rng)
-            ops.gemm("nt", H2, P[pre + "att2_fc2.weight"], cHat, bias=P[pre + "att2_fc2.bias"], act=ACT_TANH)
-
-        self._par([att2,
-                   lambda: ops.gemm("nt", Attended, Wg1[:, :2 * H], G1pre, bias=P[pre + "gamma1_fc1.bias"]),
-                   lambda: ops.gemm("nt", Attended, Wg2[:, :2 * H], G2pre, bias=P[pre + "gamma2_fc1.bias"])])
-
-        self.mark("fwd:att2+gamma")
-        # (5) the memory recurrence (:177-180), T steps in one kernel
-        mems = buf("mems", (T + 1) * B, mem)
-        ops.mfn_mem_fwd(dict(
-            T=T, B=B, mem=mem, g1=dm.g1, g2=dm.g2, G1pre=G1pre, G2pre=G2pre, cHat=cHat,
-            W1m=Wg1[:, 2 * H:], W2m=Wg2[:, 2 * H:],
-            W12=P[pre + "gamma1_fc2.weight"], b12=P[pre + "gamma1_fc2.bias"],
-            W22=P[pre + "gamma2_fc2.weight"], b22=P[pre + "gamma2_fc2.bias"],
-            mems=mems, U1=buf("U1", TB, dm.g1), U2=buf("U2", TB, dm.g2),
-            Gam1=buf("Gam1", TB, mem), Gam2=buf("Gam2", TB, mem),
-            drop1=drop(dm.p_g1, SITE_G1), drop2=drop(dm.p_g2, SITE_G2), rng=rng))
-
-        self.mark("fwd:mem recurrence")
-        if self.mfn_only:                                     # MFN.forward returns cat(h_T^l,h_T^a,h_T^v,mem_T) (:194-198)
-            last = buf("mfn_last", B, H + mem)
-            ops.copy2d(Hall[TB:], last[:, :H])
-            ops.copy2d(mems[TB:], last[:, H:])
-            return dict(mfn_last=last)
-
-        # (6) zy = last_to_zy_fc1(cat(h_T^l, h_T^a, h_T^v, mem_T))  (:194-198, :535)
-        ZY = buf("ZY", B, dm.zy)
-        Wzy = P["last_to_zy_fc1.weight"]
-        ops.gemm("nt", Hall[TB:], Wzy[:, :H], ZY, bias=P["last_to_zy_fc1.bias"])
-        ops.gemm("nt", mems[TB:], Wzy[:, H:], ZY, accumulate=True)
-
-        # (7) MMD of z_y (the encoder latents went out in step 3); same auxiliary stream, off the critical path
-        with self._aux(3):
-            if self.kl:                                           # log-variance of z_y and its KL term (mfm_model.py:744,746)
-                Wlv = P["last_to_logvarzy_fc1.weight"]
-                LVY = buf("LVY", B, dm.zy)
-                ops.gemm("nt", Hall[TB:], Wlv[:, :H], LVY, bias=P["last_to_logvarzy_fc1.bias"])
-                ops.gemm("nt", mems[TB:], Wlv[:, H:], LVY, accumulate=True)
-                ops.kld_fwd(ZY, LVY, self.loss_buf[7:8])
-            else:
-                if self.want_mmd:
-                    self._mmd(3, ZY)
+        if self.ef:
+            ZY = self._forward_ef_head(P)
+        else:
+            ZY = self._forward_mfn_head(P, CS2, Hall, drop, rng)
+            if self.mfn_only:
+                return ZY
         for ev in (self._z_ready or []):                   # the factor MLPs read Z, produced on the auxiliary streams
             if ev is not None:
                 torch.cuda.current_stream(self.device).wait_event(ev)
@@ -355,6 +310,91 @@ class Engine:
             self._join_aux()
         return dict(x_l_hat=Xhat[0], x_a_hat=Xhat[1], x_v_hat=Xhat[2], y_hat=Yhat,
                     zl=Z[0], za=Z[1], zv=Z[2], zy=ZY, fy=FY, mmd_parts=self.loss_buf[4:8])
+
+    def _forward_mfn_head(self, P, CS2, Hall, drop, rng):
+        """Steps (4)-(7) of forward for the MFN variants: attention, memory recurrence, z_y and its regulariser.  Returns z_y
+        (or, for a standalone MFN, its output dict)."""
+        dm, ops, buf = self.dm, self.ops, self.buf
+        T, B, H, mem = dm.T, dm.B, dm.H, dm.mem
+        TB = T * B
+        # (4) MFN attention for all T at once (:171-176); only gamma*_fc1's memory columns are sequential
+        pre = self.pre
+        cStar = CS2[B:(T + 1) * B]
+        self.ws_views["cStar"] = cStar
+        H1 = buf("H1", TB, dm.a1)
+        ops.gemm("nt", cStar, P[pre + "att1_fc1.weight"], H1, bias=P[pre + "att1_fc1.bias"], act=ACT_RELU,
+                 drop=drop(dm.p_att1, SITE_ATT1), rng=rng)
+        Att = buf("Att", TB, 2 * H)
+        ops.gemm("nt", H1, P[pre + "att1_fc2.weight"], Att, bias=P[pre + "att1_fc2.bias"])
+        Attended = buf("Attended", TB, 2 * H)
+        ops.softmax_gate_fwd(Att, cStar, Attended)
+        self.mark("fwd:att1+gate")
+        H2 = buf("H2", TB, dm.a2)
+        cHat = buf("cHat", TB, mem)
+        G1pre = buf("G1pre", TB, dm.g1)
+        G2pre = buf("G2pre", TB, dm.g2)
+        Wg1, Wg2 = P[pre + "gamma1_fc1.weight"], P[pre + "gamma2_fc1.weight"]
+
+        def att2():
+            ops.gemm("nt", Attended, P[pre + "att2_fc1.weight"], H2, bias=P[pre + "att2_fc1.bias"], act=ACT_RELU,
+                     drop=drop(dm.p_att2, SITE_ATT2), rng=rng)
+            ops.gemm("nt", H2, P[pre + "att2_fc2.weight"], cHat, bias=P[pre + "att2_fc2.bias"], act=ACT_TANH)
+
+        self._par([att2,
+                   lambda: ops.gemm("nt", Attended, Wg1[:, :2 * H], G1pre, bias=P[pre + "gamma1_fc1.bias"]),
+                   lambda: ops.gemm("nt", Attended, Wg2[:, :2 * H], G2pre, bias=P[pre + "gamma2_fc1.bias"])])
+
+        self.mark("fwd:att2+gamma")
+        # (5) the memory recurrence (:177-180), T steps in one kernel
+        mems = buf("mems", (T + 1) * B, mem)
+        ops.mfn_mem_fwd(dict(
+            T=T, B=B, mem=mem, g1=dm.g1, g2=dm.g2, G1pre=G1pre, G2pre=G2pre, cHat=cHat,
+            W1m=Wg1[:, 2 * H:], W2m=Wg2[:, 2 * H:],
+            W12=P[pre + "gamma1_fc2.weight"], b12=P[pre + "gamma1_fc2.bias"],
+            W22=P[pre + "gamma2_fc2.weight"], b22=P[pre + "gamma2_fc2.bias"],
+            mems=mems, U1=buf("U1", TB, dm.g1), U2=buf("U2", TB, dm.g2),
+            Gam1=buf("Gam1", TB, mem), Gam2=buf("Gam2", TB, mem),
+            drop1=drop(dm.p_g1, SITE_G1), drop2=drop(dm.p_g2, SITE_G2), rng=rng))
+
+        self.mark("fwd:mem recurrence")
+        if self.mfn_only:                                     # MFN.forward returns cat(h_T^l,h_T^a,h_T^v,mem_T) (:194-198)
+            last = buf("mfn_last", B, H + mem)
+            ops.copy2d(Hall[TB:], last[:, :H])
+            ops.copy2d(mems[TB:], last[:, H:])
+            return dict(mfn_last=last)          # (MFN.forward's own return value)
+
+        # (6) zy = last_to_zy_fc1(cat(h_T^l, h_T^a, h_T^v, mem_T))  (:194-198, :535)
+        ZY = buf("ZY", B, dm.zy)
+        Wzy = P["last_to_zy_fc1.weight"]
+        ops.gemm("nt", Hall[TB:], Wzy[:, :H], ZY, bias=P["last_to_zy_fc1.bias"])
+        ops.gemm("nt", mems[TB:], Wzy[:, H:], ZY, accumulate=True)
+
+        # (7) MMD of z_y (the encoder latents went out in step 3); same auxiliary stream, off the critical path
+        with self._aux(3):
+            if self.kl:                                           # log-variance of z_y and its KL term (mfm_model.py:744,746)
+                Wlv = P["last_to_logvarzy_fc1.weight"]
+                LVY = buf("LVY", B, dm.zy)
+                ops.gemm("nt", Hall[TB:], Wlv[:, :H], LVY, bias=P["last_to_logvarzy_fc1.bias"])
+                ops.gemm("nt", mems[TB:], Wlv[:, H:], LVY, accumulate=True)
+                ops.kld_fwd(ZY, LVY, self.loss_buf[7:8])
+            else:
+                if self.want_mmd:
+                    self._mmd(3, ZY)
+        return ZY
+
+    def _forward_ef_head(self, P):
+        """MFM_KL_EF (mfm_model.py:639-643): z_y and its log-variance are Linears of the early-fusion encoder's output."""
+        dm, ops, buf = self.dm, self.ops, self.buf
+        B, TB, hef = dm.B, dm.T * dm.B, sum(dm.z)
+        EFlast = buf("EFlast", B, hef)
+        ops.gemm("nt", self.ws["hsEF"][TB:], P["ef_encoder.fc1.weight"], EFlast, bias=P["ef_encoder.fc1.bias"])
+        ZY = buf("ZY", B, dm.zy)
+        ops.gemm("nt", EFlast, P["last_to_zy_fc1.weight"], ZY, bias=P["last_to_zy_fc1.bias"])
+        with self._aux(3):
+            LVY = buf("LVY", B, dm.zy)
+            ops.gemm("nt", EFlast, P["last_to_logvarzy_fc1.weight"], LVY, bias=P["last_to_logvarzy_fc1.bias"])
+            ops.kld_fwd(ZY, LVY, self.loss_buf[7:8])
+        return ZY
 
     # -- losses (the fused training path) ------------------------------------------
     def losses(self, y: torch.Tensor):
@@ -665,24 +705,34 @@ class Engine:
         for k in range(4):
             ops.copy2d(dmmd[k], dlat[k], accumulate=True)
 
-        # (6') last_to_zy_fc1 over cat(h_T, mem_T)
-        Wzy = P["last_to_zy_fc1.weight"]
-        Gzy = G["last_to_zy_fc1.weight"]
-        Hall, mems = ws["Hall"], ws["mems"]
-        self._wgrad_gemm( dZY, Hall[TB:], Gzy[:, :H], accumulate=True)
-        self._wgrad_gemm( dZY, mems[TB:], Gzy[:, H:], accumulate=True)
-        bgrad(dZY, "last_to_zy_fc1.bias")
-        dHlast = buf("dHlast", B, H)
-        dmemT = buf("dmemT", B, mem)
-        ops.gemm("nn", dZY, Wzy[:, :H], dHlast)
-        ops.gemm("nn", dZY, Wzy[:, H:], dmemT)
-        if self.kl:                                               # the log-variance head of z_y reads the same cat(h_T, mem_T)
-            Wlv, Glv = P["last_to_logvarzy_fc1.weight"], G["last_to_logvarzy_fc1.weight"]
-            self._wgrad_gemm(dLV[3], Hall[TB:], Glv[:, :H], accumulate=True)
-            self._wgrad_gemm(dLV[3], mems[TB:], Glv[:, H:], accumulate=True)
-            bgrad(dLV[3], "last_to_logvarzy_fc1.bias")
-            ops.gemm("nn", dLV[3], Wlv[:, :H], dHlast, accumulate=True)
-            ops.gemm("nn", dLV[3], Wlv[:, H:], dmemT, accumulate=True)
+        dHlast = dmemT = None
+        if self.ef:
+            # (6') MFM_KL_EF: z_y and its log-variance are Linears of the early-fusion encoder's output (:640-641)
+            hef = sum(dm.z)
+            dEF = buf("dEFlast", B, hef)
+            lin_bwd(dZY, ws["EFlast"], "last_to_zy_fc1", dEF)
+            lin_bwd(dLV[3], ws["EFlast"], "last_to_logvarzy_fc1", dEF, accumulate=True)
+            dhEF = buf("dhEF", B, hef)
+            lin_bwd(dEF, ws["hsEF"][TB:], "ef_encoder.fc1", dhEF)
+        else:
+            # (6') last_to_zy_fc1 over cat(h_T, mem_T)
+            Wzy = P["last_to_zy_fc1.weight"]
+            Gzy = G["last_to_zy_fc1.weight"]
+            Hall, mems = ws["Hall"], ws["mems"]
+            self._wgrad_gemm( dZY, Hall[TB:], Gzy[:, :H], accumulate=True)
+            self._wgrad_gemm( dZY, mems[TB:], Gzy[:, H:], accumulate=True)
+            bgrad(dZY, "last_to_zy_fc1.bias")
+            dHlast = buf("dHlast", B, H)
+            dmemT = buf("dmemT", B, mem)
+            ops.gemm("nn", dZY, Wzy[:, :H], dHlast)
+            ops.gemm("nn", dZY, Wzy[:, H:], dmemT)
+            if self.kl:                                               # the log-variance head of z_y reads the same cat(h_T, mem_T)
+                Wlv, Glv = P["last_to_logvarzy_fc1.weight"], G["last_to_logvarzy_fc1.weight"]
+                self._wgrad_gemm(dLV[3], Hall[TB:], Glv[:, :H], accumulate=True)
+                self._wgrad_gemm(dLV[3], mems[TB:], Glv[:, H:], accumulate=True)
+                bgrad(dLV[3], "last_to_logvarzy_fc1.bias")
+                ops.gemm("nn", dLV[3], Wlv[:, :H], dHlast, accumulate=True)
+                ops.gemm("nn", dLV[3], Wlv[:, H:], dmemT, accumulate=True)
 
         enc_cells = []
         dhE = [buf("dhE%d" % m, B, dm.z[m]) for m in range(3)]
@@ -721,7 +771,19 @@ class Engine:
                     ops.copy2d(G[nm + ".bias_ih"].view(1, -1), G[nm + ".bias_hh"].view(1, -1), accumulate=True)
             self._enc_used = True
             enc_cells = []
-        self._backward_mfn(P, G, dHlast, dmemT, enc_cells, wgrad, bgrad, lin_bwd, relu_scale)
+        if self.ef:                                          # the early-fusion cell is the last recurrence of the step
+            hef = sum(dm.z)
+            cell = dict(T=T, B=B, h=hef, gates=ws["gatesEF"], cs=ws["csEF"], W=P["ef_encoder.lstm.weight_hh"], dh_all=None,
+                        dh_last=dhEF, dc_ext=None, dG=buf("dGEF", TB, 4 * hef), dc_scratch=buf("dcSEF", B, hef))
+            ops.lstm_bwd(enc_cells + [cell])
+            X2 = self.x_in.view(TB, dm.D)
+            jobs = [(c, "encoder_%s.lstm" % TAGS[m], self.xs[m], ws["hsE%d" % m][:TB]) for m, c in enumerate(enc_cells)]
+            jobs.append((cell, "ef_encoder.lstm", X2, ws["hsEF"][:TB]))
+            for i, (c, nm, xin, hs) in enumerate(jobs):
+                self._wgrad_pair(c["dG"], xin, G[nm + ".weight_ih"], G[nm + ".bias_ih"], hs, G[nm + ".weight_hh"],
+                                 G[nm + ".bias_hh"], index=i)
+        else:
+            self._backward_mfn(P, G, dHlast, dmemT, enc_cells, wgrad, bgrad, lin_bwd, relu_scale)
         self.mark("bwd:lstm enc+mfn")
         self._join_side()
         self.mark("bwd:join wgrads")

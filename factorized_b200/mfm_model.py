@@ -257,7 +257,7 @@ class MFM(nn.Module):
         """The four Gaussian samples of loss_MMD, drawn in the reference's order zl, za, zv, zy (:536)."""
         c = self._cfg[0]
         sizes = (c["zl_size"], c["za_size"], c["zv_size"], c["zy_size"])
-        if getattr(self, "_variant", "mfm") == "kl":          # MFM_KL draws nothing (no sampling, KL regulariser)
+        if getattr(self, "_variant", "mfm") in ("kl", "kl_ef"):   # MFM_KL / MFM_KL_EF draw nothing (no sampling, KL regulariser)
             return [torch.zeros(1, 1, device=device) for _ in sizes]
         if self.mmd_noise == "cpu":
             return [torch.randn(n, k).to(device) for k in sizes]
@@ -334,5 +334,56 @@ class MFM_KL(MFM):
         self._cfg = [dict(config), dict(NN1Config), dict(NN2Config), dict(gamma1Config), dict(gamma2Config), dict(outConfig)]
         self._param_names = [k for k, _ in self.named_parameters() if k not in UNUSED]
         self._variant = "kl"
+        self.mmd_noise = "cpu"
+        self.dropout_seed = 123
+
+
+class MFM_KL_EF(MFM):
+    """mfm_model.py:557-660 -- MFM_KL with the MFN encoder replaced by ONE early-fusion ``encoderLSTM`` over the
+    concatenated input (``ef_encoder``, hidden size zl+za+zv); z_y and its log-variance are Linears of its output.
+    ``forward(x) -> ([x_l_hat, x_a_hat, x_v_hat, y_hat], kld_loss, 0.0)``.  Same kernels as MFM_KL minus the MFN."""
+
+    def __init__(self, config, NN1Config, NN2Config, gamma1Config, gamma2Config, outConfig):
+        nn.Module.__init__(self)
+        [self.d_l, self.d_a, self.d_v] = config["input_dims"]
+        [self.dh_l, self.dh_a, self.dh_v] = config["h_dims"]
+        zy_size, zl_size, za_size, zv_size = config["zy_size"], config["zl_size"], config["za_size"], config["zv_size"]
+        fy_size, fl_size, fa_size, fv_size = config["fy_size"], config["fl_size"], config["fa_size"], config["fv_size"]
+        output_dim = config["output_dim"]
+        # construction order fixes the init RNG stream (mfm_model.py:579-619)
+        self.encoder_l = encoderLSTM(self.d_l, zl_size)
+        self.encoder_a = encoderLSTM(self.d_a, za_size)
+        self.encoder_v = encoderLSTM(self.d_v, zv_size)
+        self.decoder_l = decoderLSTM(fy_size + fl_size, self.d_l)
+        self.decoder_a = decoderLSTM(fy_size + fa_size, self.d_a)
+        self.decoder_v = decoderLSTM(fy_size + fv_size, self.d_v)
+        last_ef_size = zl_size + za_size + zv_size
+        self.ef_encoder = encoderLSTM(self.d_l + self.d_a + self.d_v, last_ef_size)
+        self.last_to_zy_fc1 = nn.Linear(last_ef_size, zy_size)
+        self.last_to_logvarzy_fc1 = nn.Linear(last_ef_size, zy_size)
+        self.last_to_zl_fc1 = nn.Linear(zl_size, zl_size)
+        self.last_to_za_fc1 = nn.Linear(za_size, za_size)
+        self.last_to_zv_fc1 = nn.Linear(zv_size, zv_size)
+        self.last_to_logvarzl_fc1 = nn.Linear(zl_size, zl_size)
+        self.last_to_logvarza_fc1 = nn.Linear(za_size, za_size)
+        self.last_to_logvarzv_fc1 = nn.Linear(zv_size, zv_size)
+        self.zy_to_fy_fc1 = nn.Linear(zy_size, fy_size)
+        self.zy_to_fy_fc2 = nn.Linear(fy_size, fy_size)
+        self.zy_to_fy_dropout = nn.Dropout(config["zy_to_fy_dropout"])
+        self.zl_to_fl_fc1 = nn.Linear(zl_size, fl_size)
+        self.zl_to_fl_fc2 = nn.Linear(fl_size, fl_size)
+        self.zl_to_fl_dropout = nn.Dropout(config["zl_to_fl_dropout"])
+        self.za_to_fa_fc1 = nn.Linear(za_size, fa_size)
+        self.za_to_fa_fc2 = nn.Linear(fa_size, fa_size)
+        self.za_to_fa_dropout = nn.Dropout(config["za_to_fa_dropout"])
+        self.zv_to_fv_fc1 = nn.Linear(zv_size, fv_size)
+        self.zv_to_fv_fc2 = nn.Linear(fv_size, fv_size)
+        self.zv_to_fv_dropout = nn.Dropout(config["zv_to_fv_dropout"])
+        self.fy_to_y_fc1 = nn.Linear(fy_size, fy_size)
+        self.fy_to_y_fc2 = nn.Linear(fy_size, output_dim)
+        self.fy_to_y_dropout = nn.Dropout(config["fy_to_y_dropout"])
+        self._cfg = [dict(config), dict(NN1Config), dict(NN2Config), dict(gamma1Config), dict(gamma2Config), dict(outConfig)]
+        self._param_names = [k for k, _ in self.named_parameters()]
+        self._variant = "kl_ef"
         self.mmd_noise = "cpu"
         self.dropout_seed = 123

@@ -115,7 +115,7 @@ class MFMTrainer:
         """forward + losses + backward into the flat gradient buffer (no communication)."""
         ops, eng = self.ops, self.eng
         ops.rng_tick(self.rng)
-        if self.variant != "kl":
+        if self.variant not in ("kl", "kl_ef"):
             for k in range(4):                                # loss_MMD's Gaussian samples (mfm_model.py:26)
                 ops.randn(self.noise[k], self.rng, SITE_NOISE + k)
         eng.forward(self.P, self.x, self.noise, train=True, rng=self.rng)

@@ -39,12 +39,13 @@ def import_reference():
 
 def run_reference(ref, configs, seed, T, n, head, data_seed, noise_seed, variant="mfm"):
     torch.manual_seed(seed)
-    model = (ref.MFM_KL if variant == "kl" else ref.MFM)(*configs).eval()              # eval(): the 9 dropouts become identity
+    cls = dict(mfm=ref.MFM, kl=ref.MFM_KL, kl_ef=ref.MFM_KL_EF)[variant]
+    model = cls(*configs).eval()                                                       # eval(): the 9 dropouts become identity
     params0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
     x, y = O.synthetic_batch(configs, T, n, data_seed, head)
     lat = {}
     hooks = dict(zl=model.encoder_l.fc1, za=model.encoder_a.fc1, zv=model.encoder_v.fc1, zy=model.last_to_zy_fc1)
-    if variant == "kl":                              # the latents are the means: one more Linear after the encoders
+    if variant in ("kl", "kl_ef"):                   # the latents are the means: one more Linear after the encoders
         hooks = dict(zl=model.last_to_zl_fc1, za=model.last_to_za_fc1, zv=model.last_to_zv_fc1, zy=model.last_to_zy_fc1)
     for k, m in hooks.items():
         m.register_forward_hook(lambda mod, i, o, k=k: lat.__setitem__(k, o.detach().clone()))
@@ -158,6 +159,27 @@ def main():
     for k, v in r["losses"].items():
         blob["loss/" + k] = np.float64(v)
     np.savez_compressed(os.path.join(outdir, "tiny_kl_l1_out1.npz"), **blob)
+
+    # ---- (1c) MFM_KL_EF (mfm_model.py:557-660): the early-fusion variant of the same family ----
+    configs = O.tiny_configs(output_dim=1)
+    seed, T, n, data_seed, noise_seed = 654, 5, 7, 13, 78
+    r = run_reference(ref, configs, seed, T, n, "l1", data_seed, noise_seed, variant="kl_ef")
+    check_oracle(r, configs, seed, n, "l1", noise_seed, "tiny_kl_ef/l1/out1", variant="kl_ef")
+    blob = dict(meta=np.array([seed, T, n, data_seed, noise_seed, 1]), x=r["x"].numpy(), y=r["y"].numpy())
+    for k, v in r["params0"].items():
+        blob["p0/" + k] = v.numpy()
+    for k, v in r["params1"].items():
+        blob["p1/" + k] = v.numpy()
+    for k, v in r["grads"].items():
+        if v is not None:
+            blob["g/" + k] = v.numpy()
+    for k, v in r["lat"].items():
+        blob["lat/" + k] = v.numpy()
+    for k in ("x_l_hat", "x_a_hat", "x_v_hat", "y_hat"):
+        blob[k] = r[k].numpy()
+    for k, v in r["losses"].items():
+        blob["loss/" + k] = np.float64(v)
+    np.savez_compressed(os.path.join(outdir, "tiny_kl_ef_l1_out1.npz"), **blob)
 
     # ---- (2) BASELINE configs[0]: MOSI shapes, best_acc dims, B=32, T=20 --------------
     # parameters are regenerated from the seed (2.9 MB otherwise); the fixture keeps

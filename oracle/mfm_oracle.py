@@ -75,7 +75,8 @@ def tiny_configs(output_dim=1):
 def param_shapes(configs, variant: str = "mfm") -> "OrderedDict[str, Tuple[int, ...]]":
     """state_dict names and shapes in the reference's construction order
     (mfm_model.py:491-520 for MFM; :43-44 encoderLSTM; :67-68 decoderLSTM;
-    :116-137 MFN).  90 tensors.  variant "kl": MFM_KL (mfm_model.py:683-721), 104 tensors."""
+    :116-137 MFN).  90 tensors.  variant "kl": MFM_KL (mfm_model.py:683-721), 104 tensors.  variant "kl_ef": MFM_KL_EF
+    (mfm_model.py:579-619): the MFN encoder is replaced by ONE early-fusion encoderLSTM over the concatenated input."""
     config, nn1, nn2, g1, g2, out = configs
     d = config["input_dims"]
     hm = config["h_dims"]
@@ -102,6 +103,24 @@ def param_shapes(configs, variant: str = "mfm") -> "OrderedDict[str, Tuple[int, 
         hd = fy + f[m]
         lstm("decoder_%s.lstm" % tag, hd, hd)
         lin("decoder_%s.fc1" % tag, hd, d[m])
+    if variant == "kl_ef":                                    # mfm_model.py:587-599
+        ef = sum(z)
+        lstm("ef_encoder.lstm", sum(d), ef)
+        lin("ef_encoder.fc1", ef, ef)
+        lin("last_to_zy_fc1", ef, zy)
+        lin("last_to_logvarzy_fc1", ef, zy)
+        for m, tag in enumerate("lav"):
+            lin("last_to_z%s_fc1" % tag, z[m], z[m])
+        for m, tag in enumerate("lav"):
+            lin("last_to_logvarz%s_fc1" % tag, z[m], z[m])
+        lin("zy_to_fy_fc1", zy, fy)
+        lin("zy_to_fy_fc2", fy, fy)
+        for m, tag in enumerate("lav"):
+            lin("z%s_to_f%s_fc1" % (tag, tag), z[m], f[m])
+            lin("z%s_to_f%s_fc2" % (tag, tag), f[m], f[m])
+        lin("fy_to_y_fc1", fy, fy)
+        lin("fy_to_y_fc2", fy, config["output_dim"])
+        return shapes
     for m, tag in enumerate("lav"):
         lstm("mfn_encoder.lstm_%s" % tag, d[m], hm[m])
     att_in = H * config["windowsize"]
@@ -384,6 +403,35 @@ def mfm_kl_forward(x: Tensor, P, configs, train=False, masks=None, branches=None
                 mfn_last=mfn_last)
 
 
+def mfm_kl_ef_forward(x: Tensor, P, configs, train=False, masks=None, branches=None):
+    """MFM_KL_EF.forward, mfm_model.py:621-660: MFM_KL with the MFN encoder replaced by one early-fusion encoderLSTM over
+    the whole input (``ef_encoder``, hidden size zl+za+zv); z_y and its log-variance are Linears of its output."""
+    config = configs[0]
+    d_l, d_a, d_v = config["input_dims"]
+    T = x.shape[0]
+    x_l, x_a, x_v = x[:, :, :d_l], x[:, :, d_l:d_l + d_a], x[:, :, d_l + d_a:]
+    lasts = [encoder_lstm(x_l, P, "encoder_l"), encoder_lstm(x_a, P, "encoder_a"), encoder_lstm(x_v, P, "encoder_v")]    # :629-631
+    zs = [linear(lasts[m], P, "last_to_z%s_fc1" % tag) for m, tag in enumerate("lav")]                                  # :632-634
+    lvs = [linear(lasts[m], P, "last_to_logvarz%s_fc1" % tag) for m, tag in enumerate("lav")]                           # :635-637
+    ef_last = encoder_lstm(x, P, "ef_encoder")                                                                           # :639
+    zy = linear(ef_last, P, "last_to_zy_fc1")
+    lvy = linear(ef_last, P, "last_to_logvarzy_fc1")                                                                     # :640-641
+    kld = loss_kld(zs[0], lvs[0]) + loss_kld(zs[1], lvs[1]) + loss_kld(zs[2], lvs[2]) + loss_kld(zy, lvy)               # :643
+    zl, za, zv = zs
+    mk = (lambda k: None if masks is None else masks.get(k))
+    fy = factor_mlp(zy, P, "zy_to_fy", config["zy_to_fy_dropout"], train, mk("fy"), branches, "fy")
+    fl = factor_mlp(zl, P, "zl_to_fl", config["zl_to_fl_dropout"], train, mk("fl"), branches, "fl")
+    fa = factor_mlp(za, P, "za_to_fa", config["za_to_fa_dropout"], train, mk("fa"), branches, "fa")
+    fv = factor_mlp(zv, P, "zv_to_fv", config["zv_to_fv_dropout"], train, mk("fv"), branches, "fv")
+    x_l_hat = decoder_lstm(torch.cat([fy, fl], 1), T, P, "decoder_l")
+    x_a_hat = decoder_lstm(torch.cat([fy, fa], 1), T, P, "decoder_a")
+    x_v_hat = decoder_lstm(torch.cat([fy, fv], 1), T, P, "decoder_v")
+    y1 = dropout(relu(linear(fy, P, "fy_to_y_fc1"), branches, "y1"), config["fy_to_y_dropout"], train, mk("y"))
+    y_hat = linear(y1, P, "fy_to_y_fc2")
+    return dict(x_l_hat=x_l_hat, x_a_hat=x_a_hat, x_v_hat=x_v_hat, y_hat=y_hat, mmd=kld,
+                zl=zl, za=za, zv=zv, zy=zy, lvl=lvs[0], lva=lvs[1], lvv=lvs[2], lvy=lvy, fy=fy, fl=fl, fa=fa, fv=fv)
+
+
 def mfm_losses(out: Dict[str, Tensor], x: Tensor, y: Tensor, configs, head: str = "l1") -> Dict[str, Tensor]:
     """Loss assembly of the train step: mfm_mosi.py:432-439 (L1 head) and
     mfm_mosi_acc.py:441-451 / mfm_moud.py:495-508 (cross-entropy head)."""
@@ -432,6 +480,8 @@ def train_step(P, x, y, configs, noise, state, head="l1", lr=1e-3, train=False, 
     Pg = OrderedDict((k, v.detach().clone().requires_grad_(k not in UNUSED_PARAMS)) for k, v in P.items())
     if variant == "kl":
         out = mfm_kl_forward(x, Pg, configs, train=train, masks=masks, branches=branches)
+    elif variant == "kl_ef":
+        out = mfm_kl_ef_forward(x, Pg, configs, train=train, masks=masks, branches=branches)
     else:
         out = mfm_forward(x, Pg, configs, noise, train=train, masks=masks, branches=branches)
     losses = mfm_losses(out, x, y, configs, head)

@@ -59,10 +59,11 @@ def train_masks_and_branches(eng, rng_cpu):
             taken = torch.where(k > 0, taken, torch.full_like(taken, -1.0))
             masks[key] = k.view(shape3) if shape3 else k
         br[bkey] = taken.view(shape3) if shape3 else taken
-    site("att1", "att1", dm.p_att1, ws["H1"], T * n, (T, n, -1))
-    site("att2", "att2", dm.p_att2, ws["H2"], T * n, (T, n, -1))
-    site("gamma1", "gamma1", dm.p_g1, ws["U1"], T * n, (T, n, -1))
-    site("gamma2", "gamma2", dm.p_g2, ws["U2"], T * n, (T, n, -1))
+    if not getattr(eng, "ef", False):                       # (MFM_KL_EF has no MFN: no attention / gamma dropouts)
+        site("att1", "att1", dm.p_att1, ws["H1"], T * n, (T, n, -1))
+        site("att2", "att2", dm.p_att2, ws["H2"], T * n, (T, n, -1))
+        site("gamma1", "gamma1", dm.p_g1, ws["U1"], T * n, (T, n, -1))
+        site("gamma2", "gamma2", dm.p_g2, ws["U2"], T * n, (T, n, -1))
     site("fy", "fy1", dm.p_fy, ws["F1y"], n)
     site("y", "y1", dm.p_y, ws["Y1"], n)
     for m, tag in enumerate("lav"):

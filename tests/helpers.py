@@ -45,3 +45,13 @@ def tiny_kl_case():
     x = torch.from_numpy(g["x"].copy())
     y = torch.from_numpy(g["y"].copy())
     return g, configs, P, x, y, T, n
+
+
+def tiny_kl_ef_case():
+    g = load_golden("tiny_kl_ef_l1_out1.npz")
+    seed, T, n, data_seed, noise_seed, od_ = [int(v) for v in g["meta"]]
+    configs = O.tiny_configs(output_dim=1)
+    P = golden_params(g)
+    x = torch.from_numpy(g["x"].copy())
+    y = torch.from_numpy(g["y"].copy())
+    return g, configs, P, x, y, T, n

@@ -10,7 +10,7 @@ import torch
 from oracle import mfm_oracle as O
 from factorized_b200.engine import Engine
 from emu_ops import EmuOps
-from helpers import rel_l2, tiny_case, tiny_kl_case
+from helpers import rel_l2, tiny_case, tiny_kl_case, tiny_kl_ef_case
 
 
 def run_engine(configs, P, x, y, noise, T, n, head, dtype=torch.float32, train=False, rng=None):
@@ -147,4 +147,30 @@ def test_engine_kl_variant_matches_reference_golden():
                 bad.append((k, e))
         else:
             assert float(G[k].abs().max()) == 0.0, k
+    assert not bad, bad
+
+
+def test_engine_kl_ef_variant_matches_reference_golden():
+    """MFM_KL_EF (mfm_model.py:557-660: one early-fusion encoder cell instead of the MFN): schedule + hand-derived backward
+    against the golden vectors of the unmodified reference class."""
+    g, configs, P, x, y, T, n = tiny_kl_ef_case()
+    P = OrderedDict(P)
+    assert "ef_encoder.lstm.weight_ih" in P and not any(k.startswith("mfn_encoder") for k in P)
+    eng = Engine(configs, T, n, "cpu", EmuOps(), head="l1", variant="kl_ef")
+    out = eng.forward(P, x.contiguous(), [torch.zeros(1, 1)] * 4)
+    dX, dY = eng.losses(y)
+    G = OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    eng.backward(P, G, dX, dY, eng.dm.lda_mmd)
+    tol = 1e-4
+    for k in ("zl", "za", "zv", "zy"):
+        assert rel_l2(out[k], g["lat/" + k]) < tol, k
+    assert rel_l2(out["y_hat"], g["y_hat"]) < tol
+    lb = eng.loss_buf
+    assert abs(float(lb[4:8].sum()) * configs[0]["lda_mmd"] - float(g["loss/mmd"])) < tol * abs(float(g["loss/mmd"]))
+    assert abs(float(lb[8]) - float(g["loss/total"])) < tol * abs(float(g["loss/total"]))
+    bad = []
+    for k in P:
+        e = rel_l2(G[k], g["g/" + k])
+        if e > 2e-4:
+            bad.append((k, e))
     assert not bad, bad

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import mfm_oracle as O
-from helpers import load_golden, rel_l2, tiny_case, tiny_kl_case
+from helpers import load_golden, rel_l2, tiny_case, tiny_kl_case, tiny_kl_ef_case
 
 pytestmark = pytest.mark.gpu
 
@@ -512,3 +512,79 @@ def test_mfm_kl_train_mode_step_and_train_mfm_dispatch(tmp_path):
     Xtr, ytr = rs.randn(40, 5, D).astype(np.float32), rs.randn(40).astype(np.float32)
     out = F.train_mfm(Xtr, ytr, Xtr[:16], ytr[:16], Xtr[:16], ytr[:16], cfg, verbose=False, save_dir=str(tmp_path))
     assert type(out["model"]).__name__ == "MFM_KL" and np.isfinite(out["history"][0][1])
+
+
+@pytest.mark.gpu
+def test_mfm_kl_ef_variant_golden_module_and_trainer():
+    """MFM_KL_EF (mfm_model.py:557-660: one early-fusion encoder cell over the whole input instead of the MFN) on the GPU: the
+    drop-in module under torch autograd against the golden vectors of the unmodified reference, then the fused trainer."""
+    import factorized_b200 as F
+    from factorized_b200.train import MFMTrainer
+    g, configs, P, x, y, T, n = tiny_kl_ef_case()
+    torch.manual_seed(int(g["meta"][0]))
+    model = F.MFM_KL_EF(*configs).cuda().eval()
+    sd = model.state_dict()
+    assert list(sd) == list(P)
+    for k, v in sd.items():
+        assert torch.equal(v.cpu(), P[k]), k                      # same construction order -> same init stream
+    xd, yd = x.cuda(), y.cuda()
+    decoded, kld, missing = model.forward(xd)
+    c = configs[0]
+    d_l, d_a, d_v = c["input_dims"]
+    Fn = torch.nn.functional
+    gen = c["lda_xl"] * Fn.mse_loss(decoded[0], xd[:, :, :d_l]) + c["lda_xa"] * Fn.mse_loss(decoded[1], xd[:, :, d_l:d_l + d_a]) \
+        + c["lda_xv"] * Fn.mse_loss(decoded[2], xd[:, :, d_l + d_a:])
+    loss = Fn.l1_loss(decoded[3].squeeze(1), yd) + gen + c["lda_mmd"] * kld + missing
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss/total"])) < TOL * abs(float(g["loss/total"]))
+    for k in ("zl", "za", "zv", "zy"):
+        assert rel_l2(model.latents[k], g["lat/" + k]) < TOL
+    bad = {k: rel_l2(p.grad, g["g/" + k]) for k, p in model.named_parameters() if not rel_l2(p.grad, g["g/" + k]) < TOL}
+    assert not bad, bad
+    # fused trainer (dropout is 0 in the tiny configuration: its train-mode step equals the reference's golden step)
+    torch.manual_seed(int(g["meta"][0]))
+    model2 = F.MFM_KL_EF(*configs).cuda()
+    tr = MFMTrainer(model2, T, n, head="l1", use_graph=False)
+    tr.x.copy_(xd)
+    tr.y.copy_(yd.reshape(-1))
+    tr.step_device()
+    torch.cuda.synchronize()
+    assert abs(float(tr.eng.loss_buf[8]) - float(g["loss/total"])) < TOL * abs(float(g["loss/total"]))
+    sd2 = model2.state_dict()
+    bad = {k: rel_l2(sd2[k].cpu() - P[k], g["p1/" + k] - P[k].numpy()) for k in P}
+    bad = {k: v for k, v in bad.items() if not v < 5e-3}
+    assert not bad, bad
+
+
+def test_mfm_kl_ef_train_mode_step_at_mosi_shapes():
+    """MFM_KL_EF at MOSI shapes (early-fusion cell h = 120: the CUDA-core recurrence serves it beside the tensor-core encoder
+    cells), train mode, CUDA graph, dropout masks replayed in the oracle."""
+    import factorized_b200 as F
+    from factorized_b200.train import MFMTrainer
+    from oracle.rng_replay import train_masks_and_branches
+    configs = O.best_acc_configs(dropout=True)
+    T, n = 20, 96
+    torch.manual_seed(123)
+    model = F.MFM_KL_EF(*configs).cuda().train()
+    P = OrderedDict((k, v.detach().cpu().clone()) for k, v in model.state_dict().items())
+    tr = MFMTrainer(model, T, n, head="l1", use_graph=True, seed=99)
+    x, y = O.synthetic_batch(configs, T, n, 5)
+    lb = tr.step(x.cuda(), y.cuda())
+    torch.cuda.synchronize()
+    masks, br = train_masks_and_branches(tr.eng, tr.rng.cpu())
+    del O.RELU_REPLAY_VIOLATIONS[:]
+    newP, losses, Go, outo = O.train_step(P, x, y, configs, None, {}, head="l1", train=True, masks=masks, branches=br, variant="kl_ef")
+    assert not O.RELU_REPLAY_VIOLATIONS
+    lbc = lb.cpu()
+    assert abs(float(lbc[8]) - losses["total"]) < TOL * abs(losses["total"])
+    bad = {k: rel_l2(tr.G[k], go) for k, go in Go.items() if go is not None and not rel_l2(tr.G[k], go) < TOL}
+    assert not bad, bad
+    # post-Adam parameters: the first Adam step is lr * g / (|g| + eps), i.e. sign-like, so entries with |g| ~ eps (the text
+    # cell's input weights have thousands) turn a 1e-7 gradient difference into a visible step difference: looser bound on
+    # the step, tight bound on the parameters themselves
+    sd = model.state_dict()
+    bad = {k: rel_l2(sd[k].cpu() - P[k], newP[k] - P[k]) for k in P if Go[k] is not None}
+    bad = {k: v for k, v in bad.items() if not v < 3e-2}
+    assert not bad, bad
+    bad = {k: rel_l2(sd[k].cpu(), newP[k]) for k in P if not rel_l2(sd[k].cpu(), newP[k]) < 1e-4}
+    assert not bad, bad

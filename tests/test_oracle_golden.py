@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import mfm_oracle as O
-from helpers import load_golden, golden_params, rel_l2, tiny_case, tiny_kl_case
+from helpers import load_golden, golden_params, rel_l2, tiny_case, tiny_kl_case, tiny_kl_ef_case
 
 TOL = 2e-5   # fp32 op-order noise between two torch formulations of the same math
 
@@ -86,4 +86,23 @@ def test_tiny_kl_full_step():
         else:
             assert G[k] is None and k in O.UNUSED_PARAMS
     for k in P:
+        assert rel_l2(newP[k], g["p1/" + k]) < TOL, k
+
+
+def test_tiny_kl_ef_full_step():
+    """MFM_KL_EF (mfm_model.py:557-660) restated in oracle.mfm_kl_ef_forward, against the unmodified reference's class."""
+    g, configs, P, x, y, T, n = tiny_kl_ef_case()
+    P2 = O.init_params(configs, int(g["meta"][0]), variant="kl_ef")
+    assert list(P2) == list(P) and len(P) == 78
+    for k in P:
+        assert torch.equal(P[k], P2[k]), k
+    newP, losses, G, out = O.train_step(P, x, y, configs, None, {}, head="l1", variant="kl_ef")
+    for k in ("zl", "za", "zv", "zy"):
+        assert rel_l2(out[k], g["lat/" + k]) < TOL, k
+    for k in ("x_l_hat", "x_a_hat", "x_v_hat", "y_hat"):
+        assert rel_l2(out[k], g[k]) < TOL, k
+    for k, v in losses.items():
+        assert abs(v - float(g["loss/" + k])) <= TOL * abs(float(g["loss/" + k])) + 1e-7, k
+    for k in P:
+        assert rel_l2(G[k], g["g/" + k]) < TOL, k
         assert rel_l2(newP[k], g["p1/" + k]) < TOL, k
