@@ -76,7 +76,7 @@ __device__ __forceinline__ void tc_epilogue_t(const TcArgs& ta, uint32_t tmem_ba
     float v[32];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (c0 + 8 * q < cend && !(ta.dbg & 32)) {          // warp-uniform  (dbg 32: experiment, no TMEM loads)
+      if (c0 + 8 * q < cend) {                            // warp-uniform
         uint32_t r[8];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -165,7 +165,6 @@ __device__ __forceinline__ void tc_epilogue_t(const TcArgs& ta, uint32_t tmem_ba
               }
             }
             float* cp = e_C + (long long)(mbase + rr) * e_ldc + n;
-            if (ta.dbg & 16) continue;                        // experiment: no global stores
             if (full4) {
               if (e_acc) {
                 const float4 o = *reinterpret_cast<const float4*>(cp);
