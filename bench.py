@@ -404,6 +404,31 @@ def main():
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
     pk = peaks()
 
+    # ---- (C) the other scaling mode, briefly: a weak run also reports the STRONG-scaling rate of the same global batch ------
+    # (every rank runs this identically: the second trainer's all-reduce is a collective)
+    other = None
+    if world > 1 and scaling == "weak" and batch % world == 0 and batch // world >= 16:
+        Bs = batch // world
+        torch.manual_seed(123)
+        model_s = F.MFM(*configs).to(dev).train()
+        tr_s = MFMTrainer(model_s, T, Bs, head=head, use_graph=not args.no_graph, seed=123)
+        xs_s = [t[:, :Bs].contiguous() for t in xs_dev[:2]]
+        ys_s = [t.view(B, -1)[:Bs].reshape(-1).contiguous() for t in ys_dev[:2]]
+        for i in range(max(args.warmup, 3)):
+            tr_s.x.copy_(xs_s[i % 2]); tr_s.y.copy_(ys_s[i % 2]); tr_s.step_device()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(args.steps):
+            tr_s.x.copy_(xs_s[i % 2]); tr_s.y.copy_(ys_s[i % 2]); tr_s.step_device()
+        g1.record()
+        barrier()
+        ms_s = max_over_ranks(g0.elapsed_time(g1))
+        other = dict(scaling="strong", global_batch=batch, per_gpu_batch=Bs, ms_per_step=ms_s / args.steps,
+                     value=world * Bs * args.steps / (ms_s * 1e-3), unit="samples/s",
+                     note="same workload with the GLOBAL batch held at %d (split over the ranks); %d timed steps after the main run" % (batch, args.steps))
+        del tr_s, model_s
+
     # ---- replicas must hold identical parameters after the same number of steps (the all-reduce keeps them in sync) -----
     replicas = None
     if world > 1:
@@ -477,6 +502,7 @@ def main():
                          d2h_bytes_per_step=64 * world, ms_per_step=ms_e2e / args.steps),
                 gpu_launches=trainer.launches_per_step * args.steps, launches_per_step=trainer.launches_per_step,
                 cuda_graph=not args.no_graph, clocks=clocks, roofline=roof, kernels=kernels, final_loss=final_loss,
+                strong_scaling=other,
                 parity_check=parity, replicas=replicas,
                 workspace_mb=round(trainer.eng.workspace_bytes() / 2 ** 20, 1))
     if rank == 0 and os.environ.get("MFM_BENCH_GEMM_SHAPES"):
