@@ -72,6 +72,41 @@ def test_gemm_strided_views_and_epilogues(ops):
     assert rel_l2(o_gpu, o_cpu) < TOL
 
 
+@pytest.mark.parametrize("mode,M,N,K,act,drop,persistent", [
+    ("nt", 40960, 400, 128, 0, None, True),          # resident weight image, three N tiles (160 / 160 / 96)
+    ("nt", 8192, 128, 400, 1, None, True),           # streaming mode (the image does not fit beside the ring)
+    ("nn", 12288, 400, 384, 0, None, True),          # NN: MN-major weight image
+    ("nt", 4100, 36, 20, 2, None, True),             # ragged last row tile, N tail clipped by the TMA store, K < one stage
+    ("nn", 5000, 300, 104, 3, None, True),           # K tail (104 = 3 stages + 8)
+    ("nt", 8192, 64, 128, 2, (0.3, 5), True),        # dropout in the epilogue
+    ("nt", 6000, 480, 300, 1, (0.5, 2), True),       # three streaming N tiles, odd tile count per CTA (unpaired last tile)
+    ("nt", 4096, 34, 64, 0, None, False),            # N not a multiple of 4: the per-tile kernel serves it
+    ("nt", 4000, 128, 128, 0, None, False),          # M < 4096: no weight-image workspace, per-tile kernel
+])
+def test_gemm_persistent_kernel(ops, mode, M, N, K, act, drop, persistent):
+    """The persistent streamed GEMM (csrc/gemm_ps.cu: TMA-fed ring, two MMA issuers, TMA-store epilogue) on the shapes /
+    epilogues it accepts, against fp64; the launch counter proves which kernel served the call; the padding columns of a
+    wider output buffer must stay untouched."""
+    gen = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=gen).cuda()
+    B = (torch.randn((N, K) if mode == "nt" else (K, N), generator=gen) / K ** 0.5).cuda()
+    ldc = (N + 3) // 4 * 4 + 4
+    Cfull = torch.full((M, ldc), 7.0).cuda()
+    C = Cfull[:, :N]
+    bias = torch.randn(N, generator=gen).cuda()
+    rng = torch.tensor([1234, 3], dtype=torch.int64)
+    n0 = ops.lib.mfm_debug_gemm_ps_count()
+    ops.gemm(mode, A, B, C, bias=bias, act=act, drop=drop, rng=rng.cuda())
+    torch.cuda.synchronize()
+    assert ops.lib.mfm_debug_gemm_ps_count() - n0 == (1 if persistent else 0)
+    ref = A.double() @ (B.double().t() if mode == "nt" else B.double()) + bias.double()
+    ref = [ref, ref.clamp_min(0), torch.tanh(ref), torch.sigmoid(ref)][act]
+    if drop:
+        ref = ref * keep_mask(rng, drop[1], drop[0], M, N).cuda().double() / (1 - drop[0])
+    assert rel_l2(C.double(), ref) < TOL
+    assert bool((Cfull[:, N:] == 7.0).all())
+
+
 @pytest.mark.parametrize("path", ["simt_fp32", "tcgen05_bf16x3"])
 @pytest.mark.parametrize("M,N,K,ldx,want_xhat", [(640, 300, 104, 300, False), (4500, 300, 104, 300, True), (700, 5, 24, 8, True),
                                                    (333, 20, 24, 20, False), (64, 7, 9, 7, True)])
