@@ -27,7 +27,8 @@
 // Tensor memory: 2 x BN accumulator columns + 32 S operand columns <= 512 (one CTA per SM owns all of it).
 // Scope (else the caller uses gemm_tcp.cu): NT / NN with a pre-split B image (weights), M >= 4096, 16 B-aligned A and C
 // with leading dimensions that are multiples of 4, N a multiple of 4 (the TMA store clips whole 16 B units), epilogue =
-// bias (+ bias2) + activation + dropout.
+// bias (+ bias2) + activation + dropout, or -- on the plain product -- ONE operand tile (TMA-loaded one block ahead, same box and
+// swizzle as the output): ReLU mask, accumulate into C, or the fused MSE head (residual, its square sum, its gradient).
 #include <cstdio>
 #include "tcp_shared.cuh"
 
@@ -53,7 +54,9 @@ struct PsArgs {
   int resident;        // 1: each CTA serves ONE N tile and keeps that tile's whole weight image in shared memory
   int S, stage_bytes;
   int passes;
-  int off_res, off_stag, off_bias, off_bar;
+  int off_res, off_stag, off_aux, off_bias, off_bar;
+  int aux;             // epilogue operand tile, TMA-loaded beside the output box: 0 none, 1 ReLU mask (C = mask > 0 ? v * scale : 0),
+                       // 2 accumulate (C += v; the operand is C itself), 3 fused MSE head (operand x: C = grad_scale (v - x))
   long long* trace;    // PS_DEBUG builds only
 };
 
@@ -134,11 +137,19 @@ __device__ __forceinline__ void ps_convert(const unsigned char* st, uint32_t tco
                  "r"(l[2]), "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]) : "memory");
 }
 
-template <int ACT>
-__device__ __forceinline__ void ps_epilogue(const PsArgs& pa, const CUtensorMap* tmC, uint32_t tmem_base, unsigned char* smem,
-                                            unsigned long long* acc_full, unsigned long long* acc_free, int ew, int lane,
-                                            long long pa_t0) {
+#define PS_AUX_MASK 1
+#define PS_AUX_ACC 2
+#define PS_AUX_MSE 3
+template <int ACT, int AUX>
+__device__ __forceinline__ void ps_epilogue(const PsArgs& pa, const CUtensorMap* tmC, const CUtensorMap* tmX, uint32_t tmem_base,
+                                            unsigned char* smem, unsigned long long* acc_full, unsigned long long* acc_free,
+                                            unsigned long long* aux_bar_all, int ew, int lane, long long pa_t0) {
   const GemmArgs& a = pa.g;
+  // AUX: the operand tile of block k+1 is TMA-loaded (same 32x32 box, same 128 B swizzle as the output box; rows / columns
+  // beyond M / N are zero-filled) into one of two buffers while block k is processed
+  const uint32_t auxb = AUX ? smem_u32(smem + pa.off_aux) + (uint32_t)ew * 8192u : 0u;
+  unsigned long long* const aux_bar = aux_bar_all + ew * 2;
+  float sq = 0.0f;
   const float* sbias = reinterpret_cast<const float*>(smem + pa.off_bias);
   const uint32_t stag = smem_u32(smem + pa.off_stag) + (uint32_t)ew * 8192u;
   const bool do_drop = a.drop_p > 0.0f;
@@ -150,6 +161,14 @@ __device__ __forceinline__ void ps_epilogue(const PsArgs& pa, const CUtensorMap*
   int blk = 0;
   const PsWalk walk(pa);
   if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmC)) : "memory");
+  if (AUX && lane == 0) {
+    int mt0, j0;
+    if (walk.get(0, mt0, j0)) {
+      const uint32_t ab = smem_u32(&aux_bar[0]);
+      mbar_expect_tx(ab, 4096u);
+      tma_load_2d(auxb, tmX, j0 * pa.BN, mt0 * P_BM + ew * 32, ab);
+    }
+  }
   for (int i = 0, mt, j; walk.get(i, mt, j); ++i) {
     const int bn = (j == pa.NT - 1) ? pa.BN_last : pa.BN;
     const int n0 = j * pa.BN, mrow = mt * P_BM + ew * 32;
@@ -180,6 +199,21 @@ __device__ __forceinline__ void ps_epilogue(const PsArgs& pa, const CUtensorMap*
       __syncwarp();
       const int n = n0 + c0;
       const uint32_t e0 = (uint32_t)(mrow + lane) * (uint32_t)a.N + (uint32_t)n;
+      uint32_t ax = 0u;
+      if (AUX) {
+        int ni = i, nc0 = c0 + 32, nmt = mt, nj = j;          // the next block of this warp: same tile, or the next tile's first
+        bool have = true;
+        if (nc0 >= bn) { ni = i + 1; nc0 = 0; have = walk.get(ni, nmt, nj); }
+        if (have && lane == 0) {                               // (every lane finished reading that buffer two blocks ago: the
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     //  __syncwarp above orders it before this issue)
+          const uint32_t ab = smem_u32(&aux_bar[(blk + 1) & 1]);
+          mbar_expect_tx(ab, 4096u);
+          tma_load_2d(auxb + (uint32_t)((blk + 1) & 1) * 4096u, tmX, nj * pa.BN + nc0, nmt * P_BM + ew * 32, ab);
+        }
+        mbar_wait(smem_u32(&aux_bar[blk & 1]), (uint32_t)((blk >> 1) & 1));
+        ax = auxb + (uint32_t)(blk & 1) * 4096u + (uint32_t)lane * 128u;
+      }
+      const bool row_ok = mrow + lane < a.M;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 b4 = *reinterpret_cast<const float4*>(sbias + n + 4 * q);
@@ -188,6 +222,21 @@ __device__ __forceinline__ void ps_epilogue(const PsArgs& pa, const CUtensorMap*
         v.y = act_t<ACT>(__uint_as_float(r[4 * q + 1]) + b4.y);
         v.z = act_t<ACT>(__uint_as_float(r[4 * q + 2]) + b4.z);
         v.w = act_t<ACT>(__uint_as_float(r[4 * q + 3]) + b4.w);
+        if (AUX) {
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                       : "r"(ax + (((uint32_t)q ^ swz) << 4)));
+          if (AUX == PS_AUX_MASK) {
+            v.x = x.x > 0.0f ? v.x * a.mask_scale : 0.0f; v.y = x.y > 0.0f ? v.y * a.mask_scale : 0.0f;
+            v.z = x.z > 0.0f ? v.z * a.mask_scale : 0.0f; v.w = x.w > 0.0f ? v.w * a.mask_scale : 0.0f;
+          } else if (AUX == PS_AUX_ACC) {
+            v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+          } else {                                             // MSE head: residual, its square (valid elements only), its gradient
+            v.x -= x.x; v.y -= x.y; v.z -= x.z; v.w -= x.w;
+            if (row_ok && n + 4 * q < a.N) sq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, sq))));
+            v.x *= a.mse.grad_scale; v.y *= a.mse.grad_scale; v.z *= a.mse.grad_scale; v.w *= a.mse.grad_scale;
+          }
+        }
         if (do_drop) {
           v.x = drop_keep(sseed, e0 + 4 * q, a.drop_p) ? v.x * keep_scale : 0.0f;
           v.y = drop_keep(sseed, e0 + 4 * q + 1, a.drop_p) ? v.y * keep_scale : 0.0f;
@@ -210,11 +259,16 @@ __device__ __forceinline__ void ps_epilogue(const PsArgs& pa, const CUtensorMap*
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __syncwarp();
+  if (AUX == PS_AUX_MSE) {                          // one atomic per warp
+    sq = warp_sum(sq);
+    if (lane == 0) atomicAdd(a.mse.slot, sq * a.mse.loss_scale);
+  }
 }
 
 template <bool B_MN>
 __global__ void __launch_bounds__(PS_THREADS, 1) gemm_ps_kernel(const PsArgs pa, const __grid_constant__ CUtensorMap tmA,
-                                                                const __grid_constant__ CUtensorMap tmC) {
+                                                                const __grid_constant__ CUtensorMap tmC,
+                                                                const __grid_constant__ CUtensorMap tmX) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const GemmArgs& a = pa.g;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -227,6 +281,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) gemm_ps_kernel(const PsArgs pa,
   unsigned long long* const acc_free = bars + 3 * PS_MAXRING + 2; // [2] accumulator drained (4 epilogue warps)
   unsigned long long* const res_bar = bars + 3 * PS_MAXRING + 4;  // resident weight image landed
   uint32_t& tmem_holder = *reinterpret_cast<uint32_t*>(bars + 3 * PS_MAXRING + 5);
+  unsigned long long* const aux_bar = bars + 3 * PS_MAXRING + 6;  // [4 epilogue warps][2] epilogue operand tile landed
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
@@ -238,6 +293,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) gemm_ps_kernel(const PsArgs pa,
       mbar_init(smem_u32(&acc_free[b]), 4);
     }
     mbar_init(smem_u32(res_bar), 1);
+    for (int b = 0; b < 8; ++b) mbar_init(smem_u32(&aux_bar[b]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
@@ -293,11 +349,14 @@ __global__ void __launch_bounds__(PS_THREADS, 1) gemm_ps_kernel(const PsArgs pa,
   } else if (warp < PS_WPROD) {
     // ================================ EPILOGUE ================================
     const int ew = warp - PS_WEPI;
-    switch (a.act) {                               // CTA-uniform
-      case MFM_ACT_RELU: ps_epilogue<MFM_ACT_RELU>(pa, &tmC, tmem_base, smem, acc_full, acc_free, ew, lane, pa_t0); break;
-      case MFM_ACT_TANH: ps_epilogue<MFM_ACT_TANH>(pa, &tmC, tmem_base, smem, acc_full, acc_free, ew, lane, pa_t0); break;
-      case MFM_ACT_SIGMOID: ps_epilogue<MFM_ACT_SIGMOID>(pa, &tmC, tmem_base, smem, acc_full, acc_free, ew, lane, pa_t0); break;
-      default: ps_epilogue<MFM_ACT_NONE>(pa, &tmC, tmem_base, smem, acc_full, acc_free, ew, lane, pa_t0); break;
+    if (pa.aux == PS_AUX_MASK)     ps_epilogue<MFM_ACT_NONE, PS_AUX_MASK>(pa, &tmC, &tmX, tmem_base, smem, acc_full, acc_free, aux_bar, ew, lane, pa_t0);
+    else if (pa.aux == PS_AUX_ACC) ps_epilogue<MFM_ACT_NONE, PS_AUX_ACC>(pa, &tmC, &tmC, tmem_base, smem, acc_full, acc_free, aux_bar, ew, lane, pa_t0);
+    else if (pa.aux == PS_AUX_MSE) ps_epilogue<MFM_ACT_NONE, PS_AUX_MSE>(pa, &tmC, &tmX, tmem_base, smem, acc_full, acc_free, aux_bar, ew, lane, pa_t0);
+    else switch (a.act) {                          // CTA-uniform
+      case MFM_ACT_RELU: ps_epilogue<MFM_ACT_RELU, 0>(pa, &tmC, &tmX, tmem_base, smem, acc_full, acc_free, aux_bar, ew, lane, pa_t0); break;
+      case MFM_ACT_TANH: ps_epilogue<MFM_ACT_TANH, 0>(pa, &tmC, &tmX, tmem_base, smem, acc_full, acc_free, aux_bar, ew, lane, pa_t0); break;
+      case MFM_ACT_SIGMOID: ps_epilogue<MFM_ACT_SIGMOID, 0>(pa, &tmC, &tmX, tmem_base, smem, acc_full, acc_free, aux_bar, ew, lane, pa_t0); break;
+      default: ps_epilogue<MFM_ACT_NONE, 0>(pa, &tmC, &tmX, tmem_base, smem, acc_full, acc_free, aux_bar, ew, lane, pa_t0); break;
     }
   } else if (warp == PS_WPROD) {
     // ================================ PRODUCER (one thread) ================================
@@ -411,8 +470,8 @@ extern "C" int mfm_debug_gemm_ps_count(void) { return g_ps_launches; }
 // accumulators + >= 4 operand stages in 512 TMEM columns), the last as narrow as N allows.  Per chunk a tile costs three
 // MMAs of max(~110 cycles fixed, bn/2), 8 KB of A and -- streaming -- its weight image from L2 (~40 B/cycle/SM when every SM
 // pulls), and the ring's round trip (~3 000 cycles) divided by its depth.  Env MFM_PS_NT / MFM_PS_RES pin the choice.
-struct PsPlan { int BN, BN_last, NT, resident, S, stage_bytes, off_res, off_stag, off_bias, off_bar; double cost; };
-static bool ps_plan_one(int MT, int N, int nck, int sms, int nt, int resident, PsPlan* pl) {
+struct PsPlan { int BN, BN_last, NT, resident, S, stage_bytes, off_res, off_stag, off_aux, off_bias, off_bar; double cost; };
+static bool ps_plan_one(int MT, int N, int nck, int sms, int nt, int resident, bool aux, PsPlan* pl) {
   const int bn = round_up((N + nt - 1) / nt, 32);
   if (bn > 224 || (long long)bn * (nt - 1) >= N || nt > sms) return false;
   const int bn_last = round_up(N - bn * (nt - 1), 32);
@@ -420,7 +479,8 @@ static bool ps_plan_one(int MT, int N, int nck, int sms, int nt, int resident, P
   const int stage = resident ? PS_STA : ((PS_STA + 2 * img + 1023) & ~1023);
   const int npad = (nt - 1) * bn + bn_last;
   const int res_bytes = resident ? ((nck * img + 1023) & ~1023) : 0;
-  const int fixed = res_bytes + PS_STAG_BYTES + round_up(npad * 4, 128) + 512;
+  const int aux_bytes = aux ? PS_STAG_BYTES : 0;           // two operand boxes per epilogue warp
+  const int fixed = res_bytes + PS_STAG_BYTES + aux_bytes + round_up(npad * 4, 128) + 512;
   int S = (PS_SMEM_BUDGET - fixed) / stage;
   const int by_tmem = (512 - 2 * bn) / 32;
   if (S > by_tmem) S = by_tmem;
@@ -435,12 +495,13 @@ static bool ps_plan_one(int MT, int N, int nck, int sms, int nt, int resident, P
   pl->BN = bn; pl->BN_last = bn_last; pl->NT = nt; pl->resident = resident; pl->S = S; pl->stage_bytes = stage;
   pl->off_res = S * stage;
   pl->off_stag = pl->off_res + res_bytes;
-  pl->off_bias = pl->off_stag + PS_STAG_BYTES;
+  pl->off_aux = pl->off_stag + PS_STAG_BYTES;
+  pl->off_bias = pl->off_aux + aux_bytes;
   pl->off_bar = pl->off_bias + round_up(npad * 4, 128);
   pl->cost = cost;
   return true;
 }
-static bool ps_plan(int M, int N, int K, int sms, PsPlan* best) {
+static bool ps_plan(int M, int N, int K, int sms, bool aux, PsPlan* best) {
   static int pin_nt = -1, pin_res = -1;
   if (pin_nt < 0) { const char* e = getenv("MFM_PS_NT"); pin_nt = e ? atoi(e) : 0; }
   if (pin_res < 0) { const char* e = getenv("MFM_PS_RES"); pin_res = e ? atoi(e) : 2; }
@@ -452,7 +513,7 @@ static bool ps_plan(int M, int N, int K, int sms, PsPlan* best) {
     for (int res = 0; res < 2; ++res) {
       if (pin_res < 2 && res != pin_res) continue;
       PsPlan pl;
-      if (!ps_plan_one(MT, N, nck, sms, nt, res, &pl)) continue;
+      if (!ps_plan_one(MT, N, nck, sms, nt, res, aux, &pl)) continue;
       if (!found || pl.cost < best->cost) { *best = pl; found = true; }
     }
   }
@@ -460,15 +521,24 @@ static bool ps_plan(int M, int N, int K, int sms, PsPlan* best) {
 }
 
 int gemm_ps_launch(int passes, int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
-                   float* C, long long ldc, const float* bias, const float* bias2, int act, float drop_p, int drop_site,
-                   const long long* rng, void* ws, size_t ws_bytes, cudaStream_t st) {
+                   float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate, const float* mask,
+                   long long ldmask, float mask_scale, float drop_p, int drop_site, const long long* rng, const GemmMse& mse,
+                   void* ws, size_t ws_bytes, cudaStream_t st) {
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("MFM_PS"); enabled = e ? atoi(e) : 1; }
   if (!enabled || mode == MFM_GEMM_TN || M < 4096 || N > PS_MAXN || N < 1 || (N & 3) || K < 1 || !ws) return MFM_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(C) & 15) || (ldc & 3) || (reinterpret_cast<uintptr_t>(ws) & 127)) return MFM_ERR_UNSUPPORTED;
+  // one epilogue operand at most, and only on the plain (no activation, no dropout) product; x_hat is not written here
+  const int naux = (mask ? 1 : 0) + (accumulate ? 1 : 0) + (mse.x ? 1 : 0);
+  if (naux > 1 || (naux && (act != MFM_ACT_NONE || drop_p > 0.0f)) || (mse.x && mse.xhat)) return MFM_ERR_UNSUPPORTED;
+  const float* auxp = mask ? mask : mse.x ? mse.x : nullptr;
+  const long long auxld = mask ? ldmask : mse.x ? mse.ldx : 0;
+  if (auxp && ((reinterpret_cast<uintptr_t>(auxp) & 15) || (auxld & 3))) return MFM_ERR_UNSUPPORTED;
   PsArgs pa;
-  pa.g = GemmArgs{M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, 0, nullptr, 0, 1.0f, drop_p, drop_site, rng, K, 0, nullptr};
-  pa.g.mse = GemmMse{nullptr, 0, 0.0f, 0.0f, nullptr, nullptr, 0};
+  pa.g = GemmArgs{M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask, mask_scale, drop_p, drop_site, rng,
+                  K, 0, nullptr};
+  pa.g.mse = mse;
+  pa.aux = mask ? PS_AUX_MASK : accumulate ? PS_AUX_ACC : mse.x ? PS_AUX_MSE : 0;
   pa.passes = passes;
 #if PS_DEBUG
   pa.trace = g_ps_trace;
@@ -477,12 +547,12 @@ int gemm_ps_launch(int passes, int mode, int M, int N, int K, const float* A, lo
 #endif
   const int sms = mfm_dev_info().sms;
   PsPlan pl;
-  if (!ps_plan(M, N, K, sms, &pl)) return MFM_ERR_UNSUPPORTED;
+  if (!ps_plan(M, N, K, sms, naux > 0, &pl)) return MFM_ERR_UNSUPPORTED;
   static int verbose = -1;
   if (verbose < 0) { const char* e = getenv("MFM_PS_VERBOSE"); verbose = e ? atoi(e) : 0; }
   if (verbose) fprintf(stderr, "gemm_ps %dx%dx%d: NT %d BN %d/%d resident %d S %d cost %.0f\n", M, N, K, pl.NT, pl.BN, pl.BN_last, pl.resident, pl.S, pl.cost);
   pa.BN = pl.BN; pa.BN_last = pl.BN_last; pa.NT = pl.NT; pa.resident = pl.resident; pa.S = pl.S; pa.stage_bytes = pl.stage_bytes;
-  pa.off_res = pl.off_res; pa.off_stag = pl.off_stag; pa.off_bias = pl.off_bias; pa.off_bar = pl.off_bar;
+  pa.off_res = pl.off_res; pa.off_stag = pl.off_stag; pa.off_aux = pl.off_aux; pa.off_bias = pl.off_bias; pa.off_bar = pl.off_bar;
   pa.nck = (K + P_BK - 1) / P_BK;
   pa.nst = (K + PS_BK - 1) / PS_BK;
   pa.MT = (M + P_BM - 1) / P_BM;
@@ -491,8 +561,10 @@ int gemm_ps_launch(int passes, int mode, int M, int N, int K, const float* A, lo
   if (img_full * (pa.NT - 1) + img_last > ws_bytes) return MFM_ERR_UNSUPPORTED;
   pa.bimg = static_cast<const unsigned char*>(ws);
   const size_t smem = (size_t)pa.off_bar + 512;
-  CUtensorMap tmA, tmC;
+  CUtensorMap tmA, tmC, tmX;
   if (!make_map(&tmA, A, lda, K, M, PS_BK, P_BM) || !make_map(&tmC, C, ldc, N, M, 32, 32)) return MFM_ERR_UNSUPPORTED;
+  tmX = tmC;
+  if (auxp && !make_map(&tmX, auxp, auxld, N, M, 32, 32)) return MFM_ERR_UNSUPPORTED;
   dim3 pg(pa.NT, pa.nck, 1);
   if (mode == MFM_GEMM_NT) {
     if (int e = mfm_func_smem_t(gemm_ps_kernel<false>, PS_SMEM_BUDGET)) return e;
@@ -510,8 +582,8 @@ int gemm_ps_launch(int passes, int mode, int M, int N, int K, const float* A, lo
     const long long tiles = (long long)pa.MT * pa.NT;
     grid = tiles < sms ? (int)tiles : sms;
   }
-  if (mode == MFM_GEMM_NT) gemm_ps_kernel<false><<<grid, PS_THREADS, smem, st>>>(pa, tmA, tmC);
-  else                     gemm_ps_kernel<true><<<grid, PS_THREADS, smem, st>>>(pa, tmA, tmC);
+  if (mode == MFM_GEMM_NT) gemm_ps_kernel<false><<<grid, PS_THREADS, smem, st>>>(pa, tmA, tmC, tmX);
+  else                     gemm_ps_kernel<true><<<grid, PS_THREADS, smem, st>>>(pa, tmA, tmC, tmX);
   MFM_LAUNCH_CHECK();
   ++g_ps_launches;
   return MFM_OK;

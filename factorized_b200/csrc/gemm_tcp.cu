@@ -348,8 +348,9 @@ bool gemm_tcp_eligible(int mode, int M, int N, int K, const float* A, long long 
 }
 
 int gemm_ps_launch(int passes, int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
-                   float* C, long long ldc, const float* bias, const float* bias2, int act, float drop_p, int drop_site,
-                   const long long* rng, void* ws, size_t ws_bytes, cudaStream_t st);
+                   float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate, const float* mask,
+                   long long ldmask, float mask_scale, float drop_p, int drop_site, const long long* rng, const GemmMse& mse,
+                   void* ws, size_t ws_bytes, cudaStream_t st);
 
 int gemm_tcp_launch(int passes, int mode, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
                     float* C, long long ldc, const float* bias, const float* bias2, int act, int accumulate,
@@ -383,9 +384,9 @@ int gemm_tcp_launch(int passes, int mode, int M, int N, int K, const float* A, l
   const int n16 = round_up(N + (colsum_out ? 1 : 0), 16);
   const int ntiles = (n16 + maxbn - 1) / maxbn;
   ta.BN = round_up((n16 + ntiles - 1) / ntiles, 16);
-  if (bpre && !mask && !accumulate && !colsum_out && !g_pending_mse.x) {       // persistent kernel (gemm_ps.cu) where it applies
-    const int rc = gemm_ps_launch(passes, mode, M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, drop_p, drop_site, rng, ws,
-                                  ws_bytes, st);
+  if (bpre && !colsum_out) {                                                   // persistent kernel (gemm_ps.cu) where it applies
+    const int rc = gemm_ps_launch(passes, mode, M, N, K, A, lda, B, ldb, C, ldc, bias, bias2, act, accumulate, mask, ldmask,
+                                  mask_scale, drop_p, drop_site, rng, g_pending_mse, ws, ws_bytes, st);
     if (rc != MFM_ERR_UNSUPPORTED) return rc;
   }
   if (bpre) {

@@ -107,8 +107,36 @@ def test_gemm_persistent_kernel(ops, mode, M, N, K, act, drop, persistent):
     assert bool((Cfull[:, N:] == 7.0).all())
 
 
+@pytest.mark.parametrize("mode,M,N,K,kind", [("nn", 40960, 128, 400, "mask"), ("nn", 8192, 400, 128, "acc"), ("nt", 4100, 64, 72, "acc"),
+                                             ("nn", 6000, 128, 64, "mask"), ("nt", 5000, 36, 20, "mask")])
+def test_gemm_persistent_kernel_operand_epilogues(ops, mode, M, N, K, kind):
+    """The data-gradient epilogues of the persistent GEMM: ReLU mask (dA = (dY W) * (A > 0) * scale) and accumulate (C += ...),
+    their operand tile TMA-loaded one block ahead; against fp64, launch counter checked, padding untouched."""
+    gen = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=gen).cuda()
+    B = (torch.randn((N, K) if mode == "nt" else (K, N), generator=gen) / K ** 0.5).cuda()
+    ldc = N + 8
+    Cfull = torch.randn(M, ldc, generator=gen).cuda()
+    C0 = Cfull.clone()
+    C = Cfull[:, :N]
+    Hfull = torch.relu(torch.randn(M, N + 4, generator=gen)).cuda()
+    n0 = ops.lib.mfm_debug_gemm_ps_count()
+    ref = A.double() @ (B.double().t() if mode == "nt" else B.double())
+    if kind == "mask":
+        ops.gemm(mode, A, B, C, mask=Hfull[:, :N], mask_scale=2.0)
+        ref = torch.where(Hfull[:, :N] > 0, ref * 2.0, torch.zeros_like(ref))
+    else:
+        ops.gemm(mode, A, B, C, accumulate=True)
+        ref = ref + C0[:, :N].double()
+    torch.cuda.synchronize()
+    assert ops.lib.mfm_debug_gemm_ps_count() - n0 == 1
+    assert rel_l2(C.double(), ref) < TOL
+    assert torch.equal(Cfull[:, N:], C0[:, N:])
+
+
 @pytest.mark.parametrize("path", ["simt_fp32", "tcgen05_bf16x3"])
 @pytest.mark.parametrize("M,N,K,ldx,want_xhat", [(640, 300, 104, 300, False), (4500, 300, 104, 300, True), (700, 5, 24, 8, True),
+                                                 (4500, 300, 104, 300, False), (8200, 20, 24, 24, False),
                                                    (333, 20, 24, 20, False), (64, 7, 9, 7, True)])
 def test_gemm_mse_fused_reconstruction_head(ops, path, M, N, K, ldx, want_xhat):
     """mfm_gemm_mse: x_hat = A W^T + b with the MSE term and its gradient produced in the GEMM epilogue
