@@ -178,8 +178,12 @@ def profile_primitives(trainer, reps=3):
         rec.clear()
         shapes.clear()
         for _ in range(reps):
+            # The eager pass is host-bound (~30 us of Python per primitive): on an idle GPU every event bracket would also
+            # hold the host's launch latency (tensor-map encoding, two launches).  A spinning kernel in front of the pass keeps
+            # the GPU busy until the whole pass is queued, so the brackets measure device time only.
+            torch.cuda._sleep(int(4.0e7))
             trainer._schedule()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
         for tag, e0, e1, fl, by in rec:
             a = agg.setdefault(tag, [0.0, 0.0, 0, 0.0])
             a[0] += e0.elapsed_time(e1)
