@@ -153,18 +153,39 @@ class Engine:
         self.xs = xs
         drop = (lambda p, site: (p, site) if (train and p > 0.0) else None)
 
-        # (1) hoisted input projections  G_x = X W_ih^T + b_ih + b_hh   (encoders :56, MFN :167-169); one branch per modality
+        # (1) hoisted input projections  G_x = X W_ih^T + b_ih + b_hh   (encoders :56, MFN :167-169); one branch per modality.
+        #     The encoder cell and the MFN cell of a modality read the same x: their G_x are column blocks of ONE matrix, and
+        #     when the trainer has laid the two input weights (and bias vectors) out back to back the two projections are one
+        #     GEMM with N = 4(z + h) -- x is streamed once (text: 93 -> 57 us).
+        def adjacent(a, b):
+            return (a.is_contiguous() and b.is_contiguous() and a.dim() == b.dim() and a.shape[1:] == b.shape[1:]
+                    and a.untyped_storage().data_ptr() == b.untyped_storage().data_ptr()
+                    and a.data_ptr() + a.numel() * 4 == b.data_ptr())
+
+        def joined(a, b):
+            shape = (a.shape[0] + b.shape[0],) + tuple(a.shape[1:])
+            return torch.as_strided(a, shape, a.stride())
+
         def project(m):
             def run():
                 tag = TAGS[m]
                 e, n = "encoder_%s.lstm" % tag, self.pre + "lstm_%s" % tag
                 ops.copy2d(X2[:, dm.off[m]:dm.off[m] + dm.d[m]], xs[m])
+                ze, zn = (4 * dm.z[m] if full else 0), (0 if self.ef else 4 * dm.hm[m])
+                gcat = buf("GxCat%d" % m, TB, ze + zn)
                 if full:
-                    ops.gemm("nt", xs[m], P[e + ".weight_ih"], buf("GxE%d" % m, TB, 4 * dm.z[m]),
-                             bias=P[e + ".bias_ih"], bias2=P[e + ".bias_hh"])
+                    self.ws["GxE%d" % m] = gcat[:, :ze]
                 if not self.ef:
-                    ops.gemm("nt", xs[m], P[n + ".weight_ih"], buf("GxN%d" % m, TB, 4 * dm.hm[m]),
-                             bias=P[n + ".bias_ih"], bias2=P[n + ".bias_hh"])
+                    self.ws["GxN%d" % m] = gcat[:, ze:]
+                if full and not self.ef and all(
+                        adjacent(P[e + leaf], P[n + leaf]) for leaf in (".weight_ih", ".bias_ih", ".bias_hh")):
+                    ops.gemm("nt", xs[m], joined(P[e + ".weight_ih"], P[n + ".weight_ih"]), gcat,
+                             bias=joined(P[e + ".bias_ih"], P[n + ".bias_ih"]), bias2=joined(P[e + ".bias_hh"], P[n + ".bias_hh"]))
+                    return
+                if full:
+                    ops.gemm("nt", xs[m], P[e + ".weight_ih"], gcat[:, :ze], bias=P[e + ".bias_ih"], bias2=P[e + ".bias_hh"])
+                if not self.ef:
+                    ops.gemm("nt", xs[m], P[n + ".weight_ih"], gcat[:, ze:], bias=P[n + ".bias_ih"], bias2=P[n + ".bias_hh"])
             return run
 
         def project_ef():                                      # the early-fusion cell reads the whole row of x (:639)

@@ -59,6 +59,15 @@ class MFMTrainer:
             self.world = torch.distributed.get_world_size(process_group)
         pd = dict(model.named_parameters())
         self.names = [k for k in pd if k not in UNUSED]
+        # The encoder cell and the MFN cell of a modality read the same input: with their input weights (and bias vectors) ADJACENT
+        # in the flat buffer the two input projections are one GEMM over a [4(z+h), d] view (engine.forward step 1).  Order only;
+        # a tensor whose size is not a multiple of the alignment leaves a gap and the engine then keeps two GEMMs.
+        if "mfn_encoder.lstm_l.weight_ih" in pd and "encoder_l.lstm.weight_ih" in pd:
+            moved = []
+            for leaf in ("weight_ih", "bias_ih", "bias_hh"):
+                for tag in "lav":
+                    moved += ["encoder_%s.lstm.%s" % (tag, leaf), "mfn_encoder.lstm_%s.%s" % (tag, leaf)]
+            self.names = moved + [k for k in self.names if k not in moved]
         # every tensor starts 256 B aligned inside the flat buffers (the cp.async-staged GEMM needs 16 B-aligned
         # operands); the gaps stay zero in all four buffers, so Adam and the all-reduce leave them zero
         ALIGN = 64
