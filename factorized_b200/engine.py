@@ -97,6 +97,7 @@ class Engine:
         self._z_ready = None             # events: encoder latents written (they are produced on the auxiliary streams)
         self._mmd_pending = False        # MMD accumulators (double) not yet folded into loss_buf[4:8]
         self.want_mmd = True             # False: forward-only inference skips the O(B^2) MMD (its parts read 0)
+        self.fused_dcext = os.environ.get("MFM_FUSED_DCEXT", "1") == "1"   # see _backward_mfn (0: separate gather pass)
         self.stamps, self.stamp_names = None, []      # debug timeline (mark)
         # two launches for the last backward recurrence (heavy cells first, their weight gradients start early): measured
         # SLOWER (3.67 vs 3.56 ms/step: the gradient GEMMs delay the second launch), kept as an experiment switch
@@ -856,13 +857,19 @@ class Engine:
         dH1 = buf("dH1", TB, dm.a1)
         lin_bwd(dL, ws["H1"], pre + "att1_fc2", dH1, mask=ws["H1"], mask_scale=relu_scale(dm.p_att1))
         lin_bwd(dH1, cStar, pre + "att1_fc1", dcStar, accumulate=True)
-        # c_t enters cStar twice: as "new" at step t and as "prev" at step t+1.  (The recurrence kernel can add the two
-        # halves itself -- dc_ext2 -- but reading the 2H-wide gradient inside the latency-bound backward recurrence
-        # measured slower than this one compact gather pass.)
-        dCext = buf("dCext", TB, H)                          # row block t = grad wrt c of cell step t
-        ops.copy2d(dcStar[:, H:], dCext)
-        if T > 1:
-            ops.copy2d(dcStar[B:, :H], dCext[:TB - B], accumulate=True)
+        # c_t enters cStar twice: as "new" at step t and as "prev" at step t+1.  The recurrence kernel adds the two halves
+        # itself (dc_ext + dc_ext2: two column blocks of the 2H-wide gradient, L2-prefetched a step ahead by its idle issuer
+        # warps); the separate gather pass it replaces (two strided copies, 165 MB) cost 1.7 % of the step.  (With round 1's
+        # recurrence kernel, which had no prefetch, the gather pass was the faster of the two.)
+        gather = not self.fused_dcext
+        if gather:
+            dCext = buf("dCext", TB, H)                      # row block t = grad wrt c of cell step t
+            ops.copy2d(dcStar[:, H:], dCext)
+            if T > 1:
+                ops.copy2d(dcStar[B:, :H], dCext[:TB - B], accumulate=True)
+            dc1, dc2 = dCext, None
+        else:                                                # the recurrence adds the two halves itself (dc_ext + dc_ext2)
+            dc1, dc2 = dcStar[:, H:], (dcStar[B:, :H] if T > 1 else None)
 
         self.mark("bwd:att1+dCext")
         # (2') the recurrences reversed and (1') the weight gradients of the 6 input-side cells, all T at once
@@ -873,7 +880,8 @@ class Engine:
             o = dm.hoff[m]
             cell = dict(T=T, B=B, h=dm.hm[m], gates=ws["gatesN%d" % m], cs=Call[:, o:o + dm.hm[m]],
                         W=P[pre + "lstm_%s.weight_hh" % tag], dh_all=None,
-                        dh_last=dHlast[:, o:o + dm.hm[m]], dc_ext=dCext[:, o:o + dm.hm[m]],
+                        dh_last=dHlast[:, o:o + dm.hm[m]], dc_ext=dc1[:, o:o + dm.hm[m]],
+                        dc_ext2=(None if dc2 is None else dc2[:, o:o + dm.hm[m]]),
                         dG=buf("dGN%d" % m, TB, 4 * dm.hm[m]), dc_scratch=buf("dcSN%d" % m, B, dm.hm[m]))
             todo.append((cell, (pre + "lstm_%s" % tag, "dGN%d" % m, m, Hall[:TB, o:o + dm.hm[m]])))
         for m, c in enumerate(enc_cells):
