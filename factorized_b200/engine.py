@@ -96,6 +96,7 @@ class Engine:
         self._pool = []                  # streams for _par branches
         self._z_ready = None             # events: encoder latents written (they are produced on the auxiliary streams)
         self._mmd_pending = False        # MMD accumulators (double) not yet folded into loss_buf[4:8]
+        self._wcat_ready = False         # backward() built WcatAtt on an auxiliary stream
         self.want_mmd = True             # False: forward-only inference skips the O(B^2) MMD (its parts read 0)
         self.fused_dcext = os.environ.get("MFM_FUSED_DCEXT", "1") == "1"   # see _backward_mfn (0: separate gather pass)
         self.stamps, self.stamp_names = None, []      # debug timeline (mark)
@@ -659,6 +660,10 @@ class Engine:
         lat = [ws["Z0"], ws["Z1"], ws["Z2"], ws["ZY"]]
         dmmd = [buf("dZmmd%d" % k, B, lat[k].shape[1]) for k in range(4)]
         dLV = [buf("dLV%d" % k, B, lat[k].shape[1]) for k in range(4)] if self.kl else None
+        if not self.ef:                                      # (parameters only: off the main stream, joined with the MMD streams)
+            with self._aux(0):
+                self._build_wcat(P)
+            self._wcat_ready = True
         for k in range(4):
             with self._aux(k):
                 ops.zero(dmmd[k])
@@ -810,6 +815,15 @@ class Engine:
         self._join_side()
         self.mark("bwd:join wgrads")
 
+    def _build_wcat(self, P):
+        """The row-concatenated weights of the three consumers of `attended` (gamma1_fc1, gamma2_fc1, att2_fc1): the data
+        gradient of `attended` is then one GEMM.  Depends on the parameters only."""
+        dm, ops, pre = self.dm, self.ops, self.pre
+        Wcat = self.buf("WcatAtt", dm.g1 + dm.g2 + dm.a2, 2 * dm.H)
+        ops.copy2d(P[pre + "gamma1_fc1.weight"][:, :2 * dm.H], Wcat[:dm.g1])
+        ops.copy2d(P[pre + "gamma2_fc1.weight"][:, :2 * dm.H], Wcat[dm.g1:dm.g1 + dm.g2])
+        ops.copy2d(P[pre + "att2_fc1.weight"], Wcat[dm.g1 + dm.g2:])
+
     def _backward_mfn(self, P, G, dHlast, dmemT, enc_cells, wgrad, bgrad, lin_bwd, relu_scale):
         """Adjoint of steps (5),(4),(2),(1): memory recurrence, attention MLPs, then the MFN cells together
         with any encoder cells handed in (one launch), then all input-side weight gradients."""
@@ -846,9 +860,9 @@ class Engine:
         lin_bwd(dPc, ws["H2"], pre + "att2_fc2", dH2, mask=ws["H2"], mask_scale=relu_scale(dm.p_att2))
         lin_bwd(dH2, Attended, pre + "att2_fc1")
         Wcat = buf("WcatAtt", dm.g1 + dm.g2 + dm.a2, 2 * H)
-        ops.copy2d(Wg1[:, :2 * H], Wcat[:dm.g1])
-        ops.copy2d(Wg2[:, :2 * H], Wcat[dm.g1:dm.g1 + dm.g2])
-        ops.copy2d(P[pre + "att2_fc1.weight"], Wcat[dm.g1 + dm.g2:])
+        if not self._wcat_ready:
+            self._build_wcat(P)
+        self._wcat_ready = False
         ops.gemm("nn", dUcat, Wcat, dAtt)
         dL = buf("dL", TB, 2 * H)
         dcStar = buf("dcStar", TB, 2 * H)
