@@ -180,6 +180,11 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_seq_bwd_kernel(LstmBatch bt
   if (wsm)
     for (int idx = tid; idx < H4 * h; idx += LSTM_THREADS) Ws[idx] = __ldg(c.W + idx);
   for (int idx = tid; idx < 2 * RT * h; idx += LSTM_THREADS) dhs[idx] = 0.0f;   // dhs and dcs
+  if (c.dc_last)                                                                // time-split recurrence: carried dc comes in
+    for (int idx = tid; idx < RT * h; idx += LSTM_THREADS) {
+      const int r = idx / h, j = idx - r * h;
+      if (row0 + r < B) dcs[idx] = __ldg(c.dc_last + (long long)(row0 + r) * h + j);
+    }
   for (int idx = tid; idx < 2 * RT * H4; idx += LSTM_THREADS) dGs[idx] = 0.0f;
   __syncthreads();
   const int gid = tid / jstride;
@@ -206,7 +211,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_seq_bwd_kernel(LstmBatch bt
           const float tc = gate_tanh(cn);
           float dc = dcs[(rbase + r) * h + j] + dh * og * (1.0f - tc * tc);
           if (c.dc_ext) dc += __ldg(c.dc_ext + tr * c.ld_dc_ext + j);
-          if (c.dc_ext2 && t < c.T - 1) dc += __ldg(c.dc_ext2 + tr * c.ld_dc_ext + j);
+          if (c.dc_ext2 && (t < c.T - 1 || c.dc_ext2_full)) dc += __ldg(c.dc_ext2 + tr * c.ld_dc_ext + j);
           const float d_o = dh * tc * og * (1.0f - og);
           const float d_i = dc * gg * ig * (1.0f - ig);
           const float d_f = dc * cp * fg * (1.0f - fg);
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_seq_bwd_kernel(LstmBatch bt
       }
     }
     __syncthreads();
-    if (active && t > 0) {
+    if (active && (t > 0 || c.dh_out)) {
       for (int j = j0; j < h; j += jstride) {
         float acc[LSTM_R];
 #pragma unroll
@@ -249,6 +254,16 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_seq_bwd_kernel(LstmBatch bt
     }
     // no second barrier: the next step writes the other dG buffer, and dhs/dcs entries are thread-private
   }
+  if (active && c.dh_out) {                                   // time-split recurrence: the carried state goes out
+    for (int j = j0; j < h; j += jstride)
+#pragma unroll
+      for (int r = 0; r < LSTM_R; ++r) {
+        const int row = row0 + rbase + r;
+        if (row >= B) continue;
+        c.dh_out[(long long)row * h + j] = dhs[(rbase + r) * h + j];
+        c.dc_out[(long long)row * h + j] = dcs[(rbase + r) * h + j];
+      }
+  }
 }
 
 static int lstm_validate(const mfm_lstm_cell* cells, int n, bool bwd) {
@@ -258,6 +273,7 @@ static int lstm_validate(const mfm_lstm_cell* cells, int n, bool bwd) {
     if (c.T <= 0 || c.B <= 0 || c.h <= 0 || !c.W || !c.cs || !c.gates) return MFM_ERR_ARG;
     if (!bwd && (!c.hs || !c.gx || c.gx_steps <= 0 || c.gx_steps > c.T)) return MFM_ERR_ARG;
     if (bwd && !c.dG) return MFM_ERR_ARG;
+    if (bwd && ((c.dh_out == nullptr) != (c.dc_out == nullptr))) return MFM_ERR_ARG;
   }
   return MFM_OK;
 }

@@ -453,6 +453,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_bwd_kernel(const __grid
   const float* __restrict__ const dce2_base = wc.c.dc_ext2;
   float* __restrict__ const dG_base = wc.c.dG;
   const int lddhl = (int)wc.c.ld_dh_last;
+  // time-split recurrence (mfm_lstm_cell): carried dc in; W^T dG_0 and dc_0 f_0 out after one more product
+  const float* __restrict__ const dcl_base = wc.c.dc_last;
+  float* __restrict__ const dho_base = wc.c.dh_out;
+  float* __restrict__ const dco_base = wc.c.dc_out;
+  const bool carry = dho_base != nullptr;
+  const bool e2full = wc.c.dc_ext2_full != 0;
   unsigned char* Ahi = smem;                                // W^T: A[j][k'], k' = 4*unit + gate
   unsigned char* Alo = Ahi + slabs * lboA;
   unsigned char* Bbase = Alo + slabs * lboA;                // per chain: dG tile [hi | lo]
@@ -517,7 +523,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_bwd_kernel(const __grid
         if (base && ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((ld & 3) == 0) && ((h & 3) == 0))
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + row * ld), "r"((uint32_t)(h * 4)) : "memory");
       };
-      for (int n = 0; n < T; ++n) {                         // n-th product: dG of step T-n (zero for n = 0) -> dh of step T-1-n
+      const int nprod = T + (carry ? 1 : 0);               // (the carried-out dh is one more product)
+      for (int n = 0; n < nprod; ++n) {                     // n-th product: dG of step T-n (zero for n = 0) -> dh of step T-1-n
 #pragma unroll 1
         for (int ch = 0; ch < NCH; ++ch) {
           if (lane == 0) {
@@ -586,7 +593,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_bwd_kernel(const __grid
 #pragma unroll
       for (int a = 0; a < NCH; ++a)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dc[a][i] = 0.0f;
+        for (int i = 0; i < 8; ++i)
+          dc[a][i] = (dcl_base && i < ro.ncol) ? __ldg(dcl_base + (long long)(rbase + min(a * NB + i, cmax)) * h + jc) : 0.0f;
       const int nsg = ro.ncol >> 1;                           // groups of TWO columns per chain: 2 or 4 (even: static parity)
 
       for (int t = T - 1; t >= 0; --t) {
@@ -605,7 +613,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_bwd_kernel(const __grid
             v.dhx = dhp ? __ldg(dhp + (unsigned)(ci * lddh)) : 0.0f;
             if (last && dhlp) v.dhx += __ldg(dhlp + (unsigned)(ci * lddhl));
             v.dcx = dcp ? __ldg(dcp + (unsigned)(ci * lddc)) : 0.0f;
-            if (!last && dc2p) v.dcx += __ldg(dc2p + (unsigned)(ci * lddc));
+            if ((!last || e2full) && dc2p) v.dcx += __ldg(dc2p + (unsigned)(ci * lddc));
             d[cc] = v;
           }
         };
@@ -642,7 +650,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_bwd_kernel(const __grid
                 const unsigned o4 = (unsigned)(ci * H4);
                 st_if(dgp[0] + o4, d_i, ok); st_if(dgp[1] + o4, d_f, ok); st_if(dgp[2] + o4, d_g, ok); st_if(dgp[3] + o4, d_o, ok);
                 if (!ok) d_i = d_f = d_g = d_o = 0.0f;
-                if (jb && t > 0) {                             // B operand: row = batch column, k' = 4j..4j+3 (8 contiguous bytes)
+                if (jb && (t > 0 || carry)) {                  // B operand: row = batch column, k' = 4j..4j+3 (8 contiguous bytes)
                   const float v4[4] = {d_i, d_f, d_g, d_o};
                   unsigned short hb[4], lb[4];
 #pragma unroll
@@ -659,7 +667,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_bwd_kernel(const __grid
               }
             }
           }
-          if (t > 0) {
+          if (t > 0 || carry) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -672,6 +680,34 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lstm_ws_bwd_kernel(const __grid
         if (dhp) dhp -= dh_step;
         if (dcp) dcp -= dc_step;
         if (dc2p) dc2p -= dc_step;
+      }
+      if (carry) {                                            // product T: W^T dG_0, and the carried dc, go out
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          ws_wait(smem_u32(&bar_done[ch]), (uint32_t)(T & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int sg = 0; sg < 4; ++sg) {
+            if (sg < nsg) {
+              float dh[4][2];
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                if (a < nacc) tmem_ld2(tl + (uint32_t)((ch * 4 + a) * NB + sg * 2), dh[a]);
+                else dh[a][0] = dh[a][1] = 0.0f;
+              }
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc) {
+                const int col = sg * 2 + cc, gcol = ch * NB + col;
+                const int ci = min(gcol, cmax);
+                const int ok = (on && gcol < bvalid) ? 1 : 0;
+                const long long o = (long long)(rbase + ci) * h + jc;
+                st_if(dho_base + o, (dh[0][cc] + dh[1][cc]) + (dh[2][cc] + dh[3][cc]), ok);
+                st_if(dco_base + o, dc[ch][col], ok);
+              }
+            }
+          }
+        }
       }
     }
   }

@@ -28,7 +28,8 @@ class LstmCell(C.Structure):
                 ("hs", c_f), ("ld_hs", LL), ("cs", c_f), ("ld_cs", LL), ("gates", c_f),
                 ("dh_all", c_f), ("ld_dh_all", LL), ("dh_last", c_f), ("ld_dh_last", LL),
                 ("dc_ext", c_f), ("ld_dc_ext", LL), ("dG", c_f), ("dc_scratch", c_f),
-                ("cs_dup", c_f), ("dc_ext2", c_f), ("ld_gx", LL)]
+                ("cs_dup", c_f), ("dc_ext2", c_f), ("ld_gx", LL),
+                ("dc_last", c_f), ("dh_out", c_f), ("dc_out", c_f), ("dc_ext2_full", C.c_int)]
 
 
 class MemArgs(C.Structure):
@@ -341,11 +342,22 @@ class CudaOps:
                     if (r_, c_) != (c["T"] * c["B"], c["h"]):
                         raise MfmCudaError("lstm dc_ext shape")
                     s.dc_ext, s.ld_dc_ext = p_, l_
-                if c.get("dc_ext2") is not None and c["T"] > 1:
+                full2 = bool(c.get("dc_ext2_full"))
+                if c.get("dc_ext2") is not None and (c["T"] > 1 or full2):
                     p_, r_, c_, l_ = _mat(c["dc_ext2"], "lstm dc_ext2")
-                    if c.get("dc_ext") is None or (r_, c_) != ((c["T"] - 1) * c["B"], c["h"]) or l_ != s.ld_dc_ext:
-                        raise MfmCudaError("lstm dc_ext2 must be [(T-1)*B,h] with the leading dimension of dc_ext")
+                    want = (c["T"] if full2 else c["T"] - 1) * c["B"]
+                    if c.get("dc_ext") is None or (r_, c_) != (want, c["h"]) or l_ != s.ld_dc_ext:
+                        raise MfmCudaError("lstm dc_ext2 must be [(T-1)*B,h] ([T*B,h] with dc_ext2_full) with the leading dimension of dc_ext")
                     s.dc_ext2 = p_
+                    s.dc_ext2_full = 1 if full2 else 0
+                for key in ("dc_last", "dh_out", "dc_out"):           # time-split recurrence: carried state in / out
+                    if c.get(key) is not None:
+                        p_, r_, c_, l_ = _mat(c[key], "lstm " + key)
+                        if (r_, c_) != (c["B"], c["h"]) or (r_ > 1 and l_ != c["h"]):
+                            raise MfmCudaError("lstm %s must be contiguous [B,h]" % key)
+                        setattr(s, key, p_)
+                if (c.get("dh_out") is None) != (c.get("dc_out") is None):
+                    raise MfmCudaError("lstm dh_out and dc_out go together")
         return arr
 
     def lstm_fwd(self, cells):

@@ -99,6 +99,7 @@ class Engine:
         self._wcat_ready = False         # backward() built WcatAtt on an auxiliary stream
         self.want_mmd = True             # False: forward-only inference skips the O(B^2) MMD (its parts read 0)
         self.fused_dcext = os.environ.get("MFM_FUSED_DCEXT", "1") == "1"   # see _backward_mfn (0: separate gather pass)
+        self.time_split = os.environ.get("MFM_TIME_SPLIT", "0") == "1"     # experiment, see _backward_mfn (default: one launch)
         self.stamps, self.stamp_names = None, []      # debug timeline (mark)
         # two launches for the last backward recurrence (heavy cells first, their weight gradients start early): measured
         # SLOWER (3.67 vs 3.56 ms/step: the gradient GEMMs delay the second launch), kept as an experiment switch
@@ -901,6 +902,37 @@ class Engine:
         for m, c in enumerate(enc_cells):
             todo.append((c, ("encoder_%s.lstm" % TAGS[m], "dGE%d" % m, m, ws["hsE%d" % m][:TB])))
         todo.sort(key=lambda cj: -cj[0]["h"])
+        if self.time_split and T >= 4 and not self.split_last_recurrence:
+            # The step ends when the weight gradients of these cells are done, and they cannot start before dG exists.  With
+            # this switch the recurrence is launched in two halves in TIME -- steps [t0, T), then [0, t0), the carried
+            # (dh, dc) handed from one to the other (mfm_lstm_cell.dh_out / dc_out / dc_last) -- and the gradient GEMMs over
+            # the late half's rows run under the early half.  Measured (same box, A/B): 2.273 -> 2.298 ms, i.e. SLOWER -- the
+            # gradient GEMMs' CTAs hold the SMs the second recurrence launch needs (one 200 KB CTA per SM), and each launch
+            # pays its own weight-image prologue.  Kept as an experiment switch; the kernels' carry path is tested.
+            t0 = T // 2
+            carry = [(buf("dhCarry_" + job[1], B, c["h"]), buf("dcCarry_" + job[1], B, c["h"])) for c, job in todo]
+
+            def sub(c, lo, hi, i):
+                d = dict(c)
+                d.update(T=hi - lo, gates=c["gates"][lo * B:hi * B], cs=c["cs"][lo * B:(hi + 1) * B], dG=c["dG"][lo * B:hi * B])
+                for k in ("dh_all", "dc_ext"):
+                    if c.get(k) is not None:
+                        d[k] = c[k][lo * B:hi * B]
+                if c.get("dc_ext2") is not None:             # block t applies at step t < T-1
+                    d["dc_ext2"] = c["dc_ext2"][lo * B:min(hi, T - 1) * B]
+                    d["dc_ext2_full"] = hi < T
+                if hi == T:
+                    d.update(dh_out=carry[i][0], dc_out=carry[i][1])
+                else:
+                    d.update(dh_last=carry[i][0], dc_last=carry[i][1])
+                return d
+            for lo, hi in ((t0, T), (0, t0)):
+                ops.lstm_bwd([sub(c, lo, hi, i) for i, (c, _) in enumerate(todo)])
+                for i, (_, (nm, dGn, m, hs)) in enumerate(todo):      # both halves of a cell on ONE side stream, in order
+                    rows = slice(lo * B, hi * B)
+                    self._wgrad_pair(ws[dGn][rows], self.xs[m][rows], G[nm + ".weight_ih"], G[nm + ".bias_ih"], hs[rows],
+                                     G[nm + ".weight_hh"], G[nm + ".bias_hh"] if lo == 0 else None, index=i)
+            return
         half = (len(todo) + 1) // 2 if (self.split_last_recurrence and len(todo) > 3) else len(todo)
         for part in (todo[:half], todo[half:]):
             if not part:

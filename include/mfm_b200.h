@@ -125,6 +125,14 @@ typedef struct mfm_lstm_cell {
   const float* dc_ext2;     /* backward only: [(T-1)*B, h]                                            */
   long long ld_gx;          /* row pitch of gx in floats (0 = 4h): lets the hoisted projections of the two cells that
                                read the same modality (encoder + MFN cell) be column blocks of ONE GEMM's output  */
+  /* Backward only: a recurrence split in TIME into two launches -- steps [t0, T) first, then [0, t0) -- so that the
+   * weight-gradient GEMM of the late half can start while the early half is still running.  The first launch hands the
+   * recurrent state on (dh_out, dc_out), the second takes it (dh_last = that dh_out, dc_last = that dc_out).  All NULL / 0
+   * for an unsplit recurrence. */
+  const float* dc_last;     /* [B, h] contiguous: dL/dc carried INTO the last step of this launch, or NULL       */
+  float* dh_out;            /* [B, h] contiguous: receives W^T dG_0, the gradient w.r.t. h before step 0, or NULL */
+  float* dc_out;            /* [B, h] contiguous: receives dc_0 * f_0 (w.r.t. c before step 0); set with dh_out  */
+  int dc_ext2_full;         /* dc_ext2 has T blocks and also applies at the last step of this launch             */
 } mfm_lstm_cell;
 #define MFM_MAX_CELLS 8
 /* all cells of one call run concurrently (blockIdx.y = cell) */

@@ -103,6 +103,8 @@ class EmuOps:
             gates, cs, W, dG = c["gates"], c["cs"], c["W"], c["dG"]
             dh = torch.zeros(B, h, dtype=gates.dtype)
             dc = torch.zeros(B, h, dtype=gates.dtype)
+            if c.get("dc_last") is not None:                 # time-split recurrence: carried dc comes in
+                dc = dc + c["dc_last"]
             for t in range(T - 1, -1, -1):
                 r = slice(t * B, (t + 1) * B)
                 if c["dh_all"] is not None:
@@ -116,7 +118,7 @@ class EmuOps:
                 dc = dc + dh * o * (1 - tc * tc)
                 if c["dc_ext"] is not None:
                     dc = dc + c["dc_ext"][r]
-                if c.get("dc_ext2") is not None and t < T - 1:
+                if c.get("dc_ext2") is not None and (t < T - 1 or c.get("dc_ext2_full")):
                     dc = dc + c["dc_ext2"][r]
                 d_o = dh * tc * o * (1 - o)
                 d_i = dc * g * i * (1 - i)
@@ -126,6 +128,9 @@ class EmuOps:
                 dG[r] = dg4
                 dh = dg4 @ W
                 dc = dc * f
+            if c.get("dh_out") is not None:                  # ... and goes out
+                c["dh_out"].copy_(dh)
+                c["dc_out"].copy_(dc)
 
     # ---- MFN memory recurrence ----
     def mfn_mem_fwd(self, a):

@@ -86,11 +86,11 @@ def test_engine_dropout_masks_replay():
 
 def test_engine_schedule_variants_agree():
     """The trainer's variants of the schedule (MMD joined only in backward, total summed there; reconstruction MSE fused
-    into the decoder heads' GEMM) and the experiment switch that splits the last backward recurrence into two launches
-    give the same losses and gradients as the default."""
+    into the decoder heads' GEMM) and the experiment switches that split the last backward recurrence into two launches (by
+    cells, or in time with the carried state handed on) give the same losses and gradients as the default."""
     g, configs, P, x, y, noise, T, n = tiny_case("l1", 1)
     ref_eng, _, Gref = run_engine(configs, P, x, y, noise, T, n, "l1")
-    for variant in ("defer_mmd_join", "split_last_recurrence", "fuse_mse"):
+    for variant in ("defer_mmd_join", "split_last_recurrence", "fuse_mse", "time_split"):
         eng = Engine(configs, T, n, "cpu", EmuOps(), head="l1")
         setattr(eng, variant, True)
         eng.forward(OrderedDict(P), x.contiguous(), noise)

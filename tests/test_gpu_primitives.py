@@ -354,6 +354,47 @@ def test_lstm_gx_leading_dimension(ops):
         assert rel_l2(d["hs"], c["hs"]) < 1e-4 and rel_l2(d["gates"], c["gates"]) < 1e-4
 
 
+@pytest.mark.parametrize("T,B,h,dec,t0", [(6, 40, 88, False, 3), (5, 33, 24, True, 2), (4, 70, 104, True, 1), (7, 19, 130, False, 4)])
+def test_lstm_bwd_split_in_time(ops, T, B, h, dec, t0):
+    """A backward recurrence launched as two halves in time -- steps [t0, T) handing (dh, dc) to steps [0, t0) -- equals the
+    single launch: tensor-core kernel (h <= 128) and CUDA-core kernel (h = 130), with dc_ext / dc_ext2 or dh_all."""
+    H4 = 4 * h
+    gates = torch.sigmoid(g(T * B, H4, seed=1)).cuda()
+    cs = g((T + 1) * B, h, seed=2).cuda()
+    cs[:B] = 0
+    W = g(H4, h, seed=3, scale=0.2).cuda()
+    base = dict(T=T, B=B, h=h, gates=gates, cs=cs, W=W, dh_all=g(T * B, h, seed=4).cuda() if dec else None,
+                dh_last=None if dec else g(B, h, seed=5).cuda(), dc_ext=None if dec else g(T * B, h, seed=6).cuda(),
+                dc_ext2=None if dec else g((T - 1) * B, h, seed=7).cuda(), dc_scratch=torch.zeros(B, h).cuda())
+    one = dict(base, dG=torch.zeros(T * B, H4).cuda())
+    ops.lstm_bwd([one])
+    dG2 = torch.zeros(T * B, H4).cuda()
+    dho, dco = torch.zeros(B, h).cuda(), torch.zeros(B, h).cuda()
+
+    def sub(lo, hi):
+        d = dict(base, T=hi - lo, gates=gates[lo * B:hi * B], cs=cs[lo * B:(hi + 1) * B], dG=dG2[lo * B:hi * B])
+        for k in ("dh_all", "dc_ext"):
+            if base[k] is not None:
+                d[k] = base[k][lo * B:hi * B]
+        if base["dc_ext2"] is not None:
+            d["dc_ext2"] = base["dc_ext2"][lo * B:min(hi, T - 1) * B]
+            d["dc_ext2_full"] = hi < T
+        if hi == T:
+            d.update(dh_out=dho, dc_out=dco)
+        else:
+            d.update(dh_last=dho, dc_last=dco)
+        return d
+    ops.lstm_bwd([sub(t0, T)])
+    ops.lstm_bwd([sub(0, t0)])
+    torch.cuda.synchronize()
+    assert rel_l2(dG2, one["dG"]) < 2e-5
+    # and against the torch statement
+    ref = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in base.items()}
+    ref["dG"] = torch.zeros(T * B, H4)
+    EmuOps().lstm_bwd([ref])
+    assert rel_l2(dG2, ref["dG"]) < 1e-4
+
+
 @pytest.mark.parametrize("simt", [False, True])
 @pytest.mark.parametrize("T,B,mem,g1,g2,drop", [(3, 5, 9, 12, 13, False), (4, 21, 64, 128, 128, True), (2, 7, 300, 256, 32, False),
                                                 (20, 64, 64, 128, 128, False), (1, 16, 32, 128, 40, True), (5, 161, 64, 100, 128, True),
