@@ -97,6 +97,8 @@ class Engine:
         self._z_ready = None             # events: encoder latents written (they are produced on the auxiliary streams)
         self._mmd_pending = False        # MMD accumulators (double) not yet folded into loss_buf[4:8]
         self._wcat_ready = False         # backward() built WcatAtt on an auxiliary stream
+        self.n_side = max(1, int(os.environ.get("MFM_SIDE_STREAMS", "6")))    # weight-gradient streams
+        self.n_aux = max(1, int(os.environ.get("MFM_AUX_STREAMS", "4")))      # MMD / KL streams (one per latent)
         self.want_mmd = True             # False: forward-only inference skips the O(B^2) MMD (its parts read 0)
         self.fused_dcext = os.environ.get("MFM_FUSED_DCEXT", "1") == "1"   # see _backward_mfn (0: separate gather pass)
         self.time_split = os.environ.get("MFM_TIME_SPLIT", "0") == "1"     # experiment, see _backward_mfn (default: one launch)
@@ -468,7 +470,7 @@ class Engine:
             return
         main = torch.cuda.current_stream(self.device)
         if self._side is None:
-            self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(self.n_side)]
         st = self._side[((key >> 8) if index is None else index) % len(self._side)]
         ev = torch.cuda.Event()
         ev.record(main)
@@ -499,7 +501,7 @@ class Engine:
             return
         main = torch.cuda.current_stream(self.device)
         if self._side is None:
-            self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(self.n_side)]
         # independent weight gradients also overlap each other; two GEMMs into the same tensor share a stream
         st = self._side[((stream_key if stream_key is not None else Gout.data_ptr()) >> 8) % len(self._side)]
         ev = torch.cuda.Event()
@@ -551,7 +553,7 @@ class Engine:
         """``with eng._aux(k):`` runs the body on auxiliary stream k, forked from the main stream at entry."""
 
         def __init__(self, eng, k):
-            self.eng, self.k, self.ctx = eng, k, None
+            self.eng, self.k, self.ctx = eng, k % eng.n_aux, None
 
         def __enter__(self):
             e = self.eng
@@ -581,7 +583,7 @@ class Engine:
         if self.device.type != "cuda" or not self.use_side_stream:
             return None
         ev = torch.cuda.Event()
-        ev.record(self._aux_streams[k])
+        ev.record(self._aux_streams[k % self.n_aux])
         return ev
 
     def _mmd(self, k, zk):
