@@ -88,7 +88,7 @@ class Engine:
         self.mmd_acc = torch.zeros(4, dtype=torch.float64, device=self.device)     # the four MMD terms, summed in double
         self.use_side_stream = True
         self._side = None
-        self._side_used = False
+        self._side_used = set()   # side streams that received work in this schedule
         self._enc_stream = None          # the encoder cells' backward runs beside the MFN backward
         self._enc_used = False
         self._aux_streams = {}           # the MMD / KL terms of the four latents run on their own streams, side by side
@@ -471,13 +471,14 @@ class Engine:
         main = torch.cuda.current_stream(self.device)
         if self._side is None:
             self._side = [torch.cuda.Stream(device=self.device) for _ in range(self.n_side)]
-        st = self._side[((key >> 8) if index is None else index) % len(self._side)]
+        i = ((key >> 8) if index is None else index) % len(self._side)
+        st = self._side[i]
         ev = torch.cuda.Event()
         ev.record(main)
         st.wait_event(ev)
         with torch.cuda.stream(st):
             fn()
-        self._side_used = True
+        self._side_used.add(i)
 
     def _wgrad_pair(self, dY, A1, G1, b1, A2, G2, b2=None, index=None):
         """dW1 += dY^T A1, dW2 += dY^T A2 and the bias gradient(s) = column sums of dY, in one launch on a side stream: the
@@ -503,20 +504,23 @@ class Engine:
         if self._side is None:
             self._side = [torch.cuda.Stream(device=self.device) for _ in range(self.n_side)]
         # independent weight gradients also overlap each other; two GEMMs into the same tensor share a stream
-        st = self._side[((stream_key if stream_key is not None else Gout.data_ptr()) >> 8) % len(self._side)]
+        i = ((stream_key if stream_key is not None else Gout.data_ptr()) >> 8) % len(self._side)
+        st = self._side[i]
         ev = torch.cuda.Event()
         ev.record(main)
         st.wait_event(ev)
         with torch.cuda.stream(st):
             ops.gemm("tn", dY, A, Gout, **kw)
-        self._side_used = True
+        self._side_used.add(i)
 
     def _join_side(self):
         if self._side is not None and self._side_used:
+            # only the streams that received work in this schedule: inside a graph capture, waiting on a stream that was never
+            # forked from the capturing stream is an error (cudaErrorStreamCaptureIsolation)
             main = torch.cuda.current_stream(self.device)
-            for st in self._side:
-                main.wait_stream(st)
-            self._side_used = False
+            for i in sorted(self._side_used):
+                main.wait_stream(self._side[i])
+            self._side_used = set()
         if self._enc_used:
             torch.cuda.current_stream(self.device).wait_stream(self._enc_stream)
             self._enc_used = False
