@@ -19,8 +19,9 @@
 //                                      The accumulator is handed back as soon as its last column block sits in registers.
 //
 // Tiles are (128 rows) x (BN columns), BN a multiple of 32 and <= 192, the last N tile possibly narrower.
-//   resident mode   (the tile's whole weight image fits next to the ring): CTA b serves N tile b % NT for every
-//                   (gridDim.x / NT)-th row tile and loads the image ONCE -- no weight traffic in the loop, 16 KB stages
+//   resident mode   (the tile's whole weight image fits next to the ring; OFF by default, MFM_PS_RES=2 lets the model choose):
+//                   CTA b serves N tile b % NT for every (gridDim.x / NT)-th row tile and loads the image ONCE -- no weight
+//                   traffic in the loop, 16 KB stages; measured slower than streaming, see ps_plan()
 //   streaming mode  tiles (row tile, N tile), N fastest, dealt round-robin; every stage carries its weight images (they are
 //                   re-read from L2 by every row tile: as many bytes as A when BN = 128)
 // ps_plan() picks N tiling and mode per shape with a small cost model.
@@ -501,20 +502,33 @@ static bool ps_plan_one(int MT, int N, int nck, int sms, int nt, int resident, b
   pl->cost = cost;
   return true;
 }
+static int g_ps_res = -1;                 // residency: 0 streaming only (default), 1 resident only, 2 by the cost model
+extern "C" int mfm_debug_gemm_ps_residency(int mode) {
+  if (mode < 0 || mode > 2) return MFM_ERR_ARG;
+  g_ps_res = mode;
+  return MFM_OK;
+}
 static bool ps_plan(int M, int N, int K, int sms, bool aux, PsPlan* best) {
-  static int pin_nt = -1, pin_res = -1;
+  static int pin_nt = -1;
+  int& pin_res = g_ps_res;
   if (pin_nt < 0) { const char* e = getenv("MFM_PS_NT"); pin_nt = e ? atoi(e) : 0; }
-  if (pin_res < 0) { const char* e = getenv("MFM_PS_RES"); pin_res = e ? atoi(e) : 2; }
+  // default 0 = streaming only: the resident mode's model cost is lower but it measured SLOWER, alone (36.7 vs 34.2 us on
+  // 40960x400x128) and in the step (all-resident 2.337 ms, model's choice 2.243, all-streaming 2.221, same box): a CTA pinned
+  // to one N tile starts with a ~100 KB image load and the row tiles divide unevenly over (SMs / NT) CTAs.  2 = by the model.
+  if (pin_res < 0) { const char* e = getenv("MFM_PS_RES"); pin_res = e ? atoi(e) : 0; }
   const int MT = (M + P_BM - 1) / P_BM, nck = (K + P_BK - 1) / P_BK;
   bool found = false;
   const int nt0 = (N + 223) / 224;
-  for (int nt = nt0; nt <= nt0 + 5; ++nt) {
-    if (pin_nt > 0 && nt != pin_nt) continue;
-    for (int res = 0; res < 2; ++res) {
-      if (pin_res < 2 && res != pin_res) continue;
-      PsPlan pl;
-      if (!ps_plan_one(MT, N, nck, sms, nt, res, aux, &pl)) continue;
-      if (!found || pl.cost < best->cost) { *best = pl; found = true; }
+  for (int pass = 0; pass < 2 && !found; ++pass) {         // (resident only: shapes it does not hold are streamed)
+    for (int nt = nt0; nt <= nt0 + 5; ++nt) {
+      if (pin_nt > 0 && nt != pin_nt) continue;
+      for (int res = 0; res < 2; ++res) {
+        if (pass == 0 && pin_res < 2 && res != pin_res) continue;
+        if (pass == 1 && res != 0) continue;
+        PsPlan pl;
+        if (!ps_plan_one(MT, N, nck, sms, nt, res, aux, &pl)) continue;
+        if (!found || pl.cost < best->cost) { *best = pl; found = true; }
+      }
     }
   }
   return found;

@@ -66,6 +66,7 @@ _SIGS = {
     "mfm_debug_set_lstm_trace": (C.c_int, [c_f]),
     "mfm_debug_lstm_variant_count": (C.c_ulonglong, [C.c_int]),
     "mfm_debug_gemm_ps_count": (C.c_int, []),
+    "mfm_debug_gemm_ps_residency": (C.c_int, [C.c_int]),
     "mfm_debug_set_gemm_ps_trace": (C.c_int, [c_f]),
     "mfm_debug_mem_force_simt": (C.c_int, [C.c_int]),
     "mfm_debug_mem_ws_trace": (C.c_int, [c_f]),

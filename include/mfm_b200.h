@@ -149,6 +149,9 @@ int mfm_debug_set_lstm_trace(void* device_buf);
 unsigned long long mfm_debug_lstm_variant_count(int variant);
 /* Launches of the persistent streaming GEMM (csrc/gemm_ps.cu) since load: the tests assert that the large-M layers run on it. */
 int mfm_debug_gemm_ps_count(void);
+/* Residency of the persistent GEMM's weight image: 0 = stream it with every ring stage (default), 1 = keep the N tile's whole image
+ * in shared memory where it fits (each CTA then serves one N tile), 2 = let the cost model choose.  (env MFM_PS_RES sets the start-up value.) */
+int mfm_debug_gemm_ps_residency(int mode);
 /* Debug aid (scripts/gemm_ps_trace.py; library built with -DPS_DEBUG=1, else MFM_ERR_UNSUPPORTED): while a device buffer of
  * 148 * (4 + 6*64 + 4*16) int64 is registered, every CTA of the persistent GEMM records clock stamps of its roles. */
 int mfm_debug_set_gemm_ps_trace(void* device_buf);

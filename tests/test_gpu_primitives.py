@@ -73,7 +73,7 @@ def test_gemm_strided_views_and_epilogues(ops):
 
 
 @pytest.mark.parametrize("mode,M,N,K,act,drop,persistent", [
-    ("nt", 40960, 400, 128, 0, None, True),          # resident weight image, three N tiles (160 / 160 / 96)
+    ("nt", 40960, 400, 128, 0, None, True),          # three N tiles (160 / 160 / 96)
     ("nt", 8192, 128, 400, 1, None, True),           # streaming mode (the image does not fit beside the ring)
     ("nn", 12288, 400, 384, 0, None, True),          # NN: MN-major weight image
     ("nt", 4100, 36, 20, 2, None, True),             # ragged last row tile, N tail clipped by the TMA store, K < one stage
@@ -83,10 +83,20 @@ def test_gemm_strided_views_and_epilogues(ops):
     ("nt", 4096, 34, 64, 0, None, False),            # N not a multiple of 4: the per-tile kernel serves it
     ("nt", 4000, 128, 128, 0, None, False),          # M < 4096: no weight-image workspace, per-tile kernel
 ])
-def test_gemm_persistent_kernel(ops, mode, M, N, K, act, drop, persistent):
+@pytest.mark.parametrize("residency", [0, 1])
+def test_gemm_persistent_kernel(ops, mode, M, N, K, act, drop, persistent, residency):
     """The persistent streamed GEMM (csrc/gemm_ps.cu: TMA-fed ring, two MMA issuers, TMA-store epilogue) on the shapes /
-    epilogues it accepts, against fp64; the launch counter proves which kernel served the call; the padding columns of a
-    wider output buffer must stay untouched."""
+    epilogues it accepts, against fp64, with the weight image streamed (the default) and resident in shared memory where it
+    fits; the launch counter proves which kernel served the call; the padding columns of a wider output buffer must stay
+    untouched."""
+    ops.lib.mfm_debug_gemm_ps_residency(residency)
+    try:
+        _gemm_persistent_case(ops, mode, M, N, K, act, drop, persistent)
+    finally:
+        ops.lib.mfm_debug_gemm_ps_residency(0)
+
+
+def _gemm_persistent_case(ops, mode, M, N, K, act, drop, persistent):
     gen = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=gen).cuda()
     B = (torch.randn((N, K) if mode == "nt" else (K, N), generator=gen) / K ** 0.5).cuda()
