@@ -125,6 +125,26 @@ class encoderLSTM(nn.Module):
         return encoder_forward(self, x)
 
 
+class EFLSTM(nn.Module):
+    """The early-fusion LSTM baseline of the reference's MOSI script (test_mosi.py:130-157): one LSTMCell over the
+    concatenated input, ``fc2(dropout(relu(fc1(h_T))))``.  Same parameter names (``lstm``, ``fc1``, ``fc2``); the recurrence
+    and ``fc1`` run on the CUDA kernels of ``encoderLSTM``, the [N, h] head is three small torch ops."""
+
+    def __init__(self, d, h, output_dim, dropout):
+        super(EFLSTM, self).__init__()
+        self.h = h
+        self.lstm = nn.LSTMCell(d, h)
+        self.fc1 = nn.Linear(h, h)
+        self.fc2 = nn.Linear(h, output_dim)
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, x):
+        from .standalone import encoder_forward
+        _require_cuda(x, "EFLSTM.forward")
+        output = torch.relu(encoder_forward(self, x))       # encoder_forward = fc1(h_T), no activation
+        return self.fc2(self.dropout(output))
+
+
 class decoderLSTM(nn.Module):
     """mfm_model.py:64-91.  ``forward(hT[N,h], t) -> [t,N,d]``."""
 

@@ -260,6 +260,21 @@ def encoder_lstm(x: Tensor, P, prefix: str) -> Tensor:
     return linear(h, P, prefix + ".fc1")
 
 
+def eflstm_forward(x: Tensor, P, train=False, p_drop=0.0, keep=None) -> Tensor:
+    """EFLSTM.forward, test_mosi.py:139-157 (the early-fusion LSTM baseline): zero state, T cell steps over the whole input
+    row, ``fc2(dropout(relu(fc1(h_T))))``.  P holds lstm.*, fc1.*, fc2.*."""
+    T, n, _ = x.shape
+    hs = P["lstm.weight_hh"].shape[1]
+    h = x.new_zeros(n, hs)
+    c = x.new_zeros(n, hs)
+    for t in range(T):
+        h, c = lstm_cell(x[t], h, c, P, "lstm")
+    out = torch.relu(linear(h, P, "fc1"))
+    if train and p_drop > 0.0:
+        out = out * keep / (1.0 - p_drop)
+    return linear(out, P, "fc2")
+
+
 def decoder_lstm(emb: Tensor, T: int, P, prefix: str) -> Tensor:
     """decoderLSTM.forward, mfm_model.py:72-91: step 0 eats the embedding,
     step t>0 eats the previous hidden state; fc1 over all T hiddens."""

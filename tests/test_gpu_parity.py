@@ -588,3 +588,24 @@ def test_mfm_kl_ef_train_mode_step_at_mosi_shapes():
     assert not bad, bad
     bad = {k: rel_l2(sd[k].cpu(), newP[k]) for k in P if not rel_l2(sd[k].cpu(), newP[k]) < 1e-4}
     assert not bad, bad
+
+
+def test_eflstm_baseline_vs_oracle():
+    """The early-fusion LSTM baseline (test_mosi.py:130-157) on the encoder kernels: forward, loss and every gradient against the
+    oracle's restatement, eval mode (the dropout of the [N, h] head is torch's own)."""
+    import factorized_b200 as F
+    torch.manual_seed(5)
+    T, n, d, h, od = 9, 37, 25, 48, 1
+    model = F.EFLSTM(d, h, od, 0.3).cuda().eval()
+    P = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    assert sorted(P) == sorted(["lstm.weight_ih", "lstm.weight_hh", "lstm.bias_ih", "lstm.bias_hh", "fc1.weight", "fc1.bias",
+                                "fc2.weight", "fc2.bias"])
+    x = torch.randn(T, n, d)
+    y = torch.randn(n)
+    out_ref = O.eflstm_forward(x, P)
+    torch.nn.functional.l1_loss(out_ref.squeeze(1), y).backward()
+    out = model.forward(x.cuda())
+    torch.nn.functional.l1_loss(out.squeeze(1), y.cuda()).backward()
+    assert rel_l2(out, out_ref) < TOL
+    bad = {k: rel_l2(p.grad, P[k].grad) for k, p in model.named_parameters() if not rel_l2(p.grad, P[k].grad) < TOL}
+    assert not bad, bad
