@@ -299,8 +299,16 @@ def train_mfm(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, head:
     if head == "l1" and y_hat.ndim == 1:
         scores["mae"] = float(np.mean(np.absolute(y_hat - y_test)))                            # :484
         scores["corr"] = float(np.corrcoef(y_hat, y_test)[0][1])                               # :486
-        scores["mult_acc"] = float(np.mean(np.round(y_hat) == np.round(y_test)))               # :488
-        scores["binary_acc"] = float(np.mean((y_hat >= 0) == (y_test >= 0)))                   # :492-498
+        scores["mult_acc"] = round(float(np.mean(np.round(y_hat) == np.round(y_test))), 5)     # :488
+        true_label, predicted_label = (y_test >= 0), (y_hat >= 0)                              # :492-493
+        scores["binary_acc"] = float(np.mean(predicted_label == true_label))                   # :498 accuracy_score
+        try:                                                                                   # :490,495-497 (sklearn, as the reference)
+            from sklearn.metrics import classification_report, confusion_matrix, f1_score
+            scores["mult_f_score"] = round(float(f1_score(np.round(y_hat), np.round(y_test), average="weighted")), 5)
+            scores["confusion_matrix"] = confusion_matrix(true_label, predicted_label).tolist()
+            scores["classification_report"] = classification_report(true_label, predicted_label, digits=5, zero_division=0)
+        except ImportError:
+            pass
     elif head == "ce":
         scores["acc"] = float(np.mean(np.argmax(y_hat, 1) == y_test))
     if verbose:

@@ -423,7 +423,10 @@ def test_train_mfm_entry_point(tmp_path):
         assert abs(tl - otl) < 1e-3 * abs(otl), (ep, tl, otl)
         assert abs(vl - ovl) < 1e-3 * abs(ovl), (ep, vl, ovl)
     assert out["predictions"].shape == (48,) and np.isfinite(out["predictions"]).all()
-    assert set(out["scores"]) == {"mae", "corr", "mult_acc", "binary_acc"}
+    # the reference's score block (mfm_mosi.py:483-498): mae, corr, mult_acc, weighted F-score, confusion matrix, report, accuracy
+    assert set(out["scores"]) == {"mae", "corr", "mult_acc", "binary_acc", "mult_f_score", "confusion_matrix", "classification_report"}
+    cm = np.asarray(out["scores"]["confusion_matrix"])
+    assert cm.sum() == 48 and abs(np.trace(cm) / 48.0 - out["scores"]["binary_acc"]) < 1e-9
     assert abs(out["best_valid"] - min(h[2] for h in out["history"])) < 1e-7
     reloaded = torch.load(out["checkpoint"], weights_only=False)       # whole-module pickle, as the reference saves it
     assert sorted(reloaded.state_dict()) == sorted(out["model"].state_dict())
