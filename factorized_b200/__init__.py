@@ -1,11 +1,17 @@
 """factorized_b200 -- the MFM (Multimodal Factorization Model) training step on B200 (sm_100a).
 
-Drop-in for the hot path of pliang279/factorized: ``encoderLSTM / decoderLSTM / MFN / MFM / MFM_KL / MFM_KL_EF`` and
-``train_mfm``; arithmetic in hand-written CUDA behind ``include/mfm_b200.h``.  CUDA only.
+Drop-in for the hot path of pliang279/factorized: ``encoderLSTM / decoderLSTM / MFN / MFM / MFM_KL / MFM_KL_EF / M_A..M_D`` and
+``train_mfm`` / ``train_mfm_ablation``; arithmetic in hand-written CUDA behind ``include/mfm_b200.h``.  CUDA only.
 """
 from .mfm_model import encoderLSTM, decoderLSTM, MFN, MFM, MFM_KL, MFM_KL_EF, EFLSTM  # noqa: F401
+from .ablations import M_A, M_B, M_C, M_D  # noqa: F401
 
 
 def train_mfm(*a, **k):
     from .train import train_mfm as f
+    return f(*a, **k)
+
+
+def train_mfm_ablation(*a, **k):
+    from .train import train_mfm_ablation as f
     return f(*a, **k)

@@ -67,9 +67,10 @@ class _MFMFunction(torch.autograd.Function):
         ctx.eng, ctx.P, ctx.gen = eng, P, eng_generation(eng, bump=True)
         dm = eng.dm
         mmd = eng.loss_buf[4:8].sum()
-        res = (out["x_l_hat"].view(T, B, dm.d[0]).clone(), out["x_a_hat"].view(T, B, dm.d[1]).clone(),
-               out["x_v_hat"].view(T, B, dm.d[2]).clone(), out["y_hat"].clone(), mmd)
-        module._latents = {k: out[k].clone() for k in ("zl", "za", "zv", "zy")}
+        res = (out["x_l_hat"].reshape(T, B, dm.d[0]).clone(), out["x_a_hat"].reshape(T, B, dm.d[1]).clone(),
+               out["x_v_hat"].reshape(T, B, dm.d[2]).clone(), out["y_hat"].clone(), mmd)
+        # (the ablation models of factorized_b200.ablations lack some of the four latents)
+        module._latents = {k: out[k].clone() for k in ("zl", "za", "zv", "zy") if out.get(k) is not None}
         return res
 
     @staticmethod

@@ -62,7 +62,7 @@ class MFMTrainer:
         # The encoder cell and the MFN cell of a modality read the same input: with their input weights (and bias vectors) ADJACENT
         # in the flat buffer the two input projections are one GEMM over a [4(z+h), d] view (engine.forward step 1).  Order only;
         # a tensor whose size is not a multiple of the alignment leaves a gap and the engine then keeps two GEMMs.
-        if "mfn_encoder.lstm_l.weight_ih" in pd and "encoder_l.lstm.weight_ih" in pd:
+        if getattr(model, "_variant", "mfm") in ("mfm", "kl") and "mfn_encoder.lstm_l.weight_ih" in pd:
             moved = []
             for leaf in ("weight_ih", "bias_ih", "bias_hh"):
                 for tag in "lav":
@@ -90,7 +90,8 @@ class MFMTrainer:
                 self.P[k] = view
                 self.G[k] = self.flat_g[o:o + p.numel()].view(p.shape)
         self.variant = getattr(model, "_variant", "mfm")
-        self.eng = E.Engine(model._cfg, T, B, dev, self.ops, head=head, variant=self.variant)
+        from .ablations import make_engine
+        self.eng = make_engine(model._cfg, T, B, dev, self.ops, head=head, variant=self.variant)
         self.eng.defer_mmd_join = True
         self.eng.fuse_mse = True
         dm = self.eng.dm
@@ -125,7 +126,7 @@ class MFMTrainer:
         ops, eng = self.ops, self.eng
         ops.rng_tick(self.rng)
         if self.variant not in ("kl", "kl_ef"):
-            for k in range(4):                                # loss_MMD's Gaussian samples (mfm_model.py:26)
+            for k in getattr(eng, "mmd_slots", range(4)):     # loss_MMD's Gaussian samples (mfm_model.py:26)
                 ops.randn(self.noise[k], self.rng, SITE_NOISE + k)
         eng.forward(self.P, self.x, self.noise, train=True, rng=self.rng)
         dX, dY = eng.losses(self.y)
@@ -221,8 +222,20 @@ def _to_time_major(X):
     return np.ascontiguousarray(np.swapaxes(np.asarray(X, dtype=np.float32), 0, 1))
 
 
+def train_mfm_ablation(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, head: str = "l1", verbose: bool = True,
+                       save_dir: Optional[str] = None):
+    """Drop-in for the reference's train_mfm_ablation (mfm_mosi.py:640-767): ``config['type']`` in m_a / m_b / m_c / m_d
+    selects M_A .. M_D (:651-658); the epoch loop, the step and the scores are train_mfm's (:660-767 repeat :403-503)."""
+    from .ablations import ABLATION_MODELS
+    kind = configs[0].get("type")
+    if kind not in ABLATION_MODELS:
+        raise ValueError("train_mfm_ablation: config['type'] must be one of %s, got %r" % (sorted(ABLATION_MODELS), kind))
+    return train_mfm(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, head=head, verbose=verbose,
+                     save_dir=save_dir, _model_cls=ABLATION_MODELS[kind])
+
+
 def train_mfm(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, head: str = "l1", verbose: bool = True,
-              save_dir: Optional[str] = None):
+              save_dir: Optional[str] = None, _model_cls=None):
     """Drop-in for the reference's train_mfm (mfm_mosi.py:386-503); CE head: mfm_mosi_acc.py:396-503.
     X_* are numpy [n,T,D]; y_* [n] (or [n,out]).  Returns a dict with the trained model and scores."""
     config = configs[0]
@@ -230,7 +243,7 @@ def train_mfm(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, head:
     X_train, y_train = np.asarray(X_train)[p], np.asarray(y_train)[p]
     Xt, Xv, Xte = _to_time_major(X_train), _to_time_major(X_valid), _to_time_major(X_test)    # :391-393
     dev = torch.device("cuda")
-    model = (MFM_KL if config.get("type", "mfm") == "kl" else MFM)(*configs).to(dev)      # :398-401,414
+    model = (_model_cls or (MFM_KL if config.get("type", "mfm") == "kl" else MFM))(*configs).to(dev)      # :398-401,414
     model.mmd_noise = "cuda"
     model.eval_skip_mmd = True            # evaluate / predict discard the MMD of the whole-set forward (:448,:460)
     T, total_n = Xt.shape[0], Xt.shape[1]

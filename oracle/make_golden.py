@@ -39,12 +39,16 @@ def import_reference():
 
 def run_reference(ref, configs, seed, T, n, head, data_seed, noise_seed, variant="mfm"):
     torch.manual_seed(seed)
-    cls = dict(mfm=ref.MFM, kl=ref.MFM_KL, kl_ef=ref.MFM_KL_EF)[variant]
+    cls = dict(mfm=ref.MFM, kl=ref.MFM_KL, kl_ef=ref.MFM_KL_EF, m_a=ref.M_A, m_b=ref.M_B, m_c=ref.M_C, m_d=ref.M_D)[variant]
     model = cls(*configs).eval()                                                       # eval(): the 9 dropouts become identity
     params0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
     x, y = O.synthetic_batch(configs, T, n, data_seed, head)
     lat = {}
-    hooks = dict(zl=model.encoder_l.fc1, za=model.encoder_a.fc1, zv=model.encoder_v.fc1, zy=model.last_to_zy_fc1)
+    hooks = {}
+    for k, owner, attr in (("zl", "encoder_l", "fc1"), ("za", "encoder_a", "fc1"), ("zv", "encoder_v", "fc1"),
+                           ("zy", "last_to_zy_fc1", None)):
+        if hasattr(model, owner):                    # the ablation models lack some of the four latents
+            hooks[k] = getattr(model, owner) if attr is None else getattr(getattr(model, owner), attr)
     if variant in ("kl", "kl_ef"):                   # the latents are the means: one more Linear after the encoders
         hooks = dict(zl=model.last_to_zl_fc1, za=model.last_to_za_fc1, zv=model.last_to_zv_fc1, zy=model.last_to_zy_fc1)
     for k, m in hooks.items():
@@ -82,12 +86,12 @@ def check_oracle(r, configs, seed, n, head, noise_seed, tag, variant="mfm"):
         dd = float((P[k] - v).abs().max())
         worst = max(worst, dd)
     assert worst == 0.0, "init_params does not reproduce the reference's init (max diff %g)" % worst
-    noise = O.draw_mmd_noise(configs, n, noise_seed)
+    noise = O.draw_mmd_noise(configs, n, noise_seed, variant=variant)
     newP, losses, G, out = O.train_step(P, r["x"], r["y"], configs, noise, {}, head=head, variant=variant)
     def rel(a, b):
         return float((a - b).norm() / (b.norm() + 1e-30))
     errs = {}
-    for k in ("zl", "za", "zv", "zy"):
+    for k in r["lat"]:
         errs[k] = rel(out[k], r["lat"][k])
     for k in ("x_l_hat", "x_a_hat", "x_v_hat", "y_hat"):
         errs[k] = rel(out[k], r[k])
@@ -111,10 +115,43 @@ def check_oracle(r, configs, seed, n, head, noise_seed, tag, variant="mfm"):
     return w
 
 
+def write_fixture(path, r, meta):
+    blob = dict(meta=np.array(meta), x=r["x"].numpy(), y=r["y"].numpy())
+    for k, v in r["params0"].items():
+        blob["p0/" + k] = v.numpy()
+    for k, v in r["params1"].items():
+        blob["p1/" + k] = v.numpy()
+    for k, v in r["grads"].items():
+        if v is not None:
+            blob["g/" + k] = v.numpy()
+    for k, v in r["lat"].items():
+        blob["lat/" + k] = v.numpy()
+    for k in ("x_l_hat", "x_a_hat", "x_v_hat", "y_hat"):
+        blob[k] = r[k].numpy()
+    for k, v in r["losses"].items():
+        blob["loss/" + k] = np.float64(v)
+    np.savez_compressed(path, **blob)
+
+
+def ablations(ref, outdir):
+    """(1d) the ablation models of train_mfm_ablation (mfm_mosi.py:651-658): M_A, M_B, M_C, M_D (mfm_model.py:201-467)."""
+    for i, variant in enumerate(O.ABLATIONS):
+        configs = O.tiny_configs(output_dim=1)
+        configs[0]["type"] = variant
+        seed, T, n, data_seed, noise_seed = 700 + i, 4 + (i % 2), 6 + i, 21 + i, 90 + i
+        r = run_reference(ref, configs, seed, T, n, "l1", data_seed, noise_seed, variant=variant)
+        check_oracle(r, configs, seed, n, "l1", noise_seed, "tiny_%s/l1/out1" % variant, variant=variant)
+        write_fixture(os.path.join(outdir, "tiny_%s_l1_out1.npz" % variant), r, [seed, T, n, data_seed, noise_seed, 1])
+
+
 def main():
     ref = import_reference()
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
+    if "--ablations-only" in sys.argv:               # leaves the other fixtures' files untouched
+        ablations(ref, outdir)
+        return
+    ablations(ref, outdir)
 
     # ---- (1) tiny awkward config, everything stored, L1 head and CE head -------------
     for head, od in (("l1", 1), ("ce", 3), ("l1", 4)):

@@ -96,6 +96,8 @@ def param_shapes(configs, variant: str = "mfm") -> "OrderedDict[str, Tuple[int, 
         shapes[prefix + ".weight"] = (dout, din)
         shapes[prefix + ".bias"] = (dout,)
 
+    if variant in ABLATIONS:
+        return _ablation_shapes(configs, variant, lstm, lin, shapes)
     for m, tag in enumerate("lav"):
         lstm("encoder_%s.lstm" % tag, d[m], z[m])
         lin("encoder_%s.fc1" % tag, z[m], z[m])
@@ -149,6 +151,79 @@ def param_shapes(configs, variant: str = "mfm") -> "OrderedDict[str, Tuple[int, 
         lin("z%s_to_f%s_fc2" % (tag, tag), f[m], f[m])
     lin("fy_to_y_fc1", fy, fy)
     lin("fy_to_y_fc2", fy, config["output_dim"])
+    return shapes
+
+
+ABLATIONS = ("m_a", "m_b", "m_c", "m_d")
+
+
+def _ablation_shapes(configs, variant, lstm, lin, shapes):
+    """Construction order of the ablation models M_A (mfm_model.py:223-242), M_B (:293-315), M_C (:367-380) and
+    M_D (:427-443) -- the models train_mfm_ablation builds (mfm_mosi.py:651-658)."""
+    config, nn1, nn2, g1, g2, out = configs
+    d, hm = config["input_dims"], config["h_dims"]
+    z = [config["zl_size"], config["za_size"], config["zv_size"]]
+    f = [config["fl_size"], config["fa_size"], config["fv_size"]]
+    fy, zy, mem, od = config["fy_size"], config["zy_size"], config["memsize"], config["output_dim"]
+    H = sum(hm)
+
+    def mfn():
+        for m, tag in enumerate("lav"):
+            lstm("mfn_encoder.lstm_%s" % tag, d[m], hm[m])
+        att_in = H * config["windowsize"]
+        gam_in = att_in + mem
+        lin("mfn_encoder.att1_fc1", att_in, nn1["shapes"])
+        lin("mfn_encoder.att1_fc2", nn1["shapes"], att_in)
+        lin("mfn_encoder.att2_fc1", att_in, nn2["shapes"])
+        lin("mfn_encoder.att2_fc2", nn2["shapes"], mem)
+        lin("mfn_encoder.gamma1_fc1", gam_in, g1["shapes"])
+        lin("mfn_encoder.gamma1_fc2", g1["shapes"], mem)
+        lin("mfn_encoder.gamma2_fc1", gam_in, g2["shapes"])
+        lin("mfn_encoder.gamma2_fc2", g2["shapes"], mem)
+        lin("mfn_encoder.out_fc1", H + mem, out["shapes"])
+        lin("mfn_encoder.out_fc2", out["shapes"], od)
+        lin("last_to_zy_fc1", H + mem, zy)
+
+    def decoders(hd):
+        for m, tag in enumerate("lav"):
+            lstm("decoder_%s.lstm" % tag, hd[m], hd[m])
+            lin("decoder_%s.fc1" % tag, hd[m], d[m])
+
+    def mlp(src, dst, zin, fout):
+        lin("z%s_to_f%s_fc1" % (src, dst), zin, fout)
+        lin("z%s_to_f%s_fc2" % (src, dst), fout, fout)
+
+    if variant == "m_a":                       # ONE encoder over the whole input; the three decoders read cat(fy, fl)
+        lstm("encoder_l.lstm", sum(d), z[0])
+        lin("encoder_l.fc1", z[0], z[0])
+        decoders([fy + f[0]] * 3)
+        mfn()
+        mlp("y", "y", zy, fy)
+        mlp("l", "l", z[0], f[0])
+        lin("fy_to_y_fc1", fy, fy)
+        lin("fy_to_y_fc2", fy, od)
+    elif variant == "m_b":                     # no MFN / no z_y: the label is predicted from cat(fl, fa, fv)
+        for m, tag in enumerate("lav"):
+            lstm("encoder_%s.lstm" % tag, d[m], z[m])
+            lin("encoder_%s.fc1" % tag, z[m], z[m])
+        decoders(f)
+        for m, tag in enumerate("lav"):
+            mlp(tag, tag, z[m], f[m])
+        lin("fy_to_y_fc1", sum(f), fy)
+        lin("fy_to_y_fc2", fy, od)
+    elif variant == "m_c":                     # MFN only: the three decoders read fy
+        decoders([fy] * 3)
+        mfn()
+        mlp("y", "y", zy, fy)
+        lin("fy_to_y_fc1", fy, fy)
+        lin("fy_to_y_fc2", fy, od)
+    else:                                      # m_d: purely discriminative (no decoders, no regulariser)
+        for m, tag in enumerate("lav"):
+            lstm("encoder_%s.lstm" % tag, d[m], z[m])
+            lin("encoder_%s.fc1" % tag, z[m], z[m])
+        for m, tag in enumerate("lav"):
+            mlp(tag, tag, z[m], f[m])
+        lin("fs_to_y", sum(f), od)
     return shapes
 
 
@@ -341,12 +416,15 @@ def loss_mmd(z: Tensor, gauss: Tensor) -> Tensor:
         - 2.0 * compute_kernel(gauss, z).mean()
 
 
-def draw_mmd_noise(configs, n: int, seed: int, dtype=torch.float32) -> List[Tensor]:
+def draw_mmd_noise(configs, n: int, seed: int, dtype=torch.float32, variant: str = "mfm") -> List[Tensor]:
     """The four draws loss_MMD makes inside MFM.forward, in order zl, za, zv, zy
-    (mfm_model.py:536), after torch.manual_seed(seed)."""
+    (mfm_model.py:536), after torch.manual_seed(seed).  The ablation models regularise fewer latents (M_A zl, zy :255;
+    M_B zl, za, zv :328; M_C zy :392; M_D none :456): the list keeps four slots, None where nothing is drawn."""
     c = configs[0]
     torch.manual_seed(seed)
-    return [torch.randn(n, k).to(dtype) for k in (c["zl_size"], c["za_size"], c["zv_size"], c["zy_size"])]
+    sizes = (c["zl_size"], c["za_size"], c["zv_size"], c["zy_size"])
+    used = dict(m_a=(0, 3), m_b=(0, 1, 2), m_c=(3,), m_d=()).get(variant, (0, 1, 2, 3))
+    return [torch.randn(n, k).to(dtype) if i in used else None for i, k in enumerate(sizes)]
 
 
 def factor_mlp(z: Tensor, P, name: str, p: float, train: bool, mask=None, branches=None, key="") -> Tensor:
@@ -447,6 +525,62 @@ def mfm_kl_ef_forward(x: Tensor, P, configs, train=False, masks=None, branches=N
                 zl=zl, za=za, zv=zv, zy=zy, lvl=lvs[0], lva=lvs[1], lvv=lvs[2], lvy=lvy, fy=fy, fl=fl, fa=fa, fv=fv)
 
 
+def ablation_forward(x: Tensor, P, configs, noise: Sequence[Tensor], variant: str, train=False, masks=None, branches=None):
+    """M_A / M_B / M_C / M_D .forward (mfm_model.py:244-269, 317-343, 382-403, 445-467): MFM with parts removed.  Returns
+    the same dict as mfm_forward (latents a model does not have are absent; "mmd" is the python float 0.0 for M_D)."""
+    config = configs[0]
+    d_l, d_a, d_v = config["input_dims"]
+    T = x.shape[0]
+    x_l, x_a, x_v = x[:, :, :d_l], x[:, :, d_l:d_l + d_a], x[:, :, d_l + d_a:]
+    mk = (lambda k: None if masks is None else masks.get(k))
+    out = {}
+
+    def fmlp(zk, name, pkey, key):
+        return factor_mlp(zk, P, name, config[pkey], train, mk(key), branches, key)
+
+    def y_head(fin):
+        y1 = dropout(relu(linear(fin, P, "fy_to_y_fc1"), branches, "y1"), config["fy_to_y_dropout"], train, mk("y"))
+        return linear(y1, P, "fy_to_y_fc2")
+
+    if variant in ("m_a", "m_c"):
+        if variant == "m_a":
+            out["zl"] = zl = encoder_lstm(x, P, "encoder_l")                                  # :252 (the WHOLE input)
+        out["mfn_last"] = mfn_last = mfn_encoder(x, P, configs, train, masks, branches)       # :253 / :390
+        out["zy"] = zy = linear(mfn_last, P, "last_to_zy_fc1")
+        if variant == "m_a":
+            out["mmd"] = loss_mmd(zl, noise[0]) + loss_mmd(zy, noise[3])                      # :255
+        else:
+            out["mmd"] = loss_mmd(zy, noise[3])                                               # :392
+        out["fy"] = fy = fmlp(zy, "zy_to_fy", "zy_to_fy_dropout", "fy")
+        emb = fy
+        if variant == "m_a":
+            out["fl"] = fl = fmlp(zl, "zl_to_fl", "zl_to_fl_dropout", "fl")
+            emb = torch.cat([fy, fl], 1)                                                      # :260
+        out["x_l_hat"] = decoder_lstm(emb, T, P, "decoder_l")                                 # :263-265 / :397-399
+        out["x_a_hat"] = decoder_lstm(emb, T, P, "decoder_a")
+        out["x_v_hat"] = decoder_lstm(emb, T, P, "decoder_v")
+        out["y_hat"] = y_head(fy)
+        return out
+    out["zl"] = zl = encoder_lstm(x_l, P, "encoder_l")                                        # :325-327 / :453-455
+    out["za"] = za = encoder_lstm(x_a, P, "encoder_a")
+    out["zv"] = zv = encoder_lstm(x_v, P, "encoder_v")
+    out["fl"] = fl = fmlp(zl, "zl_to_fl", "zl_to_fl_dropout", "fl")
+    out["fa"] = fa = fmlp(za, "za_to_fa", "za_to_fa_dropout", "fa")
+    out["fv"] = fv = fmlp(zv, "zv_to_fv", "zv_to_fv_dropout", "fv")
+    fs = torch.cat([fl, fa, fv], 1)
+    if variant == "m_b":
+        out["mmd"] = loss_mmd(zl, noise[0]) + loss_mmd(za, noise[1]) + loss_mmd(zv, noise[2])  # :328
+        out["x_l_hat"] = decoder_lstm(fl, T, P, "decoder_l")                                  # :336-338
+        out["x_a_hat"] = decoder_lstm(fa, T, P, "decoder_a")
+        out["x_v_hat"] = decoder_lstm(fv, T, P, "decoder_v")
+        out["y_hat"] = y_head(fs)                                                             # :339-340
+    else:
+        out["mmd"] = 0.0                                                                      # :456
+        out["x_l_hat"], out["x_a_hat"], out["x_v_hat"] = x_l, x_a, x_v                        # :465 the inputs themselves
+        out["y_hat"] = linear(fs, P, "fs_to_y")                                               # :464
+    return out
+
+
 def mfm_losses(out: Dict[str, Tensor], x: Tensor, y: Tensor, configs, head: str = "l1") -> Dict[str, Tensor]:
     """Loss assembly of the train step: mfm_mosi.py:432-439 (L1 head) and
     mfm_mosi_acc.py:441-451 / mfm_moud.py:495-508 (cross-entropy head)."""
@@ -497,13 +631,16 @@ def train_step(P, x, y, configs, noise, state, head="l1", lr=1e-3, train=False, 
         out = mfm_kl_forward(x, Pg, configs, train=train, masks=masks, branches=branches)
     elif variant == "kl_ef":
         out = mfm_kl_ef_forward(x, Pg, configs, train=train, masks=masks, branches=branches)
+    elif variant in ABLATIONS:                                # train_mfm_ablation runs the same step (mfm_mosi.py:677-697)
+        out = ablation_forward(x, Pg, configs, noise, variant, train=train, masks=masks, branches=branches)
     else:
         out = mfm_forward(x, Pg, configs, noise, train=train, masks=masks, branches=branches)
     losses = mfm_losses(out, x, y, configs, head)
     losses["total"].backward()
     G = OrderedDict((k, (None if v.grad is None else v.grad.detach().clone())) for k, v in Pg.items())
     newP = adam_step(OrderedDict((k, v.detach().clone()) for k, v in P.items()), G, state, lr=lr)
-    return newP, {k: float(v.detach()) for k, v in losses.items()}, G, {k: v.detach() for k, v in out.items()}
+    return newP, {k: float(v.detach()) if torch.is_tensor(v) else float(v) for k, v in losses.items()}, G, \
+        {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}
 
 
 def synthetic_batch(configs, T: int, n: int, seed: int, head="l1", dtype=torch.float32):

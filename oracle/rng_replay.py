@@ -59,15 +59,23 @@ def train_masks_and_branches(eng, rng_cpu):
             taken = torch.where(k > 0, taken, torch.full_like(taken, -1.0))
             masks[key] = k.view(shape3) if shape3 else k
         br[bkey] = taken.view(shape3) if shape3 else taken
-    if not getattr(eng, "ef", False):                       # (MFM_KL_EF has no MFN: no attention / gamma dropouts)
+    abl = getattr(eng, "abl", None)                         # factorized_b200.ablations.AblationEngine: M_A .. M_D
+    has_mfn = eng.has_mfn if abl else not getattr(eng, "ef", False)
+    if has_mfn:                                             # (MFM_KL_EF, M_B and M_D have no MFN: no attention / gamma dropouts)
         site("att1", "att1", dm.p_att1, ws["H1"], T * n, (T, n, -1))
         site("att2", "att2", dm.p_att2, ws["H2"], T * n, (T, n, -1))
         site("gamma1", "gamma1", dm.p_g1, ws["U1"], T * n, (T, n, -1))
         site("gamma2", "gamma2", dm.p_g2, ws["U2"], T * n, (T, n, -1))
-    site("fy", "fy1", dm.p_fy, ws["F1y"], n)
-    site("y", "y1", dm.p_y, ws["Y1"], n)
+    if abl is None or has_mfn:
+        site("fy", "fy1", dm.p_fy, ws["F1y"], n)
+        br["fy"] = (ws["FY"] > 0).float().cpu()
+    if abl != "m_d":
+        site("y", "y1", dm.p_y, ws["Y1"], n)
     for m, tag in enumerate("lav"):
-        site("f" + tag, "f%s1" % tag, dm.p_f[m], ws["F1_%d" % m], n)
-        br["f" + tag] = (ws["EMB%d" % m][:, dm.fy:] > 0).float().cpu()
-    br["fy"] = (ws["FY"] > 0).float().cpu()
+        if abl is None:
+            site("f" + tag, "f%s1" % tag, dm.p_f[m], ws["F1_%d" % m], n)
+            br["f" + tag] = (ws["EMB%d" % m][:, dm.fy:] > 0).float().cpu()
+        elif m in eng.fdst:
+            site("f" + tag, "f%s1" % tag, dm.p_f[m], ws["F1_%d" % m], n)
+            br["f" + tag] = (eng.fdst[m] > 0).float().cpu()
     return masks, br

@@ -55,3 +55,17 @@ def tiny_kl_ef_case():
     x = torch.from_numpy(g["x"].copy())
     y = torch.from_numpy(g["y"].copy())
     return g, configs, P, x, y, T, n
+
+
+def tiny_ablation_case(variant):
+    """Golden vectors of the unmodified reference's M_A / M_B / M_C / M_D (oracle/make_golden.py, section 1d)."""
+    g = load_golden("tiny_%s_l1_out1.npz" % variant)
+    seed, T, n, data_seed, noise_seed, od_ = [int(v) for v in g["meta"]]
+    configs = O.tiny_configs(output_dim=1)
+    configs[0]["type"] = variant
+    P = golden_params(g)
+    x = torch.from_numpy(g["x"].copy())
+    y = torch.from_numpy(g["y"].copy())
+    noise = O.draw_mmd_noise(configs, n, noise_seed, variant=variant)
+    noise = [torch.zeros(1, 1) if v is None else v for v in noise]
+    return g, configs, P, x, y, noise, T, n

@@ -174,3 +174,129 @@ def test_engine_kl_ef_variant_matches_reference_golden():
         if e > 2e-4:
             bad.append((k, e))
     assert not bad, bad
+
+
+def check_ablation_against_golden(g, eng, out, G, P, configs, T, n, tol=1e-4, gtol=2e-4):
+    for k in ("zl", "za", "zv", "zy"):
+        if "lat/" + k in g:
+            assert rel_l2(out[k], g["lat/" + k]) < tol, k
+        else:
+            assert out[k] is None, k
+    for k in ("x_l_hat", "x_a_hat", "x_v_hat"):
+        assert rel_l2(out[k].reshape(T, n, -1), g[k]) < tol, k
+    assert rel_l2(out["y_hat"], g["y_hat"]) < tol
+    lb = eng.loss_buf
+    assert abs(float(lb[0]) - float(g["loss/disc"])) < tol * abs(float(g["loss/disc"])) + 1e-7
+    for i, k in enumerate(("mse_l", "mse_a", "mse_v")):
+        assert abs(float(lb[1 + i]) - float(g["loss/" + k])) <= tol * float(g["loss/" + k]), k
+    assert abs(float(lb[4:8].sum()) * configs[0]["lda_mmd"] - float(g["loss/mmd"])) <= tol * abs(float(g["loss/mmd"])) + 1e-9
+    assert abs(float(lb[8]) - float(g["loss/total"])) < tol * abs(float(g["loss/total"]))
+    bad = []
+    for k in P:
+        if "g/" + k in g:
+            e = rel_l2(G[k], g["g/" + k])
+            if e > gtol:
+                bad.append((k, e))
+        else:
+            assert float(G[k].abs().max()) == 0.0, k
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("variant", ["m_a", "m_b", "m_c", "m_d"])
+@pytest.mark.parametrize("fused", [False, True])
+def test_engine_ablation_variants_match_reference_golden(variant, fused):
+    """M_A .. M_D (mfm_model.py:201-467, the models of train_mfm_ablation mfm_mosi.py:651-658): schedule + hand-derived
+    backward of factorized_b200.ablations against the golden vectors of the unmodified reference classes, in the module's
+    configuration and in the trainer's (MSE fused into the decoder heads, MMD joined in backward)."""
+    from helpers import tiny_ablation_case
+    from factorized_b200.ablations import AblationEngine
+    g, configs, P, x, y, noise, T, n = tiny_ablation_case(variant)
+    P = OrderedDict(P)
+    eng = AblationEngine(configs, T, n, "cpu", EmuOps(), head="l1", variant=variant)
+    eng.fuse_mse = eng.defer_mmd_join = fused
+    out = eng.forward(P, x.contiguous(), noise)
+    dX, dY = eng.losses(y)
+    G = OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    eng.backward(P, G, dX, dY, eng.dm.lda_mmd)
+    if fused:
+        out = dict(out)
+        for k in ("x_l_hat", "x_a_hat", "x_v_hat"):       # the fused heads never write x_hat: compare the losses and gradients
+            if out[k] is None:
+                out[k] = torch.from_numpy(g[k].copy())
+    check_ablation_against_golden(g, eng, out, G, P, configs, T, n)
+
+
+@pytest.mark.parametrize("variant", ["m_a", "m_b", "m_c", "m_d"])
+def test_engine_ablation_dropout_masks_replay(variant):
+    """train=True with every dropout on: the counter-based masks the schedule applies, replayed through the oracle."""
+    from emu_ops import keep_mask
+    from factorized_b200 import engine as E
+    from helpers import tiny_ablation_case
+    from factorized_b200.ablations import AblationEngine
+    g, configs, P, x, y, noise, T, n = tiny_ablation_case(variant)
+    configs = [dict(c) for c in configs]
+    configs[0].update(zy_to_fy_dropout=0.3, zl_to_fl_dropout=0.2, za_to_fa_dropout=0.5, zv_to_fv_dropout=0.4,
+                      fy_to_y_dropout=0.25)
+    for c, p in zip(configs[1:5], (0.5, 0.3, 0.2, 0.4)):
+        c["drop"] = p
+    rng = torch.tensor([4321, 3], dtype=torch.int64)
+    P = OrderedDict(P)
+    eng = AblationEngine(configs, T, n, "cpu", EmuOps(), head="l1", variant=variant)
+    out = eng.forward(P, x.contiguous(), noise, train=True, rng=rng)
+    dX, dY = eng.losses(y)
+    G = OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    eng.backward(P, G, dX, dY, eng.dm.lda_mmd)
+    c = configs[0]
+    nn1, nn2, g1, g2 = configs[1:5]
+    masks = dict(
+        att1=keep_mask(rng, E.SITE_ATT1, nn1["drop"], T * n, nn1["shapes"]).view(T, n, -1),
+        att2=keep_mask(rng, E.SITE_ATT2, nn2["drop"], T * n, nn2["shapes"]).view(T, n, -1),
+        gamma1=keep_mask(rng, E.SITE_G1, g1["drop"], T * n, g1["shapes"]).view(T, n, -1),
+        gamma2=keep_mask(rng, E.SITE_G2, g2["drop"], T * n, g2["shapes"]).view(T, n, -1),
+        fy=keep_mask(rng, E.SITE_FY, c["zy_to_fy_dropout"], n, c["fy_size"]),
+        fl=keep_mask(rng, E.SITE_FL, c["zl_to_fl_dropout"], n, c["fl_size"]),
+        fa=keep_mask(rng, E.SITE_FA, c["za_to_fa_dropout"], n, c["fa_size"]),
+        fv=keep_mask(rng, E.SITE_FV, c["zv_to_fv_dropout"], n, c["fv_size"]),
+        y=keep_mask(rng, E.SITE_Y, c["fy_to_y_dropout"], n, c["fy_size"]),
+    )
+    onoise = [None if v.shape[0] != n else v for v in noise]
+    newP, losses, Go, outo = O.train_step(P, x, y, configs, onoise, {}, head="l1", train=True, masks=masks, variant=variant)
+    assert rel_l2(out["y_hat"], outo["y_hat"]) < 1e-4
+    assert abs(float(eng.loss_buf[8]) - losses["total"]) < 1e-4 * abs(losses["total"])
+    bad = [(k, rel_l2(G[k], Go[k])) for k in P if Go[k] is not None and rel_l2(G[k], Go[k]) > 3e-4]
+    assert not bad, bad
+    assert all(float(G[k].abs().max()) == 0.0 for k in P if Go[k] is None)
+
+
+@pytest.mark.parametrize("variant", ["m_a", "m_b", "m_c", "m_d"])
+def test_ablation_modules_init_and_trainer_step_match_reference_golden(variant):
+    """The drop-in classes M_A .. M_D draw the reference's initial weights for the same seed (same construction order, same
+    state-dict keys), and one fused trainer step on them (host logic, primitives injected) lands on the reference's
+    post-Adam parameters."""
+    from helpers import tiny_ablation_case
+    from factorized_b200.ablations import ABLATION_MODELS, AblationEngine
+    from factorized_b200.train import MFMTrainer
+    g, configs, P, x, y, noise, T, n = tiny_ablation_case(variant)
+    torch.manual_seed(int(g["meta"][0]))
+    model = ABLATION_MODELS[variant](*configs).eval()
+    sd = model.state_dict()
+    assert list(sd) == list(P)
+    for k in P:
+        assert torch.equal(sd[k], P[k]), k
+    tr = MFMTrainer(model, T, n, head="l1", _test_ops=EmuOps())
+    assert isinstance(tr.eng, AblationEngine) and tr.eng.abl == variant
+    drawn = []
+    tr.ops.randn = lambda out, rng, site: drawn.append(site)        # keep the injected noise
+    for k in tr.eng.mmd_slots:
+        tr.noise[k].copy_(noise[k])
+    lb = tr.step(x, y)
+    assert len(drawn) == len(tr.eng.mmd_slots)
+    assert abs(float(lb[8]) - float(g["loss/total"])) < 1e-4 * abs(float(g["loss/total"]))
+    worst = 0.0
+    for k, v in model.state_dict().items():
+        d_ref, d_got = torch.from_numpy(g["p1/" + k]) - P[k], v - P[k]
+        if float(d_ref.norm()) == 0.0:
+            assert float(d_got.abs().max()) == 0.0, k
+            continue
+        worst = max(worst, float((d_got - d_ref).norm() / d_ref.norm()))
+    assert worst < 2e-3, worst

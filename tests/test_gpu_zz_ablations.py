@@ -1,0 +1,148 @@
+"""The ablation models M_A .. M_D (mfm_model.py:201-467; train_mfm_ablation, mfm_mosi.py:640-767) on the GPU through the C ABI:
+golden vectors of the unmodified reference classes, train-mode steps at MOSI shapes against the oracle with the masks replayed,
+and the train_mfm_ablation entry point.  Tolerance 1e-3 relative, fp32 (BASELINE.json north_star)."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mfm_oracle as O
+from helpers import rel_l2, tiny_ablation_case
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+VARIANTS = ["m_a", "m_b", "m_c", "m_d"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_ablation_golden_module_and_trainer(variant):
+    """The drop-in class under torch autograd against the golden vectors (same init for the same seed; outputs, latents, loss,
+    every gradient), then one fused trainer step against the reference's post-Adam parameters."""
+    from factorized_b200.ablations import ABLATION_MODELS
+    from factorized_b200.train import MFMTrainer
+    g, configs, P, x, y, noise, T, n = tiny_ablation_case(variant)
+    torch.manual_seed(int(g["meta"][0]))
+    model = ABLATION_MODELS[variant](*configs).cuda().eval()
+    sd = model.state_dict()
+    assert list(sd) == list(P)
+    for k, v in sd.items():
+        assert torch.equal(v.cpu(), P[k]), k
+    xd, yd = x.cuda(), y.cuda()
+    torch.manual_seed(int(g["meta"][4]))                             # fixes loss_MMD's draws (CPU generator, reference order)
+    decoded, mmd, missing = model.forward(xd)
+    if variant == "m_d":
+        assert mmd == 0.0 and isinstance(mmd, float)
+        assert torch.equal(decoded[0], xd[:, :, :configs[0]["input_dims"][0]])
+    c = configs[0]
+    d_l, d_a, d_v = c["input_dims"]
+    Fn = torch.nn.functional
+    for i, k in enumerate(("x_l_hat", "x_a_hat", "x_v_hat", "y_hat")):
+        assert rel_l2(decoded[i], g[k]) < TOL, k
+    gen = c["lda_xl"] * Fn.mse_loss(decoded[0], xd[:, :, :d_l]) + c["lda_xa"] * Fn.mse_loss(decoded[1], xd[:, :, d_l:d_l + d_a]) \
+        + c["lda_xv"] * Fn.mse_loss(decoded[2], xd[:, :, d_l + d_a:])
+    loss = Fn.l1_loss(decoded[3].squeeze(1), yd) + gen + c["lda_mmd"] * mmd + missing
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss/total"])) < TOL * abs(float(g["loss/total"]))
+    lat = model.latents
+    assert sorted(lat) == sorted(k[4:] for k in g if k.startswith("lat/"))
+    for k in lat:
+        assert rel_l2(lat[k], g["lat/" + k]) < TOL, k
+    bad = {}
+    for k, p in model.named_parameters():
+        if "g/" + k in g:
+            e = rel_l2(p.grad, g["g/" + k])
+            if not e < TOL:
+                bad[k] = e
+        else:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+    assert not bad, bad
+    # fused trainer, CUDA graph (dropout is 0 in the tiny configuration: its train-mode step equals the golden step)
+    torch.manual_seed(int(g["meta"][0]))
+    model2 = ABLATION_MODELS[variant](*configs).cuda()
+    tr = MFMTrainer(model2, T, n, head="l1", use_graph=True)
+    real_randn = tr.ops.randn
+    try:
+        tr.ops.randn = lambda *a, **k: None                           # keep the injected Gaussian samples
+        for k in tr.eng.mmd_slots:
+            tr.noise[k].copy_(noise[k])
+        tr.x.copy_(xd)
+        tr.y.copy_(yd.reshape(-1))
+        tr.step_device()
+        torch.cuda.synchronize()
+    finally:
+        tr.ops.randn = real_randn
+    assert abs(float(tr.eng.loss_buf[8]) - float(g["loss/total"])) < TOL * abs(float(g["loss/total"]))
+    sd2 = model2.state_dict()
+    bad = {}
+    for k in P:
+        d_ref = g["p1/" + k] - P[k].numpy()
+        if float(np.abs(d_ref).max()) == 0.0:
+            assert torch.equal(sd2[k].cpu(), P[k]), k
+            continue
+        e = rel_l2(sd2[k].cpu() - P[k], d_ref)
+        if not e < 5e-3:
+            bad[k] = e
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_ablation_train_mode_step_at_mosi_shapes(variant):
+    """MOSI shapes (best_acc dims, T=20), train mode with every dropout on, CUDA graph; the masks the step drew are replayed
+    in the oracle.  Batch 192: the recurrences take their tensor-core path, the projections the tcgen05 GEMM."""
+    from factorized_b200.ablations import ABLATION_MODELS
+    from factorized_b200.train import MFMTrainer
+    from oracle.rng_replay import train_masks_and_branches
+    configs = O.best_acc_configs(dropout=True)
+    configs[0]["type"] = variant
+    T, n = 20, 192
+    torch.manual_seed(123)
+    model = ABLATION_MODELS[variant](*configs).cuda().train()
+    P = OrderedDict((k, v.detach().cpu().clone()) for k, v in model.state_dict().items())
+    tr = MFMTrainer(model, T, n, head="l1", use_graph=True, seed=77)
+    x, y = O.synthetic_batch(configs, T, n, 5)
+    lb = tr.step(x.cuda(), y.cuda())
+    torch.cuda.synchronize()
+    masks, br = train_masks_and_branches(tr.eng, tr.rng.cpu())
+    noise = [tr.noise[k].cpu() if k in tr.eng.mmd_slots else None for k in range(4)]
+    del O.RELU_REPLAY_VIOLATIONS[:]
+    newP, losses, Go, outo = O.train_step(P, x, y, configs, noise, {}, head="l1", train=True, masks=masks, branches=br,
+                                          variant=variant)
+    assert not O.RELU_REPLAY_VIOLATIONS, O.RELU_REPLAY_VIOLATIONS[:5]
+    lbc = lb.cpu()
+    assert abs(float(lbc[0]) - losses["disc"]) < TOL * abs(losses["disc"])
+    assert abs(float(lbc[8]) - losses["total"]) < TOL * abs(losses["total"])
+    for i, k in enumerate(("mse_l", "mse_a", "mse_v")):
+        assert abs(float(lbc[1 + i]) - losses[k]) <= TOL * abs(losses[k]), k
+    bad = {k: rel_l2(tr.G[k], go) for k, go in Go.items() if go is not None and not rel_l2(tr.G[k], go) < TOL}
+    assert not bad, bad
+    sd = model.state_dict()
+    bad = {k: rel_l2(sd[k].cpu(), newP[k]) for k in P if not rel_l2(sd[k].cpu(), newP[k]) < 1e-4}
+    assert not bad, bad
+    # a second step replays the captured graph
+    loss1 = float(lbc[8])
+    lb = tr.step(x.cuda(), y.cuda())
+    torch.cuda.synchronize()
+    assert np.isfinite(float(lb[8])) and float(lb[8]) != loss1
+
+
+def test_train_mfm_ablation_entry_point(tmp_path):
+    """train_mfm_ablation (mfm_mosi.py:640-767): model selected by config['type'], the epoch loop of train_mfm."""
+    import factorized_b200 as F
+    configs = O.tiny_configs()
+    configs[0].update(type="m_b", batchsize=8, num_epochs=3)
+    rs = np.random.RandomState(3)
+    D, T = sum(configs[0]["input_dims"]), 5
+    Xtr, ytr = rs.randn(40, T, D).astype(np.float32), rs.randn(40).astype(np.float32)
+    Xva, yva = rs.randn(16, T, D).astype(np.float32), rs.randn(16).astype(np.float32)
+    Xte, yte = rs.randn(24, T, D).astype(np.float32), rs.randn(24).astype(np.float32)
+    np.random.seed(1)
+    torch.manual_seed(2)
+    out = F.train_mfm_ablation(Xtr, ytr, Xva, yva, Xte, yte, configs, verbose=False, save_dir=str(tmp_path))
+    assert type(out["model"]).__name__ == "M_B"
+    assert len(out["history"]) == 3 and all(np.isfinite(v) for h in out["history"] for v in h[1:])
+    assert out["predictions"].shape == (24,) and np.isfinite(out["scores"]["mae"])
+    configs[0]["type"] = "mfm"
+    with pytest.raises(ValueError):
+        F.train_mfm_ablation(Xtr, ytr, Xva, yva, Xte, yte, configs, verbose=False, save_dir=str(tmp_path))

@@ -106,3 +106,29 @@ def test_tiny_kl_ef_full_step():
     for k in P:
         assert rel_l2(G[k], g["g/" + k]) < TOL, k
         assert rel_l2(newP[k], g["p1/" + k]) < TOL, k
+
+
+@pytest.mark.parametrize("variant,ntensors", [("m_a", 70), ("m_b", 52), ("m_c", 60), ("m_d", 32)])
+def test_tiny_ablation_full_step(variant, ntensors):
+    """M_A .. M_D (mfm_model.py:201-467) restated in oracle.ablation_forward, against the unmodified reference's classes:
+    same init for the same seed, and one train step (mfm_mosi.py:677-697) -- outputs, losses, gradients, post-Adam."""
+    from helpers import tiny_ablation_case
+    g, configs, P, x, y, noise, T, n = tiny_ablation_case(variant)
+    P2 = O.init_params(configs, int(g["meta"][0]), variant=variant)
+    assert list(P2) == list(P) and len(P) == ntensors
+    for k in P:
+        assert torch.equal(P[k], P2[k]), k
+    newP, losses, G, out = O.train_step(P, x, y, configs, noise, {}, head="l1", variant=variant)
+    for k in ("zl", "za", "zv", "zy"):
+        if "lat/" + k in g:
+            assert rel_l2(out[k], g["lat/" + k]) < TOL, k
+    for k in ("x_l_hat", "x_a_hat", "x_v_hat", "y_hat"):
+        assert rel_l2(out[k], g[k]) < TOL, k
+    for k, v in losses.items():
+        assert abs(v - float(g["loss/" + k])) <= TOL * abs(float(g["loss/" + k])) + 1e-7, k
+    for k in P:
+        if "g/" + k in g:
+            assert rel_l2(G[k], g["g/" + k]) < TOL, k
+        else:
+            assert G[k] is None, k
+        assert rel_l2(newP[k], g["p1/" + k]) < TOL, k
