@@ -15,3 +15,8 @@ def train_mfm(*a, **k):
 def train_mfm_ablation(*a, **k):
     from .train import train_mfm_ablation as f
     return f(*a, **k)
+
+
+def train_mfm_test_zeros(*a, **k):
+    from .train import train_mfm_test_zeros as f
+    return f(*a, **k)

@@ -222,6 +222,56 @@ def _to_time_major(X):
     return np.ascontiguousarray(np.swapaxes(np.asarray(X, dtype=np.float32), 0, 1))
 
 
+def score(predictions, y_test, head: str = "l1"):
+    """The reference's score block (mfm_mosi.py:483-498) as a dict instead of prints."""
+    scores = {}
+    y_hat, y_test = np.asarray(predictions), np.asarray(y_test)
+    if head == "l1" and y_hat.ndim == 1:
+        scores["mae"] = float(np.mean(np.absolute(y_hat - y_test)))                            # :484
+        scores["corr"] = float(np.corrcoef(y_hat, y_test)[0][1])                               # :486
+        scores["mult_acc"] = round(float(np.mean(np.round(y_hat) == np.round(y_test))), 5)     # :488
+        true_label, predicted_label = (y_test >= 0), (y_hat >= 0)                              # :492-493
+        scores["binary_acc"] = float(np.mean(predicted_label == true_label))                   # :498 accuracy_score
+        try:                                                                                   # :490,495-497 (sklearn, as the reference)
+            from sklearn.metrics import classification_report, confusion_matrix, f1_score
+            scores["mult_f_score"] = round(float(f1_score(np.round(y_hat), np.round(y_test), average="weighted")), 5)
+            scores["confusion_matrix"] = confusion_matrix(true_label, predicted_label).tolist()
+            scores["classification_report"] = classification_report(true_label, predicted_label, digits=5, zero_division=0)
+        except ImportError:
+            pass
+    elif head == "ce":
+        scores["acc"] = float(np.mean(np.argmax(y_hat, 1) == y_test))
+    return scores
+
+
+def train_mfm_test_zeros(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, verbose: bool = True,
+                         save_dir: Optional[str] = None):
+    """Drop-in for the reference's train_mfm_test_zeros (mfm_mosi.py:505-638): train MFM exactly as train_mfm does, then predict
+    the test set three times with one modality zeroed out -- language, acoustic, visual (:571-578) -- and score each (:632-638).
+    Returns train_mfm's dict plus ``predictions_nol/noa/nov``, ``scores_nol/noa/nov`` and the reconstruction errors of the zeroed
+    modality the reference prints (:592-595)."""
+    configs = [dict(c) for c in configs]
+    configs[0]["type"] = "mfm"                                        # (:516 builds MFM whatever the type)
+    out = train_mfm(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, head="l1", verbose=verbose, save_dir=save_dir)
+    model = out["model"].eval()
+    d_l, d_a, d_v = configs[0]["input_dims"]
+    dev = next(model.parameters()).device
+    X = torch.from_numpy(_to_time_major(X_test)).to(dev)
+    spans = dict(nol=(0, d_l), noa=(d_l, d_l + d_a), nov=(d_l + d_a, d_l + d_a + d_v))
+    with torch.no_grad():
+        for i, (tag, (lo, hi)) in enumerate(spans.items()):
+            Xz = X.clone()
+            Xz[:, :, lo:hi] = 0.0
+            decoded, _, _ = model.forward(Xz)
+            y_hat = decoded[3].squeeze(1).cpu().numpy()
+            out["predictions_" + tag] = y_hat
+            out["scores_" + tag] = score(y_hat, y_test)
+            out["recon_" + tag] = float(torch.nn.functional.mse_loss(decoded[i], X[:, :, lo:hi]))
+            if verbose:
+                print("scoring y_hat_" + tag, out["scores_" + tag])
+    return out
+
+
 def train_mfm_ablation(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, head: str = "l1", verbose: bool = True,
                        save_dir: Optional[str] = None):
     """Drop-in for the reference's train_mfm_ablation (mfm_mosi.py:640-767): ``config['type']`` in m_a / m_b / m_c / m_d
@@ -307,23 +357,7 @@ def train_mfm(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, head:
     if os.path.exists(path):
         model = torch.load(path, weights_only=False)                 # :481
     y_hat = predict(Xte)
-    scores = {}
-    y_test = np.asarray(y_test)
-    if head == "l1" and y_hat.ndim == 1:
-        scores["mae"] = float(np.mean(np.absolute(y_hat - y_test)))                            # :484
-        scores["corr"] = float(np.corrcoef(y_hat, y_test)[0][1])                               # :486
-        scores["mult_acc"] = round(float(np.mean(np.round(y_hat) == np.round(y_test))), 5)     # :488
-        true_label, predicted_label = (y_test >= 0), (y_hat >= 0)                              # :492-493
-        scores["binary_acc"] = float(np.mean(predicted_label == true_label))                   # :498 accuracy_score
-        try:                                                                                   # :490,495-497 (sklearn, as the reference)
-            from sklearn.metrics import classification_report, confusion_matrix, f1_score
-            scores["mult_f_score"] = round(float(f1_score(np.round(y_hat), np.round(y_test), average="weighted")), 5)
-            scores["confusion_matrix"] = confusion_matrix(true_label, predicted_label).tolist()
-            scores["classification_report"] = classification_report(true_label, predicted_label, digits=5, zero_division=0)
-        except ImportError:
-            pass
-    elif head == "ce":
-        scores["acc"] = float(np.mean(np.argmax(y_hat, 1) == y_test))
+    scores = score(y_hat, y_test, head)
     if verbose:
         print(scores)
     return dict(model=model, scores=scores, history=history, best_valid=best_valid, checkpoint=path, predictions=y_hat)

@@ -144,6 +144,73 @@ def ablations(ref, outdir):
         write_fixture(os.path.join(outdir, "tiny_%s_l1_out1.npz" % variant), r, [seed, T, n, data_seed, noise_seed, 1])
 
 
+def reference_baseline_classes():
+    """EFLSTM and MFN of /root/reference/test_mosi.py (:130-157, :158-265).  That script cannot be imported (Python-2 prints,
+    argparse and data loading at module level), so only its two class statements are executed -- read from the file at run time,
+    unmodified -- in a namespace holding what the script's own imports bind (torch, nn, F)."""
+    import ast
+    import torch.nn as nn
+    import torch.nn.functional as F
+    src = open(os.path.join(REF, "test_mosi.py")).read().split("\n")
+    starts = [i for i, ln in enumerate(src) if ln.startswith("class EFLSTM") or ln.startswith("class MFN")]
+    assert len(starts) == 2
+    ns = dict(torch=torch, nn=nn, F=F)
+    for a in starts:
+        b = a + 1
+        while b < len(src) and (src[b].strip() == "" or src[b][0] in "\t "):
+            b += 1
+        code = "\n".join(src[a:b])
+        ast.parse(code)
+        exec(compile(code, "test_mosi.py:%d" % (a + 1), "exec"), ns)
+    return ns["EFLSTM"], ns["MFN"]
+
+
+def baselines(ref, outdir):
+    """(1e) the MOSI script's baselines: the oracle restatements (eflstm_forward, mfn_baseline_forward) against the live classes,
+    and a fixture with their outputs and gradients."""
+    EF, MFNB = reference_baseline_classes()
+    configs = O.tiny_configs(output_dim=1)
+    T, n = 5, 9
+    x, y = O.synthetic_batch(configs, T, n, 4)
+    blob = dict(x=x.numpy(), y=y.numpy())
+    Fn = torch.nn.functional
+    # MFN with its output head
+    torch.manual_seed(17)
+    m = MFNB(*configs).eval()
+    out = m.forward(x)
+    Fn.l1_loss(out.squeeze(1), y).backward()
+    P = {"mfn_encoder." + k: v.detach().clone() for k, v in m.state_dict().items()}
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    o2 = O.mfn_baseline_forward(x, Pg, configs)
+    Fn.l1_loss(o2.squeeze(1), y).backward()
+    w = float((o2 - out).abs().max())
+    for k, p in m.named_parameters():
+        w = max(w, float((Pg["mfn_encoder." + k].grad - p.grad).norm() / (p.grad.norm() + 1e-30)))
+        blob["mfn/p/" + k] = p.detach().numpy()
+        blob["mfn/g/" + k] = p.grad.numpy()
+    blob["mfn/out"] = out.detach().numpy()
+    print("[baseline MFN] oracle vs live reference: worst err %.3g" % w)
+    assert w < 2e-5
+    # early-fusion LSTM
+    D, h = sum(configs[0]["input_dims"]), 6
+    torch.manual_seed(5)
+    e = EF(D, h, 1, 0.3).eval()
+    out = e.forward(x)
+    Fn.l1_loss(out.squeeze(1), y).backward()
+    Pg = {k: v.detach().clone().requires_grad_(True) for k, v in e.state_dict().items()}
+    o2 = O.eflstm_forward(x, Pg)
+    Fn.l1_loss(o2.squeeze(1), y).backward()
+    w = float((o2 - out).abs().max())
+    for k, p in e.named_parameters():
+        w = max(w, float((Pg[k].grad - p.grad).norm() / (p.grad.norm() + 1e-30)))
+        blob["ef/p/" + k] = p.detach().numpy()
+        blob["ef/g/" + k] = p.grad.numpy()
+    blob["ef/out"] = out.detach().numpy()
+    print("[baseline EFLSTM] oracle vs live reference: worst err %.3g" % w)
+    assert w < 2e-5
+    np.savez_compressed(os.path.join(outdir, "tiny_baselines.npz"), **blob)
+
+
 def main():
     ref = import_reference()
     outdir = os.path.join(ROOT, "tests", "golden")
@@ -151,7 +218,11 @@ def main():
     if "--ablations-only" in sys.argv:               # leaves the other fixtures' files untouched
         ablations(ref, outdir)
         return
+    if "--baselines-only" in sys.argv:
+        baselines(ref, outdir)
+        return
     ablations(ref, outdir)
+    baselines(ref, outdir)
 
     # ---- (1) tiny awkward config, everything stored, L1 head and CE head -------------
     for head, od in (("l1", 1), ("ce", 3), ("l1", 4)):

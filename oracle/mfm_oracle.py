@@ -402,6 +402,15 @@ def mfn_encoder(x: Tensor, P, configs, train=False, masks=None, branches=None) -
     return torch.cat([hcs[0][0], hcs[1][0], hcs[2][0], mem], 1)             # :194-198
 
 
+def mfn_baseline_forward(x: Tensor, P, configs, train=False, masks=None, branches=None, prefix="mfn_encoder.") -> Tensor:
+    """The MFN baseline of the reference's MOSI script (test_mosi.py:158-265): the MFN of mfm_model.py plus the output head
+    ``out_fc2(out_dropout(relu(out_fc1(last_hs))))`` (:264) that mfm_model.MFN constructs and never uses."""
+    last = mfn_encoder(x, P, configs, train, masks, branches)
+    mk = None if masks is None else masks.get("out")
+    h = dropout(relu(linear(last, P, prefix + "out_fc1"), branches, "out1"), configs[5]["drop"], train, mk)
+    return linear(h, P, prefix + "out_fc2")
+
+
 def compute_kernel(x: Tensor, y: Tensor) -> Tensor:
     """mfm_model.py:14-23: exp(-mean_k((x_ik-y_jk)^2)/dim) = exp(-|x_i-y_j|^2/dim^2)."""
     dim = x.shape[1]

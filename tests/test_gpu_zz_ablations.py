@@ -146,3 +146,65 @@ def test_train_mfm_ablation_entry_point(tmp_path):
     configs[0]["type"] = "mfm"
     with pytest.raises(ValueError):
         F.train_mfm_ablation(Xtr, ytr, Xva, yva, Xte, yte, configs, verbose=False, save_dir=str(tmp_path))
+
+
+def test_baselines_of_the_mosi_script_vs_reference_golden():
+    """The baselines of the reference's MOSI script (test_mosi.py): MFN with its out_fc1/out_fc2 head (:158-265) and the
+    early-fusion LSTM (:130-157) -- output and every gradient against the fixture made from the reference's own classes, eval
+    mode; same initial weights for the same seed."""
+    from factorized_b200 import baselines
+    from helpers import load_golden
+    g = load_golden("tiny_baselines.npz")
+    configs = O.tiny_configs()
+    x, y = torch.from_numpy(g["x"].copy()), torch.from_numpy(g["y"].copy())
+    n = x.shape[1]
+    Fn = torch.nn.functional
+    torch.manual_seed(17)
+    mfn = baselines.MFN(*configs).cuda().eval()
+    for k, v in mfn.state_dict().items():
+        assert torch.equal(v.cpu(), torch.from_numpy(g["mfn/p/" + k])), k
+    out = mfn.forward(x.cuda())
+    assert out.shape == (n, 1)
+    Fn.l1_loss(out.squeeze(1), y.cuda()).backward()
+    assert rel_l2(out.detach(), g["mfn/out"]) < TOL
+    bad = {k: rel_l2(p.grad, g["mfn/g/" + k]) for k, p in mfn.named_parameters() if not rel_l2(p.grad, g["mfn/g/" + k]) < TOL}
+    assert not bad, bad
+    torch.manual_seed(5)
+    ef = baselines.EFLSTM(x.shape[2], 6, 1, 0.3).cuda().eval()
+    for k, v in ef.state_dict().items():
+        assert torch.equal(v.cpu(), torch.from_numpy(g["ef/p/" + k])), k
+    out = ef.forward(x.cuda())
+    Fn.l1_loss(out.squeeze(1), y.cuda()).backward()
+    assert rel_l2(out.detach(), g["ef/out"]) < TOL
+    bad = {k: rel_l2(p.grad, g["ef/g/" + k]) for k, p in ef.named_parameters() if not rel_l2(p.grad, g["ef/g/" + k]) < TOL}
+    assert not bad, bad
+
+
+def test_train_mfm_test_zeros_entry_point(tmp_path):
+    """train_mfm_test_zeros (mfm_mosi.py:505-638): MFM trained as train_mfm does, then three test-set predictions with one
+    modality zeroed.  The predictions must be the oracle's forward of the TRAINED weights on the same zeroed inputs."""
+    import factorized_b200 as F
+    rs = np.random.RandomState(7)
+    configs = O.tiny_configs()
+    configs[0].update(batchsize=8, num_epochs=2, type="kl")             # the type is ignored: the reference builds MFM (:516)
+    T, D = 4, sum(configs[0]["input_dims"])
+    d_l, d_a, d_v = configs[0]["input_dims"]
+    Xtr, ytr = rs.randn(32, T, D).astype(np.float32), rs.randn(32).astype(np.float32)
+    Xva, yva = rs.randn(16, T, D).astype(np.float32), rs.randn(16).astype(np.float32)
+    Xte, yte = rs.randn(20, T, D).astype(np.float32), rs.randn(20).astype(np.float32)
+    np.random.seed(3)
+    torch.manual_seed(4)
+    out = F.train_mfm_test_zeros(Xtr, ytr, Xva, yva, Xte, yte, configs, verbose=False, save_dir=str(tmp_path))
+    assert type(out["model"]).__name__ == "MFM"
+    P = OrderedDict((k, v.detach().cpu()) for k, v in out["model"].state_dict().items())
+    Xt = torch.from_numpy(np.ascontiguousarray(np.swapaxes(Xte, 0, 1)))
+    noise = O.draw_mmd_noise(configs, 20, 1)
+    for i, (tag, lo, hi) in enumerate((("nol", 0, d_l), ("noa", d_l, d_l + d_a), ("nov", d_l + d_a, D))):
+        Xz = Xt.clone()
+        Xz[:, :, lo:hi] = 0.0
+        ref = O.mfm_forward(Xz, P, configs, noise)
+        assert rel_l2(out["predictions_" + tag], ref["y_hat"].squeeze(1)) < TOL, tag
+        rec = float(torch.nn.functional.mse_loss(ref[("x_l_hat", "x_a_hat", "x_v_hat")[i]], Xt[:, :, lo:hi]))
+        assert abs(out["recon_" + tag] - rec) < TOL * rec, tag
+        assert abs(out["scores_" + tag]["mae"] - float(np.mean(np.abs(out["predictions_" + tag] - yte)))) < 1e-6
+    assert not np.allclose(out["predictions_nol"], out["predictions"])

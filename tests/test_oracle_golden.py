@@ -132,3 +132,25 @@ def test_tiny_ablation_full_step(variant, ntensors):
         else:
             assert G[k] is None, k
         assert rel_l2(newP[k], g["p1/" + k]) < TOL, k
+
+
+def test_baselines_of_the_mosi_script():
+    """EFLSTM and MFN-with-head (test_mosi.py:130-157, 158-265) restated in oracle.eflstm_forward / mfn_baseline_forward, against
+    outputs and gradients of the reference's own classes (oracle/make_golden.py section 1e)."""
+    g = load_golden("tiny_baselines.npz")
+    configs = O.tiny_configs(output_dim=1)
+    x, y = torch.from_numpy(g["x"].copy()), torch.from_numpy(g["y"].copy())
+    Fn = torch.nn.functional
+    Pg = {"mfn_encoder." + k[len("mfn/p/"):]: torch.from_numpy(v.copy()).requires_grad_(True) for k, v in g.items() if k.startswith("mfn/p/")}
+    assert len(Pg) == 32
+    out = O.mfn_baseline_forward(x, Pg, configs)
+    Fn.l1_loss(out.squeeze(1), y).backward()
+    assert rel_l2(out.detach(), g["mfn/out"]) < TOL
+    for k, p in Pg.items():
+        assert rel_l2(p.grad, g["mfn/g/" + k[len("mfn_encoder."):]]) < TOL, k
+    Pe = {k[len("ef/p/"):]: torch.from_numpy(v.copy()).requires_grad_(True) for k, v in g.items() if k.startswith("ef/p/")}
+    out = O.eflstm_forward(x, Pe)
+    Fn.l1_loss(out.squeeze(1), y).backward()
+    assert rel_l2(out.detach(), g["ef/out"]) < TOL
+    for k, p in Pe.items():
+        assert rel_l2(p.grad, g["ef/g/" + k]) < TOL, k
