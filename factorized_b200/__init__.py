@@ -5,6 +5,7 @@ Drop-in for the hot path of pliang279/factorized: ``encoderLSTM / decoderLSTM / 
 """
 from .mfm_model import encoderLSTM, decoderLSTM, MFN, MFM, MFM_KL, MFM_KL_EF, EFLSTM  # noqa: F401
 from .ablations import M_A, M_B, M_C, M_D  # noqa: F401
+from .missing import MFM_missing  # noqa: F401
 
 
 def train_mfm(*a, **k):
@@ -19,4 +20,9 @@ def train_mfm_ablation(*a, **k):
 
 def train_mfm_test_zeros(*a, **k):
     from .train import train_mfm_test_zeros as f
+    return f(*a, **k)
+
+
+def train_mfm_missing(*a, **k):
+    from .train import train_mfm_missing as f
     return f(*a, **k)

@@ -382,6 +382,9 @@ def make_engine(configs, T, B, device, ops, head="l1", variant="mfm"):
     """The schedule object of a model variant."""
     if variant in VARIANTS:
         return AblationEngine(configs, T, B, device, ops, head=head, variant=variant)
+    if variant == "missing":
+        from .missing import MissingEngine
+        return MissingEngine(configs, T, B, device, ops, head=head)
     return E.Engine(configs, T, B, device, ops, head=head, variant=variant)
 
 

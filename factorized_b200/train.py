@@ -272,6 +272,98 @@ def train_mfm_test_zeros(X_train, y_train, X_valid, y_valid, X_test, y_test, con
     return out
 
 
+def train_mfm_missing(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, verbose: bool = True,
+                      save_dir: Optional[str] = None):
+    """Drop-in for the reference's train_mfm_missing (mfm_mosi.py:918-1105): MFM_missing trained with the four-pass loss
+    (:962-982, fused step of ``missing.MissingEngine``); the epoch's training figure is the mean all-present text reconstruction
+    MSE (:984-985); validation is the FULL loss of the whole validation set in eval mode, MMD included (:987-1021), which drives
+    ReduceLROnPlateau and save-best; the test set is predicted with all modalities and with each one inferred (:1023-1060) and
+    every prediction scored (:1097-1105).  Returns a dict with the model, the four prediction vectors and their scores, the
+    twelve reconstruction errors the reference prints, and the history."""
+    from .missing import MFM_missing, PASSES
+    config = configs[0]
+    p = np.random.permutation(X_train.shape[0])                     # :919-921
+    X_train, y_train = np.asarray(X_train)[p], np.asarray(y_train)[p]
+    Xt, Xv, Xte = _to_time_major(X_train), _to_time_major(X_valid), _to_time_major(X_test)
+    dev = torch.device("cuda")
+    model = MFM_missing(*configs).to(dev)                            # :929
+    model.mmd_noise = "cuda"
+    d_l, d_a, d_v = config["input_dims"]
+    T, total_n = Xt.shape[0], Xt.shape[1]
+    bs = int(config["batchsize"])
+    num_batches = total_n // bs                                      # :951
+    lr = 1e-3                                                        # optim.Adam(model.parameters()), :931
+    trainer = MFMTrainer(model, T, bs, head="l1", lr=lr)
+    sched_opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=lr)
+    scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(sched_opt, "min")   # :945
+    ytr = np.asarray(y_train, dtype=np.float32)
+    Xpin = torch.empty((max(num_batches, 1), T, bs, Xt.shape[2]), dtype=torch.float32).pin_memory()
+    ypin = torch.empty((max(num_batches, 1), bs), dtype=torch.float32).pin_memory()
+    for b in range(num_batches):
+        Xpin[b].copy_(torch.from_numpy(Xt[:, b * bs:(b + 1) * bs]))
+        ypin[b].copy_(torch.from_numpy(ytr[b * bs:(b + 1) * bs]))
+    Fn = torch.nn.functional
+
+    def full_loss(out, bx, by):                                      # :962-982 / :1003-1019
+        dec, nol, noa, nov, mmd, missing = out
+        x_l, x_a, x_v = bx[:, :, :d_l], bx[:, :, d_l:d_l + d_a], bx[:, :, d_l + d_a:]
+        gen = config["lda_xl"] * Fn.mse_loss(dec[0], x_l) + config["lda_xa"] * Fn.mse_loss(dec[1], x_a) \
+            + config["lda_xv"] * Fn.mse_loss(dec[2], x_v) + config["lda_xl"] * Fn.mse_loss(nol[0], x_l) \
+            + config["lda_xa"] * Fn.mse_loss(noa[1], x_a) + config["lda_xv"] * Fn.mse_loss(noa[2], x_v)
+        disc = sum(Fn.l1_loss(d[3].squeeze(1), by) for d in (dec, nol, noa, nov))
+        return disc + gen + config["lda_mmd"] * mmd + missing
+
+    def evaluate(X, y):
+        model.eval()
+        with torch.no_grad():
+            bx = torch.from_numpy(X).to(dev)
+            by = torch.from_numpy(np.asarray(y, dtype=np.float32)).to(dev)
+            return float(full_loss(model.forward(bx), bx, by))
+
+    def predict(X):
+        model.eval()
+        with torch.no_grad():
+            bx = torch.from_numpy(X).to(dev)
+            out = model.forward(bx)
+            xm = (bx[:, :, :d_l], bx[:, :, d_l:d_l + d_a], bx[:, :, d_l + d_a:])
+            recon = {"x_%s_hat%s" % (t, s): float(Fn.mse_loss(out[p][m], xm[m]))
+                     for p, s in enumerate(PASSES) for m, t in enumerate("lav")}
+            return [out[p][3].squeeze(1).cpu().numpy() for p in range(4)], recon
+
+    best_valid = 999999.0
+    save_dir = save_dir or tempfile.mkdtemp(prefix="res_mfm2_")
+    path = os.path.join(save_dir, "mfn_%d.pt" % random.randint(0, 100000))
+    history = []
+    for epoch in range(int(config["num_epochs"])):
+        model.train()
+        acc = torch.zeros((), dtype=torch.float32, device=dev)
+        for b in range(num_batches):
+            lb = trainer.step(Xpin[b], ypin[b])
+            acc += lb[10]                                            # l2_loss(x_l_hat, x_l), :984
+        train_loss = float(acc) / max(num_batches, 1)
+        valid_loss = evaluate(Xv, y_valid)
+        scheduler.step(valid_loss)
+        trainer.set_lr(sched_opt.param_groups[0]["lr"])
+        history.append((epoch, train_loss, valid_loss))
+        if valid_loss <= best_valid:
+            best_valid = valid_loss
+            torch.save(model, path)
+            if verbose:
+                print(epoch, train_loss, valid_loss, "saving model")
+        elif verbose:
+            print(epoch, train_loss, valid_loss)
+    if os.path.exists(path):
+        model = torch.load(path, weights_only=False)
+    preds, recon = predict(Xte)
+    out = dict(model=model, history=history, best_valid=best_valid, checkpoint=path, recon=recon)
+    for p, s in enumerate(PASSES):
+        out["predictions" + s] = preds[p]
+        out["scores" + s] = score(preds[p], y_test)
+        if verbose:
+            print("scoring y_hat" + s, out["scores" + s])
+    return out
+
+
 def train_mfm_ablation(X_train, y_train, X_valid, y_valid, X_test, y_test, configs, head: str = "l1", verbose: bool = True,
                        save_dir: Optional[str] = None):
     """Drop-in for the reference's train_mfm_ablation (mfm_mosi.py:640-767): ``config['type']`` in m_a / m_b / m_c / m_d

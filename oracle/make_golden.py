@@ -144,6 +144,61 @@ def ablations(ref, outdir):
         write_fixture(os.path.join(outdir, "tiny_%s_l1_out1.npz" % variant), r, [seed, T, n, data_seed, noise_seed, 1])
 
 
+def missing(ref, outdir):
+    """(1f) MFM_missing (mfm_model.py:766-885) through the step of train_mfm_missing (mfm_mosi.py:957-982)."""
+    configs = O.tiny_configs(output_dim=1)
+    seed, T, n, data_seed, noise_seed = 808, 4, 7, 31, 95
+    torch.manual_seed(seed)
+    model = ref.MFM_missing(*configs).eval()
+    params0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    x, y = O.synthetic_batch(configs, T, n, data_seed, "l1")
+    opt = torch.optim.Adam(model.parameters())                                         # mfm_mosi.py:931
+    opt.zero_grad()
+    torch.manual_seed(noise_seed)
+    decoded, decoded_nol, decoded_noa, decoded_nov, mmd, missing_loss = model.forward(x)
+    c = configs[0]
+    d_l, d_a, d_v = c["input_dims"]
+    x_l, x_a, x_v = x[:, :, :d_l], x[:, :, d_l:d_l + d_a], x[:, :, d_l + d_a:]
+    l1, l2 = torch.nn.L1Loss(), torch.nn.MSELoss()
+    gen = c["lda_xl"] * l2(decoded[0], x_l) + c["lda_xa"] * l2(decoded[1], x_a) + c["lda_xv"] * l2(decoded[2], x_v) \
+        + c["lda_xl"] * l2(decoded_nol[0], x_l) + c["lda_xa"] * l2(decoded_noa[1], x_a) + c["lda_xv"] * l2(decoded_noa[2], x_v)
+    disc = l1(decoded[3].squeeze(1), y) + l1(decoded_nol[3].squeeze(1), y) + l1(decoded_noa[3].squeeze(1), y) \
+        + l1(decoded_nov[3].squeeze(1), y)
+    loss = disc + gen + c["lda_mmd"] * mmd + missing_loss                                # :977-982
+    loss.backward()
+    grads = {k: (None if p.grad is None else p.grad.detach().clone()) for k, p in model.named_parameters()}
+    opt.step()
+    params1 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    # oracle restatement vs the live class
+    P = O.init_params(configs, seed, variant="missing")
+    assert list(P) == list(params0) and all(torch.equal(P[k], params0[k]) for k in P), "init differs"
+    noise = O.draw_mmd_noise(configs, n, noise_seed)
+    newP, losses, G, out = O.train_step(P, x, y, configs, noise, {}, variant="missing")
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-30))
+    w = abs(losses["total"] - float(loss)) / abs(float(loss))
+    w = max(w, abs(losses["missing"] - float(missing_loss)) / abs(float(missing_loss)))
+    blob = dict(meta=np.array([seed, T, n, data_seed, noise_seed, 1]), x=x.numpy(), y=y.numpy())
+    for sfx, dec in zip(O.MISSING_PASSES, (decoded, decoded_nol, decoded_noa, decoded_nov)):
+        for name, t in zip(("x_l_hat", "x_a_hat", "x_v_hat", "y_hat"), dec):
+            w = max(w, rel(out[name + sfx], t.detach()))
+            blob[name + sfx] = t.detach().numpy()
+    for k, g in grads.items():
+        if g is None:
+            assert G[k] is None, k
+        else:
+            w = max(w, rel(G[k], g))
+            blob["g/" + k] = g.numpy()
+    for k in params0:
+        w = max(w, rel(newP[k], params1[k]))
+        blob["p0/" + k] = params0[k].numpy()
+        blob["p1/" + k] = params1[k].numpy()
+    print("[tiny_missing] oracle vs live reference: worst rel err %.3g" % w)
+    assert w < 2e-5, "oracle restatement disagrees with the reference"
+    for k, v in dict(total=loss, disc=disc, gen=gen, mmd=c["lda_mmd"] * mmd, missing=missing_loss).items():
+        blob["loss/" + k] = np.float64(float(v))
+    np.savez_compressed(os.path.join(outdir, "tiny_missing_l1_out1.npz"), **blob)
+
+
 def reference_baseline_classes():
     """EFLSTM and MFN of /root/reference/test_mosi.py (:130-157, :158-265).  That script cannot be imported (Python-2 prints,
     argparse and data loading at module level), so only its two class statements are executed -- read from the file at run time,
@@ -221,8 +276,12 @@ def main():
     if "--baselines-only" in sys.argv:
         baselines(ref, outdir)
         return
+    if "--missing-only" in sys.argv:
+        missing(ref, outdir)
+        return
     ablations(ref, outdir)
     baselines(ref, outdir)
+    missing(ref, outdir)
 
     # ---- (1) tiny awkward config, everything stored, L1 head and CE head -------------
     for head, od in (("l1", 1), ("ce", 3), ("l1", 4)):

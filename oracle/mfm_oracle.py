@@ -101,6 +101,10 @@ def param_shapes(configs, variant: str = "mfm") -> "OrderedDict[str, Tuple[int, 
     for m, tag in enumerate("lav"):
         lstm("encoder_%s.lstm" % tag, d[m], z[m])
         lin("encoder_%s.fc1" % tag, z[m], z[m])
+    if variant == "missing":                                  # MFM_missing, mfm_model.py:792-798: six cross-modal encoders
+        for name, (a, b), zo in MISSING_ENCODERS(config):
+            lstm(name + ".lstm", d[a] + d[b], zo)
+            lin(name + ".fc1", zo, zo)
     for m, tag in enumerate("lav"):
         hd = fy + f[m]
         lstm("decoder_%s.lstm" % tag, hd, hd)
@@ -155,6 +159,14 @@ def param_shapes(configs, variant: str = "mfm") -> "OrderedDict[str, Tuple[int, 
 
 
 ABLATIONS = ("m_a", "m_b", "m_c", "m_d")
+
+
+def MISSING_ENCODERS(config):
+    """The six cross-modal encoders of MFM_missing in construction order (mfm_model.py:792-798): (name, the two modalities whose
+    columns it reads, output size).  encoder_XY_to_Z infers the latent of the missing modality Z from the other two."""
+    zl, za, zv, zy = config["zl_size"], config["za_size"], config["zv_size"], config["zy_size"]
+    return [("encoder_la_to_v", (0, 1), zv), ("encoder_lv_to_a", (0, 2), za), ("encoder_av_to_l", (1, 2), zl),
+            ("encoder_la_to_y", (0, 1), zy), ("encoder_lv_to_y", (0, 2), zy), ("encoder_av_to_y", (1, 2), zy)]
 
 
 def _ablation_shapes(configs, variant, lstm, lin, shapes):
@@ -590,6 +602,74 @@ def ablation_forward(x: Tensor, P, configs, noise: Sequence[Tensor], variant: st
     return out
 
 
+MISSING_PASSES = ("", "_nol", "_noa", "_nov")
+
+
+def mfm_missing_forward(x: Tensor, P, configs, noise: Sequence[Tensor], train=False, masks=None, branches=None):
+    """MFM_missing.forward, mfm_model.py:827-885: MFM plus six cross-modal encoders that infer the latents of a missing modality
+    (and z_y) from the other two, an MSE between inferred and true latents (``missing``), and FOUR passes through the shared
+    generative half -- all present, language / acoustic / visual inferred.  Output keys carry the reference's suffixes
+    ("x_l_hat_nol", ...).  Dropout: every pass draws its own masks; masks / branches of pass p > 0 are keyed "<site>@p"."""
+    config = configs[0]
+    d_l, d_a, d_v = config["input_dims"]
+    T = x.shape[0]
+    xm = [x[:, :, :d_l], x[:, :, d_l:d_l + d_a], x[:, :, d_l + d_a:]]
+    zl = encoder_lstm(xm[0], P, "encoder_l")                                  # :836-838
+    za = encoder_lstm(xm[1], P, "encoder_a")
+    zv = encoder_lstm(xm[2], P, "encoder_v")
+    mfn_last = mfn_encoder(x, P, configs, train, masks, branches)             # :839
+    zy = linear(mfn_last, P, "last_to_zy_fc1")
+    inf = {}
+    for name, (a, b), _ in MISSING_ENCODERS(config):                          # :843-850
+        inf[name] = encoder_lstm(torch.cat([xm[a], xm[b]], dim=2), P, name)
+    zv_nov, za_noa, zl_nol = inf["encoder_la_to_v"], inf["encoder_lv_to_a"], inf["encoder_av_to_l"]
+    zy_nov, zy_noa, zy_nol = inf["encoder_la_to_y"], inf["encoder_lv_to_y"], inf["encoder_av_to_y"]
+    mmd = loss_mmd(zl, noise[0]) + loss_mmd(za, noise[1]) + loss_mmd(zv, noise[2]) + loss_mmd(zy, noise[3])   # :852
+    F = torch.nn.functional
+    missing = F.mse_loss(zv_nov, zv) + F.mse_loss(za_noa, za) + F.mse_loss(zl_nol, zl) \
+        + F.mse_loss(zy_nov, zy) + F.mse_loss(zy_noa, zy) + F.mse_loss(zy_nol, zy)                           # :853-858
+    out = dict(mmd=mmd, missing=missing, zl=zl, za=za, zv=zv, zy=zy, zl_nol=zl_nol, za_noa=za_noa, zv_nov=zv_nov,
+               zy_nol=zy_nol, zy_noa=zy_noa, zy_nov=zy_nov)
+
+    def decode(p, zl_, za_, zv_, zy_):                                        # :860-875
+        sfx = "" if p == 0 else "@%d" % p
+        mk = (lambda k: None if masks is None else masks.get(k + sfx))
+        fy = factor_mlp(zy_, P, "zy_to_fy", config["zy_to_fy_dropout"], train, mk("fy"), branches, "fy" + sfx)
+        fl = factor_mlp(zl_, P, "zl_to_fl", config["zl_to_fl_dropout"], train, mk("fl"), branches, "fl" + sfx)
+        fa = factor_mlp(za_, P, "za_to_fa", config["za_to_fa_dropout"], train, mk("fa"), branches, "fa" + sfx)
+        fv = factor_mlp(zv_, P, "zv_to_fv", config["zv_to_fv_dropout"], train, mk("fv"), branches, "fv" + sfx)
+        s = MISSING_PASSES[p]
+        out["x_l_hat" + s] = decoder_lstm(torch.cat([fy, fl], 1), T, P, "decoder_l")
+        out["x_a_hat" + s] = decoder_lstm(torch.cat([fy, fa], 1), T, P, "decoder_a")
+        out["x_v_hat" + s] = decoder_lstm(torch.cat([fy, fv], 1), T, P, "decoder_v")
+        y1 = dropout(relu(linear(fy, P, "fy_to_y_fc1"), branches, "y1" + sfx), config["fy_to_y_dropout"], train, mk("y"))
+        out["y_hat" + s] = linear(y1, P, "fy_to_y_fc2")
+
+    decode(0, zl, za, zv, zy)                                                 # :876-883
+    decode(1, zl_nol, za, zv, zy_nol)
+    decode(2, zl, za_noa, zv, zy_noa)
+    decode(3, zl, za, zv_nov, zy_nov)
+    return out
+
+
+def mfm_missing_losses(out: Dict[str, Tensor], x: Tensor, y: Tensor, configs) -> Dict[str, Tensor]:
+    """Loss of train_mfm_missing's step, mfm_mosi.py:962-982.  Six reconstruction terms -- the three of the all-present pass,
+    x_l of the language-inferred pass and x_a AND x_v of the acoustic-inferred pass (the reference reads x_v_hat_noa, :976; the
+    visual-inferred pass contributes its label only) -- four L1 label terms, the MMD and the latent-matching MSE."""
+    config = configs[0]
+    d_l, d_a, d_v = config["input_dims"]
+    F = torch.nn.functional
+    x_l, x_a, x_v = x[:, :, :d_l], x[:, :, d_l:d_l + d_a], x[:, :, d_l + d_a:]
+    mse_l = F.mse_loss(out["x_l_hat"], x_l) + F.mse_loss(out["x_l_hat_nol"], x_l)
+    mse_a = F.mse_loss(out["x_a_hat"], x_a) + F.mse_loss(out["x_a_hat_noa"], x_a)
+    mse_v = F.mse_loss(out["x_v_hat"], x_v) + F.mse_loss(out["x_v_hat_noa"], x_v)
+    gen = config["lda_xl"] * mse_l + config["lda_xa"] * mse_a + config["lda_xv"] * mse_v
+    disc = sum(F.l1_loss(out["y_hat" + s].squeeze(1), y) for s in MISSING_PASSES)
+    mmd = config["lda_mmd"] * out["mmd"]
+    total = disc + gen + mmd + out["missing"]
+    return dict(total=total, disc=disc, gen=gen, mmd=mmd, mse_l=mse_l, mse_a=mse_a, mse_v=mse_v, missing=out["missing"])
+
+
 def mfm_losses(out: Dict[str, Tensor], x: Tensor, y: Tensor, configs, head: str = "l1") -> Dict[str, Tensor]:
     """Loss assembly of the train step: mfm_mosi.py:432-439 (L1 head) and
     mfm_mosi_acc.py:441-451 / mfm_moud.py:495-508 (cross-entropy head)."""
@@ -642,9 +722,11 @@ def train_step(P, x, y, configs, noise, state, head="l1", lr=1e-3, train=False, 
         out = mfm_kl_ef_forward(x, Pg, configs, train=train, masks=masks, branches=branches)
     elif variant in ABLATIONS:                                # train_mfm_ablation runs the same step (mfm_mosi.py:677-697)
         out = ablation_forward(x, Pg, configs, noise, variant, train=train, masks=masks, branches=branches)
+    elif variant == "missing":                                # train_mfm_missing (mfm_mosi.py:918-982): its own loss
+        out = mfm_missing_forward(x, Pg, configs, noise, train=train, masks=masks, branches=branches)
     else:
         out = mfm_forward(x, Pg, configs, noise, train=train, masks=masks, branches=branches)
-    losses = mfm_losses(out, x, y, configs, head)
+    losses = mfm_missing_losses(out, x, y, configs) if variant == "missing" else mfm_losses(out, x, y, configs, head)
     losses["total"].backward()
     G = OrderedDict((k, (None if v.grad is None else v.grad.detach().clone())) for k, v in Pg.items())
     newP = adam_step(OrderedDict((k, v.detach().clone()) for k, v in P.items()), G, state, lr=lr)

@@ -69,3 +69,15 @@ def tiny_ablation_case(variant):
     noise = O.draw_mmd_noise(configs, n, noise_seed, variant=variant)
     noise = [torch.zeros(1, 1) if v is None else v for v in noise]
     return g, configs, P, x, y, noise, T, n
+
+
+def tiny_missing_case():
+    """Golden vectors of the unmodified reference's MFM_missing through train_mfm_missing's step (make_golden.py, section 1f)."""
+    g = load_golden("tiny_missing_l1_out1.npz")
+    seed, T, n, data_seed, noise_seed, od_ = [int(v) for v in g["meta"]]
+    configs = O.tiny_configs(output_dim=1)
+    P = golden_params(g)
+    x = torch.from_numpy(g["x"].copy())
+    y = torch.from_numpy(g["y"].copy())
+    noise = O.draw_mmd_noise(configs, n, noise_seed)
+    return g, configs, P, x, y, noise, T, n

@@ -300,3 +300,158 @@ def test_ablation_modules_init_and_trainer_step_match_reference_golden(variant):
             continue
         worst = max(worst, float((d_got - d_ref).norm() / d_ref.norm()))
     assert worst < 2e-3, worst
+
+
+MISSING_OUT = ["%s%s" % (k, s) for s in ("", "_nol", "_noa", "_nov") for k in ("x_l_hat", "x_a_hat", "x_v_hat", "y_hat")]
+
+
+@pytest.mark.parametrize("deferred", [False, True])
+def test_engine_missing_variant_matches_reference_golden(deferred):
+    """MFM_missing (mfm_model.py:766-885) through train_mfm_missing's step (mfm_mosi.py:957-982): schedule + hand-derived
+    backward of factorized_b200.missing against the golden vectors of the unmodified reference class -- all sixteen decoded
+    tensors, the losses, all 122 gradients."""
+    from helpers import tiny_missing_case
+    from factorized_b200.missing import MissingEngine
+    g, configs, P, x, y, noise, T, n = tiny_missing_case()
+    P = OrderedDict(P)
+    eng = MissingEngine(configs, T, n, "cpu", EmuOps(), head="l1")
+    eng.defer_mmd_join = deferred
+    out = eng.forward(P, x.contiguous(), noise)
+    dX, dY = eng.losses(y)
+    assert sorted(dX) == [(0, 0), (0, 1), (0, 2), (1, 0), (2, 1), (2, 2)] and len(dY) == 4
+    G = OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    eng.backward(P, G, dX, dY, eng.dm.lda_mmd)
+    tol = 1e-4
+    for k in MISSING_OUT:
+        got = out[k] if k.startswith("y_hat") else out[k].reshape(T, n, -1)
+        assert rel_l2(got, g[k]) < tol, k
+    lb = eng.loss_buf
+    for slot, k, w in ((0, "disc", 1.0), (9, "missing", 1.0), (8, "total", 1.0)):
+        assert abs(float(lb[slot]) - float(g["loss/" + k])) < tol * abs(float(g["loss/" + k])), k
+    assert abs(float(lb[4:8].sum()) * configs[0]["lda_mmd"] - float(g["loss/mmd"])) < tol * abs(float(g["loss/mmd"]))
+    c = configs[0]
+    gen = c["lda_xl"] * float(lb[1]) + c["lda_xa"] * float(lb[2]) + c["lda_xv"] * float(lb[3])
+    assert abs(gen - float(g["loss/gen"])) < tol * float(g["loss/gen"])
+    d_l = c["input_dims"][0]
+    assert abs(float(lb[10]) - float(((torch.from_numpy(g["x_l_hat"]) - x[:, :, :d_l]) ** 2).mean())) < tol * float(lb[10])
+    bad = []
+    for k in P:
+        if "g/" + k in g:
+            e = rel_l2(G[k], g["g/" + k])
+            if e > 2e-4:
+                bad.append((k, e))
+        else:
+            assert float(G[k].abs().max()) == 0.0, k
+    assert not bad, bad
+
+
+def missing_masks(rng, configs, n):
+    """The keep-masks of the MFM_missing schedule: the MFN sites as in MFM, the generative half's sites once per pass
+    (site + 32 p), keyed for oracle.mfm_missing_forward ("<site>@p")."""
+    from emu_ops import keep_mask
+    from factorized_b200 import engine as E
+    c = configs[0]
+    masks = {}
+    for p in range(4):
+        sfx = "" if p == 0 else "@%d" % p
+        masks["fy" + sfx] = keep_mask(rng, E.SITE_FY + 32 * p, c["zy_to_fy_dropout"], n, c["fy_size"])
+        masks["fl" + sfx] = keep_mask(rng, E.SITE_FL + 32 * p, c["zl_to_fl_dropout"], n, c["fl_size"])
+        masks["fa" + sfx] = keep_mask(rng, E.SITE_FA + 32 * p, c["za_to_fa_dropout"], n, c["fa_size"])
+        masks["fv" + sfx] = keep_mask(rng, E.SITE_FV + 32 * p, c["zv_to_fv_dropout"], n, c["fv_size"])
+        masks["y" + sfx] = keep_mask(rng, E.SITE_Y + 32 * p, c["fy_to_y_dropout"], n, c["fy_size"])
+    return masks
+
+
+def test_engine_missing_dropout_masks_replay():
+    """train=True with every dropout on: each of the four passes draws its own masks; replayed through the oracle."""
+    from emu_ops import keep_mask
+    from factorized_b200 import engine as E
+    from helpers import tiny_missing_case
+    from factorized_b200.missing import MissingEngine
+    g, configs, P, x, y, noise, T, n = tiny_missing_case()
+    configs = [dict(c) for c in configs]
+    configs[0].update(zy_to_fy_dropout=0.3, zl_to_fl_dropout=0.2, za_to_fa_dropout=0.5, zv_to_fv_dropout=0.4,
+                      fy_to_y_dropout=0.25)
+    for c, p in zip(configs[1:5], (0.5, 0.3, 0.2, 0.4)):
+        c["drop"] = p
+    rng = torch.tensor([999, 11], dtype=torch.int64)
+    P = OrderedDict(P)
+    eng = MissingEngine(configs, T, n, "cpu", EmuOps(), head="l1")
+    out = eng.forward(P, x.contiguous(), noise, train=True, rng=rng)
+    dX, dY = eng.losses(y)
+    G = OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    eng.backward(P, G, dX, dY, eng.dm.lda_mmd)
+    nn1, nn2, g1, g2 = configs[1:5]
+    masks = missing_masks(rng, configs, n)
+    masks.update(
+        att1=keep_mask(rng, E.SITE_ATT1, nn1["drop"], T * n, nn1["shapes"]).view(T, n, -1),
+        att2=keep_mask(rng, E.SITE_ATT2, nn2["drop"], T * n, nn2["shapes"]).view(T, n, -1),
+        gamma1=keep_mask(rng, E.SITE_G1, g1["drop"], T * n, g1["shapes"]).view(T, n, -1),
+        gamma2=keep_mask(rng, E.SITE_G2, g2["drop"], T * n, g2["shapes"]).view(T, n, -1))
+    assert not torch.equal(masks["fy"], masks["fy@1"])
+    newP, losses, Go, outo = O.train_step(P, x, y, configs, noise, {}, train=True, masks=masks, variant="missing")
+    for k in ("y_hat", "y_hat_nol", "y_hat_noa", "y_hat_nov", "x_a_hat_noa"):
+        got = out[k] if k.startswith("y_hat") else out[k].reshape(T, n, -1)
+        assert rel_l2(got, outo[k]) < 1e-4, k
+    assert abs(float(eng.loss_buf[8]) - losses["total"]) < 1e-4 * abs(losses["total"])
+    bad = [(k, rel_l2(G[k], Go[k])) for k in P if Go[k] is not None and rel_l2(G[k], Go[k]) > 3e-4]
+    assert not bad, bad
+
+
+def test_missing_module_init_and_trainer_step_match_reference_golden():
+    from helpers import tiny_missing_case
+    from factorized_b200.missing import MFM_missing, MissingEngine
+    from factorized_b200.train import MFMTrainer
+    g, configs, P, x, y, noise, T, n = tiny_missing_case()
+    torch.manual_seed(int(g["meta"][0]))
+    model = MFM_missing(*configs).eval()
+    sd = model.state_dict()
+    assert list(sd) == list(P) and len(P) == 126
+    for k in P:
+        assert torch.equal(sd[k], P[k]), k
+    tr = MFMTrainer(model, T, n, head="l1", _test_ops=EmuOps())
+    assert isinstance(tr.eng, MissingEngine)
+    tr.ops.randn = lambda *a, **k: None
+    for k in range(4):
+        tr.noise[k].copy_(noise[k])
+    lb = tr.step(x, y)
+    assert abs(float(lb[8]) - float(g["loss/total"])) < 1e-4 * abs(float(g["loss/total"]))
+    worst = 0.0
+    for k, v in model.state_dict().items():
+        d_ref, d_got = torch.from_numpy(g["p1/" + k]) - P[k], v - P[k]
+        if float(d_ref.norm()) == 0.0:
+            assert float(d_got.abs().max()) == 0.0, k
+            continue
+        worst = max(worst, float((d_got - d_ref).norm() / d_ref.norm()))
+    assert worst < 2e-3, worst
+
+
+@pytest.mark.parametrize("variant", ["m_a", "m_b", "m_c", "m_d", "missing"])
+def test_rng_replay_helper_reads_the_variant_engines(variant):
+    """oracle.rng_replay.train_masks_and_branches (what the GPU train-mode tests and bench.py's parity check use to replay a CUDA
+    step's dropout masks and ReLU branches in the oracle) against the ablation and MFM_missing schedules, on the test double."""
+    from helpers import tiny_ablation_case, tiny_missing_case
+    from oracle.rng_replay import train_masks_and_branches
+    from factorized_b200.ablations import make_engine
+    g, configs, P, x, y, noise, T, n = tiny_missing_case() if variant == "missing" else tiny_ablation_case(variant)
+    configs = [dict(c) for c in configs]
+    configs[0].update(zy_to_fy_dropout=0.3, zl_to_fl_dropout=0.2, za_to_fa_dropout=0.5, zv_to_fv_dropout=0.4,
+                      fy_to_y_dropout=0.25)
+    for c, p in zip(configs[1:5], (0.5, 0.3, 0.2, 0.4)):
+        c["drop"] = p
+    rng = torch.tensor([31337, 5], dtype=torch.int64)
+    P = OrderedDict(P)
+    eng = make_engine(configs, T, n, "cpu", EmuOps(), head="l1", variant=variant)
+    eng.forward(P, x.contiguous(), noise, train=True, rng=rng)
+    dX, dY = eng.losses(y)
+    G = OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    eng.backward(P, G, dX, dY, eng.dm.lda_mmd)
+    masks, br = train_masks_and_branches(eng, rng)
+    onoise = [None if v.shape[0] != n else v for v in noise]
+    del O.RELU_REPLAY_VIOLATIONS[:]
+    newP, losses, Go, outo = O.train_step(P, x, y, configs, onoise, {}, head="l1", train=True, masks=masks, branches=br,
+                                          variant=variant)
+    assert not O.RELU_REPLAY_VIOLATIONS, O.RELU_REPLAY_VIOLATIONS[:3]
+    assert abs(float(eng.loss_buf[8]) - losses["total"]) < 1e-4 * abs(losses["total"])
+    bad = [(k, rel_l2(G[k], Go[k])) for k in P if Go[k] is not None and rel_l2(G[k], Go[k]) > 3e-4]
+    assert not bad, bad

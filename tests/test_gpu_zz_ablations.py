@@ -208,3 +208,127 @@ def test_train_mfm_test_zeros_entry_point(tmp_path):
         assert abs(out["recon_" + tag] - rec) < TOL * rec, tag
         assert abs(out["scores_" + tag]["mae"] - float(np.mean(np.abs(out["predictions_" + tag] - yte)))) < 1e-6
     assert not np.allclose(out["predictions_nol"], out["predictions"])
+
+
+MISSING_OUT = ["%s%s" % (k, s) for s in ("", "_nol", "_noa", "_nov") for k in ("x_l_hat", "x_a_hat", "x_v_hat", "y_hat")]
+
+
+def test_mfm_missing_golden_module_and_trainer():
+    """MFM_missing (mfm_model.py:766-885) on the GPU: the drop-in module under torch autograd through train_mfm_missing's loss
+    (mfm_mosi.py:962-982) against the golden vectors of the unmodified reference -- sixteen decoded tensors, loss, every
+    gradient -- then the fused trainer step against the reference's post-Adam parameters."""
+    from helpers import tiny_missing_case
+    from factorized_b200.missing import MFM_missing
+    from factorized_b200.train import MFMTrainer
+    g, configs, P, x, y, noise, T, n = tiny_missing_case()
+    torch.manual_seed(int(g["meta"][0]))
+    model = MFM_missing(*configs).cuda().eval()
+    sd = model.state_dict()
+    assert list(sd) == list(P)
+    for k, v in sd.items():
+        assert torch.equal(v.cpu(), P[k]), k
+    xd, yd = x.cuda(), y.cuda()
+    torch.manual_seed(int(g["meta"][4]))
+    dec, nol, noa, nov, mmd, missing = model.forward(xd)
+    flat = list(dec) + list(nol) + list(noa) + list(nov)
+    for k, t in zip(MISSING_OUT, flat):
+        assert rel_l2(t, g[k]) < TOL, k
+    c = configs[0]
+    d_l, d_a, d_v = c["input_dims"]
+    Fn = torch.nn.functional
+    x_l, x_a, x_v = xd[:, :, :d_l], xd[:, :, d_l:d_l + d_a], xd[:, :, d_l + d_a:]
+    gen = c["lda_xl"] * Fn.mse_loss(dec[0], x_l) + c["lda_xa"] * Fn.mse_loss(dec[1], x_a) + c["lda_xv"] * Fn.mse_loss(dec[2], x_v) \
+        + c["lda_xl"] * Fn.mse_loss(nol[0], x_l) + c["lda_xa"] * Fn.mse_loss(noa[1], x_a) + c["lda_xv"] * Fn.mse_loss(noa[2], x_v)
+    disc = sum(Fn.l1_loss(d[3].squeeze(1), yd) for d in (dec, nol, noa, nov))
+    loss = disc + gen + c["lda_mmd"] * mmd + missing
+    loss.backward()
+    assert abs(float(missing.detach()) - float(g["loss/missing"])) < TOL * float(g["loss/missing"])
+    assert abs(float(loss.detach()) - float(g["loss/total"])) < TOL * abs(float(g["loss/total"]))
+    bad = {}
+    for k, p in model.named_parameters():
+        if "g/" + k in g:
+            e = rel_l2(p.grad, g["g/" + k])
+            if not e < TOL:
+                bad[k] = e
+        else:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+    assert not bad, bad
+    torch.manual_seed(int(g["meta"][0]))
+    model2 = MFM_missing(*configs).cuda()
+    tr = MFMTrainer(model2, T, n, head="l1", use_graph=True)
+    real_randn = tr.ops.randn
+    try:
+        tr.ops.randn = lambda *a, **k: None
+        for k in range(4):
+            tr.noise[k].copy_(noise[k])
+        tr.x.copy_(xd)
+        tr.y.copy_(yd.reshape(-1))
+        tr.step_device()
+        torch.cuda.synchronize()
+    finally:
+        tr.ops.randn = real_randn
+    assert abs(float(tr.eng.loss_buf[8]) - float(g["loss/total"])) < TOL * abs(float(g["loss/total"]))
+    sd2 = model2.state_dict()
+    bad = {}
+    for k in P:
+        d_ref = g["p1/" + k] - P[k].numpy()
+        if float(np.abs(d_ref).max()) == 0.0:
+            assert torch.equal(sd2[k].cpu(), P[k]), k
+            continue
+        e = rel_l2(sd2[k].cpu() - P[k], d_ref)
+        if not e < 5e-3:
+            bad[k] = e
+    assert not bad, bad
+
+
+def test_mfm_missing_train_mode_step_at_mosi_shapes_and_entry_point(tmp_path):
+    """MOSI shapes, train mode with every dropout on, CUDA graph, each of the four generative passes drawing its own masks; replayed
+    in the oracle.  Then train_mfm_missing (mfm_mosi.py:918-1105) end to end on a small problem."""
+    import factorized_b200 as F
+    from factorized_b200.train import MFMTrainer
+    from oracle.rng_replay import train_masks_and_branches
+    configs = O.best_acc_configs(dropout=True)
+    T, n = 20, 128
+    torch.manual_seed(123)
+    model = F.MFM_missing(*configs).cuda().train()
+    P = OrderedDict((k, v.detach().cpu().clone()) for k, v in model.state_dict().items())
+    tr = MFMTrainer(model, T, n, head="l1", use_graph=True, seed=55)
+    x, y = O.synthetic_batch(configs, T, n, 5)
+    lb = tr.step(x.cuda(), y.cuda())
+    torch.cuda.synchronize()
+    masks, br = train_masks_and_branches(tr.eng, tr.rng.cpu())
+    noise = [t.cpu() for t in tr.noise]
+    del O.RELU_REPLAY_VIOLATIONS[:]
+    newP, losses, Go, outo = O.train_step(P, x, y, configs, noise, {}, train=True, masks=masks, branches=br, variant="missing")
+    assert not O.RELU_REPLAY_VIOLATIONS, O.RELU_REPLAY_VIOLATIONS[:5]
+    lbc = lb.cpu()
+    assert abs(float(lbc[0]) - losses["disc"]) < TOL * abs(losses["disc"])
+    assert abs(float(lbc[9]) - losses["missing"]) < TOL * abs(losses["missing"])
+    assert abs(float(lbc[8]) - losses["total"]) < TOL * abs(losses["total"])
+    bad = {k: rel_l2(tr.G[k], go) for k, go in Go.items() if go is not None and not rel_l2(tr.G[k], go) < TOL}
+    assert not bad, bad
+    sd = model.state_dict()
+    bad = {k: rel_l2(sd[k].cpu(), newP[k]) for k in P if not rel_l2(sd[k].cpu(), newP[k]) < 1e-4}
+    assert not bad, bad
+    # the entry point
+    cfg = O.tiny_configs()
+    cfg[0].update(batchsize=8, num_epochs=2)
+    rs = np.random.RandomState(5)
+    D, T2 = sum(cfg[0]["input_dims"]), 4
+    Xtr, ytr = rs.randn(32, T2, D).astype(np.float32), rs.randn(32).astype(np.float32)
+    Xva, yva = rs.randn(16, T2, D).astype(np.float32), rs.randn(16).astype(np.float32)
+    Xte, yte = rs.randn(24, T2, D).astype(np.float32), rs.randn(24).astype(np.float32)
+    np.random.seed(1)
+    torch.manual_seed(2)
+    out = F.train_mfm_missing(Xtr, ytr, Xva, yva, Xte, yte, cfg, verbose=False, save_dir=str(tmp_path))
+    assert type(out["model"]).__name__ == "MFM_missing" and len(out["history"]) == 2
+    assert all(np.isfinite(v) for h in out["history"] for v in h[1:]) and len(out["recon"]) == 12
+    Pm = OrderedDict((k, v.detach().cpu()) for k, v in out["model"].state_dict().items())
+    Xt = torch.from_numpy(np.ascontiguousarray(np.swapaxes(Xte, 0, 1)))
+    ref = O.mfm_missing_forward(Xt, Pm, cfg, O.draw_mmd_noise(cfg, 24, 1))
+    for s in ("", "_nol", "_noa", "_nov"):
+        assert rel_l2(out["predictions" + s], ref["y_hat" + s].squeeze(1)) < TOL, s
+        assert np.isfinite(out["scores" + s]["mae"])
+    d_l = cfg[0]["input_dims"][0]
+    rec = float(torch.nn.functional.mse_loss(ref["x_l_hat_nol"], Xt[:, :, :d_l]))
+    assert abs(out["recon"]["x_l_hat_nol"] - rec) < TOL * rec

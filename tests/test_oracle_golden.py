@@ -154,3 +154,26 @@ def test_baselines_of_the_mosi_script():
     assert rel_l2(out.detach(), g["ef/out"]) < TOL
     for k, p in Pe.items():
         assert rel_l2(p.grad, g["ef/g/" + k]) < TOL, k
+
+
+def test_tiny_missing_full_step():
+    """MFM_missing (mfm_model.py:766-885) through train_mfm_missing's step (mfm_mosi.py:957-982), restated in
+    oracle.mfm_missing_forward / mfm_missing_losses, against the unmodified reference's class."""
+    from helpers import tiny_missing_case
+    g, configs, P, x, y, noise, T, n = tiny_missing_case()
+    P2 = O.init_params(configs, int(g["meta"][0]), variant="missing")
+    assert list(P2) == list(P) and len(P) == 126
+    for k in P:
+        assert torch.equal(P[k], P2[k]), k
+    newP, losses, G, out = O.train_step(P, x, y, configs, noise, {}, variant="missing")
+    for s in O.MISSING_PASSES:
+        for k in ("x_l_hat", "x_a_hat", "x_v_hat", "y_hat"):
+            assert rel_l2(out[k + s], g[k + s]) < TOL, k + s
+    for k in ("total", "disc", "gen", "mmd", "missing"):
+        assert abs(losses[k] - float(g["loss/" + k])) <= TOL * abs(float(g["loss/" + k])) + 1e-7, k
+    for k in P:
+        if "g/" + k in g:
+            assert rel_l2(G[k], g["g/" + k]) < TOL, k
+        else:
+            assert G[k] is None, k
+        assert rel_l2(newP[k], g["p1/" + k]) < TOL, k
