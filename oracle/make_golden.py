@@ -199,6 +199,60 @@ def missing(ref, outdir):
     np.savez_compressed(os.path.join(outdir, "tiny_missing_l1_out1.npz"), **blob)
 
 
+def toy_missing_models(ref, outdir):
+    """(1g) seq2seq and basic_missing (mfm_model.py:887-1017) with the losses of train_seq2seq / train_basic_missing
+    (mfm_mosi.py:819-823, :1153-1157): reconstruction MSEs (resp. three L1 label terms) + lda_mmd * MMD."""
+    configs = O.tiny_configs(output_dim=1)
+    c = configs[0]
+    d_l, d_a, d_v = c["input_dims"]
+    T, n = 4, 8
+    x, y = O.synthetic_batch(configs, T, n, 41, "l1")
+    x_l, x_a, x_v = x[:, :, :d_l], x[:, :, d_l:d_l + d_a], x[:, :, d_l + d_a:]
+    blob = dict(x=x.numpy(), y=y.numpy(), noise_seed=np.array([61, 62]))
+    l1, l2 = torch.nn.L1Loss(), torch.nn.MSELoss()
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-30))
+    for tag, cls, seed, nseed in (("s2s", ref.seq2seq, 901, 61), ("bm", ref.basic_missing, 902, 62)):
+        torch.manual_seed(seed)
+        m = cls(*configs).eval()
+        torch.manual_seed(nseed)
+        res = m.forward(x)
+        mmd = res[-1]
+        if tag == "s2s":
+            outs = dict(x_l_hat_nol=res[0][0], x_a_hat_noa=res[1][0], x_v_hat_nov=res[2][0])
+            loss = c["lda_xl"] * l2(res[0][0], x_l) + c["lda_xa"] * l2(res[1][0], x_a) + c["lda_xv"] * l2(res[2][0], x_v) \
+                + c["lda_mmd"] * mmd
+            sizes = (c["zv_size"], c["za_size"], c["zl_size"])
+        else:
+            outs = dict(y_hat_nol=res[0], y_hat_noa=res[1], y_hat_nov=res[2])
+            loss = l1(res[0].squeeze(1), y) + l1(res[1].squeeze(1), y) + l1(res[2].squeeze(1), y) + c["lda_mmd"] * mmd
+            sizes = (c["zy_size"],) * 3
+        loss.backward()
+        P = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+        torch.manual_seed(nseed)
+        noise = [torch.randn(n, k) for k in sizes]
+        o = (O.seq2seq_forward if tag == "s2s" else O.basic_missing_forward)(x, P, configs, noise)
+        if tag == "s2s":
+            lo = c["lda_xl"] * l2(o["x_l_hat_nol"], x_l) + c["lda_xa"] * l2(o["x_a_hat_noa"], x_a) \
+                + c["lda_xv"] * l2(o["x_v_hat_nov"], x_v) + c["lda_mmd"] * o["mmd"]
+        else:
+            lo = sum(l1(o[k].squeeze(1), y) for k in ("y_hat_nol", "y_hat_noa", "y_hat_nov")) + c["lda_mmd"] * o["mmd"]
+        lo.backward()
+        w = abs(float(lo) - float(loss)) / abs(float(loss))
+        for k, t in outs.items():
+            w = max(w, rel(o[k].detach(), t.detach()))
+            blob["%s/%s" % (tag, k)] = t.detach().numpy()
+        for k, p in m.named_parameters():
+            w = max(w, rel(P[k].grad, p.grad))
+            blob["%s/p/%s" % (tag, k)] = p.detach().numpy()
+            blob["%s/g/%s" % (tag, k)] = p.grad.numpy()
+        blob["%s/loss" % tag] = np.float64(float(loss))
+        blob["%s/mmd" % tag] = np.float64(float(mmd))
+        blob["%s/seed" % tag] = np.array([seed])
+        print("[%s] oracle vs live reference: worst rel err %.3g" % (cls.__name__, w))
+        assert w < 2e-5
+    np.savez_compressed(os.path.join(outdir, "tiny_toy_missing.npz"), **blob)
+
+
 def reference_baseline_classes():
     """EFLSTM and MFN of /root/reference/test_mosi.py (:130-157, :158-265).  That script cannot be imported (Python-2 prints,
     argparse and data loading at module level), so only its two class statements are executed -- read from the file at run time,
@@ -279,9 +333,13 @@ def main():
     if "--missing-only" in sys.argv:
         missing(ref, outdir)
         return
+    if "--toy-only" in sys.argv:
+        toy_missing_models(ref, outdir)
+        return
     ablations(ref, outdir)
     baselines(ref, outdir)
     missing(ref, outdir)
+    toy_missing_models(ref, outdir)
 
     # ---- (1) tiny awkward config, everything stored, L1 head and CE head -------------
     for head, od in (("l1", 1), ("ce", 3), ("l1", 4)):

@@ -602,6 +602,41 @@ def ablation_forward(x: Tensor, P, configs, noise: Sequence[Tensor], variant: st
     return out
 
 
+def seq2seq_forward(x: Tensor, P, configs, noise: Sequence[Tensor], train=False):
+    """seq2seq.forward, mfm_model.py:929-958: every modality reconstructed from the other two.  ``noise``: the Gaussian samples
+    of the three loss_MMD calls in the reference's order (zv_nov, za_noa, zl_nol; :942).  Dropout off (train=False) only."""
+    assert not train
+    config = configs[0]
+    d_l, d_a, d_v = config["input_dims"]
+    T = x.shape[0]
+    x_l, x_a, x_v = x[:, :, :d_l], x[:, :, d_l:d_l + d_a], x[:, :, d_l + d_a:]
+    zv_nov = encoder_lstm(torch.cat([x_l, x_a], 2), P, "encoder_la_to_v")
+    za_noa = encoder_lstm(torch.cat([x_l, x_v], 2), P, "encoder_lv_to_a")
+    zl_nol = encoder_lstm(torch.cat([x_a, x_v], 2), P, "encoder_av_to_l")
+    mmd = loss_mmd(zv_nov, noise[0]) + loss_mmd(za_noa, noise[1]) + loss_mmd(zl_nol, noise[2])
+    fl = factor_mlp(zl_nol, P, "zl_to_fl", 0.0, False)
+    fa = factor_mlp(za_noa, P, "za_to_fa", 0.0, False)
+    fv = factor_mlp(zv_nov, P, "zv_to_fv", 0.0, False)
+    return dict(x_l_hat_nol=decoder_lstm(fl, T, P, "decoder_l"), x_a_hat_noa=decoder_lstm(fa, T, P, "decoder_a"),
+                x_v_hat_nov=decoder_lstm(fv, T, P, "decoder_v"), mmd=mmd)
+
+
+def basic_missing_forward(x: Tensor, P, configs, noise: Sequence[Tensor], train=False):
+    """basic_missing.forward, mfm_model.py:998-1017: the label from two modalities.  ``noise`` in the order zy_nov, zy_noa,
+    zy_nol (:1011).  Dropout off only."""
+    assert not train
+    config = configs[0]
+    d_l, d_a, d_v = config["input_dims"]
+    x_l, x_a, x_v = x[:, :, :d_l], x[:, :, d_l:d_l + d_a], x[:, :, d_l + d_a:]
+    zy_nov = encoder_lstm(torch.cat([x_l, x_a], 2), P, "encoder_la_to_y")
+    zy_noa = encoder_lstm(torch.cat([x_l, x_v], 2), P, "encoder_lv_to_y")
+    zy_nol = encoder_lstm(torch.cat([x_a, x_v], 2), P, "encoder_av_to_y")
+    mmd = loss_mmd(zy_nov, noise[0]) + loss_mmd(zy_noa, noise[1]) + loss_mmd(zy_nol, noise[2])
+    head = lambda z, n: linear(torch.relu(linear(z, P, n + "_fc1")), P, n + "_fc2")
+    return dict(y_hat_nol=head(zy_nol, "zy_nol_to_y"), y_hat_noa=head(zy_noa, "zy_noa_to_y"),
+                y_hat_nov=head(zy_nov, "zy_nov_to_y"), mmd=mmd)
+
+
 MISSING_PASSES = ("", "_nol", "_noa", "_nov")
 
 

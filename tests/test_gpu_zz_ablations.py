@@ -332,3 +332,62 @@ def test_mfm_missing_train_mode_step_at_mosi_shapes_and_entry_point(tmp_path):
     d_l = cfg[0]["input_dims"][0]
     rec = float(torch.nn.functional.mse_loss(ref["x_l_hat_nol"], Xt[:, :, :d_l]))
     assert abs(out["recon"]["x_l_hat_nol"] - rec) < TOL * rec
+
+
+def test_seq2seq_basic_missing_and_module_level_functions():
+    """The rest of the reference's mfm_model surface (mfm_mosi.py:30 imports it all): seq2seq / basic_missing (mfm_model.py:887-1017)
+    against the fixture made from the reference's own classes -- outputs, loss, every gradient -- and compute_kernel / loss_MMD /
+    loss_KLD (:14-38) against the oracle."""
+    import mfm_model as shim
+    from helpers import load_golden
+    g = load_golden("tiny_toy_missing.npz")
+    configs = O.tiny_configs(output_dim=1)
+    c = configs[0]
+    d_l, d_a, d_v = c["input_dims"]
+    x, y = torch.from_numpy(g["x"].copy()).cuda(), torch.from_numpy(g["y"].copy()).cuda()
+    Fn = torch.nn.functional
+    for tag, cls, nseed in (("s2s", shim.seq2seq, 61), ("bm", shim.basic_missing, 62)):
+        torch.manual_seed(int(g[tag + "/seed"][0]))
+        m = cls(*configs).cuda().eval()
+        for k, v in m.state_dict().items():
+            assert torch.equal(v.cpu(), torch.from_numpy(g["%s/p/%s" % (tag, k)])), (tag, k)
+        torch.manual_seed(nseed)                                       # loss_MMD draws on the CPU generator, reference order
+        res = m.forward(x)
+        if tag == "s2s":
+            outs = dict(x_l_hat_nol=res[0][0], x_a_hat_noa=res[1][0], x_v_hat_nov=res[2][0])
+            loss = c["lda_xl"] * Fn.mse_loss(res[0][0], x[:, :, :d_l]) + c["lda_xa"] * Fn.mse_loss(res[1][0], x[:, :, d_l:d_l + d_a]) \
+                + c["lda_xv"] * Fn.mse_loss(res[2][0], x[:, :, d_l + d_a:]) + c["lda_mmd"] * res[3]
+        else:
+            outs = dict(y_hat_nol=res[0], y_hat_noa=res[1], y_hat_nov=res[2])
+            loss = sum(Fn.l1_loss(r.squeeze(1), y) for r in res[:3]) + c["lda_mmd"] * res[3]
+        loss.backward()
+        for k, t in outs.items():
+            assert rel_l2(t.detach(), g["%s/%s" % (tag, k)]) < TOL, (tag, k)
+        assert abs(float(res[-1].detach()) - float(g[tag + "/mmd"])) < TOL * abs(float(g[tag + "/mmd"]))
+        assert abs(float(loss.detach()) - float(g[tag + "/loss"])) < TOL * abs(float(g[tag + "/loss"]))
+        bad = {k: rel_l2(p.grad, g["%s/g/%s" % (tag, k)]) for k, p in m.named_parameters()
+               if not rel_l2(p.grad, g["%s/g/%s" % (tag, k)]) < TOL}
+        assert not bad, (tag, bad)
+    # module-level functions
+    gen = torch.Generator().manual_seed(3)
+    a, b = torch.randn(37, 11, generator=gen), torch.randn(29, 11, generator=gen)
+    assert rel_l2(shim.compute_kernel(a.cuda(), b.cuda()), O.compute_kernel(a, b)) < 1e-5
+    mu, lv = torch.randn(19, 7, generator=gen), 0.3 * torch.randn(19, 7, generator=gen)
+    mu_r, lv_r = mu.clone().requires_grad_(True), lv.clone().requires_grad_(True)
+    (2.5 * O.loss_kld(mu_r, lv_r)).backward()
+    mu_g, lv_g = mu.cuda().requires_grad_(True), lv.cuda().requires_grad_(True)
+    kl = shim.loss_KLD(mu_g, lv_g)
+    (2.5 * kl).backward()
+    assert abs(float(kl.detach()) - float(O.loss_kld(mu, lv))) < 1e-5 * abs(float(O.loss_kld(mu, lv)))
+    assert rel_l2(mu_g.grad, mu_r.grad) < 1e-5 and rel_l2(lv_g.grad, lv_r.grad) < 1e-5
+    z = torch.randn(33, 9, generator=gen)
+    torch.manual_seed(8)
+    noise = torch.randn(33, 9)
+    z_r = z.clone().requires_grad_(True)
+    (0.7 * O.loss_mmd(z_r, noise)).backward()
+    z_g = z.cuda().requires_grad_(True)
+    torch.manual_seed(8)
+    mm = shim.loss_MMD(z_g)
+    (0.7 * mm).backward()
+    assert abs(float(mm.detach()) - float(O.loss_mmd(z, noise))) < 1e-4 * abs(float(O.loss_mmd(z, noise)))
+    assert rel_l2(z_g.grad, z_r.grad) < 1e-4

@@ -177,3 +177,30 @@ def test_tiny_missing_full_step():
         else:
             assert G[k] is None, k
         assert rel_l2(newP[k], g["p1/" + k]) < TOL, k
+
+
+def test_seq2seq_and_basic_missing_restatements():
+    """seq2seq / basic_missing (mfm_model.py:887-1017) restated in the oracle, against outputs, loss and gradients of the
+    reference's own classes under the losses of train_seq2seq / train_basic_missing (make_golden.py section 1g)."""
+    g = load_golden("tiny_toy_missing.npz")
+    configs = O.tiny_configs(output_dim=1)
+    c = configs[0]
+    d_l, d_a, d_v = c["input_dims"]
+    x, y = torch.from_numpy(g["x"].copy()), torch.from_numpy(g["y"].copy())
+    n = x.shape[1]
+    Fn = torch.nn.functional
+    for tag, fwd, nseed, sizes in (("s2s", O.seq2seq_forward, 61, (c["zv_size"], c["za_size"], c["zl_size"])),
+                                   ("bm", O.basic_missing_forward, 62, (c["zy_size"],) * 3)):
+        P = {k[len(tag) + 3:]: torch.from_numpy(v.copy()).requires_grad_(True) for k, v in g.items() if k.startswith(tag + "/p/")}
+        torch.manual_seed(nseed)
+        noise = [torch.randn(n, k) for k in sizes]
+        o = fwd(x, P, configs, noise)
+        if tag == "s2s":
+            loss = c["lda_xl"] * Fn.mse_loss(o["x_l_hat_nol"], x[:, :, :d_l]) + c["lda_xa"] * Fn.mse_loss(o["x_a_hat_noa"], x[:, :, d_l:d_l + d_a]) \
+                + c["lda_xv"] * Fn.mse_loss(o["x_v_hat_nov"], x[:, :, d_l + d_a:]) + c["lda_mmd"] * o["mmd"]
+        else:
+            loss = sum(Fn.l1_loss(o[k].squeeze(1), y) for k in ("y_hat_nol", "y_hat_noa", "y_hat_nov")) + c["lda_mmd"] * o["mmd"]
+        loss.backward()
+        assert abs(float(loss) - float(g[tag + "/loss"])) < TOL * abs(float(g[tag + "/loss"]))
+        for k, p in P.items():
+            assert rel_l2(p.grad, g["%s/g/%s" % (tag, k)]) < TOL, (tag, k)
