@@ -633,11 +633,13 @@ class Engine:
     # -- backward ------------------------------------------------------------------
     def backward(self, P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], dXhat: Sequence[torch.Tensor],
                  dYhat: torch.Tensor, mmd_scale: float, mmd_scale_dev: Optional[torch.Tensor] = None,
-                 d_mfn_last: Optional[torch.Tensor] = None):
+                 d_mfn_last: Optional[torch.Tensor] = None, d_latents: Optional[Sequence[torch.Tensor]] = None):
         """Adjoint of ``forward``.  ``dXhat[m]`` [T*B,d_m] and ``dYhat`` [B,out] are
         d(loss)/d(output); d(loss)/d(mmd) = ``mmd_scale`` (host float) times the optional
         device scalar ``mmd_scale_dev``.  Parameter gradients are ACCUMULATED into ``G``
-        (same names as ``P``), which the caller zeroes."""
+        (same names as ``P``), which the caller zeroes.  ``d_latents`` (zl, za, zv, zy): gradients a caller formed on the
+        latents OUTSIDE the step (the MFM of mfm_mosi_acc.py returns them and its loop applies loss_MMD itself, :394, :441);
+        they take the place of the regulariser's own gradient."""
         dm, ops, buf, ws = self.dm, self.ops, self.buf, self.ws
         T, B, H, mem = dm.T, dm.B, dm.H, dm.mem
         TB = T * B
@@ -674,7 +676,9 @@ class Engine:
         for k in range(4):
             with self._aux(k):
                 ops.zero(dmmd[k])
-                if self.kl:                                       # d KLD / d mu and / d logvar, scaled by dLoss/dKLD
+                if d_latents is not None:
+                    ops.copy2d(d_latents[k], dmmd[k])
+                elif self.kl:                                     # d KLD / d mu and / d logvar, scaled by dLoss/dKLD
                     ops.kld_bwd(lat[k], ws["LV%d" % k] if k < 3 else ws["LVY"], mmd_scale, dmmd[k], dLV[k], mmd_scale_dev)
                 else:
                     rc, t12 = ws["mmd_rc%d" % k], ws["mmd_t12_%d" % k]

@@ -455,3 +455,26 @@ def test_rng_replay_helper_reads_the_variant_engines(variant):
     assert abs(float(eng.loss_buf[8]) - losses["total"]) < 1e-4 * abs(losses["total"])
     bad = [(k, rel_l2(G[k], Go[k])) for k in P if Go[k] is not None and rel_l2(G[k], Go[k]) > 3e-4]
     assert not bad, bad
+
+
+def test_engine_backward_with_external_latent_gradients():
+    """Engine.backward(d_latents=...): the MFM of mfm_mosi_acc.py returns its latents and the loop applies loss_MMD to them itself
+    (:394, :441).  Forward without the in-step MMD + the MMD gradient formed outside and handed in must reproduce the golden
+    step's gradients."""
+    g, configs, P, x, y, noise, T, n = tiny_case("l1", 1)
+    P = OrderedDict(P)
+    eng = Engine(configs, T, n, "cpu", EmuOps(), head="l1")
+    eng.want_mmd = False
+    out = eng.forward(P, x.contiguous(), [None] * 4)
+    assert float(eng.loss_buf[4:8].abs().sum()) == 0.0
+    dX, dY = eng.losses(y)
+    lda = configs[0]["lda_mmd"]
+    dlat = []
+    for k, key in enumerate(("zl", "za", "zv", "zy")):
+        z = out[key].clone().requires_grad_(True)
+        (lda * O.loss_mmd(z, noise[k])).backward()
+        dlat.append(z.grad)
+    G = OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    eng.backward(P, G, dX, dY, 0.0, d_latents=dlat)
+    bad = [(k, rel_l2(G[k], g["g/" + k])) for k in P if "g/" + k in g and rel_l2(G[k], g["g/" + k]) > 2e-4]
+    assert not bad, bad

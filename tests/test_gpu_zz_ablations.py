@@ -391,3 +391,44 @@ def test_seq2seq_basic_missing_and_module_level_functions():
     (0.7 * mm).backward()
     assert abs(float(mm.detach()) - float(O.loss_mmd(z, noise))) < 1e-4 * abs(float(O.loss_mmd(z, noise)))
     assert rel_l2(z_g.grad, z_r.grad) < 1e-4
+
+
+def test_mfm_of_the_classification_script_returns_differentiable_latents():
+    """mfm_mosi_acc.py carries its own MFM (:311-394): output_dim 2, forward returns (zl, za, zv, zy, x_l_hat, x_a_hat, x_v_hat,
+    y_hat), and ITS loop applies loss_MMD to the latents (:441) before the cross-entropy step (:446-448).  The drop-in class run
+    through that loop body against the oracle's CE train step: loss and every gradient."""
+    from factorized_b200 import mfm_acc
+    from factorized_b200.functional import loss_MMD
+    configs = O.tiny_configs(output_dim=2)
+    c = configs[0]
+    d_l, d_a, d_v = c["input_dims"]
+    T, n = 5, 9
+    x, y = O.synthetic_batch(configs, T, n, 8, "ce")
+    cfg_in = [dict(v) for v in configs]
+    cfg_in[0]["output_dim"] = 7                                      # ignored: the script hard-codes 2
+    torch.manual_seed(77)
+    model = mfm_acc.MFM(*cfg_in).cuda().eval()
+    P = O.init_params(configs, 77)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), P[k]), k
+    xd, yd = x.cuda(), y.cuda()
+    torch.manual_seed(5)
+    zl, za, zv, zy, x_l_hat, x_a_hat, x_v_hat, y_hat = model.forward(xd)
+    assert y_hat.shape == (n, 2)
+    Fn = torch.nn.functional
+    mmd = c["lda_mmd"] * (loss_MMD(zl) + loss_MMD(za) + loss_MMD(zv) + loss_MMD(zy))
+    gen = c["lda_xl"] * Fn.mse_loss(x_l_hat, xd[:, :, :d_l]) + c["lda_xa"] * Fn.mse_loss(x_a_hat, xd[:, :, d_l:d_l + d_a]) \
+        + c["lda_xv"] * Fn.mse_loss(x_v_hat, xd[:, :, d_l + d_a:])
+    loss = Fn.cross_entropy(y_hat, yd.long()) + gen + mmd
+    loss.backward()
+    noise = O.draw_mmd_noise(configs, n, 5)
+    _, losses, Go, outo = O.train_step(P, x, y, configs, noise, {}, head="ce")
+    assert abs(float(loss.detach()) - losses["total"]) < TOL * abs(losses["total"])
+    assert rel_l2(zy.detach(), outo["zy"]) < TOL and rel_l2(y_hat.detach(), outo["y_hat"]) < TOL
+    bad = {}
+    for k, p in model.named_parameters():
+        if Go[k] is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+        elif not rel_l2(p.grad, Go[k]) < TOL:
+            bad[k] = rel_l2(p.grad, Go[k])
+    assert not bad, bad
