@@ -432,3 +432,38 @@ def test_mfm_of_the_classification_script_returns_differentiable_latents():
         elif not rel_l2(p.grad, Go[k]) < TOL:
             bad[k] = rel_l2(p.grad, Go[k])
     assert not bad, bad
+
+
+def test_input_staging_feeds_every_step_its_own_batch():
+    """SURVEY section 8 f2, the input staging of MFMTrainer.step: host batches travel on a copy stream into one of two device
+    staging buffers while the previous step computes (the reference does a blocking pageable copy per step, mfm_mosi.py:428-429).
+    Six distinct batches are queued back to back without a synchronisation -- pinned, then one pageable -- and every step's
+    losses must equal those of an identically seeded trainer fed from device tensors."""
+    import factorized_b200 as F
+    from factorized_b200.train import MFMTrainer
+    configs = O.tiny_configs()
+    T, n, steps = 5, 16, 6
+    gen = torch.Generator().manual_seed(9)
+    D = sum(configs[0]["input_dims"])
+    xs = [(1.0 + 0.5 * i) * torch.randn(T, n, D, generator=gen) for i in range(steps)]
+    ys = [torch.randn(n, generator=gen) + i for i in range(steps)]
+    trainers = []
+    for _ in range(2):
+        torch.manual_seed(31)
+        trainers.append(MFMTrainer(F.MFM(*configs).cuda(), T, n, head="l1", use_graph=True, seed=5))
+    host, dev = trainers
+    xp = [x.clone().pin_memory() if i < steps - 1 else x.clone() for i, x in enumerate(xs)]     # the last one pageable
+    yp = [y.clone().pin_memory() if i < steps - 1 else y.clone() for i, y in enumerate(ys)]
+    got = [host.step(xp[i], yp[i]).clone() for i in range(steps)]          # no sync in between: the double buffer is live
+    torch.cuda.synchronize()
+    want = []
+    for i in range(steps):
+        want.append(dev.step(xs[i].cuda(), ys[i].cuda()).clone())
+        torch.cuda.synchronize()
+    for i in range(steps):
+        for slot in (0, 1, 2, 3, 8):
+            a, b = float(got[i][slot]), float(want[i][slot])
+            assert abs(a - b) <= 1e-4 * abs(b), (i, slot, a, b)
+    assert len({round(float(w[8]), 3) for w in want}) == steps             # the batches are distinguishable by their loss
+    sh, sd = host.model.state_dict(), dev.model.state_dict()
+    assert max(rel_l2(sh[k], sd[k]) for k in sh) < 1e-4
