@@ -76,3 +76,63 @@ def test_two_rank_gloo_matches_shard_averaged_oracle():
     assert len(ret) == world + 1 and ret["solo"] == ret["solo"]       # the single-rank step finished (and is not NaN)
     for r in range(world):
         assert ret[r] < 2e-3, dict(ret)
+
+
+def _variant_worker(rank, world, port, ret, variant):
+    """Same check for a model variant's trainer (ablation / MFM_missing engines behind the same flat-buffer all-reduce)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from oracle import mfm_oracle as O
+    from factorized_b200.ablations import ABLATION_MODELS
+    from factorized_b200.missing import MFM_missing
+    from factorized_b200.train import MFMTrainer
+    from emu_ops import EmuOps
+    configs = O.tiny_configs()
+    T, n_global = 4, 8
+    n = n_global // world
+    x, y = O.synthetic_batch(configs, T, n_global, 6)
+    xs, ys = x[:, rank * n:(rank + 1) * n].contiguous(), y[rank * n:(rank + 1) * n].contiguous()
+    torch.manual_seed(43)
+    model = (MFM_missing if variant == "missing" else ABLATION_MODELS[variant])(*configs)
+    tr = MFMTrainer(model, T, n, head="l1", _test_ops=EmuOps())
+    ov = "missing" if variant == "missing" else variant
+    draw = lambda r: O.draw_mmd_noise(configs, n, 200 + r, variant=ov)
+    noise = draw(rank)
+    tr.ops.randn = lambda *a, **k: None
+    for k in range(4):
+        if noise[k] is not None:
+            tr.noise[k].copy_(noise[k])
+    tr.step(xs, ys)
+    got = OrderedDict((k, v.detach().clone()) for k, v in model.state_dict().items())
+    P = O.init_params(configs, 43, variant=ov)
+    Gs = []
+    for r in range(world):
+        xr, yr = x[:, r * n:(r + 1) * n].contiguous(), y[r * n:(r + 1) * n].contiguous()
+        _, _, G, _ = O.train_step(P, xr, yr, configs, draw(r), {}, variant=ov)
+        Gs.append(G)
+    Gavg = OrderedDict((k, None if Gs[0][k] is None else sum(g[k] for g in Gs) / world) for k in P)
+    ref = O.adam_step(OrderedDict((k, v.clone()) for k, v in P.items()), Gavg, {})
+    worst = 0.0
+    for k in P:
+        if Gavg[k] is None:
+            continue
+        d_ref, d_got = ref[k] - P[k], got[k] - P[k]
+        worst = max(worst, float((d_got - d_ref).norm() / (d_ref.norm() + 1e-30)))
+    ret[rank] = worst
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("variant", ["m_a", "missing"])
+def test_two_rank_gloo_variant_trainers(variant):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000) + (7 if variant == "missing" else 0)
+    mp.spawn(_variant_worker, args=(world, port, ret, variant), nprocs=world, join=True)
+    for r in range(world):
+        assert ret[r] < 2e-3, dict(ret)
