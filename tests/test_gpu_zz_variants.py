@@ -1,6 +1,9 @@
-"""The ablation models M_A .. M_D (mfm_model.py:201-467; train_mfm_ablation, mfm_mosi.py:640-767) on the GPU through the C ABI:
-golden vectors of the unmodified reference classes, train-mode steps at MOSI shapes against the oracle with the masks replayed,
-and the train_mfm_ablation entry point.  Tolerance 1e-3 relative, fp32 (BASELINE.json north_star)."""
+"""Everything either side of the MFM step, on the GPU through the C ABI (this file sorts last: the hot path's own parity tests
+run first).  The ablation models M_A .. M_D (mfm_model.py:201-467; train_mfm_ablation, mfm_mosi.py:640-767), MFM_missing (:766-885;
+train_mfm_missing), train_mfm_test_zeros, the MOSI script's baselines (test_mosi.py:130-265), seq2seq / basic_missing and the
+module-level functions, the classification script's own MFM (mfm_mosi_acc.py:311-394) and the trainer's input staging: golden
+vectors of the unmodified reference classes, train-mode steps at MOSI shapes against the oracle with the masks replayed, and the
+entry points.  Tolerance 1e-3 relative, fp32 (BASELINE.json north_star)."""
 from collections import OrderedDict
 
 import numpy as np
