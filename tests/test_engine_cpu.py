@@ -478,3 +478,47 @@ def test_engine_backward_with_external_latent_gradients():
     eng.backward(P, G, dX, dY, 0.0, d_latents=dlat)
     bad = [(k, rel_l2(G[k], g["g/" + k])) for k in P if "g/" + k in g and rel_l2(G[k], g["g/" + k]) > 2e-4]
     assert not bad, bad
+
+
+def _random_configs(seed):
+    """Small configurations drawn from the shape of the reference's search space (mfm_mosi.py:1304-1351): unequal modality
+    widths, cell sizes, latent / factor sizes, memory and hidden-layer widths; every dropout on."""
+    import random
+    r = random.Random(seed)
+    pick = lambda lo, hi: r.randint(lo, hi)
+    config = dict(input_dims=[pick(5, 9), pick(2, 4), pick(3, 6)], h_dims=[pick(3, 7), pick(2, 5), pick(2, 6)],
+                  zy_size=pick(2, 6), zl_size=pick(2, 7), za_size=pick(2, 4), zv_size=pick(3, 8),
+                  fy_size=pick(2, 5), fl_size=pick(2, 6), fa_size=pick(2, 4), fv_size=pick(2, 5), memsize=pick(3, 9),
+                  zy_to_fy_dropout=0.3, zl_to_fl_dropout=0.2, za_to_fa_dropout=0.4, zv_to_fv_dropout=0.1, fy_to_y_dropout=0.25,
+                  lda_mmd=r.choice([0.5, 1.0, 2.0]), lda_xl=r.choice([0.1, 1.0]), lda_xa=r.choice([0.01, 0.5]), lda_xv=r.choice([0.5, 2.0]),
+                  missing=0, windowsize=2, batchsize=4, num_epochs=1, lr=0.01, momentum=0.9, output_dim=1, type="mfm")
+    nn_ = lambda: dict(shapes=pick(4, 12), drop=r.choice([0.2, 0.5]))
+    return [config, nn_(), nn_(), nn_(), nn_(), nn_()], pick(2, 5), pick(3, 9)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("variant", ["mfm", "kl", "kl_ef", "m_a", "m_b", "m_c", "m_d", "missing"])
+def test_every_schedule_on_random_configurations(variant, seed):
+    """All eight schedules (MFM, MFM_KL, MFM_KL_EF, M_A..M_D, MFM_missing) on randomly drawn small configurations, train mode with
+    every dropout on: losses and all gradients against the oracle's autograd with the masks and ReLU branches replayed."""
+    from oracle.rng_replay import train_masks_and_branches
+    from factorized_b200.ablations import make_engine
+    configs, T, n = _random_configs(100 * seed + len(variant))
+    configs[0]["type"] = variant
+    P = OrderedDict(O.init_params(configs, seed, variant=variant))
+    x, y = O.synthetic_batch(configs, T, n, seed + 10)
+    noise = O.draw_mmd_noise(configs, n, seed + 20, variant=variant if variant.startswith("m_") else "mfm")
+    rng = torch.tensor([77 + seed, 2], dtype=torch.int64)
+    eng = make_engine(configs, T, n, "cpu", EmuOps(), head="l1", variant=variant)
+    eng.forward(P, x.contiguous(), [torch.zeros(1, 1) if v is None else v for v in noise], train=True, rng=rng)
+    dX, dY = eng.losses(y)
+    G = OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    eng.backward(P, G, dX, dY, eng.dm.lda_mmd)
+    masks, br = train_masks_and_branches(eng, rng)
+    del O.RELU_REPLAY_VIOLATIONS[:]
+    _, losses, Go, _ = O.train_step(P, x, y, configs, noise, {}, head="l1", train=True, masks=masks, branches=br, variant=variant)
+    assert not O.RELU_REPLAY_VIOLATIONS
+    assert abs(float(eng.loss_buf[8]) - losses["total"]) < 1e-4 * abs(losses["total"]), (float(eng.loss_buf[8]), losses["total"])
+    bad = [(k, rel_l2(G[k], Go[k])) for k in P if Go[k] is not None and float(Go[k].abs().max()) > 0 and rel_l2(G[k], Go[k]) > 5e-4]
+    assert not bad, bad
+    assert all(float(G[k].abs().max()) == 0.0 for k in P if Go[k] is None)
