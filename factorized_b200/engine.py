@@ -19,7 +19,7 @@ state histories have T+1 blocks with block 0 the zero initial state.
 from __future__ import annotations
 
 import os
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional, Sequence
 
 import torch
 

@@ -14,7 +14,7 @@ reference, which hard-codes ``.cuda()`` -- and no fallback.
 from __future__ import annotations
 
 from collections import OrderedDict
-from typing import Dict, List
+from typing import Dict
 
 import torch
 import torch.nn as nn

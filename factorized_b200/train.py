@@ -15,7 +15,6 @@ validation L1, save-best / reload, score) -- mfm_mosi.py:386-503.
 """
 from __future__ import annotations
 
-import math
 import os
 import random
 import tempfile
@@ -25,7 +24,6 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from . import engine as E
 from .mfm_model import MFM, MFM_KL, UNUSED, _ops
 
 SITE_NOISE = 20   # RNG sites 20..23: the four MMD Gaussian samples
