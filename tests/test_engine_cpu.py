@@ -522,3 +522,25 @@ def test_every_schedule_on_random_configurations(variant, seed):
     bad = [(k, rel_l2(G[k], Go[k])) for k in P if Go[k] is not None and float(Go[k].abs().max()) > 0 and rel_l2(G[k], Go[k]) > 5e-4]
     assert not bad, bad
     assert all(float(G[k].abs().max()) == 0.0 for k in P if Go[k] is None)
+
+
+@pytest.mark.parametrize("T,n", [(1, 3), (3, 1), (1, 1)])
+@pytest.mark.parametrize("variant", ["mfm", "missing", "m_c"])
+def test_degenerate_sequence_length_and_batch(variant, T, n):
+    """One time step (no c_{t-1} block from a previous step, no second half of the attention gradient) and a batch of one row
+    (the MMD of a single sample): the schedules against the oracle's autograd."""
+    from factorized_b200.ablations import make_engine
+    configs = O.tiny_configs()
+    configs[0]["type"] = variant
+    P = OrderedDict(O.init_params(configs, 9, variant=variant))
+    x, y = O.synthetic_batch(configs, T, n, 12)
+    noise = O.draw_mmd_noise(configs, n, 13, variant=variant if variant.startswith("m_") else "mfm")
+    eng = make_engine(configs, T, n, "cpu", EmuOps(), head="l1", variant=variant)
+    eng.forward(P, x.contiguous(), [torch.zeros(1, 1) if v is None else v for v in noise])
+    dX, dY = eng.losses(y)
+    G = OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    eng.backward(P, G, dX, dY, eng.dm.lda_mmd)
+    _, losses, Go, _ = O.train_step(P, x, y, configs, noise, {}, head="l1", variant=variant)
+    assert abs(float(eng.loss_buf[8]) - losses["total"]) < 1e-4 * abs(losses["total"])
+    bad = [(k, rel_l2(G[k], Go[k])) for k in P if Go[k] is not None and float(Go[k].abs().max()) > 1e-12 and rel_l2(G[k], Go[k]) > 5e-4]
+    assert not bad, bad
