@@ -88,3 +88,27 @@ def test_score_block():
     if "confusion_matrix" in s:
         assert s["confusion_matrix"] == [[2, 1], [0, 3]] and 0.0 <= s["mult_f_score"] <= 1.0
     assert score(np.array([[0.1, 0.9], [0.8, 0.2]]), np.array([1, 1]), head="ce") == {"acc": 0.5}
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(lib, tmp_path):
+    """The drop-in boundary is a C ABI: include/mfm_b200.h must compile as C99 (no C++, no torch types) and a C program must
+    link against the library and call it.  ``mfm_version`` and an argument-check error path only: no GPU work."""
+    import shutil
+    import subprocess
+    from factorized_b200 import cuda_ops
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "mfm_b200.h"\n'
+                   'int main(void) {\n'
+                   '  int rc = mfm_zero(0, 0, (void*)0);           /* bad argument: must return an error code, not crash */\n'
+                   '  printf("%d %d\\n", mfm_version(), rc);\n  return 0;\n}\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)], check=True)
+    libdir = os.path.dirname(cuda_ops.LIB_PATH)
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-lmfm_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    env = dict(os.environ)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True, env=env).stdout.split()
+    assert out[0] == "100" and int(out[1]) != 0
