@@ -237,8 +237,15 @@ def score(predictions, y_test, head: str = "l1"):
             scores["classification_report"] = classification_report(true_label, predicted_label, digits=5, zero_division=0)
         except ImportError:
             pass
-    elif head == "ce":
-        scores["acc"] = float(np.mean(np.argmax(y_hat, 1) == y_test))
+    elif head == "ce":                                   # mfm_moud.py:421-428 / mfm_you.py:399-406: argmax, confusion matrix, report
+        predicted_label = np.argmax(y_hat, axis=1)
+        scores["acc"] = float(np.mean(predicted_label == y_test))
+        try:
+            from sklearn.metrics import classification_report, confusion_matrix
+            scores["confusion_matrix"] = confusion_matrix(y_test, predicted_label).tolist()
+            scores["classification_report"] = classification_report(y_test, predicted_label, digits=5, zero_division=0)
+        except ImportError:
+            pass
     return scores
 
 

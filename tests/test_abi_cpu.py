@@ -87,7 +87,10 @@ def test_score_block():
     assert abs(s["binary_acc"] - 5.0 / 6.0) < 1e-12
     if "confusion_matrix" in s:
         assert s["confusion_matrix"] == [[2, 1], [0, 3]] and 0.0 <= s["mult_f_score"] <= 1.0
-    assert score(np.array([[0.1, 0.9], [0.8, 0.2]]), np.array([1, 1]), head="ce") == {"acc": 0.5}
+    c = score(np.array([[0.1, 0.9], [0.8, 0.2], [0.3, 0.7]]), np.array([1, 1, 0]), head="ce")      # mfm_moud.py:421-428
+    assert abs(c["acc"] - 1.0 / 3.0) < 1e-12
+    if "confusion_matrix" in c:
+        assert c["confusion_matrix"] == [[0, 1], [1, 1]] and "accuracy" in c["classification_report"]
 
 
 def test_header_is_plain_c_and_links_from_a_c_program(lib, tmp_path):
