@@ -204,3 +204,52 @@ def test_seq2seq_and_basic_missing_restatements():
         assert abs(float(loss) - float(g[tag + "/loss"])) < TOL * abs(float(g[tag + "/loss"]))
         for k, p in P.items():
             assert rel_l2(p.grad, g["%s/g/%s" % (tag, k)]) < TOL, (tag, k)
+
+
+def test_oracle_ops_match_their_published_definitions():
+    """The torch ops the oracle is built from against oracle/numpy_restatement.py (documented LSTMCell gate order i,f,g,o; mean
+    reductions; Adam with eps outside the bias-corrected root; the reference's own MMD with its [n,m,dim] tensor), in float64."""
+    from oracle import numpy_restatement as N
+    rs = np.random.RandomState(0)
+    T, n, d, h = 4, 5, 7, 3
+    P = {"e.lstm.weight_ih": rs.randn(4 * h, d), "e.lstm.weight_hh": rs.randn(4 * h, h), "e.lstm.bias_ih": rs.randn(4 * h),
+         "e.lstm.bias_hh": rs.randn(4 * h), "e.fc1.weight": rs.randn(h, h), "e.fc1.bias": rs.randn(h)}
+    Pt = {k: torch.from_numpy(v) for k, v in P.items()}
+    x = rs.randn(T, n, d)
+    hh, cc = rs.randn(n, h), rs.randn(n, h)
+    h2, c2 = O.lstm_cell(torch.from_numpy(x[0]), torch.from_numpy(hh), torch.from_numpy(cc), Pt, "e.lstm")
+    h2n, c2n = N.lstm_cell(x[0], hh, cc, P["e.lstm.weight_ih"], P["e.lstm.weight_hh"], P["e.lstm.bias_ih"], P["e.lstm.bias_hh"])
+    assert np.allclose(h2.numpy(), h2n, atol=1e-12) and np.allclose(c2.numpy(), c2n, atol=1e-12)
+    # the same through torch's own nn.LSTMCell (what the reference calls)
+    cell = torch.nn.LSTMCell(d, h).double()
+    with torch.no_grad():
+        for leaf in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+            getattr(cell, leaf).copy_(Pt["e.lstm." + leaf])
+        h3, c3 = cell(torch.from_numpy(x[0]), (torch.from_numpy(hh), torch.from_numpy(cc)))
+    assert np.allclose(h3.numpy(), h2n, atol=1e-12) and np.allclose(c3.numpy(), c2n, atol=1e-12)
+    z = O.encoder_lstm(torch.from_numpy(x), Pt, "e")
+    zn = N.encoder_lstm(x, *(P["e." + k] for k in ("lstm.weight_ih", "lstm.weight_hh", "lstm.bias_ih", "lstm.bias_hh", "fc1.weight", "fc1.bias")))
+    assert np.allclose(z.numpy(), zn, atol=1e-12)
+    a, b = rs.randn(6, 4), rs.randn(6, 4)
+    Fn = torch.nn.functional
+    assert abs(float(torch.nn.MSELoss()(torch.from_numpy(a), torch.from_numpy(b))) - N.mse_loss(a, b)) < 1e-14
+    assert abs(float(torch.nn.L1Loss()(torch.from_numpy(a), torch.from_numpy(b))) - N.l1_loss(a, b)) < 1e-14
+    lab = rs.randint(0, 4, 6)
+    assert abs(float(torch.nn.CrossEntropyLoss()(torch.from_numpy(a), torch.from_numpy(lab))) - N.cross_entropy(a, lab)) < 1e-13
+    assert np.allclose(Fn.softmax(torch.from_numpy(a), dim=1).numpy(), N.softmax_rows(a), atol=1e-14)
+    zz, gg = rs.randn(9, 5), rs.randn(9, 5)
+    assert abs(float(O.loss_mmd(torch.from_numpy(zz), torch.from_numpy(gg))) - N.loss_mmd(zz, gg)) < 1e-13
+    assert np.allclose(O.compute_kernel(torch.from_numpy(zz), torch.from_numpy(gg)).numpy(), N.compute_kernel(zz, gg), atol=1e-14)
+    # Adam: three steps of torch.optim.Adam, of the oracle's adam_step and of the published update
+    p0 = rs.randn(5, 3)
+    grads = [rs.randn(5, 3) * (10.0 ** -k) for k in range(3)]
+    tp = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = torch.optim.Adam([tp])
+    Po, st = {"w": torch.from_numpy(p0.copy())}, {}
+    pn, mn, vn = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+    for t, g_ in enumerate(grads, 1):
+        tp.grad = torch.from_numpy(g_.copy())
+        opt.step()
+        Po = O.adam_step(Po, {"w": torch.from_numpy(g_.copy())}, st)
+        pn, mn, vn = N.adam_step(pn, g_, mn, vn, t)
+        assert np.allclose(tp.detach().numpy(), pn, atol=1e-14) and np.allclose(Po["w"].numpy(), pn, atol=1e-14)
